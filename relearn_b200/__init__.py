@@ -1,0 +1,13 @@
+"""relearn_b200 -- B200-native rollout/update hot path of edlanglois/relearn.
+
+Host-side mirror of the reference's interfaces for that path over a C-ABI CUDA library
+(`include/relearn_b200.h`, built in-tree by `__graft_entry__.build()`).  No CPU fallback exists.
+"""
+from . import _lib  # noqa: F401
+from .envs import (BatchedEnv, CartPole, CartPoleConfig, Chain, MemoryGame, MetaEnv, Successor,  # noqa: F401
+                   TrialEpisodeLimit, UniformBernoulliBandits, VisibleStepLimit, build_env)
+from .modules import Mlp, MlpConfig, init_params  # noqa: F401
+from .runtime import Context, DeviceBuffer  # noqa: F401
+from .simulation import ActorSpec, HistoryDataBound, Trajectory, rollout  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,87 @@
+// common.cuh -- context, error plumbing and launch accounting shared by every translation unit.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/relearn_b200.h"
+
+struct rl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int sm_count = 148;
+    int cc_major = 0, cc_minor = 0;
+    size_t total_mem = 0;
+    uint64_t launches = 0;
+    std::string last_error;
+    // NCCL data-parallel group (nccl.cu)
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    // scratch for small reductions (lazily grown)
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // pinned host scratch for scalar read-backs
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+std::string &rl_tls_error();
+
+inline rl_status rl_fail(rl_ctx *ctx, rl_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->last_error = buf;
+    rl_tls_error() = buf;
+    return st;
+}
+
+#define RL_CUDA(ctx, expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return rl_fail((ctx), _e == cudaErrorMemoryAllocation ? RL_ERR_OOM : RL_ERR_CUDA,       \
+                           "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define RL_REQUIRE(ctx, cond, msg)                                                                  \
+    do {                                                                                            \
+        if (!(cond)) return rl_fail((ctx), RL_ERR_INVALID_ARG, "%s (%s:%d)", msg, __FILE__, __LINE__); \
+    } while (0)
+
+#define RL_TRY(expr)                                                                                \
+    do {                                                                                            \
+        rl_status _s = (expr);                                                                      \
+        if (_s != RL_OK) return _s;                                                                 \
+    } while (0)
+
+// Every kernel launch goes through this so that rl_ctx_launch_count() is the library's own count.
+#define RL_LAUNCH(ctx, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                            \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                            \
+        (ctx)->launches += 1;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess)                                                                      \
+            return rl_fail((ctx), RL_ERR_CUDA, "launch of %s failed: %s (%s:%d)", #kernel,          \
+                           cudaGetErrorString(_e), __FILE__, __LINE__);                             \
+    } while (0)
+
+void rl_nccl_teardown(rl_ctx *ctx);
+rl_status rl_allreduce_f64_inplace(rl_ctx *ctx, double *buf_dev, size_t n);
+rl_status rl_ctx_scratch(rl_ctx *ctx, size_t bytes, void **out);
+rl_status rl_ctx_pinned(rl_ctx *ctx, size_t bytes, void **out);
+
+inline unsigned rl_div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Grid for an elementwise pass over n items with `block` threads: enough CTAs to cover n, which the
+// hardware schedules in waves of sm_count * resident CTAs.
+inline unsigned rl_grid_for(uint64_t n, unsigned block) { return rl_div_up(n ? n : 1, block); }

@@ -1,0 +1,90 @@
+// handles.cuh -- definitions of the opaque C-ABI handles, shared between translation units.
+#pragma once
+
+#include "common.cuh"
+#include "envs.cuh"
+
+struct rl_env {
+    rl_ctx *ctx = nullptr;
+    rl_env_kind kind = RL_ENV_CARTPOLE;
+    uint64_t E = 0, lane_offset = 0;
+    CartPoleEnv::Params cartpole{};
+    ChainEnv::Params chain{};
+    MemoryEnv::Params memory{};
+    BanditMetaEnv::Params bandit{};
+    rl_env_structure structure{};
+    EnvStatePtrs state{};
+    NoiseSource noise{};
+    // outputs of the unfused step
+    float *obs = nullptr, *reward = nullptr, *next_obs = nullptr;
+    uint8_t *succ = nullptr;
+};
+
+struct rl_mlp {
+    rl_ctx *ctx = nullptr;
+    int in_dim = 0, hidden = 0, out_dim = 0;
+    rl_activation act = RL_ACT_RELU;
+    uint64_t n_params = 0;
+    float *params = nullptr;  // device, flat in Module::variables() order
+    __host__ __device__ static uint64_t count(int in, int hidden, int out) {
+        return (uint64_t)hidden * in + hidden + (uint64_t)out * hidden + out;
+    }
+};
+
+struct rl_adam {
+    rl_mlp *mlp = nullptr;
+    rl_adam_cfg cfg{};
+    float *m = nullptr, *v = nullptr;  // device, n_params each
+    uint64_t step = 0;
+};
+
+struct rl_traj {
+    rl_ctx *ctx = nullptr;
+    rl_env *env = nullptr;
+    uint64_t E = 0, T = 0, F = 0;
+    float *obs = nullptr, *reward = nullptr, *next_obs = nullptr;
+    uint8_t *action = nullptr, *succ = nullptr;
+    uint32_t *lane_len = nullptr;
+    uint64_t num_steps = 0;     // valid steps (host copy, refreshed by rollout / load)
+    uint64_t num_episodes = 0;
+    uint64_t used_T = 0;        // number of time slots in use (<= T)
+    double *counts_dev = nullptr;  // device: [0] = num_steps, [1] = num_episodes (f64 for all-reduce)
+};
+
+struct rl_tabq {
+    rl_ctx *ctx = nullptr;
+    uint64_t R = 0;
+    int S = 0, A = 0;
+    double discount = 1.0;
+    double *q = nullptr;        // f64 [R][S][A]
+    unsigned long long *counts = nullptr;  // u64 [R][S][A]
+};
+
+// Mlp weights passed by value into kernels
+struct MlpView {
+    const float *params;
+    int in_dim, hidden, out_dim, act;
+    __device__ const float *w1() const { return params; }
+    __device__ const float *b1() const { return params + (size_t)hidden * in_dim; }
+    __device__ const float *w2() const { return b1() + hidden; }
+    __device__ const float *b2() const { return w2() + (size_t)out_dim * hidden; }
+};
+
+inline MlpView rl_mlp_view(const rl_mlp *m) {
+    MlpView v;
+    v.params = m ? m->params : nullptr;
+    v.in_dim = m ? m->in_dim : 0;
+    v.hidden = m ? m->hidden : 0;
+    v.out_dim = m ? m->out_dim : 0;
+    v.act = m ? (int)m->act : 0;
+    return v;
+}
+
+__device__ __forceinline__ float rl_activate(int act, float v) {
+    switch (act) {
+    case RL_ACT_RELU: return v < 0.0f ? 0.0f : v;  // NaN propagates like torch.relu
+    case RL_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
+    case RL_ACT_TANH: return tanhf(v);
+    default: return v;
+    }
+}

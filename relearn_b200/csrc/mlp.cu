@@ -1,0 +1,120 @@
+// mlp.cu -- Mlp module handle (src/torch/modules/ff/mlp.rs) and a plain batched forward.
+// The hot loops do not call this kernel: the rollout fuses the policy forward into the step kernel
+// (rollout.cu) and the updates fuse forward/backward into their own passes (update.cu).  This is the
+// Module::forward entry point used for evaluation and parity checks.
+#include "handles.cuh"
+
+namespace {
+
+// One thread per sample; weights staged in shared memory and read as warp-wide broadcasts.
+template <int FT, int OT>
+__global__ void __launch_bounds__(256) mlp_forward_kernel(MlpView m, const float *__restrict__ x, uint64_t n,
+                                                         float *__restrict__ out) {
+    extern __shared__ float sw[];
+    const uint64_t np = rl_mlp::count(m.in_dim, m.hidden, m.out_dim);
+    for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
+    __syncthreads();
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const int F = m.in_dim, H = m.hidden, O = m.out_dim;
+    const float *w1 = sw, *b1 = w1 + (size_t)H * F, *w2 = b1 + H, *b2 = w2 + (size_t)O * H;
+    float xi[FT], z[OT];
+#pragma unroll
+    for (int f = 0; f < FT; ++f) xi[f] = f < F ? x[(uint64_t)f * n + s] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < OT; ++k) z[k] = k < O ? b2[k] : 0.0f;
+    for (int j = 0; j < H; ++j) {
+        float acc = b1[j];
+#pragma unroll
+        for (int f = 0; f < FT; ++f)
+            if (f < F) acc = fmaf(w1[j * F + f], xi[f], acc);
+        const float h = rl_activate(m.act, acc);
+#pragma unroll
+        for (int k = 0; k < OT; ++k)
+            if (k < O) z[k] = fmaf(w2[k * H + j], h, z[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < OT; ++k)
+        if (k < O) out[(uint64_t)k * n + s] = z[k];
+}
+
+}  // namespace
+
+extern "C" {
+
+rl_status rl_mlp_create(rl_ctx *ctx, int32_t in_dim, const int32_t *hidden_sizes, int32_t n_hidden, int32_t out_dim,
+                        rl_activation activation, rl_mlp **out) {
+    RL_REQUIRE(ctx, ctx && out && hidden_sizes, "rl_mlp_create: NULL argument");
+    if (n_hidden != 1)
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED,
+                       "rl_mlp_create: only one hidden layer is implemented (MlpConfig default hidden_sizes=[128])");
+    RL_REQUIRE(ctx, in_dim >= 1 && in_dim <= 36 && out_dim >= 1 && out_dim <= 32, "rl_mlp_create: dims out of range");
+    RL_REQUIRE(ctx, hidden_sizes[0] >= 1 && hidden_sizes[0] <= 1024, "rl_mlp_create: hidden size out of range");
+    RL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rl_mlp *m = new (std::nothrow) rl_mlp();
+    if (!m) return rl_fail(ctx, RL_ERR_OOM, "rl_mlp_create: host allocation failed");
+    m->ctx = ctx;
+    m->in_dim = in_dim;
+    m->hidden = hidden_sizes[0];
+    m->out_dim = out_dim;
+    m->act = activation;
+    m->n_params = rl_mlp::count(in_dim, m->hidden, out_dim);
+    cudaError_t e = cudaMalloc((void **)&m->params, m->n_params * sizeof(float));
+    if (e != cudaSuccess) {
+        delete m;
+        return rl_fail(ctx, RL_ERR_OOM, "rl_mlp_create: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(m->params, 0, m->n_params * sizeof(float), ctx->stream);
+    *out = m;
+    return RL_OK;
+}
+
+rl_status rl_mlp_destroy(rl_mlp *m) {
+    if (!m) return RL_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    cudaFree(m->params);
+    delete m;
+    return RL_OK;
+}
+
+rl_status rl_mlp_num_params(rl_mlp *m, uint64_t *n) {
+    if (!m || !n) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_num_params: NULL argument");
+    *n = m->n_params;
+    return RL_OK;
+}
+
+rl_status rl_mlp_set_weights(rl_mlp *m, const float *host, uint64_t n) {
+    if (!m || !host) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_set_weights: NULL argument");
+    RL_REQUIRE(m->ctx, n == m->n_params, "rl_mlp_set_weights: wrong parameter count");
+    RL_CUDA(m->ctx, cudaMemcpyAsync(m->params, host, n * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+    RL_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+    return RL_OK;
+}
+
+rl_status rl_mlp_get_weights(rl_mlp *m, float *host, uint64_t n) {
+    if (!m || !host) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_get_weights: NULL argument");
+    RL_REQUIRE(m->ctx, n == m->n_params, "rl_mlp_get_weights: wrong parameter count");
+    RL_CUDA(m->ctx, cudaMemcpyAsync(host, m->params, n * sizeof(float), cudaMemcpyDeviceToHost, m->ctx->stream));
+    RL_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+    return RL_OK;
+}
+
+rl_status rl_mlp_forward(rl_mlp *m, const float *x_dev, uint64_t n, float *out_dev) {
+    if (!m || !x_dev || !out_dev) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_forward: NULL argument");
+    rl_ctx *ctx = m->ctx;
+    if (n == 0) return RL_OK;
+    const size_t smem = m->n_params * sizeof(float);
+    const unsigned block = 256, grid = rl_grid_for(n, block);
+    MlpView v = rl_mlp_view(m);
+    if (m->in_dim <= 8 && m->out_dim <= 2) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_forward_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (mlp_forward_kernel<8, 2>), grid, block, smem, v, x_dev, n, out_dev);
+    } else {
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_forward_kernel<36, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (mlp_forward_kernel<36, 32>), grid, block, smem, v, x_dev, n, out_dev);
+    }
+    return RL_OK;
+}
+
+}  // extern "C"

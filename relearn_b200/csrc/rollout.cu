@@ -1,0 +1,695 @@
+// rollout.cu -- trajectories and the fused rollout kernels.
+//
+// One launch = Agent::actor + Steps + TakeAlignedSteps + write_experience + OnlineStepsSummary for
+// every lane (src/simulation/steps.rs:113-168, take_steps.rs:18-89, agents/buffers/vec.rs:113-141,
+// buffers/mod.rs:237-261, simulation/summary.rs:198-216, train.rs:98-158).  Environment state lives
+// in registers for the whole rollout, the policy MLP is evaluated inside the step loop, and the only
+// HBM traffic is the trajectory write stream (26 B per env-step for CartPole: obs 20 + action 1 +
+// reward 4 + succ 1).
+//
+//  K2a rollout_kernel<EnvT>            one thread per lane; weights in shared memory (broadcast LDS)
+//  K2b rollout_cartpole_coop_kernel<L> L threads per lane split the 128 hidden units and keep their
+//                                      slice of the weights in registers; logits are combined by
+//                                      an xor-shuffle butterfly.  Used when there are too few
+//                                      lanes to fill the GPU with one thread each (E = 4096).
+#include "handles.cuh"
+
+namespace {
+
+enum { ST_STEPS = 0, ST_R, ST_R2, ST_EPS, ST_ER, ST_ER2, ST_EL, ST_EL2, ST_STORED_STEPS, ST_STORED_EPS, ST_COUNT };
+
+struct RolloutArgs {
+    uint64_t E, lane_offset, Tcap;
+    NoiseSource noise;
+    uint32_t min_steps, slack;
+    float *obs, *reward, *next_obs;
+    uint8_t *action, *succ;
+    uint32_t *lane_len;
+    int actor_kind;
+    MlpView net;
+    const uint8_t *actions;
+    double eps;
+    int training;
+    const double *qtable;
+    int S, A, F;
+    double *partials;  // f64 [gridDim.x][ST_COUNT]
+};
+
+struct LaneStats {
+    double v[ST_COUNT];
+    double cur_reward;
+    uint32_t cur_len;
+    __device__ void init() {
+#pragma unroll
+        for (int i = 0; i < ST_COUNT; ++i) v[i] = 0.0;
+        cur_reward = 0.0;
+        cur_len = 0;
+    }
+    // OnlineStepsSummary::push (summary.rs:198-216), kept as raw f64 sums (count, sum, sum of squares)
+    __device__ void push(float reward, int succ) {
+        const double r = (double)reward;
+        v[ST_STEPS] += 1.0; v[ST_R] += r; v[ST_R2] += r * r;
+        cur_len += 1;
+        cur_reward += r;
+        if (succ != RL_CONTINUE) {
+            const double L = (double)cur_len;
+            v[ST_EPS] += 1.0; v[ST_ER] += cur_reward; v[ST_ER2] += cur_reward * cur_reward;
+            v[ST_EL] += L; v[ST_EL2] += L * L;
+            cur_reward = 0.0;
+            cur_len = 0;
+        }
+    }
+};
+
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// Deterministic block reduction of the per-lane statistics into partials[blockIdx.x][*].
+__device__ void block_reduce_stats(const LaneStats &st, bool contributes, double *partials) {
+    __shared__ double red[32][ST_COUNT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < ST_COUNT; ++i) {
+        const double s = warp_sum(contributes ? st.v[i] : 0.0);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < ST_COUNT) {
+        double s = 0.0;
+        for (int w = 0; w < nwarps; ++w) s += red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * ST_COUNT + threadIdx.x] = s;
+    }
+}
+
+// Categorical::new + sample (categorical.rs:29-33,52-54) as inverse CDF over exp(log_softmax(z)).
+template <int MAXA>
+__device__ __forceinline__ uint32_t categorical_sample(const float *z, int A, float u) {
+    float m = z[0];
+#pragma unroll
+    for (int k = 1; k < MAXA; ++k)
+        if (k < A) m = fmaxf(m, z[k]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MAXA; ++k)
+        if (k < A) sum += expf(z[k] - m);
+    const float lse = m + logf(sum);
+    float c = 0.0f;
+    uint32_t a = (uint32_t)(A - 1);
+    bool found = false;
+#pragma unroll
+    for (int k = 0; k < MAXA; ++k)
+        if (k < A && !found) {
+            c += expf(z[k] - lse);
+            if (u < c) { a = (uint32_t)k; found = true; }
+        }
+    return a;
+}
+
+template <int MAXA>
+__device__ __forceinline__ uint32_t argmax_first(const float *z, int A) {
+    uint32_t best = 0;
+    float bv = z[0];
+#pragma unroll
+    for (int k = 1; k < MAXA; ++k)
+        if (k < A && z[k] > bv) { bv = z[k]; best = (uint32_t)k; }
+    return best;
+}
+
+// Weights in shared memory.  PACK8: per hidden unit 8 floats {w1[j][0..4], b1[j], w2[0][j], w2[1][j]}
+// (F <= 5, A <= 2: two broadcast LDS.128 per unit).  Otherwise the reference layout verbatim.
+template <bool PACK8>
+__device__ void stage_weights(const MlpView &m, float *sw) {
+    if (m.params == nullptr) return;
+    const int F = m.in_dim, H = m.hidden, A = m.out_dim;
+    if (PACK8) {
+        for (int i = threadIdx.x; i < H * 8; i += blockDim.x) {
+            const int j = i >> 3, c = i & 7;
+            float v = 0.0f;
+            if (c < 5) v = c < F ? m.w1()[j * F + c] : 0.0f;
+            else if (c == 5) v = m.b1()[j];
+            else v = (c - 6) < A ? m.w2()[(c - 6) * H + j] : 0.0f;
+            sw[i] = v;
+        }
+        if (threadIdx.x < 2) sw[H * 8 + threadIdx.x] = (int)threadIdx.x < A ? m.b2()[threadIdx.x] : 0.0f;
+    } else {
+        const uint64_t np = rl_mlp::count(F, H, A);
+        for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
+    }
+}
+
+template <class EnvT, bool PACK8>
+__device__ __forceinline__ void mlp_logits(const MlpView &m, const float *sw, const float *obs, float *z) {
+    const int F = m.in_dim, H = m.hidden, A = m.out_dim;
+    if constexpr (PACK8) {
+        float z0 = sw[H * 8], z1 = sw[H * 8 + 1];
+        const float4 *w4 = reinterpret_cast<const float4 *>(sw);
+#pragma unroll 4
+        for (int j = 0; j < H; ++j) {
+            const float4 a = w4[2 * j], b = w4[2 * j + 1];
+            float acc = b.y;
+            acc = fmaf(a.x, obs[0], acc);
+            acc = fmaf(a.y, obs[1], acc);
+            acc = fmaf(a.z, obs[2], acc);
+            acc = fmaf(a.w, obs[3], acc);
+            acc = fmaf(b.x, obs[4], acc);
+            const float h = rl_activate(m.act, acc);
+            z0 = fmaf(b.z, h, z0);
+            z1 = fmaf(b.w, h, z1);
+        }
+        z[0] = z0;
+        z[1] = z1;
+    } else {
+        const float *w1 = sw, *b1 = w1 + (size_t)H * F, *w2 = b1 + H, *b2 = w2 + (size_t)A * H;
+#pragma unroll
+        for (int k = 0; k < EnvT::MAXA; ++k) z[k] = k < A ? b2[k] : 0.0f;
+        for (int j = 0; j < H; ++j) {
+            float acc = b1[j];
+#pragma unroll
+            for (int f = 0; f < EnvT::MAXF; ++f)
+                if (f < F) acc = fmaf(w1[j * F + f], obs[f], acc);
+            const float h = rl_activate(m.act, acc);
+#pragma unroll
+            for (int k = 0; k < EnvT::MAXA; ++k)
+                if (k < A) z[k] = fmaf(w2[k * H + j], h, z[k]);
+        }
+    }
+}
+
+// True when the actor evaluates its network on this step (uniform over the grid, so that the
+// cooperative kernel can shuffle logits without divergence).
+__device__ __forceinline__ bool actor_needs_logits(const RolloutArgs &a) {
+    return a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY || (a.actor_kind == RL_ACTOR_EPS_GREEDY_Q && a.eps < 1.0);
+}
+
+// Actor::act for every actor kind (steps.rs:126-128); z holds the network output when needed.
+template <class EnvT, bool REPLAY>
+__device__ __forceinline__ uint32_t actor_act(const RolloutArgs &a, const typename EnvT::Params &p,
+                                              const typename EnvT::State &s, LaneNoise<REPLAY> &nz, uint64_t e,
+                                              uint32_t t, const float *z) {
+    switch (a.actor_kind) {
+    case RL_ACTOR_REPLAY_ACTIONS: return a.actions[(uint64_t)t * a.E + e];
+    case RL_ACTOR_RANDOM: return rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, (uint32_t)a.A);
+    case RL_ACTOR_CATEGORICAL_POLICY: {  // policies/actor.rs:42-55
+        const float u = rl_u32_to_f32(nz.template next_u32<RL_STREAM_ACTOR>());
+        return categorical_sample<EnvT::MAXA>(z, a.A, u);
+    }
+    case RL_ACTOR_EPS_GREEDY_Q: {  // dqn.rs:360-379
+        if (rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps)) return rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, (uint32_t)a.A);
+        return argmax_first<EnvT::MAXA>(z, a.A);
+    }
+    case RL_ACTOR_TABULAR_EPS_GREEDY: {  // tabular.rs:222-232
+        if (a.training && rl_u64_to_f64(nz.template next_u64<RL_STREAM_ACTOR>()) < a.eps)
+            return rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, (uint32_t)a.A);
+        const double *row = a.qtable + ((uint64_t)e * a.S + EnvT::observe_index(p, s)) * a.A;
+        uint32_t best = 0;
+        double bv = row[0];
+        for (int k = 1; k < a.A; ++k)
+            if (row[k] > bv) { bv = row[k]; best = (uint32_t)k; }
+        return best;
+    }
+    }
+    return 0;
+}
+
+__device__ __forceinline__ float pick5(const float *v, int i) {
+    return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : i == 3 ? v[3] : v[4];
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2a: one thread per lane
+// ------------------------------------------------------------------------------------------------
+template <class EnvT, bool REPLAY>
+__global__ void __launch_bounds__(128) rollout_kernel(typename EnvT::Params p, RolloutArgs a) {
+    constexpr bool PACK8 = EnvT::MAXF <= 5 && EnvT::MAXA <= 2;
+    extern __shared__ __align__(16) float sw[];
+    stage_weights<PACK8>(a.net, sw);
+    __syncthreads();
+
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < a.E;
+    const bool needs_logits = actor_needs_logits(a);
+    LaneStats st;
+    st.init();
+    if (valid) {
+        const int F = a.F;
+        LaneNoise<REPLAY> nz;
+        nz.init(a.noise, a.lane_offset + e, e);
+        const uint32_t t0 = a.noise.step_counter;
+        typename EnvT::State s;
+        float obs[EnvT::MAXF], last_obs[EnvT::MAXF];
+#pragma unroll
+        for (int f = 0; f < EnvT::MAXF; ++f) obs[f] = last_obs[f] = 0.0f;
+        uint32_t n = a.min_steps ? a.min_steps + a.slack : 0;  // take_steps.rs:20-31
+        uint32_t i = 0;
+        int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+        if (n > 0) {  // train.rs:135: every period starts fresh episodes
+            nz.set_step(t0);
+            EnvT::template reset<REPLAY>(p, s, nz);
+            EnvT::observe(p, s, obs);
+        }
+        while (n > 0) {
+            nz.set_step(t0 + i);
+            float z[EnvT::MAXA];
+            if (needs_logits) mlp_logits<EnvT, PACK8>(a.net, sw, obs, z);
+            const uint32_t action = actor_act<EnvT, REPLAY>(a, p, s, nz, e, i, z);
+#pragma unroll
+            for (int f = 0; f < EnvT::MAXF; ++f)
+                if (f < F) {
+                    a.obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
+                    last_obs[f] = obs[f];
+                }
+            float r;
+            const int sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
+            if (sc == RL_INTERRUPT) {
+                EnvT::observe(p, s, obs);
+#pragma unroll
+                for (int f = 0; f < EnvT::MAXF; ++f)
+                    if (f < F) a.next_obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
+            }
+            if (sc != RL_CONTINUE) {
+                nz.set_step(t0 + i + 1);
+                EnvT::template reset<REPLAY>(p, s, nz);
+            }
+            EnvT::observe(p, s, obs);
+            a.action[(uint64_t)i * a.E + e] = (uint8_t)action;
+            a.reward[(uint64_t)i * a.E + e] = r;
+            a.succ[(uint64_t)i * a.E + e] = (uint8_t)sc;
+            st.push(r, sc);
+            succ_prev = succ_last;
+            succ_last = sc;
+            i += 1;
+            n -= 1;
+            if (sc != RL_CONTINUE && n <= a.slack) n = 0;  // take_steps.rs:83-88
+        }
+        // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
+        uint32_t len = i;
+        double eps = st.v[ST_EPS];
+        if (i > 0 && succ_last == RL_CONTINUE) {
+            len = i - 1;
+            a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (len > 0 && succ_prev == RL_CONTINUE) {
+                a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+#pragma unroll
+                for (int f = 0; f < EnvT::MAXF; ++f)
+                    if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
+                eps += 1.0;
+            }
+        }
+        a.lane_len[e] = len;
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = eps;
+        nz.finish(a.noise, e);
+    }
+    block_reduce_stats(st, valid, a.partials);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2b: CartPole, LANES threads per lane, H = 128 hidden units split across them, weights in registers.
+// Every thread of a group carries the full (redundant) f64 physics so that no state is exchanged;
+// only the two partial logits cross lanes (log2(LANES) xor-shuffles each).
+// ------------------------------------------------------------------------------------------------
+template <int LANES, bool REPLAY>
+__global__ void __launch_bounds__(128) rollout_cartpole_coop_kernel(CartPoleEnv::Params p, RolloutArgs a) {
+    using EnvT = CartPoleEnv;
+    constexpr int H = 128, UNITS = H / LANES;
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t e = gtid / LANES;
+    const int sub = (int)(gtid % LANES);
+    const bool valid = e < a.E;
+    const int F = a.F;
+
+    // this thread's slice of the network: units sub, sub + LANES, ...
+    float w1[UNITS][5], b1[UNITS], w2a[UNITS], w2b[UNITS];
+    float b2a = 0.0f, b2b = 0.0f;
+    const bool has_net = a.net.params != nullptr;
+    if (has_net) {
+#pragma unroll
+        for (int u = 0; u < UNITS; ++u) {
+            const int j = sub + u * LANES;
+#pragma unroll
+            for (int f = 0; f < 5; ++f) w1[u][f] = f < F ? a.net.w1()[j * F + f] : 0.0f;
+            b1[u] = a.net.b1()[j];
+            w2a[u] = a.net.w2()[j];
+            w2b[u] = a.net.w2()[H + j];
+        }
+        b2a = a.net.b2()[0];
+        b2b = a.net.b2()[1];
+    }
+
+    const bool needs_logits = actor_needs_logits(a);
+    LaneStats st;
+    st.init();
+    LaneNoise<REPLAY> nz;
+    const uint64_t e_safe = valid ? e : 0;  // out-of-range threads shadow lane 0 without storing anything
+    nz.init(a.noise, a.lane_offset + e_safe, e_safe);
+    const uint32_t t0 = a.noise.step_counter;
+    EnvT::State s;
+    float obs[5] = {0, 0, 0, 0, 0}, last_obs[5] = {0, 0, 0, 0, 0};
+    uint32_t n = (valid && a.min_steps) ? a.min_steps + a.slack : 0;
+    uint32_t i = 0;
+    int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+    s.x = s.xd = s.th = s.thd = 0.0;
+    s.meta = 0x80000000u | p.max_steps;
+    if (n > 0) {
+        nz.set_step(t0);
+        EnvT::reset<REPLAY>(p, s, nz);
+        EnvT::observe(p, s, obs);
+    }
+    // The loop is warp-uniform: every thread of the warp takes part in the logit shuffles until the
+    // last lane of the warp has finished (lanes only finish at different times when slack > 0).
+    while (__any_sync(0xffffffffu, n > 0)) {
+        float z[2] = {0.0f, 0.0f};
+        if (needs_logits) {
+            float z0 = 0.0f, z1 = 0.0f;
+#pragma unroll
+            for (int u = 0; u < UNITS; ++u) {
+                float acc = b1[u];
+#pragma unroll
+                for (int f = 0; f < 5; ++f) acc = fmaf(w1[u][f], obs[f], acc);
+                const float h = rl_activate(a.net.act, acc);
+                z0 = fmaf(w2a[u], h, z0);
+                z1 = fmaf(w2b[u], h, z1);
+            }
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) {
+                z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+                z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+            }
+            z[0] = z0 + b2a;
+            z[1] = z1 + b2b;
+        }
+        if (n > 0) {
+            nz.set_step(t0 + i);
+            const uint32_t action = actor_act<EnvT, REPLAY>(a, p, s, nz, e, i, z);
+#pragma unroll
+            for (int f = 0; f < 5; ++f) last_obs[f] = obs[f];
+            float r;
+            const int sc = EnvT::step<REPLAY>(p, s, action, nz, r);
+            // trajectory writes are spread over the group: thread `sub` owns one column of the record
+            if (sub < F) a.obs[((uint64_t)i * F + sub) * a.E + e] = pick5(last_obs, sub);
+            if (sc == RL_INTERRUPT) {
+                EnvT::observe(p, s, obs);
+                if (sub < F) a.next_obs[((uint64_t)i * F + sub) * a.E + e] = pick5(obs, sub);
+            }
+            if (sc != RL_CONTINUE) {
+                nz.set_step(t0 + i + 1);
+                EnvT::reset<REPLAY>(p, s, nz);
+            }
+            EnvT::observe(p, s, obs);
+            if (sub == 5) a.action[(uint64_t)i * a.E + e] = (uint8_t)action;
+            if (sub == 6) a.reward[(uint64_t)i * a.E + e] = r;
+            if (sub == 7) a.succ[(uint64_t)i * a.E + e] = (uint8_t)sc;
+            st.push(r, sc);
+            succ_prev = succ_last;
+            succ_last = sc;
+            i += 1;
+            n -= 1;
+            if (sc != RL_CONTINUE && n <= a.slack) n = 0;
+        }
+    }
+    if (valid) {
+        uint32_t len = i;
+        double eps = st.v[ST_EPS];
+        if (i > 0 && succ_last == RL_CONTINUE) {
+            len = i - 1;
+            // same thread as the in-loop store of these addresses, so program order applies
+            if (sub == 7) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (len > 0 && succ_prev == RL_CONTINUE) {
+                if (sub == 7) a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+                if (sub < F) a.next_obs[((uint64_t)(len - 1) * F + sub) * a.E + e] = pick5(last_obs, sub);
+                eps += 1.0;
+            }
+        }
+        if (sub == 0) a.lane_len[e] = len;
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = eps;
+        if (sub == 0) nz.finish(a.noise, e);
+    }
+    block_reduce_stats(st, valid && sub == 0, a.partials);
+}
+
+// Sum the per-block partials in block order (deterministic) and publish the summary.
+__global__ void rollout_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ out,
+                                        double *__restrict__ traj_counts) {
+    const int i = threadIdx.x;
+    if (i < ST_COUNT) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * ST_COUNT + i];
+        out[i] = s;
+        if (i == ST_STORED_STEPS) traj_counts[0] = s;
+        if (i == ST_STORED_EPS) traj_counts[1] = s;
+    }
+}
+
+template <class EnvT>
+size_t rollout_smem_bytes(const rl_mlp *net) {
+    if (!net) return 16;
+    constexpr bool PACK8 = EnvT::MAXF <= 5 && EnvT::MAXA <= 2;
+    return PACK8 ? ((size_t)net->hidden * 8 + 4) * sizeof(float) : net->n_params * sizeof(float);
+}
+
+template <class EnvT>
+rl_status launch_rollout(rl_ctx *ctx, const typename EnvT::Params &p, RolloutArgs &a, const rl_mlp *net, bool replay,
+                         int *nblocks_out) {
+    const unsigned block = 128, grid = rl_grid_for(a.E, block);
+    const size_t smem = rollout_smem_bytes<EnvT>(net);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    if (replay) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_kernel<EnvT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_kernel<EnvT, true>), grid, block, smem, p, a);
+    } else {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_kernel<EnvT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_kernel<EnvT, false>), grid, block, smem, p, a);
+    }
+    return RL_OK;
+}
+
+template <int LANES>
+rl_status launch_coop(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
+    const unsigned block = 128, grid = rl_grid_for(a.E * LANES, block);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    if (replay) {
+        RL_LAUNCH(ctx, (rollout_cartpole_coop_kernel<LANES, true>), grid, block, 0, p, a);
+    } else {
+        RL_LAUNCH(ctx, (rollout_cartpole_coop_kernel<LANES, false>), grid, block, 0, p, a);
+    }
+    return RL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+rl_status rl_traj_create(rl_env *env, uint64_t step_capacity, rl_traj **out) {
+    if (!env || !out) return rl_fail(env ? env->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_traj_create: NULL argument");
+    rl_ctx *ctx = env->ctx;
+    RL_REQUIRE(ctx, step_capacity > 0 && step_capacity < (1ull << 31), "rl_traj_create: step_capacity out of range");
+    RL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rl_traj *t = new (std::nothrow) rl_traj();
+    if (!t) return rl_fail(ctx, RL_ERR_OOM, "rl_traj_create: host allocation failed");
+    t->ctx = ctx; t->env = env; t->E = env->E; t->T = step_capacity; t->F = (uint64_t)env->structure.num_features;
+    const size_t TE = (size_t)t->T * t->E;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    };
+    alloc((void **)&t->obs, TE * t->F * sizeof(float));
+    alloc((void **)&t->next_obs, TE * t->F * sizeof(float));
+    alloc((void **)&t->reward, TE * sizeof(float));
+    alloc((void **)&t->action, TE);
+    alloc((void **)&t->succ, TE);
+    alloc((void **)&t->lane_len, t->E * sizeof(uint32_t));
+    alloc((void **)&t->counts_dev, 8 * sizeof(double));
+    if (e != cudaSuccess) {
+        rl_traj_destroy(t);
+        return rl_fail(ctx, e == cudaErrorMemoryAllocation ? RL_ERR_OOM : RL_ERR_CUDA, "rl_traj_create: %s",
+                       cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(t->succ, RL_PAD, TE, ctx->stream);
+    cudaMemsetAsync(t->lane_len, 0, t->E * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(t->counts_dev, 0, 8 * sizeof(double), ctx->stream);
+    *out = t;
+    return RL_OK;
+}
+
+rl_status rl_traj_destroy(rl_traj *t) {
+    if (!t) return RL_OK;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    cudaFree(t->obs); cudaFree(t->next_obs); cudaFree(t->reward); cudaFree(t->action); cudaFree(t->succ);
+    cudaFree(t->lane_len); cudaFree(t->counts_dev);
+    delete t;
+    return RL_OK;
+}
+
+rl_status rl_traj_view_of(rl_traj *t, rl_traj_view *out) {
+    if (!t || !out) return rl_fail(t ? t->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_traj_view_of: NULL argument");
+    rl_ctx *ctx = t->ctx;
+    double counts[2];
+    RL_CUDA(ctx, cudaMemcpyAsync(counts, t->counts_dev, sizeof counts, cudaMemcpyDeviceToHost, ctx->stream));
+    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    t->num_steps = (uint64_t)counts[0];
+    t->num_episodes = (uint64_t)counts[1];
+    out->num_lanes = t->E; out->step_capacity = t->T; out->num_features = t->F;
+    out->obs = t->obs; out->action = t->action; out->reward = t->reward; out->succ = t->succ;
+    out->next_obs = t->next_obs; out->lane_len = t->lane_len; out->num_steps = t->num_steps;
+    return RL_OK;
+}
+
+}  // extern "C"
+
+namespace {
+// lane_len and counts for caller-loaded trajectories
+__global__ void traj_index_kernel(const uint8_t *__restrict__ succ, uint64_t T, uint64_t E, uint32_t *lane_len,
+                                  double *partials) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    LaneStats st;
+    st.init();
+    if (e < E) {
+        uint32_t len = 0, eps = 0;
+        for (uint64_t t = 0; t < T; ++t) {
+            const uint8_t sc = succ[t * E + e];
+            if (sc == RL_PAD) break;
+            len += 1;
+            if (sc != RL_CONTINUE) eps += 1;
+        }
+        lane_len[e] = len;
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = (double)eps;
+    }
+    block_reduce_stats(st, e < E, partials);
+}
+}  // namespace
+
+extern "C" {
+
+rl_status rl_traj_load(rl_traj *t, uint64_t steps, const float *obs_dev, const uint8_t *action_dev,
+                       const float *reward_dev, const uint8_t *succ_dev, const float *next_obs_dev) {
+    if (!t || !obs_dev || !action_dev || !reward_dev || !succ_dev)
+        return rl_fail(t ? t->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_traj_load: NULL argument");
+    rl_ctx *ctx = t->ctx;
+    RL_REQUIRE(ctx, steps <= t->T, "rl_traj_load: steps exceed capacity");
+    const size_t n = (size_t)steps * t->E;
+    const cudaMemcpyKind k = cudaMemcpyDeviceToDevice;
+    RL_CUDA(ctx, cudaMemsetAsync(t->succ, RL_PAD, (size_t)t->T * t->E, ctx->stream));
+    RL_CUDA(ctx, cudaMemcpyAsync(t->obs, obs_dev, n * t->F * sizeof(float), k, ctx->stream));
+    RL_CUDA(ctx, cudaMemcpyAsync(t->action, action_dev, n, k, ctx->stream));
+    RL_CUDA(ctx, cudaMemcpyAsync(t->reward, reward_dev, n * sizeof(float), k, ctx->stream));
+    RL_CUDA(ctx, cudaMemcpyAsync(t->succ, succ_dev, n, k, ctx->stream));
+    if (next_obs_dev) RL_CUDA(ctx, cudaMemcpyAsync(t->next_obs, next_obs_dev, n * t->F * sizeof(float), k, ctx->stream));
+    const unsigned block = 128, grid = rl_grid_for(t->E, block);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    RL_LAUNCH(ctx, traj_index_kernel, grid, block, 0, t->succ, steps, t->E, t->lane_len, partials + ST_COUNT);
+    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, partials + ST_COUNT, (int)grid, partials, t->counts_dev);
+    t->used_T = steps;
+    return RL_OK;
+}
+
+rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_traj *traj, rl_steps_summary *summary) {
+    if (!env || !actor || !traj) return rl_fail(env ? env->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_rollout: NULL argument");
+    rl_ctx *ctx = env->ctx;
+    RL_REQUIRE(ctx, traj->env == env, "rl_rollout: trajectory belongs to another env");
+    const uint64_t cap = bound.min_steps ? bound.min_steps + bound.slack_steps : 0;
+    RL_REQUIRE(ctx, cap <= traj->T, "rl_rollout: min_steps + slack_steps exceeds the trajectory capacity");
+    const rl_env_structure &es = env->structure;
+    rl_mlp *net = actor->net;
+    const bool needs_net = actor->kind == RL_ACTOR_CATEGORICAL_POLICY || actor->kind == RL_ACTOR_EPS_GREEDY_Q;
+    if (needs_net) {
+        RL_REQUIRE(ctx, net != nullptr, "rl_rollout: actor needs a network");
+        RL_REQUIRE(ctx, net->in_dim == es.num_features && net->out_dim == es.num_actions,
+                   "rl_rollout: network dimensions do not match the environment");
+    } else {
+        net = nullptr;
+    }
+    if (actor->kind == RL_ACTOR_REPLAY_ACTIONS) RL_REQUIRE(ctx, actor->actions_dev, "rl_rollout: actions_dev is NULL");
+    if (actor->kind == RL_ACTOR_TABULAR_EPS_GREEDY) {
+        RL_REQUIRE(ctx, actor->table, "rl_rollout: table is NULL");
+        RL_REQUIRE(ctx, actor->table->R == env->E && actor->table->S == es.num_observations && actor->table->A == es.num_actions,
+                   "rl_rollout: table shape does not match the environment (one replica per lane)");
+    }
+    RolloutArgs a{};
+    a.E = env->E; a.lane_offset = env->lane_offset; a.Tcap = traj->T;
+    a.noise = env->noise;
+    a.min_steps = (uint32_t)bound.min_steps; a.slack = (uint32_t)bound.slack_steps;
+    a.obs = traj->obs; a.reward = traj->reward; a.next_obs = traj->next_obs; a.action = traj->action; a.succ = traj->succ;
+    a.lane_len = traj->lane_len;
+    a.actor_kind = actor->kind;
+    a.net = rl_mlp_view(net);
+    a.actions = actor->actions_dev;
+    a.eps = actor->exploration_rate;
+    a.training = actor->training;
+    a.qtable = actor->table ? actor->table->q : nullptr;
+    a.S = es.num_observations; a.A = es.num_actions; a.F = es.num_features;
+
+    RL_CUDA(ctx, cudaMemsetAsync(traj->succ, RL_PAD, (size_t)traj->T * traj->E, ctx->stream));
+    const bool replay = env->noise.mode == RL_NOISE_REPLAY;
+    int nblocks = 0;
+    switch (env->kind) {
+    case RL_ENV_CARTPOLE: {
+        int lanes = actor->lanes_per_env;
+        const bool coop_ok = net && net->hidden == 128 && es.num_actions == 2;
+        if (lanes == 0) {
+            // auto: fill ~8 warps per SM sub-partition's worth of threads when lanes are scarce
+            lanes = 1;
+            if (coop_ok) {
+                const uint64_t target_threads = (uint64_t)ctx->sm_count * 1024;
+                while (lanes < 32 && env->E * (uint64_t)lanes * 2 <= target_threads) lanes *= 2;
+                if (lanes > 1 && lanes < 8) lanes = 8;
+            }
+        }
+        if (lanes > 1 && !coop_ok)
+            return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env > 1 needs a 128-unit MLP on CartPole");
+        switch (lanes) {
+        case 1: RL_TRY((launch_rollout<CartPoleEnv>(ctx, env->cartpole, a, net, replay, &nblocks))); break;
+        case 8: RL_TRY((launch_coop<8>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 16: RL_TRY((launch_coop<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 32: RL_TRY((launch_coop<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 8, 16 or 32");
+        }
+        break;
+    }
+    case RL_ENV_CHAIN: RL_TRY((launch_rollout<ChainEnv>(ctx, env->chain, a, net, replay, &nblocks))); break;
+    case RL_ENV_MEMORY_GAME: RL_TRY((launch_rollout<MemoryEnv>(ctx, env->memory, a, net, replay, &nblocks))); break;
+    case RL_ENV_BANDIT_META: RL_TRY((launch_rollout<BanditMetaEnv>(ctx, env->bandit, a, net, replay, &nblocks))); break;
+    }
+    double *totals = a.partials - ST_COUNT;
+    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, a.partials, nblocks, totals, traj->counts_dev);
+    env->noise.step_counter += (uint32_t)cap + 1;  // fresh noise for the next period
+    traj->used_T = cap;
+    if (summary) {
+        double *host;
+        RL_TRY(rl_ctx_pinned(ctx, ST_COUNT * sizeof(double), (void **)&host));
+        RL_CUDA(ctx, cudaMemcpyAsync(host, totals, ST_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        auto mv = [&](int n_i, int s_i, int s2_i) {
+            rl_mean_var m{};
+            m.count = (uint64_t)host[n_i];
+            if (m.count) {
+                m.mean = host[s_i] / host[n_i];
+                m.squared_residual_sum = host[s2_i] - host[s_i] * m.mean;
+                if (m.squared_residual_sum < 0.0) m.squared_residual_sum = 0.0;
+            }
+            return m;
+        };
+        summary->step_reward = mv(ST_STEPS, ST_R, ST_R2);
+        summary->episode_reward = mv(ST_EPS, ST_ER, ST_ER2);
+        summary->episode_length = mv(ST_EPS, ST_EL, ST_EL2);
+        summary->num_stored_steps = (uint64_t)host[ST_STORED_STEPS];
+        summary->num_stored_episodes = (uint64_t)host[ST_STORED_EPS];
+        traj->num_steps = summary->num_stored_steps;
+        traj->num_episodes = summary->num_stored_episodes;
+    }
+    return RL_OK;
+}
+
+}  // extern "C"

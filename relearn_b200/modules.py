@@ -1,0 +1,86 @@
+"""Mlp module (src/torch/modules/ff/mlp.rs) over the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib as L
+from .runtime import Context
+
+ACTIVATIONS = {"identity": L.RL_ACT_IDENTITY, "relu": L.RL_ACT_RELU, "sigmoid": L.RL_ACT_SIGMOID, "tanh": L.RL_ACT_TANH}
+
+
+@dataclass
+class MlpConfig:
+    """mlp.rs:25-34 defaults: hidden_sizes [128], Relu, output Identity."""
+
+    hidden_sizes: list = field(default_factory=lambda: [128])
+    activation: str = "relu"
+
+    def build_module(self, ctx: Context, in_dim: int, out_dim: int) -> "Mlp":
+        return Mlp(ctx, in_dim, self.hidden_sizes, out_dim, self.activation)
+
+
+def num_params(in_dim, hidden, out_dim):
+    return hidden * in_dim + hidden + out_dim * hidden + out_dim
+
+
+def init_params(rng: np.random.Generator, in_dim: int, hidden: int, out_dim: int) -> np.ndarray:
+    """Initializer::Uniform(FanAvg) with Linear's fan_in = in_dim + 1 (initializers.rs:31-38,159-163;
+    linear.rs:56): every tensor of a Linear ~ U(+-sqrt(6 / (in+1+out))).  libtorch's generator is not
+    reproducible from relearn, so values come from numpy and are injected."""
+    parts = []
+    for (i, o) in ((in_dim, hidden), (hidden, out_dim)):
+        lim = np.sqrt(6.0 / (i + 1 + o))
+        parts.append(rng.uniform(-lim, lim, size=(o, i)).astype(np.float32).ravel())
+        parts.append(rng.uniform(-lim, lim, size=(o,)).astype(np.float32))
+    return np.concatenate(parts)
+
+
+class Mlp:
+    def __init__(self, ctx: Context, in_dim: int, hidden_sizes, out_dim: int, activation: str = "relu"):
+        self.ctx, self._lib = ctx, ctx._lib
+        self.in_dim, self.hidden_sizes, self.out_dim = in_dim, list(hidden_sizes), out_dim
+        hs = (C.c_int32 * len(self.hidden_sizes))(*self.hidden_sizes)
+        h = C.c_void_p()
+        L.check(self._lib.rl_mlp_create(ctx.handle, in_dim, hs, len(self.hidden_sizes), out_dim,
+                                        ACTIVATIONS[activation], C.byref(h)), ctx.handle)
+        self.handle = h
+        n = C.c_uint64()
+        L.check(self._lib.rl_mlp_num_params(h, C.byref(n)), ctx.handle)
+        self.num_params = n.value
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self._lib.rl_mlp_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, flat: np.ndarray):
+        """Flat f32 in Module::variables() order (kernel[out,in] row-major, bias) per Linear."""
+        a = np.ascontiguousarray(flat, dtype=np.float32)
+        L.check(self._lib.rl_mlp_set_weights(self.handle, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
+
+    def get_weights(self) -> np.ndarray:
+        a = np.empty(self.num_params, np.float32)
+        L.check(self._lib.rl_mlp_get_weights(self.handle, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
+        return a
+
+    def forward(self, x: np.ndarray) -> np.ndarray:
+        """x [n, in_dim] -> [n, out_dim] (host convenience; uploads planes, downloads planes)."""
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.in_dim)
+        n = x.shape[0]
+        xin = self.ctx.to_device(np.ascontiguousarray(x.T))
+        out = self.ctx.alloc(max(n, 1) * self.out_dim * 4)
+        L.check(self._lib.rl_mlp_forward(self.handle, xin.c, n, out.c), self.ctx.handle)
+        res = out.download((self.out_dim, n), np.float32).T.copy()
+        xin.free()
+        out.free()
+        return res

@@ -1,0 +1,224 @@
+"""GPU parity: environment dynamics, unfused step kernels and fused rollouts vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle as O
+import relearn_b200 as R
+from relearn_b200 import _lib as L
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+CARTPOLE = R.CartPoleConfig().wrap(R.VisibleStepLimit(25))
+INT_ENVS = [
+    pytest.param(R.Chain(), id="chain"),
+    pytest.param(R.Chain(size=9, discount_factor=0.9), id="chain9"),
+    pytest.param(R.MemoryGame(2, 1), id="memory-2-1"),
+    pytest.param(R.MemoryGame(4, 3), id="memory-4-3"),
+    pytest.param(R.MetaEnv(R.UniformBernoulliBandits(2), 3), id="bandit-2x3"),
+    pytest.param(R.MetaEnv(R.UniformBernoulliBandits(10), 7), id="bandit-10x7"),
+]
+
+
+def _unfused_vs_oracle(ctx, cfg, E, T, rng, exact):
+    """Drive rl_env_step with scripted actions; the oracle lane consumes the same word stream."""
+    env = R.build_env(ctx, cfg, E, seed=3)
+    A = env.num_actions
+    words = P.random_words(rng, E, 24 * T + 64)
+    env.set_noise_replay(words, None)
+    actions = rng.integers(0, A, size=(T, E), dtype=np.uint8)
+    ref = P.oracle_rollout(cfg, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=actions, env_words=words)
+    obs = env.reset_all()
+    for t in range(T):
+        live = ref["n_taken"] > t  # every lane takes exactly T steps
+        assert live.all()
+        # the observation acted on at step t (before finalize the oracle stored it at obs[t])
+        stored = ref["lane_len"] > t
+        if exact:
+            np.testing.assert_array_equal(obs[stored], ref["obs"][t][stored])
+        else:
+            np.testing.assert_allclose(obs[stored], ref["obs"][t][stored], rtol=1e-6, atol=1e-7)
+        out = env.step(actions[t])
+        # successor codes: finalize may have rewritten the oracle's last stored step to Interrupt
+        unchanged = ref["lane_len"] > t + 1
+        np.testing.assert_array_equal(out["succ"][unchanged], ref["succ"][t][unchanged])
+        np.testing.assert_array_equal(out["reward"][stored], ref["reward"][t][stored])
+        obs = out["obs"]
+    env.close()
+
+
+@pytest.mark.parametrize("cfg", INT_ENVS)
+def test_unfused_step_integer_envs_bit_exact(ctx, cfg):
+    _unfused_vs_oracle(ctx, cfg, E=97, T=40, rng=np.random.default_rng(11), exact=True)
+
+
+def test_unfused_step_cartpole(ctx):
+    _unfused_vs_oracle(ctx, CARTPOLE, E=300, T=60, rng=np.random.default_rng(12), exact=False)
+
+
+def test_cartpole_single_step_map_f64(ctx):
+    """Single-step map from random oracle states: f64 state within 1e-12 rel (sincos is the only
+    non-bit-identical primitive), successor codes and flags exact."""
+    import ctypes as C
+
+    rng = np.random.default_rng(5)
+    E = 4096
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    env = R.build_env(ctx, cfg, E, seed=0)
+    st = np.stack([rng.uniform(-2.3, 2.3, E), rng.uniform(-2, 2, E), rng.uniform(-0.2, 0.2, E), rng.uniform(-2, 2, E)])
+    meta = (rng.integers(2, 500, E).astype(np.uint32) | (rng.integers(0, 2, E).astype(np.uint32) << 31))
+    env.set_state(st, meta)
+    env.set_noise_replay(P.random_words(rng, E, 16), None)
+    actions = rng.integers(0, 2, E).astype(np.uint8)
+    out = env.step(actions)
+    f64, u32 = env.get_state()
+    oenv = O.make_env(P.oracle_cfg_for(cfg))
+    lib = O.lib()
+    n_cont = 0
+    for e in range(E):
+        s = O.State()
+        s.x, s.xd, s.th, s.thd = st[:, e]
+        s.flag = int(meta[e] >> 31)
+        s.steps_remaining = int(meta[e] & 0x7FFFFFFF)
+        rew = C.c_double()
+        rng_o = O.ScriptRng(np.zeros(4, np.uint32))
+        succ = lib.ro_env_step(C.byref(oenv), C.byref(s), int(actions[e]), rng_o.ref, C.byref(rew))
+        assert succ == out["succ"][e], e
+        if succ == O.CONTINUE:
+            n_cont += 1
+            got = f64[:, e]
+            np.testing.assert_allclose(got, [s.x, s.xd, s.th, s.thd], rtol=1e-12, atol=1e-15)
+            assert int(u32[e] >> 31) == s.flag
+            assert int(u32[e] & 0x7FFFFFFF) == s.steps_remaining
+    assert n_cont > E // 2
+    env.close()
+
+
+@pytest.mark.parametrize("cfg", INT_ENVS)
+@pytest.mark.parametrize("slack", [0, 5])
+def test_fused_rollout_replay_integer_envs_bit_exact(ctx, cfg, slack):
+    rng = np.random.default_rng(21)
+    E, T = 130, 37
+    env = R.build_env(ctx, cfg, E, seed=3)
+    words = P.random_words(rng, E, 24 * (T + slack) + 64)
+    env.set_noise_replay(words, None)
+    actions = rng.integers(0, env.num_actions, size=(T + slack, E), dtype=np.uint8)
+    traj = R.Trajectory(env, T + slack)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_REPLAY_ACTIONS, actions=actions), R.HistoryDataBound(T, slack), traj)
+    ref = P.oracle_rollout(cfg, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=actions, env_words=words)
+    P.compare_traj(traj.to_host(), ref, what="fused replay")
+    P.compare_summary(summ, ref["summary"])
+    assert summ.num_stored_steps == int(ref["lane_len"].sum())
+
+
+@pytest.mark.parametrize("slack", [0, 7])
+def test_fused_rollout_replay_cartpole(ctx, slack):
+    rng = np.random.default_rng(22)
+    E, T = 257, 64
+    env = R.build_env(ctx, CARTPOLE, E, seed=3)
+    words = P.random_words(rng, E, 8 * (T + slack) + 64)
+    env.set_noise_replay(words, None)
+    actions = rng.integers(0, 2, size=(T + slack, E), dtype=np.uint8)
+    traj = R.Trajectory(env, T + slack)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_REPLAY_ACTIONS, actions=actions), R.HistoryDataBound(T, slack), traj)
+    ref = P.oracle_rollout(CARTPOLE, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=actions, env_words=words)
+    P.compare_traj(traj.to_host(), ref, obs_rtol=1e-6, obs_atol=1e-7, what="fused cartpole replay")
+    P.compare_summary(summ, ref["summary"])
+
+
+@pytest.mark.parametrize("cfg", INT_ENVS)
+def test_fused_rollout_philox_random_actor_bit_exact(ctx, cfg):
+    """Production noise: the oracle regenerates the Philox slots and must reproduce the rollout exactly."""
+    E, T, seed, off = 150, 33, 0xC0FFEE, 1000
+    env = R.build_env(ctx, cfg, E, seed=seed, lane_offset=off)
+    env.set_noise_philox(seed, 17)
+    traj = R.Trajectory(env, T + 3)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_RANDOM), R.HistoryDataBound(T, 3), traj)
+    ref = P.oracle_rollout(cfg, E, T, 3, actor_kind=O.ACTOR_RANDOM, philox_seed=seed, lane_offset=off, t0=17)
+    P.compare_traj(traj.to_host(), ref, what="philox random")
+    P.compare_summary(summ, ref["summary"])
+
+
+def test_philox_slot_matches_oracle():
+    lib, olib = L.lib(), O.lib()
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        seed, lane = int(rng.integers(0, 2**63)), int(rng.integers(0, 2**40))
+        t, stream, draw = int(rng.integers(0, 2**32)), int(rng.integers(0, 3)), int(rng.integers(0, 9))
+        assert lib.rl_philox_slot(seed, lane, t, stream, draw) == olib.ro_philox_slot(seed, lane, t, stream, draw)
+
+
+@pytest.mark.parametrize("lanes", [1, 8, 16, 32])
+def test_fused_rollout_policy_cartpole_consistent(ctx, lanes):
+    """Categorical policy inside the step kernel: every action is the inverse-CDF choice for the recorded
+    observation (near-ties within 2e-6 of a CDF edge are tolerated and counted), and the dynamics given those
+    actions match the oracle."""
+    rng = np.random.default_rng(30 + lanes)
+    E, T = 96, 50
+    env = R.build_env(ctx, CARTPOLE, E, seed=3)
+    ewords = P.random_words(rng, E, 8 * T + 64)
+    awords = P.random_words(rng, E, 8 * T + 64)
+    env.set_noise_replay(ewords, awords)
+    params = R.init_params(rng, 5, 128, 2) * 3.0
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes),
+              R.HistoryDataBound(T, 0), traj)
+    host = traj.to_host()
+    checked, near = P.check_policy_consistency(host, params, 128, 2, awords)
+    assert checked > E * (T - 2) and near <= 3
+    # replaying the kernel's own actions through the oracle reproduces the trajectory
+    acts = host["action"].copy()
+    ref = P.oracle_rollout(CARTPOLE, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=acts, env_words=ewords)
+    P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what=f"policy lanes={lanes}")
+
+
+def test_coop_kernel_matches_single_lane_kernel(ctx):
+    """The cooperative (L threads per env) kernel and the thread-per-env kernel agree on everything but
+    logit rounding; with replayed actions they are identical."""
+    rng = np.random.default_rng(40)
+    E, T = 64, 40
+    actions = rng.integers(0, 2, size=(T, E), dtype=np.uint8)
+    words = P.random_words(rng, E, 8 * T + 64)
+    hosts = []
+    for _ in range(2):
+        env = R.build_env(ctx, CARTPOLE, E, seed=3)
+        env.set_noise_replay(words, None)
+        traj = R.Trajectory(env, T)
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_REPLAY_ACTIONS, actions=actions), R.HistoryDataBound(T, 0), traj)
+        hosts.append(traj.to_host())
+    for k in ("obs", "action", "reward", "succ", "lane_len"):
+        np.testing.assert_array_equal(hosts[0][k], hosts[1][k])
+
+
+def test_eps_greedy_q_actor_chain(ctx):
+    rng = np.random.default_rng(50)
+    cfg = R.Chain()
+    E, T, eps = 80, 30, 0.3
+    env = R.build_env(ctx, cfg, E, seed=3)
+    ewords = P.random_words(rng, E, 16 * T)
+    awords = P.random_words(rng, E, 16 * T)
+    env.set_noise_replay(ewords, awords)
+    params = R.init_params(rng, 5, 128, 2)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_EPS_GREEDY_Q, net=net, exploration_rate=eps), R.HistoryDataBound(T, 0), traj)
+    ref = P.oracle_rollout(cfg, E, T, 0, actor_kind=O.ACTOR_EPS_GREEDY_Q, params=params, env_words=ewords,
+                           actor_words=awords, exploration_rate=eps)
+    P.compare_traj(traj.to_host(), ref, what="eps-greedy chain")
+
+
+def test_rollout_lane_sharding_invariance(ctx):
+    """Philox noise is keyed by the global lane id: two half-size shards equal one full-size env."""
+    cfg, seed, E, T = R.Chain(), 99, 64, 25
+    def run(n, off):
+        env = R.build_env(ctx, cfg, n, seed=seed, lane_offset=off)
+        traj = R.Trajectory(env, T)
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_RANDOM), R.HistoryDataBound(T, 0), traj)
+        return traj.to_host()
+    full, a, b = run(E, 0), run(E // 2, 0), run(E // 2, E // 2)
+    for k in ("obs", "action", "reward", "succ"):
+        np.testing.assert_array_equal(full[k][:, : E // 2], a[k])
+        np.testing.assert_array_equal(full[k][:, E // 2 :], b[k])
