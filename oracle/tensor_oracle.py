@@ -1,0 +1,306 @@
+"""Torch-CPU restatement of the tensor side of relearn's update path.  TEST INFRASTRUCTURE ONLY.
+
+The reference computes these with `tch` -> libtorch 1.12 (not vendored, cannot be built here:
+"parity unpinned" for MLP/Adam numerics beyond the reference's own closed-form KATs, which
+tests/test_oracle_golden.py replays).  Every function follows the cited reference code op for op,
+on torch 2.11 CPU tensors, with autograd doing the first- and second-order backward passes exactly
+as `Tensor::run_backward` does in the reference.
+
+dtype: the reference runs f32 tensors with f64 host scalars; pass dtype=torch.float64 to get a
+high-precision run of the same algorithm (used to bound the f32 rounding noise of both sides).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+F32_MIN = float(torch.finfo(torch.float32).min)
+
+
+# ------------------------------------------------------------------------------------------------
+# modules (src/torch/modules/ff/mlp.rs:139-151, linear.rs:118-123)
+# ------------------------------------------------------------------------------------------------
+def unflatten_mlp(flat: torch.Tensor, n_in: int, hidden: int, n_out: int):
+    """Module::variables() order: W1[H,F], b1[H], W2[A,H], b2[A] (linear.rs:108-110, mlp.rs:126-128)."""
+    o = 0
+    shapes = [(hidden, n_in), (hidden,), (n_out, hidden), (n_out,)]
+    out = []
+    for s in shapes:
+        n = int(np.prod(s))
+        out.append(flat[o:o + n].reshape(s))
+        o += n
+    return out
+
+
+def mlp_forward(params, x):
+    w1, b1, w2, b2 = params
+    h = torch.relu(torch.nn.functional.linear(x, w1, b1))
+    return torch.nn.functional.linear(h, w2, b2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Categorical (src/torch/distributions/categorical.rs:29-76, distributions/mod.rs:25-31)
+# ------------------------------------------------------------------------------------------------
+class Categorical:
+    def __init__(self, unnormalized_log_probs: torch.Tensor):
+        self.log_probs = torch.log_softmax(unnormalized_log_probs, dim=-1)  # :29-33
+
+    def _clamp_min(self, x):
+        lo = F32_MIN if x.dtype == torch.float32 else float(torch.finfo(torch.float64).min)
+        return x.clamp_min(lo)
+
+    def log_prob(self, elements):  # :56-60
+        return self.log_probs.gather(-1, elements.unsqueeze(-1)).squeeze(-1)
+
+    def entropy(self):  # :62-68
+        return -(self._clamp_min(self.log_probs) * self.log_probs.exp()).sum(-1)
+
+    def kl_divergence_from(self, other: "Categorical"):  # :70-76  KL(self || other)
+        return (self._clamp_min(self.log_probs - other.log_probs) * self.log_probs.exp()).sum(-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# utils (src/torch/utils.rs:31-97)
+# ------------------------------------------------------------------------------------------------
+def flatten_tensors(ts):
+    return torch.cat([t.reshape(-1) for t in ts])
+
+
+def unflatten_tensors(flat, shapes):
+    out, o = [], 0
+    for s in shapes:
+        n = int(np.prod(s))
+        out.append(flat[o:o + n].reshape(s))
+        o += n
+    return out
+
+
+def flat_dot(a, b):
+    return torch.dot(a.reshape(-1), b.reshape(-1))
+
+
+# ------------------------------------------------------------------------------------------------
+# ConjugateGradientOptimizer (src/torch/optimizers/conjugate_gradient.rs:41-403)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class CgConfig:  # :55-64
+    iterations: int = 10
+    max_backtracks: int = 15
+    backtrack_ratio: float = 0.8
+    hpv_reg_coeff: float = 1e-5
+    accept_violation: bool = False
+
+
+class HessianVectorProduct:  # :262-339
+    def __init__(self, output, params, reg_coeff):
+        self.params = params
+        self.reg_coeff = reg_coeff
+        self.shapes = [tuple(p.shape) for p in params]
+        grads = torch.autograd.grad(output, params, retain_graph=True, create_graph=True, allow_unused=True)
+        self.grads = [g if g is not None else torch.zeros_like(p) for g, p in zip(grads, params)]
+
+    def mat_vec_mul(self, vector):
+        vs = unflatten_tensors(vector, self.shapes)
+        gvp = torch.stack([flat_dot(g, v) for g, v in zip(self.grads, vs)]).sum()
+        hvp = torch.autograd.grad(gvp, self.params, retain_graph=True)
+        return flatten_tensors(hvp) + self.reg_coeff * vector
+
+
+class MatrixProduct:
+    def __init__(self, m):
+        self.m = m
+
+    def mat_vec_mul(self, v):
+        return self.m.mv(v)
+
+
+def solve_conjugate_gradient(f_ax, b, iterations, residual_tol):  # :371-403
+    x = torch.zeros_like(b)
+    residual = b.clone()
+    step = b.clone()
+    rns = residual.dot(residual)
+    iters = 0
+    for _ in range(iterations):
+        iters += 1
+        z = f_ax.mat_vec_mul(step)
+        alpha = rns / step.dot(z)
+        x.addcmul_(alpha, step)
+        residual.addcmul_(-alpha, z)
+        new_rns = residual.dot(residual)
+        if float(new_rns) < residual_tol:
+            break
+        mu = new_rns / rns
+        step.mul_(mu)
+        step.add_(residual)
+        rns = new_rns
+    return x, iters
+
+
+class OptimizerStepError(Exception):
+    def __init__(self, kind, **kw):
+        super().__init__(kind)
+        self.kind = kind
+        self.info = kw
+
+
+def trust_region_backward_step(params, loss_distance_fn, max_distance, cfg: CgConfig, log: dict):  # :115-179
+    loss, distance = loss_distance_fn()
+    loss_grads = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
+    used = [(p, g) for p, g in zip(params, loss_grads) if g is not None]
+    params = [p for p, _ in used]
+    flat_loss_grads = flatten_tensors([g for _, g in used])
+    hvp_fn = HessianVectorProduct(distance, params, cfg.hpv_reg_coeff)
+    step_dir, cg_iters = solve_conjugate_gradient(hvp_fn, flat_loss_grads, cfg.iterations, 1e-10)
+    step_dir = torch.nan_to_num(step_dir, nan=0.0)
+    val = 1.0 / (float(step_dir.dot(hvp_fn.mat_vec_mul(step_dir))) + 1e-8) * max_distance * 2.0
+    step_size = math.sqrt(val) if val >= 0 else float("nan")
+    if math.isnan(step_size):
+        step_size = 1.0
+    log["step_size"] = step_size
+    log["cg_iterations"] = cg_iters
+    log["flat_grad"] = flat_loss_grads.detach().clone()
+    log["step_dir"] = step_dir.detach().clone()
+    descent_step = step_size * step_dir
+    initial_loss = float(loss)
+    backtracking_line_search(params, descent_step, loss_distance_fn, max_distance, initial_loss, cfg, log)
+    return initial_loss
+
+
+def backtracking_line_search(params, descent_step, loss_constraint_fn, max_constraint_value, initial_loss,
+                             cfg: CgConfig, log: dict):  # :183-254
+    prev_params = [p.detach().clone() for p in params]
+    shapes = [tuple(p.shape) for p in params]
+    steps = unflatten_tensors(descent_step.detach(), shapes)
+    loss = initial_loss
+    constraint_val = float("inf")
+    log["loss_initial"] = loss
+    log["num_backtracks"] = -1
+    for i in range(cfg.max_backtracks):
+        ratio = cfg.backtrack_ratio ** i
+        with torch.no_grad():
+            for step, prev, p in zip(steps, prev_params, params):
+                p.copy_(prev - ratio * step)
+        with torch.no_grad():
+            lt, ct = loss_constraint_fn()
+        loss, constraint_val = float(lt), float(ct)
+        if loss < initial_loss and constraint_val <= max_constraint_value:
+            log["num_backtracks"] = i
+            log["step_scale"] = ratio
+            break
+    log["loss_final"] = loss
+    log["constraint_val_final"] = constraint_val
+    err = None
+    if math.isnan(loss):
+        err = OptimizerStepError("NaNLoss")
+    elif math.isnan(constraint_val):
+        err = OptimizerStepError("NaNConstraint")
+    elif loss >= initial_loss:
+        err = OptimizerStepError("LossNotImproving", loss=loss, loss_before=initial_loss)
+    elif constraint_val >= max_constraint_value and not cfg.accept_violation:
+        err = OptimizerStepError("ConstraintViolated", constraint_val=constraint_val)
+    if err is not None:
+        with torch.no_grad():
+            for p, prev in zip(params, prev_params):
+                p.copy_(prev)
+        raise err
+
+
+# ------------------------------------------------------------------------------------------------
+# Trpo::update (src/torch/agents/policies/trpo.rs:97-164)
+# ------------------------------------------------------------------------------------------------
+def trpo_update(flat_params: np.ndarray, n_in, hidden, n_out, obs, actions, advantages, max_kl=0.01,
+                cfg: CgConfig | None = None, dtype=torch.float32):
+    """Returns (new_flat_params, log dict with the reference's log keys + 'error')."""
+    cfg = cfg or CgConfig()
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    act_t = torch.tensor(np.asarray(actions), dtype=torch.int64)
+    adv_t = torch.tensor(np.asarray(advantages), dtype=dtype)
+    log = {}
+    with torch.no_grad():
+        dist0 = Categorical(mlp_forward(params, obs_t))
+        logp0 = dist0.log_prob(act_t)
+        log["entropy"] = float(dist0.entropy().mean())
+
+    def loss_distance_fn():
+        dist = Categorical(mlp_forward(params, obs_t))
+        ratio = (dist.log_prob(act_t) - logp0).exp()
+        loss = -(ratio * adv_t).mean()
+        distance = dist0.kl_divergence_from(dist).mean()
+        return loss, distance
+
+    log["error"] = None
+    try:
+        trust_region_backward_step(params, loss_distance_fn, max_kl, cfg, log)
+    except OptimizerStepError as e:
+        log["error"] = e.kind
+    new_flat = flatten_tensors([p.detach() for p in params]).numpy().copy()
+    return new_flat, log
+
+
+def policy_loss_kl_grad_fvp(flat_params, n_in, hidden, n_out, obs, actions, advantages, vector, reg=0.0,
+                            dtype=torch.float64):
+    """Pieces of the TRPO step for kernel-level parity: loss, KL, flat loss gradient, (H + reg I) v."""
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    act_t = torch.tensor(np.asarray(actions), dtype=torch.int64)
+    adv_t = torch.tensor(np.asarray(advantages), dtype=dtype)
+    with torch.no_grad():
+        dist0 = Categorical(mlp_forward(params, obs_t))
+        logp0 = dist0.log_prob(act_t)
+        entropy = float(dist0.entropy().mean())
+    dist = Categorical(mlp_forward(params, obs_t))
+    loss = -((dist.log_prob(act_t) - logp0).exp() * adv_t).mean()
+    kl = dist0.kl_divergence_from(dist).mean()
+    g = flatten_tensors(torch.autograd.grad(loss, params, retain_graph=True))
+    hvp = HessianVectorProduct(kl, params, reg)
+    hv = hvp.mat_vec_mul(torch.tensor(np.asarray(vector), dtype=dtype))
+    return float(loss), float(kl), entropy, g.detach().numpy(), hv.detach().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# ValuesOpt::update + n_backward_steps + Adam (critics/opt.rs:100-127, torch/agents/mod.rs:35-72,
+# optimizers/coptimizer.rs:13-27,136-168; libtorch Adam defaults eps=1e-8, amsgrad=false)
+# ------------------------------------------------------------------------------------------------
+def value_update(flat_params, n_in, hidden, obs, targets, n_steps=80, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0,
+                 eps=1e-8, dtype=torch.float32, adam_state=None):
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, 1)]
+    opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+    if adam_state is not None:
+        opt.load_state_dict(adam_state)
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    tgt_t = torch.tensor(np.asarray(targets), dtype=dtype)
+    losses = []
+    for _ in range(n_steps):
+        loss = torch.nn.functional.mse_loss(mlp_forward(params, obs_t).squeeze(-1), tgt_t, reduction="mean")
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    new_flat = flatten_tensors([p.detach() for p in params]).numpy().copy()
+    return new_flat, losses, opt.state_dict()
+
+
+def q_update(flat_params, n_in, hidden, n_out, obs, actions, targets, n_steps=1, lr=1e-3, dtype=torch.float32):
+    """DQN loss (dqn.rs:316-326): mse(Q(obs).gather(actions), targets) + Adam steps."""
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    opt = torch.optim.Adam(params, lr=lr)
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    act_t = torch.tensor(np.asarray(actions), dtype=torch.int64).unsqueeze(-1)
+    tgt_t = torch.tensor(np.asarray(targets), dtype=dtype)
+    losses = []
+    for _ in range(n_steps):
+        q = mlp_forward(params, obs_t).gather(-1, act_t).squeeze(-1)
+        loss = torch.nn.functional.mse_loss(q, tgt_t, reduction="mean")
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses

@@ -140,7 +140,7 @@ def test_tabular_q_chain_bit_exact(ctx):
     traj = R.Trajectory(env, T)
     olib = O.lib()
     for period in range(periods):
-        ewords = P.random_words(rng, E, 4 * T)
+        ewords = P.random_words(rng, E, 6 * T)
         awords = P.random_words(rng, E, 6 * T)
         env.set_noise_replay(ewords, awords)
         R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_TABULAR_EPS_GREEDY, table=table, exploration_rate=eps, training=True),
