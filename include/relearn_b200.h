@@ -295,6 +295,13 @@ typedef struct rl_trpo_stats {
 rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const rl_trpo_cfg *cfg,
                          rl_trpo_stats *stats);
 
+/* The pieces of one TRPO step for diagnostics and parity checks: the loss_distance_fn closure of
+ * trpo.rs:124-146 at the current parameters (loss, kl, entropy of the behaviour policy), the flat
+ * loss gradient (conjugate_gradient.rs:127,143) and HessianVectorProduct::mat_vec_mul(vec)
+ * (conjugate_gradient.rs:312-338).  grad_host / fvp_host: f32 [num_params]; any output may be NULL. */
+rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const float *vec_host, double hpv_reg_coeff,
+                        double *loss, double *kl, double *entropy, float *grad_host, float *fvp_host);
+
 /* ------------------------------------------------------------------------------------------ */
 /* Critic / Adam (Critic::update src/torch/agents/critics/opt.rs:100-127; n_backward_steps      */
 /*   src/torch/agents/mod.rs:35-72; COptimizer/AdamConfig src/torch/optimizers/coptimizer.rs)   */

@@ -267,31 +267,58 @@ def policy_loss_kl_grad_fvp(flat_params, n_in, hidden, n_out, obs, actions, adva
 # ValuesOpt::update + n_backward_steps + Adam (critics/opt.rs:100-127, torch/agents/mod.rs:35-72,
 # optimizers/coptimizer.rs:13-27,136-168; libtorch Adam defaults eps=1e-8, amsgrad=false)
 # ------------------------------------------------------------------------------------------------
+class Adam112:
+    """libtorch 1.12 `torch::optim::Adam::step` (torch/csrc/api/src/optim/adam.cpp), the optimizer the
+    reference's COptimizer::adam constructs: mul_/add_ moment updates (not the lerp_ of newer Python
+    torch.optim.Adam), eps 1e-8, no amsgrad."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0, eps=1e-8):
+        self.params = params
+        self.lr, self.betas, self.wd, self.eps = lr, betas, weight_decay, eps
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.step_count = 0
+
+    @torch.no_grad()
+    def step(self, grads):
+        self.step_count += 1
+        b1, b2 = self.betas
+        bc1 = 1 - b1 ** self.step_count
+        bc2 = 1 - b2 ** self.step_count
+        for p, g, m, v in zip(self.params, grads, self.m, self.v):
+            if self.wd != 0:
+                g = g.add(p, alpha=self.wd)
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (v.sqrt() / math.sqrt(bc2)).add_(self.eps)
+            p.addcdiv_(m, denom, value=-(self.lr / bc1))
+
+
 def value_update(flat_params, n_in, hidden, obs, targets, n_steps=80, lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0,
-                 eps=1e-8, dtype=torch.float32, adam_state=None):
+                 eps=1e-8, dtype=torch.float32, opt=None):
     flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
     params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, 1)]
-    opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
-    if adam_state is not None:
-        opt.load_state_dict(adam_state)
+    if opt is None:
+        opt = Adam112(params, lr, betas, weight_decay, eps)
+    else:
+        opt.params = params
     obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
     tgt_t = torch.tensor(np.asarray(targets), dtype=dtype)
     losses = []
     for _ in range(n_steps):
         loss = torch.nn.functional.mse_loss(mlp_forward(params, obs_t).squeeze(-1), tgt_t, reduction="mean")
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
+        grads = torch.autograd.grad(loss, params)
+        opt.step(grads)
         losses.append(float(loss))
     new_flat = flatten_tensors([p.detach() for p in params]).numpy().copy()
-    return new_flat, losses, opt.state_dict()
+    return new_flat, losses, opt
 
 
 def q_update(flat_params, n_in, hidden, n_out, obs, actions, targets, n_steps=1, lr=1e-3, dtype=torch.float32):
     """DQN loss (dqn.rs:316-326): mse(Q(obs).gather(actions), targets) + Adam steps."""
     flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
     params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
-    opt = torch.optim.Adam(params, lr=lr)
+    opt = Adam112(params, lr)
     obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
     act_t = torch.tensor(np.asarray(actions), dtype=torch.int64).unsqueeze(-1)
     tgt_t = torch.tensor(np.asarray(targets), dtype=dtype)
@@ -299,8 +326,6 @@ def q_update(flat_params, n_in, hidden, n_out, obs, actions, targets, n_steps=1,
     for _ in range(n_steps):
         q = mlp_forward(params, obs_t).gather(-1, act_t).squeeze(-1)
         loss = torch.nn.functional.mse_loss(q, tgt_t, reduction="mean")
-        opt.zero_grad()
-        loss.backward()
-        opt.step()
+        opt.step(torch.autograd.grad(loss, params))
         losses.append(float(loss))
     return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses

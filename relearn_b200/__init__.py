@@ -11,3 +11,7 @@ from .runtime import Context, DeviceBuffer  # noqa: F401
 from .simulation import ActorSpec, HistoryDataBound, Trajectory, rollout  # noqa: F401
 
 __version__ = "0.1.0"
+from .agents import TabularQ  # noqa: F401,E402
+from .torch_agents import (ActorCriticAgent, ActorCriticConfig, Adam, AdamConfig,  # noqa: F401,E402
+                           ConjugateGradientOptimizerConfig, OptimizerStepError, Trpo, TrpoConfig, ValuesOpt,
+                           ValuesOptConfig)

@@ -166,6 +166,7 @@ SIGNATURES = {
     "rl_gae": (st, [vp, vp, C.c_float, C.c_float, vp, vp]),
     "rl_trpo_cfg_default": (None, [P(TrpoCfg)]),
     "rl_trpo_update": (st, [vp, vp, vp, P(TrpoCfg), P(TrpoStats)]),
+    "rl_trpo_probe": (st, [vp, vp, vp, vp, C.c_double, P(C.c_double), P(C.c_double), P(C.c_double), vp, vp]),
     "rl_adam_cfg_default": (None, [P(AdamCfg)]),
     "rl_adam_create": (st, [vp, P(AdamCfg), P(vp)]),
     "rl_adam_destroy": (st, [vp]),

@@ -4,25 +4,6 @@
 
 extern "C" {
 
-void rl_trpo_cfg_default(rl_trpo_cfg *c) {
-    // trpo.rs:29-38, conjugate_gradient.rs:55-64
-    c->max_policy_step_kl = 0.01; c->cg_iterations = 10; c->max_backtracks = 15; c->backtrack_ratio = 0.8;
-    c->hpv_reg_coeff = 1e-5; c->accept_violation = 0;
-}
-void rl_adam_cfg_default(rl_adam_cfg *c) {
-    // coptimizer.rs:136-168; eps is libtorch's default
-    c->learning_rate = 1e-3; c->beta1 = 0.9; c->beta2 = 0.999; c->weight_decay = 0.0; c->eps = 1e-8;
-}
-rl_status rl_trpo_update(rl_traj *traj, const float *, rl_mlp *, const rl_trpo_cfg *, rl_trpo_stats *) {
-    return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_UNSUPPORTED, "rl_trpo_update: not built yet");
-}
-rl_status rl_adam_create(rl_mlp *mlp, const rl_adam_cfg *, rl_adam **) {
-    return rl_fail(mlp ? mlp->ctx : nullptr, RL_ERR_UNSUPPORTED, "rl_adam_create: not built yet");
-}
-rl_status rl_adam_destroy(rl_adam *) { return RL_OK; }
-rl_status rl_value_update(rl_traj *traj, const float *, rl_mlp *, rl_adam *, int32_t, rl_opt_stats *) {
-    return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_UNSUPPORTED, "rl_value_update: not built yet");
-}
 rl_status rl_replay_create(rl_env *env, uint64_t, rl_replay **) {
     return rl_fail(env ? env->ctx : nullptr, RL_ERR_UNSUPPORTED, "rl_replay_create: not built yet");
 }

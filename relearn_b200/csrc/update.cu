@@ -1,0 +1,885 @@
+// update.cu -- the on-policy update: TRPO policy step and Adam critic step.
+//
+// Reference: Trpo::update (src/torch/agents/policies/trpo.rs:97-164),
+// ConjugateGradientOptimizer (src/torch/optimizers/conjugate_gradient.rs:115-403),
+// ValuesOpt::update (src/torch/agents/critics/opt.rs:100-127), n_backward_steps
+// (src/torch/agents/mod.rs:35-72), COptimizer/Adam (src/torch/optimizers/coptimizer.rs:13-27).
+//
+// The reference runs ~29 full-batch libtorch passes with autograd (first and second order) and a
+// host sync per CG iteration and per line-search try.  Here every pass over the batch is one fused
+// kernel (K5/K6, FP32-FMA bound) that computes forward, the per-sample softmax algebra and the
+// analytic backward / Fisher-vector product in registers, and every piece of P-vector algebra (CG
+// recurrences, step size, line-search bookkeeping, Adam) is a single-CTA kernel driven by device-side
+// flags, so the whole update is enqueued without a host round trip.
+//
+// mlp_pass_kernel<F, A, UPL, MODE>: one warp owns a tile of 32 samples; lane l owns hidden units
+// {l + 32u : u < UPL} (H = 32 * UPL) with their weights in registers.  Forward computes each lane's
+// partial logits for 8 samples at a time and combines them with a shuffle reduce-scatter; the lane
+// that loaded sample s does that sample's softmax / loss / KL algebra; the backward sweep re-derives
+// the hidden activations (cheaper than staging them through shared memory) and accumulates this
+// lane's slice of the parameter gradient in f32 registers, flushed to per-warp f64 totals in shared
+// memory every few tiles.  Blocks write f64 partial rows; rows are summed in a fixed order, so the
+// result is deterministic and independent of scheduling.
+//
+// Exactness: the Hessian of mean KL(p0 || p_theta) at theta0 equals the Fisher matrix
+// mean J^T (diag p - p p^T) J (the first-order term vanishes because p = p0 there), so the analytic
+// Fisher-vector product is the reference's double-backward Hessian-vector product.
+#include "handles.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace {
+
+enum { PASS_STATS = 0, PASS_EVAL = 1, PASS_GRAD = 2, PASS_FVP = 3, PASS_VALUE = 4, PASS_QLOSS = 5 };
+enum { SC_LOSS = 0, SC_KL = 1, SC_ENTROPY = 2, SC_COUNT = 3, NSCALAR = 4 };
+constexpr float F32_LOWEST = -3.402823466e+38f;
+constexpr int PASS_THREADS = 256;
+constexpr int FLUSH_TILES = 4;
+
+struct PassArgs {
+    const float *obs;
+    const uint8_t *action, *succ;
+    uint64_t T, E;
+    const float *theta, *vec;
+    const float *adv;
+    float *logp0;         // f32 [T*E][2]
+    const float *target;  // f32 [T*E]
+    double *partials;     // f64 [gridDim.x][P + NSCALAR]
+    const int *skip_flag;
+};
+
+template <int A>
+__device__ __forceinline__ void log_softmax(const float *z, float *lp) {
+    if (A == 1) {
+        lp[0] = 0.0f;
+        return;
+    }
+    float m = z[0];
+#pragma unroll
+    for (int k = 1; k < A; ++k) m = fmaxf(m, z[k]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < A; ++k) sum += expf(z[k] - m);
+    const float lse = m + logf(sum);
+#pragma unroll
+    for (int k = 0; k < A; ++k) lp[k] = z[k] - lse;
+}
+
+// Reduce v[0..7] across the 32 lanes; afterwards every lane of quad q (lanes 4q..4q+3) holds the
+// complete sum of element q.  9 shuffles.
+__device__ __forceinline__ float reduce_scatter8(float *v, int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? v[i] : v[i + 2], keep = b3 ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const float send = b2 ? v[0] : v[1], keep = b2 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+__device__ __forceinline__ double warp_sum_f64(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+template <int F, int A, int UPL, int MODE>
+__global__ void __launch_bounds__(PASS_THREADS, 1) mlp_pass_kernel(PassArgs a) {
+    constexpr int H = 32 * UPL;
+    constexpr int P = H * F + H + A * H + A;
+    constexpr int W = P + NSCALAR;
+    constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS;
+    constexpr bool IS_POLICY = MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP;
+    if (a.skip_flag && *a.skip_flag) return;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // per-warp regions: f64 totals [P], x tile [32][8], dz tile [32][2]
+    double *tot_all = reinterpret_cast<double *>(smem_raw);
+    double *tot = tot_all + (size_t)warp * P;
+    float *xs_all = reinterpret_cast<float *>(tot_all + (size_t)nwarps * P);
+    float *xs = xs_all + (size_t)warp * 32 * 8;
+    float *dzs = xs_all + (size_t)nwarps * 32 * 8 + (size_t)warp * 32 * 2;
+    if (BACKWARD)
+        for (int i = lane; i < P; i += 32) tot[i] = 0.0;
+
+    // this lane's slice of the parameters: units j = lane + 32 u
+    const float *tw1 = a.theta, *tb1 = tw1 + H * F, *tw2 = tb1 + H, *tb2 = tw2 + A * H;
+    float w1[UPL][F], b1[UPL], w2[A][UPL], b2[A];
+#pragma unroll
+    for (int u = 0; u < UPL; ++u) {
+        const int j = lane + 32 * u;
+#pragma unroll
+        for (int f = 0; f < F; ++f) w1[u][f] = tw1[j * F + f];
+        b1[u] = tb1[j];
+#pragma unroll
+        for (int k = 0; k < A; ++k) w2[k][u] = tw2[k * H + j];
+    }
+#pragma unroll
+    for (int k = 0; k < A; ++k) b2[k] = tb2[k];
+    // FVP direction slice
+    float vw1[MODE == PASS_FVP ? UPL : 1][F], vb1[MODE == PASS_FVP ? UPL : 1], vw2[A][MODE == PASS_FVP ? UPL : 1], vb2[A];
+    if (MODE == PASS_FVP) {
+        const float *pw1 = a.vec, *pb1 = pw1 + H * F, *pw2 = pb1 + H, *pb2 = pw2 + A * H;
+#pragma unroll
+        for (int u = 0; u < UPL; ++u) {
+            const int j = lane + 32 * u;
+#pragma unroll
+            for (int f = 0; f < F; ++f) vw1[u][f] = pw1[j * F + f];
+            vb1[u] = pb1[j];
+#pragma unroll
+            for (int k = 0; k < A; ++k) vw2[k][u] = pw2[k * H + j];
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) vb2[k] = pb2[k];
+    }
+    // gradient accumulators (f32, flushed to f64)
+    float gw1[BACKWARD ? UPL : 1][F], gb1[BACKWARD ? UPL : 1], gw2[A][BACKWARD ? UPL : 1];
+    if (BACKWARD) {
+#pragma unroll
+        for (int u = 0; u < UPL; ++u) {
+#pragma unroll
+            for (int f = 0; f < F; ++f) gw1[u][f] = 0.0f;
+            gb1[u] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < A; ++k) gw2[k][u] = 0.0f;
+        }
+    }
+    double gb2[A], sc[NSCALAR];
+#pragma unroll
+    for (int k = 0; k < A; ++k) gb2[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSCALAR; ++k) sc[k] = 0.0;
+
+    auto flush = [&]() {
+        if (!BACKWARD) return;
+#pragma unroll
+        for (int u = 0; u < UPL; ++u) {
+            const int j = lane + 32 * u;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                tot[j * F + f] += (double)gw1[u][f];
+                gw1[u][f] = 0.0f;
+            }
+            tot[H * F + j] += (double)gb1[u];
+            gb1[u] = 0.0f;
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                tot[H * F + H + k * H + j] += (double)gw2[k][u];
+                gw2[k][u] = 0.0f;
+            }
+        }
+    };
+
+    const uint64_t TE = a.T * a.E;
+    const uint64_t ntiles = (TE + 31) / 32;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * nwarps + warp, total_warps = (uint64_t)gridDim.x * nwarps;
+    int since_flush = 0;
+    for (uint64_t tile = warp_global; tile < ntiles; tile += total_warps) {
+        // ---- load this lane's sample ----
+        const uint64_t n = tile * 32 + lane;
+        const bool in_range = n < TE;
+        const uint8_t sc_code = in_range ? a.succ[n] : (uint8_t)RL_PAD;
+        const bool valid = sc_code != RL_PAD;
+        const uint64_t t = in_range ? n / a.E : 0, e = in_range ? n - t * a.E : 0;
+        float xv[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xv[f] = (f < F && valid) ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
+        __syncwarp();
+        reinterpret_cast<float4 *>(xs)[lane * 2] = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        reinterpret_cast<float4 *>(xs)[lane * 2 + 1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
+        const int act_s = (IS_POLICY || MODE == PASS_QLOSS) ? (valid ? (int)a.action[n] : 0) : 0;
+        float adv_s = 0.0f, tgt_s = 0.0f, lp0[A];
+        if (MODE == PASS_EVAL || MODE == PASS_GRAD) adv_s = valid ? a.adv[n] : 0.0f;
+        if (MODE == PASS_VALUE || MODE == PASS_QLOSS) tgt_s = valid ? a.target[n] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) lp0[k] = 0.0f;
+        if ((MODE == PASS_EVAL || MODE == PASS_GRAD) && valid) {
+            const float2 l = reinterpret_cast<const float2 *>(a.logp0)[n];
+            lp0[0] = l.x;
+            if (A > 1) lp0[A > 1 ? 1 : 0] = l.y;
+        }
+        __syncwarp();
+
+        // ---- forward: partial logits, 8 samples at a time ----
+        float z[A], zd[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) z[k] = zd[k] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float pz[A][8], pzd[MODE == PASS_FVP ? A : 1][8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 xa = reinterpret_cast<const float4 *>(xs)[(c * 8 + i) * 2];
+                const float4 xb = reinterpret_cast<const float4 *>(xs)[(c * 8 + i) * 2 + 1];
+                const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    pz[k][i] = 0.0f;
+                    if (MODE == PASS_FVP) pzd[k][i] = 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < UPL; ++u) {
+                    float pre = b1[u];
+#pragma unroll
+                    for (int f = 0; f < F; ++f) pre = fmaf(w1[u][f], x[f], pre);
+                    const float h = pre < 0.0f ? 0.0f : pre;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) pz[k][i] = fmaf(w2[k][u], h, pz[k][i]);
+                    if (MODE == PASS_FVP) {
+                        float dpre = vb1[u];
+#pragma unroll
+                        for (int f = 0; f < F; ++f) dpre = fmaf(vw1[u][f], x[f], dpre);
+                        const float dh = pre > 0.0f ? dpre : 0.0f;
+#pragma unroll
+                        for (int k = 0; k < A; ++k) pzd[k][i] = fmaf(vw2[k][u], h, fmaf(w2[k][u], dh, pzd[k][i]));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < A; ++k) {
+                const float full = reduce_scatter8(pz[k], lane);
+                const float mine = __shfl_sync(0xffffffffu, full, 4 * (lane & 7));
+                if ((lane >> 3) == c) z[k] = mine;
+                if (MODE == PASS_FVP) {
+                    const float fulld = reduce_scatter8(pzd[k], lane);
+                    const float mined = __shfl_sync(0xffffffffu, fulld, 4 * (lane & 7));
+                    if ((lane >> 3) == c) zd[k] = mined;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+            z[k] += b2[k];
+            if (MODE == PASS_FVP) zd[k] += vb2[k];
+        }
+
+        // ---- per-sample algebra on the lane that owns the sample ----
+        float dz[A];
+#pragma unroll
+        for (int k = 0; k < A; ++k) dz[k] = 0.0f;
+        if (valid) {
+            sc[SC_COUNT] += 1.0;
+            if (IS_POLICY) {
+                float lp[A], p[A];
+                log_softmax<A>(z, lp);
+#pragma unroll
+                for (int k = 0; k < A; ++k) p[k] = expf(lp[k]);
+                if (MODE == PASS_STATS) {
+                    // trpo.rs:112-122: log-probs of the behaviour policy and its entropy (categorical.rs:62-68)
+                    float ent = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) ent += fmaxf(lp[k], F32_LOWEST) * p[k];
+                    sc[SC_ENTROPY] += (double)(-ent);
+                    reinterpret_cast<float2 *>(a.logp0)[n] = make_float2(lp[0], A > 1 ? lp[A > 1 ? 1 : 0] : 0.0f);
+                }
+                if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
+                    // trpo.rs:129-144: ratio = exp(logp - logp0); loss = -mean(ratio * adv); KL(p0 || p)
+                    float lpa = lp[0], lp0a = lp0[0];
+#pragma unroll
+                    for (int k = 1; k < A; ++k)
+                        if (act_s == k) { lpa = lp[k]; lp0a = lp0[k]; }
+                    const float ratio = expf(lpa - lp0a);
+                    sc[SC_LOSS] += (double)(-(ratio * adv_s));
+                    float kl = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) kl += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
+                    sc[SC_KL] += (double)kl;
+                    if (MODE == PASS_GRAD) {
+                        const float g = -(ratio * adv_s);  // d loss_s / d logp_a
+#pragma unroll
+                        for (int k = 0; k < A; ++k) dz[k] = g * ((act_s == k ? 1.0f : 0.0f) - p[k]);
+                    }
+                }
+                if (MODE == PASS_FVP) {
+                    // u = (diag p - p p^T) zdot
+                    float pd = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) pd = fmaf(p[k], zd[k], pd);
+#pragma unroll
+                    for (int k = 0; k < A; ++k) dz[k] = p[k] * (zd[k] - pd);
+                }
+            } else if (MODE == PASS_VALUE) {
+                // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
+                const float diff = z[0] - tgt_s;
+                sc[SC_LOSS] += (double)(diff * diff);
+                dz[0] = 2.0f * diff;
+            } else if (MODE == PASS_QLOSS) {
+                // dqn.rs:316-326: mse(Q(obs).gather(action), targets)
+                float q = z[0];
+#pragma unroll
+                for (int k = 1; k < A; ++k)
+                    if (act_s == k) q = z[k];
+                const float diff = q - tgt_s;
+                sc[SC_LOSS] += (double)(diff * diff);
+#pragma unroll
+                for (int k = 0; k < A; ++k) dz[k] = act_s == k ? 2.0f * diff : 0.0f;
+            }
+        }
+
+        // ---- backward sweep ----
+        if (BACKWARD) {
+#pragma unroll
+            for (int k = 0; k < A; ++k) gb2[k] += (double)dz[k];
+            reinterpret_cast<float2 *>(dzs)[lane] = make_float2(dz[0], A > 1 ? dz[A > 1 ? 1 : 0] : 0.0f);
+            __syncwarp();
+#pragma unroll 4
+            for (int s = 0; s < 32; ++s) {
+                const float2 d2 = reinterpret_cast<const float2 *>(dzs)[s];
+                const float d[2] = {d2.x, d2.y};
+                const float4 xa = reinterpret_cast<const float4 *>(xs)[s * 2];
+                const float4 xb = reinterpret_cast<const float4 *>(xs)[s * 2 + 1];
+                const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+                for (int u = 0; u < UPL; ++u) {
+                    float pre = b1[u];
+#pragma unroll
+                    for (int f = 0; f < F; ++f) pre = fmaf(w1[u][f], x[f], pre);
+                    const float h = pre < 0.0f ? 0.0f : pre;
+                    float dh = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < A; ++k) {
+                        gw2[k][u] = fmaf(d[k], h, gw2[k][u]);
+                        dh = fmaf(d[k], w2[k][u], dh);
+                    }
+                    dh = pre > 0.0f ? dh : 0.0f;
+                    gb1[u] += dh;
+#pragma unroll
+                    for (int f = 0; f < F; ++f) gw1[u][f] = fmaf(dh, x[f], gw1[u][f]);
+                }
+            }
+            if (++since_flush == FLUSH_TILES) {
+                flush();
+                since_flush = 0;
+            }
+        }
+    }
+    flush();
+
+    // ---- block reduction into one partial row ----
+    double *red = reinterpret_cast<double *>(xs_all);  // reuse the tile region: [nwarps][NSCALAR + A]
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NSCALAR; ++k) {
+        const double s = warp_sum_f64(sc[k]);
+        if (lane == 0) red[warp * (NSCALAR + A) + k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        const double s = warp_sum_f64(gb2[k]);
+        if (lane == 0) red[warp * (NSCALAR + A) + NSCALAR + k] = s;
+    }
+    __syncthreads();
+    double *row = a.partials + (size_t)blockIdx.x * W;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        double s = 0.0;
+        if (i < P - A) {
+            if (BACKWARD)
+                for (int w = 0; w < nwarps; ++w) s += tot_all[(size_t)w * P + i];
+        } else if (i < P) {
+            if (BACKWARD)
+                for (int w = 0; w < nwarps; ++w) s += red[w * (NSCALAR + A) + NSCALAR + (i - (P - A))];
+        } else {
+            for (int w = 0; w < nwarps; ++w) s += red[w * (NSCALAR + A) + (i - P)];
+        }
+        row[i] = s;
+    }
+}
+
+// rows[B][W] -> out[W], fixed summation order
+__global__ void reduce_rows_kernel(const double *__restrict__ rows, int B, int W, double *__restrict__ out,
+                                   const int *skip_flag) {
+    if (skip_flag && *skip_flag) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W) return;
+    double s = 0.0;
+    for (int b = 0; b < B; ++b) s += rows[(size_t)b * W + i];
+    out[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// single-CTA vector kernels
+// ------------------------------------------------------------------------------------------------
+struct TrpoState {
+    double N, loss0, entropy, rr, step_size, step_scale, loss_final, kl_final;
+    int cg_done, cg_iters, accepted, num_backtracks, status, evals;
+};
+
+constexpr int VEC_THREADS = 1024;
+
+__device__ double block_sum_f64(double v) {
+    __shared__ double red[32];
+    __shared__ double result;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum_f64(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double s = lane < (int)(blockDim.x >> 5) ? red[lane] : 0.0;
+        s = warp_sum_f64(s);
+        if (lane == 0) result = s;
+    }
+    __syncthreads();
+    return result;
+}
+
+__global__ void trpo_begin_kernel(TrpoState *st, const double *sums, int P) {
+    if (threadIdx.x == 0) {
+        st->N = sums[P + SC_COUNT];
+        st->entropy = sums[P + SC_ENTROPY] / st->N;
+        st->cg_done = 0; st->cg_iters = 0; st->accepted = 0; st->num_backtracks = -1; st->status = RL_OK; st->evals = 0;
+        st->step_size = 0.0; st->step_scale = 0.0; st->rr = 0.0;
+        st->loss0 = 0.0; st->loss_final = 0.0; st->kl_final = INFINITY;
+    }
+}
+
+// g = grad / N; x = 0; r = p = g; rr = r.r  (conjugate_gradient.rs:121-143,377-384)
+__global__ void __launch_bounds__(VEC_THREADS)
+    trpo_cg_init_kernel(TrpoState *st, const double *sums, int P, float *g, float *x, float *r, float *p,
+                        const float *theta, float *theta0) {
+    const double N = st->N;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float gi = (float)(sums[i] / N);
+        g[i] = gi; x[i] = 0.0f; r[i] = gi; p[i] = gi;
+        theta0[i] = theta[i];
+        acc += (double)gi * (double)gi;
+    }
+    const double rr = block_sum_f64(acc);
+    if (threadIdx.x == 0) {
+        st->rr = (double)(float)rr;
+        st->loss0 = (double)(float)(sums[P + SC_LOSS] / N);
+        st->loss_final = st->loss0;
+    }
+}
+
+// one CG iteration given the Fisher-vector product of p (conjugate_gradient.rs:386-401, :335-337)
+__global__ void __launch_bounds__(VEC_THREADS)
+    trpo_cg_step_kernel(TrpoState *st, const double *sums, int P, float *x, float *r, float *p, float reg, double tol) {
+    if (st->cg_done) return;
+    __shared__ float s_alpha, s_mu;
+    __shared__ int s_done;
+    const double N = st->N;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float z = __fadd_rn((float)(sums[i] / N), __fmul_rn(p[i], reg));
+        acc += (double)p[i] * (double)z;
+    }
+    const double pz = block_sum_f64(acc);
+    if (threadIdx.x == 0) s_alpha = (float)st->rr / (float)pz;
+    __syncthreads();
+    const float alpha = s_alpha;
+    acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float z = __fadd_rn((float)(sums[i] / N), __fmul_rn(p[i], reg));
+        x[i] = __fadd_rn(x[i], __fmul_rn(alpha, p[i]));
+        const float ri = __fadd_rn(r[i], __fmul_rn(-alpha, z));
+        r[i] = ri;
+        acc += (double)ri * (double)ri;
+    }
+    const double rr_new = block_sum_f64(acc);
+    if (threadIdx.x == 0) {
+        const float rrn = (float)rr_new;
+        st->cg_iters += 1;
+        if ((double)rrn < tol) {
+            s_done = 1;
+            st->cg_done = 1;
+        } else {
+            s_done = 0;
+            s_mu = rrn / (float)st->rr;
+            st->rr = (double)rrn;
+        }
+    }
+    __syncthreads();
+    if (!s_done) {
+        const float mu = s_mu;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) p[i] = __fadd_rn(__fmul_rn(p[i], mu), r[i]);
+    }
+}
+
+// nan_to_num_(0.0, None, None) on the step direction (conjugate_gradient.rs:152); also re-arms the FVP pass
+__global__ void trpo_nan_to_num_kernel(TrpoState *st, float *x, int P) {
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        float v = x[i];
+        if (isnan(v)) v = 0.0f;
+        else if (isinf(v)) v = v > 0.0f ? 3.402823466e+38f : -3.402823466e+38f;
+        x[i] = v;
+    }
+    if (threadIdx.x == 0) st->cg_done = 0;  // the step-size FVP must always run
+}
+
+// step_size = sqrt(2 delta / (x.Hx + 1e-8)), NaN -> 1; descent = step_size * x  (conjugate_gradient.rs:155-166)
+__global__ void __launch_bounds__(VEC_THREADS)
+    trpo_step_size_kernel(TrpoState *st, const double *sums, int P, const float *x, float *descent, float reg,
+                          double max_kl) {
+    __shared__ float s_step;
+    const double N = st->N;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        const float hx = __fadd_rn((float)(sums[i] / N), __fmul_rn(x[i], reg));
+        acc += (double)x[i] * (double)hx;
+    }
+    const double xhx = block_sum_f64(acc);
+    if (threadIdx.x == 0) {
+        double step = sqrt(1.0 / ((double)(float)xhx + 1e-8) * max_kl * 2.0);
+        if (isnan(step)) step = 1.0;
+        st->step_size = step;
+        s_step = (float)step;
+    }
+    __syncthreads();
+    const float step = s_step;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) descent[i] = __fmul_rn(step, x[i]);
+}
+
+// theta = theta0 - ratio * descent  (conjugate_gradient.rs:201-213)
+__global__ void trpo_ls_candidate_kernel(const TrpoState *st, float *theta, const float *theta0, const float *descent,
+                                         float ratio, int P) {
+    if (st->accepted) return;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) theta[i] = __fsub_rn(theta0[i], __fmul_rn(ratio, descent[i]));
+}
+
+// accept iff loss < loss0 && kl <= max_kl  (conjugate_gradient.rs:215-223)
+__global__ void trpo_ls_check_kernel(TrpoState *st, const double *sums, int P, double max_kl, int i, double ratio) {
+    if (threadIdx.x != 0 || st->accepted) return;
+    const double loss = (double)(float)(sums[P + SC_LOSS] / st->N);
+    const double kl = (double)(float)(sums[P + SC_KL] / st->N);
+    st->loss_final = loss;
+    st->kl_final = kl;
+    st->evals += 1;
+    if (loss < st->loss0 && kl <= max_kl) {
+        st->accepted = 1;
+        st->num_backtracks = i;
+        st->step_scale = ratio;
+    }
+}
+
+// error classification and parameter rollback (conjugate_gradient.rs:228-251)
+__global__ void trpo_ls_finish_kernel(TrpoState *st, float *theta, const float *theta0, int P, double max_kl,
+                                      int accept_violation) {
+    __shared__ int s_status;
+    if (threadIdx.x == 0) {
+        const double loss = st->loss_final, kl = st->kl_final;
+        int status = RL_OK;
+        if (isnan(loss)) status = RL_STEP_NAN_LOSS;
+        else if (isnan(kl)) status = RL_STEP_NAN_CONSTRAINT;
+        else if (loss >= st->loss0) status = RL_STEP_LOSS_NOT_IMPROVING;
+        else if (kl >= max_kl && !accept_violation) status = RL_STEP_CONSTRAINT_VIOLATED;
+        st->status = status;
+        s_status = status;
+    }
+    __syncthreads();
+    if (s_status != RL_OK)
+        for (int i = threadIdx.x; i < P; i += blockDim.x) theta[i] = theta0[i];
+}
+
+// libtorch Adam::step (non-amsgrad) on the mean gradient; records the loss of this step
+struct AdamArgs {
+    double lr, beta1, beta2, weight_decay, eps;
+};
+__global__ void __launch_bounds__(VEC_THREADS)
+    adam_step_kernel(const double *sums, int P, float *theta, float *m, float *v, AdamArgs c, uint64_t step,
+                     double *loss_out) {
+    const double N = sums[P + SC_COUNT];
+    const float beta1 = (float)c.beta1, beta2 = (float)c.beta2;
+    const float omb1 = (float)(1.0 - c.beta1), omb2 = (float)(1.0 - c.beta2);
+    const double bc1 = 1.0 - pow(c.beta1, (double)step), bc2 = 1.0 - pow(c.beta2, (double)step);
+    const float step_size = (float)(c.lr / bc1), bc2_sqrt = (float)sqrt(bc2), eps = (float)c.eps;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        float g = (float)(sums[i] / N);
+        float th = theta[i];
+        if (c.weight_decay != 0.0) g = __fadd_rn(g, __fmul_rn((float)c.weight_decay, th));
+        // exp_avg.mul_(beta1).add_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float mi = __fadd_rn(__fmul_rn(m[i], beta1), __fmul_rn(omb1, g));
+        const float vi = __fadd_rn(__fmul_rn(v[i], beta2), __fmul_rn(__fmul_rn(omb2, g), g));
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+        theta[i] = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+    }
+    if (threadIdx.x == 0 && loss_out) *loss_out = sums[P + SC_LOSS] / N;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+struct PassPlan {
+    int P, W, grid;
+    size_t smem;
+    double *partials, *sums;
+};
+
+template <int F, int A, int UPL>
+size_t pass_smem_bytes() {
+    constexpr int H = 32 * UPL, P = H * F + H + A * H + A;
+    const int nwarps = PASS_THREADS / 32;
+    return (size_t)nwarps * P * sizeof(double) + (size_t)nwarps * 32 * 8 * sizeof(float) + (size_t)nwarps * 32 * 2 * sizeof(float);
+}
+
+template <int F, int A, int UPL, int MODE>
+rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
+    const size_t smem = pass_smem_bytes<F, A, UPL>();
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_pass_kernel<F, A, UPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    args.partials = plan.partials;
+    RL_LAUNCH(ctx, (mlp_pass_kernel<F, A, UPL, MODE>), plan.grid, PASS_THREADS, smem, args);
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 256), 256, 0, plan.partials, plan.grid, plan.W, plan.sums,
+              args.skip_flag);
+    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    return RL_OK;
+}
+
+rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extra_bytes, void **extra) {
+    plan->P = P;
+    plan->W = P + NSCALAR;
+    const uint64_t ntiles = (TE + 31) / 32;
+    const uint64_t want = (ntiles + (PASS_THREADS / 32) - 1) / (PASS_THREADS / 32);
+    plan->grid = (int)(want < (uint64_t)ctx->sm_count ? (want ? want : 1) : (uint64_t)ctx->sm_count);
+    const size_t rows = (size_t)plan->grid * plan->W * sizeof(double), sums = (size_t)plan->W * sizeof(double);
+    char *buf;
+    RL_TRY(rl_ctx_scratch(ctx, rows + sums + extra_bytes + 256, (void **)&buf));
+    plan->partials = (double *)buf;
+    plan->sums = (double *)(buf + rows);
+    if (extra) *extra = buf + rows + ((sums + 255) / 256) * 256;
+    return RL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void rl_trpo_cfg_default(rl_trpo_cfg *c) {
+    // trpo.rs:29-38, conjugate_gradient.rs:55-64
+    c->max_policy_step_kl = 0.01; c->cg_iterations = 10; c->max_backtracks = 15; c->backtrack_ratio = 0.8;
+    c->hpv_reg_coeff = 1e-5; c->accept_violation = 0;
+}
+
+void rl_adam_cfg_default(rl_adam_cfg *c) {
+    // coptimizer.rs:136-168; eps is libtorch's AdamOptions default
+    c->learning_rate = 1e-3; c->beta1 = 0.9; c->beta2 = 0.999; c->weight_decay = 0.0; c->eps = 1e-8;
+}
+
+rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const rl_trpo_cfg *cfg,
+                         rl_trpo_stats *stats) {
+    if (!traj || !adv_dev || !policy || !cfg)
+        return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_update: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    constexpr int F = 5, A = 2, UPL = 4;
+    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
+          policy->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED,
+                       "rl_trpo_update: built for a %d->%d->%d ReLU policy (got %d->%d->%d)", F, 32 * UPL, A,
+                       policy->in_dim, policy->hidden, policy->out_dim);
+    const int P = (int)policy->n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
+    PassPlan plan;
+    // extra: state + 6 P-vectors + logp0
+    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
+    const size_t extra = 256 + 6 * vec_bytes + TE * 2 * sizeof(float);
+    char *ex;
+    RL_TRY(make_plan(ctx, P, TE, &plan, extra, (void **)&ex));
+    TrpoState *st = (TrpoState *)ex;
+    float *theta0 = (float *)(ex + 256), *g = (float *)(ex + 256 + vec_bytes), *x = (float *)(ex + 256 + 2 * vec_bytes);
+    float *r = (float *)(ex + 256 + 3 * vec_bytes), *p = (float *)(ex + 256 + 4 * vec_bytes);
+    float *descent = (float *)(ex + 256 + 5 * vec_bytes);
+    float *logp0 = (float *)(ex + 256 + 6 * vec_bytes);
+    float *theta = policy->params;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    PassArgs pa{};
+    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
+    pa.theta = theta; pa.vec = nullptr; pa.adv = adv_dev; pa.logp0 = logp0; pa.target = nullptr; pa.skip_flag = nullptr;
+    const float reg = (float)cfg->hpv_reg_coeff;
+
+    // behaviour-policy statistics (no_grad block, trpo.rs:112-122)
+    RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
+    RL_LAUNCH(ctx, trpo_begin_kernel, 1, 32, 0, st, plan.sums, P);
+    // loss gradient at theta0 (conjugate_gradient.rs:121-143)
+    RL_TRY((launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa)));
+    RL_LAUNCH(ctx, trpo_cg_init_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, g, x, r, p, theta, theta0);
+    // conjugate gradient on the Fisher matrix (conjugate_gradient.rs:371-403)
+    pa.vec = p;
+    pa.skip_flag = &st->cg_done;
+    for (uint64_t it = 0; it < cfg->cg_iterations; ++it) {
+        RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
+        RL_LAUNCH(ctx, trpo_cg_step_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, r, p, reg, 1e-10);
+    }
+    RL_LAUNCH(ctx, trpo_nan_to_num_kernel, 1, VEC_THREADS, 0, st, x, P);
+    pa.vec = x;
+    pa.skip_flag = nullptr;
+    RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
+    RL_LAUNCH(ctx, trpo_step_size_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, descent, reg, cfg->max_policy_step_kl);
+    // backtracking line search (conjugate_gradient.rs:183-254)
+    pa.vec = nullptr;
+    pa.skip_flag = &st->accepted;
+    for (uint64_t i = 0; i < cfg->max_backtracks; ++i) {
+        const double ratio = std::pow(cfg->backtrack_ratio, (double)i);
+        RL_LAUNCH(ctx, trpo_ls_candidate_kernel, 1, VEC_THREADS, 0, st, theta, theta0, descent, (float)ratio, P);
+        RL_TRY((launch_pass<F, A, UPL, PASS_EVAL>(ctx, plan, pa)));
+        RL_LAUNCH(ctx, trpo_ls_check_kernel, 1, 32, 0, st, plan.sums, P, cfg->max_policy_step_kl, (int)i, ratio);
+    }
+    RL_LAUNCH(ctx, trpo_ls_finish_kernel, 1, VEC_THREADS, 0, st, theta, theta0, P, cfg->max_policy_step_kl,
+              cfg->accept_violation);
+    TrpoState *host;
+    RL_TRY(rl_ctx_pinned(ctx, sizeof(TrpoState), (void **)&host));
+    RL_CUDA(ctx, cudaMemcpyAsync(host, st, sizeof(TrpoState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats) RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        stats->entropy = host->entropy; stats->step_size = host->step_size; stats->loss_initial = host->loss0;
+        stats->loss_final = host->loss_final; stats->constraint_val_final = host->kl_final;
+        stats->step_scale = host->step_scale; stats->num_backtracks = host->num_backtracks;
+        stats->cg_iterations = host->cg_iters; stats->num_steps = (uint64_t)host->N;
+        cudaEventElapsedTime(&stats->policy_update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return (rl_status)host->status;
+}
+
+rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const float *vec_host, double hpv_reg_coeff,
+                        double *loss, double *kl, double *entropy, float *grad_host, float *fvp_host) {
+    if (!traj || !adv_dev || !policy) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_probe: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    constexpr int F = 5, A = 2, UPL = 4;
+    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
+          policy->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_trpo_probe: built for a %d->%d->%d ReLU policy", F, 32 * UPL, A);
+    const int P = (int)policy->n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
+    PassPlan plan;
+    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
+    char *ex;
+    RL_TRY(make_plan(ctx, P, TE, &plan, vec_bytes + TE * 2 * sizeof(float), (void **)&ex));
+    float *vec = (float *)ex, *logp0 = (float *)(ex + vec_bytes);
+    std::vector<double> host((size_t)plan.W);
+    PassArgs pa{};
+    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
+    pa.theta = policy->params; pa.adv = adv_dev; pa.logp0 = logp0;
+    auto fetch = [&]() -> rl_status {
+        RL_CUDA(ctx, cudaMemcpyAsync(host.data(), plan.sums, (size_t)plan.W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RL_OK;
+    };
+    RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
+    RL_TRY(fetch());
+    const double N = host[P + SC_COUNT];
+    if (entropy) *entropy = host[P + SC_ENTROPY] / N;
+    RL_TRY((launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa)));
+    RL_TRY(fetch());
+    if (loss) *loss = host[P + SC_LOSS] / N;
+    if (kl) *kl = host[P + SC_KL] / N;
+    if (grad_host)
+        for (int i = 0; i < P; ++i) grad_host[i] = (float)(host[i] / N);
+    if (vec_host && fvp_host) {
+        RL_CUDA(ctx, cudaMemcpyAsync(vec, vec_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        pa.vec = vec;
+        RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
+        RL_TRY(fetch());
+        for (int i = 0; i < P; ++i) fvp_host[i] = (float)(host[i] / N) + vec_host[i] * (float)hpv_reg_coeff;
+    }
+    return RL_OK;
+}
+
+rl_status rl_adam_create(rl_mlp *mlp, const rl_adam_cfg *cfg, rl_adam **out) {
+    if (!mlp || !cfg || !out) return rl_fail(mlp ? mlp->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_adam_create: NULL argument");
+    rl_ctx *ctx = mlp->ctx;
+    RL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rl_adam *a = new (std::nothrow) rl_adam();
+    if (!a) return rl_fail(ctx, RL_ERR_OOM, "rl_adam_create: host allocation failed");
+    a->mlp = mlp;
+    a->cfg = *cfg;
+    cudaError_t e = cudaMalloc((void **)&a->m, mlp->n_params * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&a->v, mlp->n_params * sizeof(float));
+    if (e != cudaSuccess) {
+        rl_adam_destroy(a);
+        return rl_fail(ctx, RL_ERR_OOM, "rl_adam_create: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(a->m, 0, mlp->n_params * sizeof(float), ctx->stream);
+    cudaMemsetAsync(a->v, 0, mlp->n_params * sizeof(float), ctx->stream);
+    *out = a;
+    return RL_OK;
+}
+
+rl_status rl_adam_destroy(rl_adam *a) {
+    if (!a) return RL_OK;
+    cudaSetDevice(a->mlp->ctx->device);
+    cudaStreamSynchronize(a->mlp->ctx->stream);
+    cudaFree(a->m); cudaFree(a->v);
+    delete a;
+    return RL_OK;
+}
+
+rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value_fn, rl_adam *adam, int32_t n_steps,
+                          rl_opt_stats *stats) {
+    if (!traj || !targets_dev || !value_fn || !adam)
+        return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_value_update: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    constexpr int F = 5, A = 1, UPL = 4;
+    RL_REQUIRE(ctx, adam->mlp == value_fn, "rl_value_update: optimizer belongs to another module");
+    RL_REQUIRE(ctx, n_steps >= 0 && n_steps <= 100000, "rl_value_update: n_steps out of range");
+    if (!((int)traj->F == F && value_fn->in_dim == F && value_fn->out_dim == A && value_fn->hidden == 32 * UPL &&
+          value_fn->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_value_update: built for a %d->%d->1 ReLU critic (got %d->%d->%d)", F,
+                       32 * UPL, value_fn->in_dim, value_fn->hidden, value_fn->out_dim);
+    const int P = (int)value_fn->n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
+    PassPlan plan;
+    double *losses;
+    RL_TRY(make_plan(ctx, P, TE, &plan, (size_t)(n_steps + 1) * sizeof(double), (void **)&losses));
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    PassArgs pa{};
+    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
+    pa.theta = value_fn->params; pa.target = targets_dev;
+    AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
+    for (int s = 0; s < n_steps; ++s) {
+        // n_backward_steps: loss -> zero_grad -> backward -> step (torch/agents/mod.rs:50-55, coptimizer.rs:13-27)
+        RL_TRY((launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa)));
+        adam->step += 1;
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, P, value_fn->params, adam->m, adam->v, ac,
+                  adam->step, losses + s);
+    }
+    if (stats) {
+        RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+        double *host;
+        RL_TRY(rl_ctx_pinned(ctx, (size_t)(n_steps + 4) * sizeof(double), (void **)&host));
+        if (n_steps > 0) RL_CUDA(ctx, cudaMemcpyAsync(host, losses, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaMemcpyAsync(host + n_steps, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        stats->loss_first = n_steps > 0 ? host[0] : 0.0;
+        stats->loss_last = n_steps > 0 ? host[n_steps - 1] : 0.0;
+        stats->num_steps = n_steps > 0 ? (uint64_t)host[n_steps] : 0;
+        stats->opt_steps = (uint64_t)n_steps;
+        cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return RL_OK;
+}
+
+}  // extern "C"
