@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the fused rollout (+ policy act) hot path, TRPO update ms, roofline.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W`; for N > 1 the driver
+launches it under torchrun (one rank per GPU, RANK/LOCAL_RANK/WORLD_SIZE/MASTER_* in the env).  One JSON
+line on stdout from rank 0.
+
+Workload = BASELINE.json configs[1] "cartpole-trpo": CartPole + VisibleStepLimit(500), MLP policy 5->128->2,
+E = 4096 lanes per GPU, T = 256 steps per lane per period (N = 1 048 576 env-steps per GPU per step of this
+bench).  A "step" is one collection period: fresh episodes on every lane, policy forward + categorical
+sample + dynamics + trajectory write for E*T env-steps.  Weak scaling: every rank owns its own E lanes
+(global lane ids rank*E ..), no data-path collective.
+
+`--impl reference` times the reference's CPU implementation of the same path: the C oracle port of
+Steps::step + PolicyActor::act on all host cores (the Rust reference cannot be built in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+B_PER_STEP_ROLLOUT = 26      # obs 5 x f32 + action u8 + reward f32 + succ u8
+B_PER_STEP_UNFUSED = 98      # K1 (f64 state)
+B_PER_STEP_SCAN = 17         # K3
+FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_setup():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist  # noqa: F811
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def max_over_ranks(dist, local, value: float) -> float:
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, ctx):
+    ctx.synchronize()
+    if dist is not None:
+        import torch
+
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (the reference's own CPU path, as the C oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_rollout_rate(params: np.ndarray, lanes: int, horizon: int, threads: int, seed: int = 1, t0: int = 0):
+    import ctypes as C
+
+    import oracle as O
+
+    cfg = O.cartpole_cfg(500)
+    mlp = O.mlp_struct(params, 5, 128, 2)
+    summ = O.Summary()
+    t = time.perf_counter()
+    O.lib().ro_rollout_lanes_philox(C.byref(cfg), C.byref(mlp), lanes, 0, horizon, 0, seed, t0, threads, C.byref(summ))
+    dt = time.perf_counter() - t
+    return lanes * horizon / dt, dt, summ
+
+
+def run_reference(args):
+    rank, world, local, _ = dist_setup() if int(os.environ.get("WORLD_SIZE", "1")) > 1 else (0, 1, 0, None)
+    if rank != 0:
+        return
+    import oracle as O  # noqa: F401
+    from relearn_b200.modules import init_params
+
+    cores = os.cpu_count() or 1
+    params = init_params(np.random.default_rng(0), 5, 128, 2)
+    horizon = args.horizon
+    # bounded sample: calibrate so that one step is ~1 s of wall time on all cores
+    rate, _, _ = cpu_rollout_rate(params, max(cores, 8), horizon, cores)
+    lanes = int(max(cores, min(args.envs, rate * 1.0 / horizon)))
+    for _ in range(args.warmup):
+        cpu_rollout_rate(params, lanes, horizon, cores)
+    t = time.perf_counter()
+    for i in range(args.steps):
+        cpu_rollout_rate(params, lanes, horizon, cores, t0=i * (horizon + 1))
+    dt = time.perf_counter() - t
+    value = lanes * horizon * args.steps / dt
+    sample = f"{lanes} lanes x {horizon} steps per step on {cores} threads (C oracle port of Steps::step + PolicyActor::act)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 dynamics / f32 policy", "data": "synthetic",
+        "config": {"workload": "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy)",
+                   "envs_per_step": lanes, "horizon": horizon, "host": "cpu"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import relearn_b200 as R
+    from relearn_b200 import _lib as L
+
+    rank, world, local, dist = dist_setup()
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    ctx = R.Context(local)
+    info = ctx.device_info()
+    E, T = args.envs, args.horizon
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    env = R.build_env(ctx, cfg, E, seed=1234, lane_offset=rank * E)
+    rng = np.random.default_rng(0)
+    params = R.init_params(rng, 5, 128, 2)
+    vparams = R.init_params(rng, 5, 128, 1)
+    agent = R.ActorCriticConfig().build_agent(env)
+    agent.policy.policy_fn.set_weights(params)
+    agent.critic.state_value_fn.set_weights(vparams)
+    traj = R.Trajectory(env, T)
+    bound = R.HistoryDataBound(T, 0)
+    actor = agent.actor(args.lanes)
+    flush = ctx.alloc(256 << 20)  # > 126 MB L2
+
+    if world > 1:  # data-parallel group for the update's all-reduces
+        ids = [R.Context.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+
+    def one_period(timed_events=None):
+        flush.zero()
+        if timed_events is not None:
+            timed_events[0].record()
+        R.rollout(env, actor, bound, traj, want_summary=False)
+        if timed_events is not None:
+            timed_events[1].record()
+
+    for _ in range(max(args.warmup, 3)):
+        one_period()
+    barrier(dist, ctx)
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = [(ctx.event(), ctx.event()) for _ in range(args.steps)]
+    launches0 = ctx.launch_count
+    barrier(dist, ctx)
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        one_period(evs[k])
+    barrier(dist, ctx)
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count - launches0
+    kernel_ms = sum(a.elapsed_ms(b) for a, b in evs)
+    total_ms = max_over_ranks(dist, local, kernel_ms)
+    clock_info = clocks.stop()
+    steps_per_period = E * T
+    value = world * steps_per_period * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e through the C ABI with host buffers: weights H2D (pinned) -> rollout -> summary D2H ----
+    w_pinned = ctx.pinned_array((params.size,), np.float32)
+    w_pinned[:] = params
+    e2e_s = 0.0
+    for k in range(max(3, min(args.warmup, 5)) + args.steps):
+        flush.zero()
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        agent.policy.policy_fn.set_weights(w_pinned)
+        summ = R.rollout(env, actor, bound, traj, want_summary=True)
+        dt = time.perf_counter() - t0
+        if k >= max(3, min(args.warmup, 5)):
+            e2e_s += dt
+    e2e_s = max_over_ranks(dist, local, e2e_s)
+    e2e_value = world * steps_per_period * args.steps / e2e_s
+    h2d = int(params.nbytes)
+    d2h = 10 * 8
+
+    # ---- roofline of the dominant kernel (fused rollout: trajectory write stream) ----
+    hbm_peak, peak_src = measured_peaks()
+    achieved = B_PER_STEP_ROLLOUT * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "rollout_cartpole (fused step+policy+sample)",
+                "note": "K2 is FP32-FMA/latency bound by design (26 B of trajectory writes per env-step); see fp32 and kernels[]"}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 dynamics / f32 policy", "data": "synthetic",
+        "config": {"workload": "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy, fused)",
+                   "envs_per_gpu": E, "horizon": T, "env_steps_per_step": world * steps_per_period,
+                   "lanes_per_env": args.lanes, "l2": "flushed between timed iterations (256 MiB memset)",
+                   "noise": "philox4x32-10", "parallelism": f"dp{world} (lanes sharded, no collective)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "rl_mlp_set_weights(pinned host) + rl_rollout + StepsSummary read-back per period"},
+        "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline,
+        "wall_s_timed_region": wall, "sm_count": info["sm_count"],
+    }
+
+    if rank == 0 and not args.quick:
+        fp32_peak = ctx.fp32_peak_tflops()
+        line["fp32"] = {"policy_tflops": FLOP_PER_STEP_POLICY * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e12,
+                        "measured_fma_peak_tflops": fp32_peak}
+    # ---- the update that consumes the rollout: GAE + TRPO + critic (ms per iteration) ----
+    if not args.no_update:
+        upd = {"adv_est_ms": [], "policy_ms": [], "critic_ms": [], "status": []}
+        for it in range(1 + args.update_iters):
+            R.rollout(env, actor, bound, traj, want_summary=False)
+            barrier(dist, ctx)
+            e0, e1 = ctx.event().record(), None
+            adv = agent.critic.advantages(traj)
+            e1 = ctx.event().record()
+            log = {}
+            status = agent.policy.update(traj, adv, log)
+            cstats = agent.critic.update(traj, log)
+            if it > 0:
+                upd["adv_est_ms"].append(e0.elapsed_ms(e1))
+                upd["policy_ms"].append(log["policy/update_time"] * 1e3)
+                upd["critic_ms"].append(cstats.update_ms)
+                upd["status"].append(int(status))
+        line["update"] = {
+            "batch_steps_per_gpu": steps_per_period, "adv_est_ms": float(np.mean(upd["adv_est_ms"])),
+            "trpo_policy_ms": max_over_ranks(dist, local, float(np.mean(upd["policy_ms"]))),
+            "critic_80_adam_ms": max_over_ranks(dist, local, float(np.mean(upd["critic_ms"]))), "status": upd["status"],
+            "all_reduce": "nccl f64 sum of grad/FVP/scalars" if world > 1 else "none (1 GPU)",
+        }
+    # ---- per-kernel rooflines for the HBM-bound kernels (rank 0, 1 GPU only) ----
+    if rank == 0 and world == 1 and not args.quick:
+        line["kernels"] = kernel_rooflines(ctx, R, L, hbm_peak)
+        # CPU baseline on this box's host cores (bounded sample)
+        cores = os.cpu_count() or 1
+        cpu_rollout_rate(params, max(cores, 8), T, cores)
+        periods, cpu_s = 0, 0.0
+        while cpu_s < 10.0 and periods < 10000:  # ~10 s of wall time on all cores
+            _, dt, _ = cpu_rollout_rate(params, E, T, cores, t0=periods * (T + 1))
+            cpu_s += dt
+            periods += 1
+        line["cpu_baseline"] = {"value": periods * E * T / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{periods} periods of {E} lanes x {T} steps ({cpu_s:.1f} s wall) of the same "
+                                          f"workload, C oracle port of Steps::step + PolicyActor::act, {cores} threads"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def kernel_rooflines(ctx, R, L, hbm_peak):
+    """Unfused step kernel (K1) and GAE scan (K3) at sizes larger than L2, timed alone with CUDA events."""
+    import ctypes as C
+
+    out = []
+    E = 1 << 22
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    env = R.build_env(ctx, cfg, E, seed=7)
+    env.reset_all()
+    actions = ctx.to_device(np.random.default_rng(0).integers(0, 2, E).astype(np.uint8))
+    for _ in range(5):
+        env.step_device(actions)
+    reps = 20
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        env.step_device(actions)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    gbs = B_PER_STEP_UNFUSED * E / (ms * 1e-3) / 1e9
+    out.append({"kernel": "env_step_kernel<CartPole> (unfused, f64 SoA state)", "envs": E, "bytes_per_step": B_PER_STEP_UNFUSED,
+                "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "env_steps_per_s": E / (ms * 1e-3),
+                "working_set_mb": E * (B_PER_STEP_UNFUSED + 20) / 1e6})
+    env.close()
+    # GAE / reward-to-go scan over [T, E] = [256, 131072] (33.5 M steps, 570 MB)
+    T, E2 = 256, 1 << 17
+    env2 = R.build_env(ctx, cfg, E2, seed=8)
+    traj = R.Trajectory(env2, T)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(R.init_params(np.random.default_rng(1), 5, 128, 2))
+    R.rollout(env2, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net), R.HistoryDataBound(T, 0), traj, want_summary=False)
+    adv, rtg = ctx.alloc(T * E2 * 4), ctx.alloc(T * E2 * 4)
+    x = ctx.alloc(T * E2 * 4)
+    x.zero()
+    v = traj.view()
+    lib = ctx._lib
+    for _ in range(3):
+        L.check(lib.rl_gae(traj.handle, None, 0.99, 0.95, adv.c, rtg.c), ctx.handle)
+    reps = 10
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        L.check(lib.rl_gae(traj.handle, None, 0.99, 0.95, adv.c, rtg.c), ctx.handle)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    # without a critic the pass reads reward 4 + succ 1 and writes adv 4 + rtg 4 = 13 B/step
+    gbs = 13 * T * E2 / (ms * 1e-3) / 1e9
+    out.append({"kernel": "gae_scan_kernel<no critic> (reward-to-go + advantages)", "steps": T * E2, "bytes_per_step": 13,
+                "ms": ms, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+    for _ in range(3):
+        L.check(lib.rl_discounted_cumsum(ctx.handle, x.c, C.c_void_p(v.succ), T, E2, 0.99, adv.c), ctx.handle)
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        L.check(lib.rl_discounted_cumsum(ctx.handle, x.c, C.c_void_p(v.succ), T, E2, 0.99, adv.c), ctx.handle)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    gbs = 9 * T * E2 / (ms * 1e-3) / 1e9
+    out.append({"kernel": "cumsum_kernel (discounted_cumsum_from_end)", "steps": T * E2, "bytes_per_step": 9, "ms": ms,
+                "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+    # large-E fused rollout: thread-per-env regime (throughput ceiling of K2a)
+    E3, T3 = 1 << 20, 64
+    env3 = R.build_env(ctx, cfg, E3, seed=9)
+    traj3 = R.Trajectory(env3, T3)
+    spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net)
+    for _ in range(2):
+        R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
+    reps = 5
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    out.append({"kernel": "rollout_kernel<CartPole> (fused, thread per env)", "envs": E3, "horizon": T3, "ms": ms,
+                "env_steps_per_s": E3 * T3 / (ms * 1e-3),
+                "trajectory_write_gbs": B_PER_STEP_ROLLOUT * E3 * T3 / (ms * 1e-3) / 1e9,
+                "policy_tflops": FLOP_PER_STEP_POLICY * E3 * T3 / (ms * 1e-3) / 1e12})
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--envs", type=int, default=4096, help="lanes per GPU")
+    ap.add_argument("--horizon", type=int, default=256, help="steps per lane per period")
+    ap.add_argument("--lanes", type=int, default=0, help="threads per env in the fused kernel (0 = auto)")
+    ap.add_argument("--update-iters", type=int, default=3)
+    ap.add_argument("--no-update", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the per-kernel rooflines and the CPU baseline")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -80,12 +80,24 @@ uint64_t rl_ctx_launch_count(rl_ctx *ctx);
 rl_status rl_ctx_device_info(rl_ctx *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor,
                              uint64_t *total_mem_bytes);
 
+/* Device timers on the context stream (cudaEvent) and a peak-FMA probe, for roofline reporting. */
+typedef struct rl_event rl_event;
+rl_status rl_event_create(rl_ctx *ctx, rl_event **out);
+rl_status rl_event_destroy(rl_event *ev);
+rl_status rl_event_record(rl_event *ev);
+/* waits for `stop`; ms = device time between the two records */
+rl_status rl_event_elapsed_ms(rl_event *start, rl_event *stop, float *ms);
+rl_status rl_probe_fp32_tflops(rl_ctx *ctx, double *tflops);
+
 /* Raw device memory for caller-supplied streams of actions / noise and for read-backs. */
 rl_status rl_malloc(rl_ctx *ctx, size_t bytes, void **out_dev);
 rl_status rl_free(rl_ctx *ctx, void *dev);
 rl_status rl_memcpy_h2d(rl_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 rl_status rl_memcpy_d2h(rl_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 rl_status rl_memset(rl_ctx *ctx, void *dst_dev, int32_t value, size_t bytes);
+/* Page-locked host memory for weights / statistics that cross the boundary every period. */
+rl_status rl_malloc_host(rl_ctx *ctx, size_t bytes, void **out_host);
+rl_status rl_free_host(rl_ctx *ctx, void *host);
 
 /* Data-parallel group over NCCL (no reference counterpart: relearn has no collectives;
  * replaces the crossbeam thread fan-out of src/simulation/train.rs:124-158 across GPUs).

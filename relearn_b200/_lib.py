@@ -127,11 +127,18 @@ SIGNATURES = {
     "rl_device_count": (C.c_int32, []),
     "rl_ctx_launch_count": (C.c_uint64, [vp]),
     "rl_ctx_device_info": (st, [vp, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_uint64)]),
+    "rl_event_create": (st, [vp, P(vp)]),
+    "rl_event_destroy": (st, [vp]),
+    "rl_event_record": (st, [vp]),
+    "rl_event_elapsed_ms": (st, [vp, vp, P(C.c_float)]),
+    "rl_probe_fp32_tflops": (st, [vp, P(C.c_double)]),
     "rl_malloc": (st, [vp, C.c_size_t, P(vp)]),
     "rl_free": (st, [vp, vp]),
     "rl_memcpy_h2d": (st, [vp, vp, vp, C.c_size_t]),
     "rl_memcpy_d2h": (st, [vp, vp, vp, C.c_size_t]),
     "rl_memset": (st, [vp, vp, C.c_int32, C.c_size_t]),
+    "rl_malloc_host": (st, [vp, C.c_size_t, P(vp)]),
+    "rl_free_host": (st, [vp, vp]),
     "rl_nccl_unique_id": (st, [vp]),
     "rl_ctx_comm_init": (st, [vp, vp, C.c_int32, C.c_int32]),
     "rl_ctx_comm_info": (st, [vp, P(C.c_int32), P(C.c_int32)]),

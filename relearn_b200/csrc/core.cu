@@ -131,6 +131,18 @@ rl_status rl_memcpy_d2h(rl_ctx *ctx, void *dst_host, const void *src_dev, size_t
     return RL_OK;
 }
 
+rl_status rl_malloc_host(rl_ctx *ctx, size_t bytes, void **out_host) {
+    RL_REQUIRE(ctx, ctx && out_host, "rl_malloc_host: NULL argument");
+    RL_CUDA(ctx, cudaMallocHost(out_host, bytes ? bytes : 1));
+    return RL_OK;
+}
+
+rl_status rl_free_host(rl_ctx *ctx, void *host) {
+    RL_REQUIRE(ctx, ctx, "ctx is NULL");
+    if (host) RL_CUDA(ctx, cudaFreeHost(host));
+    return RL_OK;
+}
+
 rl_status rl_memset(rl_ctx *ctx, void *dst_dev, int32_t value, size_t bytes) {
     RL_REQUIRE(ctx, ctx && (bytes == 0 || dst_dev), "rl_memset: NULL argument");
     RL_CUDA(ctx, cudaMemsetAsync(dst_dev, value, bytes, ctx->stream));

@@ -44,6 +44,15 @@ class Context:
                 self.handle)
         return {"sm_count": sm.value, "cc": (maj.value, mnr.value), "total_mem": mem.value}
 
+    # -- timing -------------------------------------------------------------------------------
+    def event(self) -> "Event":
+        return Event(self)
+
+    def fp32_peak_tflops(self) -> float:
+        v = C.c_double()
+        L.check(self._lib.rl_probe_fp32_tflops(self.handle, C.byref(v)), self.handle)
+        return v.value
+
     # -- data-parallel group ----------------------------------------------------------------
     def comm_init(self, unique_id: bytes, rank: int, world_size: int):
         assert len(unique_id) == L.RL_NCCL_UNIQUE_ID_BYTES
@@ -60,6 +69,16 @@ class Context:
     # -- memory -----------------------------------------------------------------------------
     def alloc(self, nbytes: int) -> "DeviceBuffer":
         return DeviceBuffer(self, nbytes)
+
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy array over page-locked host memory (kept alive by the context)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        L.check(self._lib.rl_malloc_host(self.handle, n, C.byref(p)), self.handle)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
 
     def to_device(self, array: np.ndarray) -> "DeviceBuffer":
         a = np.ascontiguousarray(array)
@@ -119,3 +138,29 @@ class DeviceBuffer:
     @property
     def c(self) -> C.c_void_p:
         return C.c_void_p(self.ptr)
+
+
+class Event:
+    """cudaEvent on the context stream."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = C.c_void_p()
+        L.check(ctx._lib.rl_event_create(ctx.handle, C.byref(h)), ctx.handle)
+        self.handle = h
+
+    def record(self):
+        L.check(self.ctx._lib.rl_event_record(self.handle), self.ctx.handle)
+        return self
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        L.check(self.ctx._lib.rl_event_elapsed_ms(self.handle, stop.handle, C.byref(ms)), self.ctx.handle)
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                self.ctx._lib.rl_event_destroy(self.handle)
+        except Exception:
+            pass
