@@ -27,6 +27,7 @@
 #include "handles.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -66,23 +67,33 @@ __device__ __forceinline__ void log_softmax(const float *z, float *lp) {
     for (int k = 0; k < A; ++k) lp[k] = z[k] - lse;
 }
 
-// Reduce v[0..7] across the 32 lanes; afterwards every lane of quad q (lanes 4q..4q+3) holds the
-// complete sum of element q.  9 shuffles.
-__device__ __forceinline__ float reduce_scatter8(float *v, int lane) {
+// Reduce v[0..CH-1] across the 32 lanes (CH = 8 or 4); afterwards every lane of group g holds the
+// complete sum of element g, where groups are 32/CH consecutive lanes.  CH=8: 9 shuffles, CH=4: 6.
+template <int CH>
+__device__ __forceinline__ float reduce_scatter(float *v, int lane) {
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    if (CH == 8) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
+        for (int i = 0; i < 4; ++i) {
+            const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = b3 ? v[i] : v[i + 2], keep = b3 ? v[i + 2] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    {
+        for (int i = 0; i < 2; ++i) {
+            const float send = b3 ? v[i] : v[i + 2], keep = b3 ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
         const float send = b2 ? v[0] : v[1], keep = b2 ? v[1] : v[0];
         v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = b4 ? v[i] : v[i + 2], keep = b4 ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+        const float send = b3 ? v[0] : v[1], keep = b3 ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 4);
     }
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
@@ -95,66 +106,77 @@ __device__ __forceinline__ double warp_sum_f64(double x) {
     return x;
 }
 
-template <int F, int A, int UPL, int MODE>
-__global__ void __launch_bounds__(PASS_THREADS, 1) mlp_pass_kernel(PassArgs a) {
+// Packed FP32x2 helpers (Blackwell FFMA2/FADD2/FMUL2: one issue slot, two FMAs)
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 dup2(float a) { return make_float2(a, a); }
+
+template <int F, int A, int UPL, int MODE, int CH, int MINB>
+__global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a) {
+    static_assert(UPL % 2 == 0, "hidden units are processed in pairs (FFMA2)");
+    constexpr int GROUP = 32 / CH;  // lanes that end up holding the same sample's logits
     constexpr int H = 32 * UPL;
+    constexpr int NP = UPL / 2;     // unit pairs per lane: pair q = units (lane + 64 q, lane + 64 q + 32)
     constexpr int P = H * F + H + A * H + A;
     constexpr int W = P + NSCALAR;
+    constexpr int XS = 12;          // floats per staged sample: F duplicated pairs (x, x), padded to 3 x float4
+    static_assert(2 * F <= XS, "sample stage too small");
     constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS;
     constexpr bool IS_POLICY = MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP;
+    constexpr bool FVP = MODE == PASS_FVP;
     if (a.skip_flag && *a.skip_flag) return;
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    // per-warp regions: f64 totals [P], x tile [32][8], dz tile [32][2]
+    // per-warp regions: f64 totals [P], x tile [32][XS]
     double *tot_all = reinterpret_cast<double *>(smem_raw);
     double *tot = tot_all + (size_t)warp * P;
     float *xs_all = reinterpret_cast<float *>(tot_all + (size_t)nwarps * P);
-    float *xs = xs_all + (size_t)warp * 32 * 8;
-    float *dzs = xs_all + (size_t)nwarps * 32 * 8 + (size_t)warp * 32 * 2;
+    float *xs = xs_all + (size_t)warp * 32 * XS;
     if (BACKWARD)
         for (int i = lane; i < P; i += 32) tot[i] = 0.0;
 
-    // this lane's slice of the parameters: units j = lane + 32 u
+    // this lane's slice of the parameters, as unit pairs (.x = unit lane + 64 q, .y = that + 32)
     const float *tw1 = a.theta, *tb1 = tw1 + H * F, *tw2 = tb1 + H, *tb2 = tw2 + A * H;
-    float w1[UPL][F], b1[UPL], w2[A][UPL], b2[A];
+    float2 w1[NP][F], b1[NP], w2[A][NP];
+    float b2[A];
 #pragma unroll
-    for (int u = 0; u < UPL; ++u) {
-        const int j = lane + 32 * u;
+    for (int q = 0; q < NP; ++q) {
+        const int j0 = lane + 64 * q, j1 = j0 + 32;
 #pragma unroll
-        for (int f = 0; f < F; ++f) w1[u][f] = tw1[j * F + f];
-        b1[u] = tb1[j];
+        for (int f = 0; f < F; ++f) w1[q][f] = f2(tw1[j0 * F + f], tw1[j1 * F + f]);
+        b1[q] = f2(tb1[j0], tb1[j1]);
 #pragma unroll
-        for (int k = 0; k < A; ++k) w2[k][u] = tw2[k * H + j];
+        for (int k = 0; k < A; ++k) w2[k][q] = f2(tw2[k * H + j0], tw2[k * H + j1]);
     }
 #pragma unroll
     for (int k = 0; k < A; ++k) b2[k] = tb2[k];
     // FVP direction slice
-    float vw1[MODE == PASS_FVP ? UPL : 1][F], vb1[MODE == PASS_FVP ? UPL : 1], vw2[A][MODE == PASS_FVP ? UPL : 1], vb2[A];
-    if (MODE == PASS_FVP) {
+    float2 vw1[FVP ? NP : 1][F], vb1[FVP ? NP : 1], vw2[A][FVP ? NP : 1];
+    float vb2[A];
+    if (FVP) {
         const float *pw1 = a.vec, *pb1 = pw1 + H * F, *pw2 = pb1 + H, *pb2 = pw2 + A * H;
 #pragma unroll
-        for (int u = 0; u < UPL; ++u) {
-            const int j = lane + 32 * u;
+        for (int q = 0; q < NP; ++q) {
+            const int j0 = lane + 64 * q, j1 = j0 + 32;
 #pragma unroll
-            for (int f = 0; f < F; ++f) vw1[u][f] = pw1[j * F + f];
-            vb1[u] = pb1[j];
+            for (int f = 0; f < F; ++f) vw1[q][f] = f2(pw1[j0 * F + f], pw1[j1 * F + f]);
+            vb1[q] = f2(pb1[j0], pb1[j1]);
 #pragma unroll
-            for (int k = 0; k < A; ++k) vw2[k][u] = pw2[k * H + j];
+            for (int k = 0; k < A; ++k) vw2[k][q] = f2(pw2[k * H + j0], pw2[k * H + j1]);
         }
 #pragma unroll
         for (int k = 0; k < A; ++k) vb2[k] = pb2[k];
     }
-    // gradient accumulators (f32, flushed to f64)
-    float gw1[BACKWARD ? UPL : 1][F], gb1[BACKWARD ? UPL : 1], gw2[A][BACKWARD ? UPL : 1];
+    // gradient accumulators (f32 pairs, flushed to f64)
+    float2 gw1[BACKWARD ? NP : 1][F], gb1[BACKWARD ? NP : 1], gw2[A][BACKWARD ? NP : 1];
     if (BACKWARD) {
 #pragma unroll
-        for (int u = 0; u < UPL; ++u) {
+        for (int q = 0; q < NP; ++q) {
 #pragma unroll
-            for (int f = 0; f < F; ++f) gw1[u][f] = 0.0f;
-            gb1[u] = 0.0f;
+            for (int f = 0; f < F; ++f) gw1[q][f] = f2(0.0f, 0.0f);
+            gb1[q] = f2(0.0f, 0.0f);
 #pragma unroll
-            for (int k = 0; k < A; ++k) gw2[k][u] = 0.0f;
+            for (int k = 0; k < A; ++k) gw2[k][q] = f2(0.0f, 0.0f);
         }
     }
     double gb2[A], sc[NSCALAR];
@@ -166,19 +188,22 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) mlp_pass_kernel(PassArgs a) {
     auto flush = [&]() {
         if (!BACKWARD) return;
 #pragma unroll
-        for (int u = 0; u < UPL; ++u) {
-            const int j = lane + 32 * u;
+        for (int q = 0; q < NP; ++q) {
+            const int j0 = lane + 64 * q, j1 = j0 + 32;
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-                tot[j * F + f] += (double)gw1[u][f];
-                gw1[u][f] = 0.0f;
+                tot[j0 * F + f] += (double)gw1[q][f].x;
+                tot[j1 * F + f] += (double)gw1[q][f].y;
+                gw1[q][f] = f2(0.0f, 0.0f);
             }
-            tot[H * F + j] += (double)gb1[u];
-            gb1[u] = 0.0f;
+            tot[H * F + j0] += (double)gb1[q].x;
+            tot[H * F + j1] += (double)gb1[q].y;
+            gb1[q] = f2(0.0f, 0.0f);
 #pragma unroll
             for (int k = 0; k < A; ++k) {
-                tot[H * F + H + k * H + j] += (double)gw2[k][u];
-                gw2[k][u] = 0.0f;
+                tot[H * F + H + k * H + j0] += (double)gw2[k][q].x;
+                tot[H * F + H + k * H + j1] += (double)gw2[k][q].y;
+                gw2[k][q] = f2(0.0f, 0.0f);
             }
         }
     };
@@ -186,184 +211,218 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) mlp_pass_kernel(PassArgs a) {
     const uint64_t TE = a.T * a.E;
     const uint64_t ntiles = (TE + 31) / 32;
     const uint64_t warp_global = (uint64_t)blockIdx.x * nwarps + warp, total_warps = (uint64_t)gridDim.x * nwarps;
+    const int quad_sample = lane / GROUP;  // sample (within a chunk) whose reduced logits this lane receives
+    const bool quad_leader = (lane % GROUP) == 0;
     int since_flush = 0;
-    for (uint64_t tile = warp_global; tile < ntiles; tile += total_warps) {
-        // ---- load this lane's sample ----
+    // Software pipeline: the global loads of the next tile are in flight while this tile is computed.
+    struct Staged {
+        float x[F];
+        float adv, tgt, lp0a, lp0b;
+        int act;
+        bool valid;
+    };
+    auto load_tile = [&](uint64_t tile, Staged &st) {
         const uint64_t n = tile * 32 + lane;
-        const bool in_range = n < TE;
-        const uint8_t sc_code = in_range ? a.succ[n] : (uint8_t)RL_PAD;
-        const bool valid = sc_code != RL_PAD;
+        const bool in_range = tile < ntiles && n < TE;
+        const uint8_t sc_code = in_range ? __ldg(a.succ + n) : (uint8_t)RL_PAD;
+        st.valid = sc_code != RL_PAD;
         const uint64_t t = in_range ? n / a.E : 0, e = in_range ? n - t * a.E : 0;
-        float xv[8];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) xv[f] = (f < F && valid) ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
-        __syncwarp();
-        reinterpret_cast<float4 *>(xs)[lane * 2] = make_float4(xv[0], xv[1], xv[2], xv[3]);
-        reinterpret_cast<float4 *>(xs)[lane * 2 + 1] = make_float4(xv[4], xv[5], xv[6], xv[7]);
-        const int act_s = (IS_POLICY || MODE == PASS_QLOSS) ? (valid ? (int)a.action[n] : 0) : 0;
-        float adv_s = 0.0f, tgt_s = 0.0f, lp0[A];
-        if (MODE == PASS_EVAL || MODE == PASS_GRAD) adv_s = valid ? a.adv[n] : 0.0f;
-        if (MODE == PASS_VALUE || MODE == PASS_QLOSS) tgt_s = valid ? a.target[n] : 0.0f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) lp0[k] = 0.0f;
-        if ((MODE == PASS_EVAL || MODE == PASS_GRAD) && valid) {
-            const float2 l = reinterpret_cast<const float2 *>(a.logp0)[n];
-            lp0[0] = l.x;
-            if (A > 1) lp0[A > 1 ? 1 : 0] = l.y;
+        for (int f = 0; f < F; ++f) st.x[f] = st.valid ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
+        st.act = ((IS_POLICY || MODE == PASS_QLOSS) && st.valid) ? (int)__ldg(a.action + n) : 0;
+        st.adv = ((MODE == PASS_EVAL || MODE == PASS_GRAD) && st.valid) ? __ldg(a.adv + n) : 0.0f;
+        st.tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && st.valid) ? __ldg(a.target + n) : 0.0f;
+        st.lp0a = st.lp0b = 0.0f;
+        if ((MODE == PASS_EVAL || MODE == PASS_GRAD) && st.valid) {
+            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n);
+            st.lp0a = l.x;
+            st.lp0b = l.y;
         }
+    };
+    Staged nxt;
+    load_tile(warp_global, nxt);
+    for (uint64_t tile = warp_global; tile < ntiles; tile += total_warps) {
+        // ---- stage this lane's sample: duplicated feature pairs to shared memory, scalars in registers ----
+        const Staged cur = nxt;
+        load_tile(tile + total_warps, nxt);
+        const bool valid = cur.valid;
+        float xv[XS];
+#pragma unroll
+        for (int i = 0; i < XS; ++i) xv[i] = (i / 2) < F ? cur.x[(i / 2) < F ? (i / 2) : 0] : 0.0f;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < XS / 4; ++i)
+            reinterpret_cast<float4 *>(xs)[lane * (XS / 4) + i] = make_float4(xv[4 * i], xv[4 * i + 1], xv[4 * i + 2], xv[4 * i + 3]);
+        const int my_act = cur.act;
+        const float my_adv = cur.adv, my_tgt = cur.tgt;
+        const float my_lp0[2] = {cur.lp0a, cur.lp0b};
+        const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
         __syncwarp();
 
-        // ---- forward: partial logits, 8 samples at a time ----
-        float z[A], zd[A];
+#pragma unroll 1
+        for (int c = 0; c < 32 / CH; ++c) {
+            // ---- forward for samples CH*c .. CH*c+CH-1: this lane's partial logits, activations kept ----
+            float2 hid[CH][NP];  // relu(pre); hid > 0 <=> pre > 0
+            float pz[A][CH], pzd[FVP ? A : 1][CH];
 #pragma unroll
-        for (int k = 0; k < A; ++k) z[k] = zd[k] = 0.0f;
+            for (int i = 0; i < CH; ++i) {
+                float2 x[XS / 2];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float pz[A][8], pzd[MODE == PASS_FVP ? A : 1][8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 xa = reinterpret_cast<const float4 *>(xs)[(c * 8 + i) * 2];
-                const float4 xb = reinterpret_cast<const float4 *>(xs)[(c * 8 + i) * 2 + 1];
-                const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+                for (int v = 0; v < XS / 4; ++v) {
+                    const float4 t4 = reinterpret_cast<const float4 *>(xs)[(c * CH + i) * (XS / 4) + v];
+                    x[2 * v] = f2(t4.x, t4.y);
+                    x[2 * v + 1] = f2(t4.z, t4.w);
+                }
+                float2 acc[A], accd[FVP ? A : 1];
 #pragma unroll
                 for (int k = 0; k < A; ++k) {
-                    pz[k][i] = 0.0f;
-                    if (MODE == PASS_FVP) pzd[k][i] = 0.0f;
+                    acc[k] = f2(0.0f, 0.0f);
+                    if (FVP) accd[k] = f2(0.0f, 0.0f);
                 }
 #pragma unroll
-                for (int u = 0; u < UPL; ++u) {
-                    float pre = b1[u];
+                for (int q = 0; q < NP; ++q) {
+                    float2 p_ = b1[q];
 #pragma unroll
-                    for (int f = 0; f < F; ++f) pre = fmaf(w1[u][f], x[f], pre);
-                    const float h = pre < 0.0f ? 0.0f : pre;
+                    for (int f = 0; f < F; ++f) p_ = __ffma2_rn(w1[q][f], x[f], p_);
+                    const float2 h = f2(fmaxf(p_.x, 0.0f), fmaxf(p_.y, 0.0f));
+                    hid[i][q] = h;
 #pragma unroll
-                    for (int k = 0; k < A; ++k) pz[k][i] = fmaf(w2[k][u], h, pz[k][i]);
-                    if (MODE == PASS_FVP) {
-                        float dpre = vb1[u];
+                    for (int k = 0; k < A; ++k) acc[k] = __ffma2_rn(w2[k][q], h, acc[k]);
+                    if (FVP) {
+                        float2 dpre = vb1[q];
 #pragma unroll
-                        for (int f = 0; f < F; ++f) dpre = fmaf(vw1[u][f], x[f], dpre);
-                        const float dh = pre > 0.0f ? dpre : 0.0f;
+                        for (int f = 0; f < F; ++f) dpre = __ffma2_rn(vw1[q][f], x[f], dpre);
+                        const float2 dh = f2(h.x > 0.0f ? dpre.x : 0.0f, h.y > 0.0f ? dpre.y : 0.0f);
 #pragma unroll
-                        for (int k = 0; k < A; ++k) pzd[k][i] = fmaf(vw2[k][u], h, fmaf(w2[k][u], dh, pzd[k][i]));
+                        for (int k = 0; k < A; ++k) accd[k] = __ffma2_rn(vw2[k][q], h, __ffma2_rn(w2[k][q], dh, accd[k]));
                     }
                 }
+#pragma unroll
+                for (int k = 0; k < A; ++k) {
+                    pz[k][i] = acc[k].x + acc[k].y;
+                    if (FVP) pzd[k][i] = accd[k].x + accd[k].y;
+                }
             }
+            // ---- reduce across lanes: group g ends up with the logits of sample CH*c + g ----
+            float z[A], zd[A];
 #pragma unroll
             for (int k = 0; k < A; ++k) {
-                const float full = reduce_scatter8(pz[k], lane);
-                const float mine = __shfl_sync(0xffffffffu, full, 4 * (lane & 7));
-                if ((lane >> 3) == c) z[k] = mine;
-                if (MODE == PASS_FVP) {
-                    const float fulld = reduce_scatter8(pzd[k], lane);
-                    const float mined = __shfl_sync(0xffffffffu, fulld, 4 * (lane & 7));
-                    if ((lane >> 3) == c) zd[k] = mined;
-                }
+                z[k] = reduce_scatter<CH>(pz[k], lane) + b2[k];
+                zd[k] = FVP ? reduce_scatter<CH>(pzd[k], lane) + vb2[k] : 0.0f;
             }
-        }
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-            z[k] += b2[k];
-            if (MODE == PASS_FVP) zd[k] += vb2[k];
-        }
+            // per-sample scalars of that sample live in lane CH*c + g
+            const int owner = c * CH + quad_sample;
+            const bool s_valid = (valid_mask >> owner) & 1u;
+            const int act_s = (IS_POLICY || MODE == PASS_QLOSS) ? __shfl_sync(0xffffffffu, my_act, owner) : 0;
+            float adv_s = 0.0f, tgt_s = 0.0f, lp0[2] = {0.0f, 0.0f};
+            if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
+                adv_s = __shfl_sync(0xffffffffu, my_adv, owner);
+                lp0[0] = __shfl_sync(0xffffffffu, my_lp0[0], owner);
+                lp0[1] = __shfl_sync(0xffffffffu, my_lp0[1], owner);
+            }
+            if (MODE == PASS_VALUE || MODE == PASS_QLOSS) tgt_s = __shfl_sync(0xffffffffu, my_tgt, owner);
 
-        // ---- per-sample algebra on the lane that owns the sample ----
-        float dz[A];
+            // ---- per-sample algebra (all lanes of a group compute the same values) ----
+            float dz[A];
 #pragma unroll
-        for (int k = 0; k < A; ++k) dz[k] = 0.0f;
-        if (valid) {
-            sc[SC_COUNT] += 1.0;
-            if (IS_POLICY) {
-                float lp[A], p[A];
-                log_softmax<A>(z, lp);
+            for (int k = 0; k < A; ++k) dz[k] = 0.0f;
+            if (s_valid) {
+                float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
+                if (IS_POLICY) {
+                    float lp[A], p[A];
+                    log_softmax<A>(z, lp);
 #pragma unroll
-                for (int k = 0; k < A; ++k) p[k] = expf(lp[k]);
-                if (MODE == PASS_STATS) {
-                    // trpo.rs:112-122: log-probs of the behaviour policy and its entropy (categorical.rs:62-68)
-                    float ent = 0.0f;
+                    for (int k = 0; k < A; ++k) p[k] = expf(lp[k]);
+                    if (MODE == PASS_STATS) {
+                        // trpo.rs:112-122: log-probs of the behaviour policy and its entropy (categorical.rs:62-68)
 #pragma unroll
-                    for (int k = 0; k < A; ++k) ent += fmaxf(lp[k], F32_LOWEST) * p[k];
-                    sc[SC_ENTROPY] += (double)(-ent);
-                    reinterpret_cast<float2 *>(a.logp0)[n] = make_float2(lp[0], A > 1 ? lp[A > 1 ? 1 : 0] : 0.0f);
-                }
-                if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
-                    // trpo.rs:129-144: ratio = exp(logp - logp0); loss = -mean(ratio * adv); KL(p0 || p)
-                    float lpa = lp[0], lp0a = lp0[0];
+                        for (int k = 0; k < A; ++k) ent_s -= fmaxf(lp[k], F32_LOWEST) * p[k];
+                        if (quad_leader)
+                            reinterpret_cast<float2 *>(a.logp0)[tile * 32 + owner] = make_float2(lp[0], A > 1 ? lp[A > 1 ? 1 : 0] : 0.0f);
+                    }
+                    if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
+                        // trpo.rs:129-144: ratio = exp(logp - logp0); loss = -mean(ratio * adv); KL(p0 || p)
+                        float lpa = lp[0], lp0a = lp0[0];
+#pragma unroll
+                        for (int k = 1; k < A; ++k)
+                            if (act_s == k) { lpa = lp[k]; lp0a = lp0[k]; }
+                        const float ratio = expf(lpa - lp0a);
+                        loss_s = -(ratio * adv_s);
+#pragma unroll
+                        for (int k = 0; k < A; ++k) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
+                        if (MODE == PASS_GRAD) {
+#pragma unroll
+                            for (int k = 0; k < A; ++k) dz[k] = loss_s * ((act_s == k ? 1.0f : 0.0f) - p[k]);
+                        }
+                    }
+                    if (FVP) {
+                        // u = (diag p - p p^T) zdot
+                        float pd = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < A; ++k) pd = fmaf(p[k], zd[k], pd);
+#pragma unroll
+                        for (int k = 0; k < A; ++k) dz[k] = p[k] * (zd[k] - pd);
+                    }
+                } else if (MODE == PASS_VALUE) {
+                    // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
+                    const float diff = z[0] - tgt_s;
+                    loss_s = diff * diff;
+                    dz[0] = 2.0f * diff;
+                } else if (MODE == PASS_QLOSS) {
+                    // dqn.rs:316-326: mse(Q(obs).gather(action), targets)
+                    float qv = z[0];
 #pragma unroll
                     for (int k = 1; k < A; ++k)
-                        if (act_s == k) { lpa = lp[k]; lp0a = lp0[k]; }
-                    const float ratio = expf(lpa - lp0a);
-                    sc[SC_LOSS] += (double)(-(ratio * adv_s));
-                    float kl = 0.0f;
+                        if (act_s == k) qv = z[k];
+                    const float diff = qv - tgt_s;
+                    loss_s = diff * diff;
 #pragma unroll
-                    for (int k = 0; k < A; ++k) kl += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
-                    sc[SC_KL] += (double)kl;
-                    if (MODE == PASS_GRAD) {
-                        const float g = -(ratio * adv_s);  // d loss_s / d logp_a
+                    for (int k = 0; k < A; ++k) dz[k] = act_s == k ? 2.0f * diff : 0.0f;
+                }
+                if (quad_leader) {
+                    sc[SC_COUNT] += 1.0;
+                    sc[SC_LOSS] += (double)loss_s;
+                    sc[SC_KL] += (double)kl_s;
+                    sc[SC_ENTROPY] += (double)ent_s;
 #pragma unroll
-                        for (int k = 0; k < A; ++k) dz[k] = g * ((act_s == k ? 1.0f : 0.0f) - p[k]);
+                    for (int k = 0; k < A; ++k) gb2[k] += (double)dz[k];
+                }
+            }
+
+            // ---- backward for the same samples ----
+            if (BACKWARD) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    float2 d[A];
+#pragma unroll
+                    for (int k = 0; k < A; ++k) d[k] = dup2(__shfl_sync(0xffffffffu, dz[k], GROUP * i));
+                    float2 x[XS / 2];
+#pragma unroll
+                    for (int v = 0; v < XS / 4; ++v) {
+                        const float4 t4 = reinterpret_cast<const float4 *>(xs)[(c * CH + i) * (XS / 4) + v];
+                        x[2 * v] = f2(t4.x, t4.y);
+                        x[2 * v + 1] = f2(t4.z, t4.w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const float2 h = hid[i][q];
+                        float2 dh = __fmul2_rn(d[0], w2[0][q]);
+#pragma unroll
+                        for (int k = 0; k < A; ++k) {
+                            gw2[k][q] = __ffma2_rn(d[k], h, gw2[k][q]);
+                            if (k > 0) dh = __ffma2_rn(d[k], w2[k][q], dh);
+                        }
+                        dh = f2(h.x > 0.0f ? dh.x : 0.0f, h.y > 0.0f ? dh.y : 0.0f);  // relu'(pre)
+                        gb1[q] = __fadd2_rn(gb1[q], dh);
+#pragma unroll
+                        for (int f = 0; f < F; ++f) gw1[q][f] = __ffma2_rn(dh, x[f], gw1[q][f]);
                     }
                 }
-                if (MODE == PASS_FVP) {
-                    // u = (diag p - p p^T) zdot
-                    float pd = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < A; ++k) pd = fmaf(p[k], zd[k], pd);
-#pragma unroll
-                    for (int k = 0; k < A; ++k) dz[k] = p[k] * (zd[k] - pd);
-                }
-            } else if (MODE == PASS_VALUE) {
-                // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
-                const float diff = z[0] - tgt_s;
-                sc[SC_LOSS] += (double)(diff * diff);
-                dz[0] = 2.0f * diff;
-            } else if (MODE == PASS_QLOSS) {
-                // dqn.rs:316-326: mse(Q(obs).gather(action), targets)
-                float q = z[0];
-#pragma unroll
-                for (int k = 1; k < A; ++k)
-                    if (act_s == k) q = z[k];
-                const float diff = q - tgt_s;
-                sc[SC_LOSS] += (double)(diff * diff);
-#pragma unroll
-                for (int k = 0; k < A; ++k) dz[k] = act_s == k ? 2.0f * diff : 0.0f;
             }
         }
-
-        // ---- backward sweep ----
-        if (BACKWARD) {
-#pragma unroll
-            for (int k = 0; k < A; ++k) gb2[k] += (double)dz[k];
-            reinterpret_cast<float2 *>(dzs)[lane] = make_float2(dz[0], A > 1 ? dz[A > 1 ? 1 : 0] : 0.0f);
-            __syncwarp();
-#pragma unroll 4
-            for (int s = 0; s < 32; ++s) {
-                const float2 d2 = reinterpret_cast<const float2 *>(dzs)[s];
-                const float d[2] = {d2.x, d2.y};
-                const float4 xa = reinterpret_cast<const float4 *>(xs)[s * 2];
-                const float4 xb = reinterpret_cast<const float4 *>(xs)[s * 2 + 1];
-                const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-                for (int u = 0; u < UPL; ++u) {
-                    float pre = b1[u];
-#pragma unroll
-                    for (int f = 0; f < F; ++f) pre = fmaf(w1[u][f], x[f], pre);
-                    const float h = pre < 0.0f ? 0.0f : pre;
-                    float dh = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < A; ++k) {
-                        gw2[k][u] = fmaf(d[k], h, gw2[k][u]);
-                        dh = fmaf(d[k], w2[k][u], dh);
-                    }
-                    dh = pre > 0.0f ? dh : 0.0f;
-                    gb1[u] += dh;
-#pragma unroll
-                    for (int f = 0; f < F; ++f) gw1[u][f] = fmaf(dh, x[f], gw1[u][f]);
-                }
-            }
-            if (++since_flush == FLUSH_TILES) {
-                flush();
-                since_flush = 0;
-            }
+        if (BACKWARD && ++since_flush == FLUSH_TILES) {
+            flush();
+            since_flush = 0;
         }
     }
     flush();
@@ -398,15 +457,27 @@ __global__ void __launch_bounds__(PASS_THREADS, 1) mlp_pass_kernel(PassArgs a) {
     }
 }
 
-// rows[B][W] -> out[W], fixed summation order
-__global__ void reduce_rows_kernel(const double *__restrict__ rows, int B, int W, double *__restrict__ out,
-                                   const int *skip_flag) {
+// rows[B][W] -> out[W] in a fixed summation order.  A block owns 32 columns; warp w sums rows
+// w, w + 8, ... (independent coalesced 256 B loads), then the 8 partials are added in warp order.
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restrict__ rows, int B, int W,
+                                                         double *__restrict__ out, const int *skip_flag) {
     if (skip_flag && *skip_flag) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W) return;
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
     double s = 0.0;
-    for (int b = 0; b < B; ++b) s += rows[(size_t)b * W + i];
-    out[i] = s;
+    if (col < W) {
+#pragma unroll 8
+        for (int b = warp; b < B; b += 8) s += rows[(size_t)b * W + col];
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && col < W) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][lane];
+        out[col] = t;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,23 +696,49 @@ template <int F, int A, int UPL>
 size_t pass_smem_bytes() {
     constexpr int H = 32 * UPL, P = H * F + H + A * H + A;
     const int nwarps = PASS_THREADS / 32;
-    return (size_t)nwarps * P * sizeof(double) + (size_t)nwarps * 32 * 8 * sizeof(float) + (size_t)nwarps * 32 * 2 * sizeof(float);
+    return (size_t)nwarps * P * sizeof(double) + (size_t)nwarps * 32 * 12 * sizeof(float);
 }
 
-template <int F, int A, int UPL, int MODE>
-rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
+template <int F, int A, int UPL, int MODE, int CH, int MINB>
+rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
     const size_t smem = pass_smem_bytes<F, A, UPL>();
     static bool configured = false;
     if (!configured) {
-        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_pass_kernel<F, A, UPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_pass_kernel<F, A, UPL, MODE, CH, MINB>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     args.partials = plan.partials;
-    RL_LAUNCH(ctx, (mlp_pass_kernel<F, A, UPL, MODE>), plan.grid, PASS_THREADS, smem, args);
-    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 256), 256, 0, plan.partials, plan.grid, plan.W, plan.sums,
+    RL_LAUNCH(ctx, (mlp_pass_kernel<F, A, UPL, MODE, CH, MINB>), plan.grid, PASS_THREADS, smem, args);
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.sums,
               args.skip_flag);
     if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
     return RL_OK;
+}
+
+int pass_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RL_PASS_VARIANT");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
+// Tile-chunk size and CTAs/SM per mode, chosen from B200 timings (profiles/r1_update_variants.md):
+// forward-only passes fit 2 CTAs/SM at CH=8; the critic pass is fastest at CH=4 with 2 CTAs/SM; the
+// gradient / Fisher-vector passes need the registers of 1 CTA/SM.  RL_PASS_VARIANT overrides (experiments).
+template <int F, int A, int UPL, int MODE>
+rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
+    switch (pass_variant()) {
+    case 1: return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args);
+    case 2: return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args);
+    case 3: return launch_pass_variant<F, A, UPL, MODE, 4, 1>(ctx, plan, args);
+    default:
+        if (MODE == PASS_VALUE || MODE == PASS_QLOSS) return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args);
+        if (MODE == PASS_STATS || MODE == PASS_EVAL) return launch_pass_variant<F, A, UPL, MODE, 8, 2>(ctx, plan, args);
+        return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args);
+    }
 }
 
 rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extra_bytes, void **extra) {
@@ -649,7 +746,8 @@ rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extr
     plan->W = P + NSCALAR;
     const uint64_t ntiles = (TE + 31) / 32;
     const uint64_t want = (ntiles + (PASS_THREADS / 32) - 1) / (PASS_THREADS / 32);
-    plan->grid = (int)(want < (uint64_t)ctx->sm_count ? (want ? want : 1) : (uint64_t)ctx->sm_count);
+    const uint64_t cap = (uint64_t)ctx->sm_count * 2;  // persistent: 2 CTAs per SM (the FVP pass fits 1 and runs 2 waves)
+    plan->grid = (int)(want < cap ? (want ? want : 1) : cap);
     const size_t rows = (size_t)plan->grid * plan->W * sizeof(double), sums = (size_t)plan->W * sizeof(double);
     char *buf;
     RL_TRY(rl_ctx_scratch(ctx, rows + sums + extra_bytes + 256, (void **)&buf));
