@@ -443,3 +443,18 @@ def gae_lane(reward, v, v_next_intr, succ, gamma, lam):
     lib().ro_gae_lane_f32(_ptr(reward, C.c_float), _ptr(v, C.c_float), _ptr(vn, C.c_float), _ptr(succ, C.c_uint8),
                           reward.size, gamma, lam, _ptr(adv, C.c_float))
     return adv
+
+
+def pack_episodes(episodes):
+    """LazyHistoryFeatures::new + PackedStructure (src/torch/agents/features.rs:70-125, packed.rs:346-420):
+    episodes sorted by length descending (stable here; the reference's sort_unstable leaves ties unordered),
+    then interleaved time-major.  `episodes` is a list of lists of per-step tuples.
+    Returns {"steps": packed list of the tuples, "batch_sizes": [...], "order": episode order}."""
+    order = sorted(range(len(episodes)), key=lambda i: -len(episodes[i]))
+    longest = len(episodes[order[0]]) if episodes else 0
+    steps, batch_sizes = [], []
+    for t in range(longest):
+        row = [episodes[i][t] for i in order if len(episodes[i]) > t]
+        steps += row
+        batch_sizes.append(len(row))
+    return {"steps": steps, "batch_sizes": batch_sizes, "order": order}
