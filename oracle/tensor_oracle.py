@@ -164,7 +164,7 @@ def trust_region_backward_step(params, loss_distance_fn, max_distance, cfg: CgCo
     log["flat_grad"] = flat_loss_grads.detach().clone()
     log["step_dir"] = step_dir.detach().clone()
     descent_step = step_size * step_dir
-    initial_loss = float(loss)
+    initial_loss = float(loss.detach())
     backtracking_line_search(params, descent_step, loss_distance_fn, max_distance, initial_loss, cfg, log)
     return initial_loss
 
