@@ -357,6 +357,27 @@ typedef struct rl_dqn_cfg {
     float discount_factor;
     uint64_t sample_seed;
 } rl_dqn_cfg;
+/* One sample_minibatch of dqn.rs:280-314 on this device: draw j takes lane j mod E (the round-robin over
+ * buffers) and a uniformly random stored episode of it (Uniform::new(0, num_episodes)), episodes are
+ * taken while the step total is below minibatch_steps, and targets are computed per cfg.  Draw words
+ * come from rl_philox_slot(sample_seed, lane = j, step = draw_index, stream = 3, draw = 0, 1, ...).
+ * Device pointers are valid until the next sample/update on this buffer. */
+typedef struct rl_minibatch_view {
+    uint64_t num_steps, num_episodes, capacity;
+    const float *obs;      /* f32 [F][capacity], columns [0, num_steps) valid, episodes in draw order */
+    const uint8_t *action; /* u8 [capacity] */
+    const float *target;   /* f32 [capacity]  StepValueTarget::targets (critics/mod.rs:203-229) */
+    const uint8_t *succ;   /* u8 [capacity]   0 = valid column, RL_PAD = unused */
+} rl_minibatch_view;
+rl_status rl_replay_sample(rl_replay *rb, const rl_dqn_cfg *cfg, rl_mlp *q, uint32_t draw_index, rl_minibatch_view *out);
+/* Debug/parity read-back of one lane's buffer, oldest step first (ReplayBuffer::steps / episodes,
+ * replay.rs:74-86).  obs/next_obs f32 [n][F] row-major; episode_len u64 [num_episodes]; any array may be NULL. */
+rl_status rl_replay_read_lane(rl_replay *rb, uint64_t lane, uint64_t max_steps, float *obs_host, uint8_t *action_host,
+                              float *reward_host, uint8_t *succ_host, float *next_obs_host, uint64_t *episode_len_host,
+                              rl_replay_stats *lane_stats);
+/* opt_steps_per_update x { sample_minibatch, mse(Q(obs).gather(action), targets), backward, Adam }
+ * (dqn.rs:263-337); with a data-parallel group every rank samples its own minibatch_steps and the
+ * gradient sums are all-reduced. */
 rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cfg *cfg, rl_opt_stats *stats);
 /* ExplorationRateSchedule::LinearAnnealed (schedules.rs:35-45) */
 double rl_exploration_rate(double start, double end, uint64_t period, uint64_t global_steps, int32_t training);

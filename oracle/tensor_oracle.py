@@ -309,7 +309,7 @@ def value_update(flat_params, n_in, hidden, obs, targets, n_steps=80, lr=1e-3, b
         loss = torch.nn.functional.mse_loss(mlp_forward(params, obs_t).squeeze(-1), tgt_t, reduction="mean")
         grads = torch.autograd.grad(loss, params)
         opt.step(grads)
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     new_flat = flatten_tensors([p.detach() for p in params]).numpy().copy()
     return new_flat, losses, opt
 
@@ -327,5 +327,51 @@ def q_update(flat_params, n_in, hidden, n_out, obs, actions, targets, n_steps=1,
         q = mlp_forward(params, obs_t).gather(-1, act_t).squeeze(-1)
         loss = torch.nn.functional.mse_loss(q, tgt_t, reduction="mean")
         opt.step(torch.autograd.grad(loss, params))
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses
+
+
+def dqn_update(flat_params, n_in, hidden, n_out, minibatches, discount, one_step_td=False, lr=1e-3,
+               dtype=torch.float32):
+    """DqnAgent::batch_update_slice_refs (dqn.rs:263-337) given the sampled episodes of every optimizer step.
+
+    `minibatches` is a list (one per optimizer step) of lists of episodes; an episode is a dict with
+    obs [L, F], action [L], reward [L], last_succ (1 = Terminate, 2 = Interrupt) and next_obs [F].
+    Targets follow StepValueTarget::targets (critics/mod.rs:203-229): RewardToGo = discounted return without
+    bootstrap; OneStepTd = r + gamma * max_a Q(next) under no_grad with the CURRENT parameters, 0 after a
+    terminal step (masked_fill_, critics/mod.rs:127-129).  Returns (new flat params, per-step losses)."""
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    opt = Adam112(params, lr)
+    g = torch.tensor(float(np.float32(discount)), dtype=dtype)
+    losses = []
+    for episodes in minibatches:
+        obs = torch.tensor(np.concatenate([ep["obs"] for ep in episodes]), dtype=dtype)
+        act = torch.tensor(np.concatenate([ep["action"] for ep in episodes]), dtype=torch.int64).unsqueeze(-1)
+        tgts = []
+        with torch.no_grad():
+            for ep in episodes:
+                r = torch.tensor(np.asarray(ep["reward"]), dtype=dtype)
+                n = r.shape[0]
+                if one_step_td:
+                    o = torch.tensor(np.asarray(ep["obs"]), dtype=dtype)
+                    v = mlp_forward(params, o).amax(dim=-1)
+                    nxt = torch.zeros(n, dtype=dtype)
+                    nxt[:-1] = v[1:]
+                    if ep["last_succ"] == 2:
+                        no = torch.tensor(np.asarray(ep["next_obs"]), dtype=dtype).unsqueeze(0)
+                        nxt[-1] = mlp_forward(params, no).amax(dim=-1)[0]
+                    tgts.append(r + g * nxt)
+                else:
+                    y = torch.zeros(n, dtype=dtype)
+                    carry = torch.zeros((), dtype=dtype)
+                    for t in range(n - 1, -1, -1):
+                        carry = r[t] + carry * g  # packed.rs:336
+                        y[t] = carry
+                    tgts.append(y)
+        tgt = torch.cat(tgts)
+        q = mlp_forward(params, obs).gather(-1, act).squeeze(-1)
+        loss = torch.nn.functional.mse_loss(q, tgt, reduction="mean")
+        opt.step(torch.autograd.grad(loss, params))
+        losses.append(float(loss.detach()))
     return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses

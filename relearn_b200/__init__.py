@@ -13,5 +13,6 @@ from .simulation import ActorSpec, HistoryDataBound, Trajectory, rollout  # noqa
 __version__ = "0.1.0"
 from .agents import TabularQ  # noqa: F401,E402
 from .torch_agents import (ActorCriticAgent, ActorCriticConfig, Adam, AdamConfig,  # noqa: F401,E402
-                           ConjugateGradientOptimizerConfig, OptimizerStepError, Trpo, TrpoConfig, ValuesOpt,
+                           ConjugateGradientOptimizerConfig, DataCollectionSchedule, DqnAgent, DqnConfig,
+                           ExplorationRateSchedule, OptimizerStepError, ReplayBuffer, Trpo, TrpoConfig, ValuesOpt,
                            ValuesOptConfig)

@@ -22,7 +22,7 @@ RL_SPACE_INTERVAL, RL_SPACE_INDEX, RL_SPACE_BOOLEAN, RL_SPACE_OPTION_INDEX = 0, 
 RL_ACT_IDENTITY, RL_ACT_RELU, RL_ACT_SIGMOID, RL_ACT_TANH = 0, 1, 2, 3
 (RL_ACTOR_REPLAY_ACTIONS, RL_ACTOR_RANDOM, RL_ACTOR_CATEGORICAL_POLICY, RL_ACTOR_EPS_GREEDY_Q,
  RL_ACTOR_TABULAR_EPS_GREEDY) = range(5)
-RL_STREAM_ENV_STEP, RL_STREAM_ENV_RESET, RL_STREAM_ACTOR = 0, 1, 2
+RL_STREAM_ENV_STEP, RL_STREAM_ENV_RESET, RL_STREAM_ACTOR, RL_STREAM_SAMPLER = 0, 1, 2, 3
 RL_NCCL_UNIQUE_ID_BYTES = 128
 
 vp = C.c_void_p
@@ -113,6 +113,11 @@ class DqnCfg(C.Structure):
                 ("target_one_step_td", C.c_int32), ("discount_factor", C.c_float), ("sample_seed", C.c_uint64)]
 
 
+class MinibatchView(C.Structure):
+    _fields_ = [("num_steps", C.c_uint64), ("num_episodes", C.c_uint64), ("capacity", C.c_uint64),
+                ("obs", vp), ("action", vp), ("target", vp), ("succ", vp)]
+
+
 P = C.POINTER
 st = C.c_int32
 
@@ -187,6 +192,8 @@ SIGNATURES = {
     "rl_replay_destroy": (st, [vp]),
     "rl_replay_append": (st, [vp, vp]),
     "rl_replay_stats_of": (st, [vp, P(ReplayStats)]),
+    "rl_replay_sample": (st, [vp, P(DqnCfg), vp, C.c_uint32, P(MinibatchView)]),
+    "rl_replay_read_lane": (st, [vp, C.c_uint64, C.c_uint64, vp, vp, vp, vp, vp, vp, P(ReplayStats)]),
     "rl_dqn_update": (st, [vp, vp, vp, P(DqnCfg), P(OptStats)]),
     "rl_exploration_rate": (C.c_double, [C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int32]),
 }

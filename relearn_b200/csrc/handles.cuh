@@ -45,11 +45,27 @@ struct rl_traj {
     float *obs = nullptr, *reward = nullptr, *next_obs = nullptr;
     uint8_t *action = nullptr, *succ = nullptr;
     uint32_t *lane_len = nullptr;
+    uint8_t *lane_flags = nullptr;  // bit 0: dangling step dropped, bit 1: previous step converted to Interrupt
     uint64_t num_steps = 0;     // valid steps (host copy, refreshed by rollout / load)
     uint64_t num_episodes = 0;
     uint64_t used_T = 0;        // number of time slots in use (<= T)
     double *counts_dev = nullptr;  // device: [0] = num_steps, [1] = num_episodes (f64 for all-reduce)
 };
+
+// Minibatch planes produced by the replay sampler (replay.cu), consumed by rl_dqn_update (update.cu).
+struct rl_minibatch_dev {
+    uint64_t capacity;       // columns allocated (valid ones have succ != RL_PAD)
+    const float *obs;        // f32 [F][capacity]
+    const uint8_t *action;   // u8 [capacity]
+    const float *target;     // f32 [capacity]
+    const uint8_t *succ;     // u8 [capacity]
+};
+rl_status rl_replay_sample_enqueue(rl_replay *rb, uint64_t minibatch_steps, uint64_t seed, uint32_t draw_index,
+                                   int one_step_td, float discount, rl_mlp *q, rl_minibatch_dev *out);
+rl_status rl_replay_sample_finish(rl_replay *rb, uint64_t *num_steps, uint64_t *num_episodes);
+uint32_t rl_replay_next_draw_index(rl_replay *rb);
+rl_ctx *rl_replay_ctx(rl_replay *rb);
+int rl_replay_num_features(rl_replay *rb);
 
 struct rl_tabq {
     rl_ctx *ctx = nullptr;

@@ -25,6 +25,7 @@ struct RolloutArgs {
     float *obs, *reward, *next_obs;
     uint8_t *action, *succ;
     uint32_t *lane_len;
+    uint8_t *lane_flags;
     int actor_kind;
     MlpView net;
     const uint8_t *actions;
@@ -286,11 +287,14 @@ __global__ void __launch_bounds__(128) rollout_kernel(typename EnvT::Params p, R
         }
         // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
         uint32_t len = i;
+        uint32_t flags = 0;
         double eps = st.v[ST_EPS];
         if (i > 0 && succ_last == RL_CONTINUE) {
             len = i - 1;
+            flags = 1;
             a.succ[(uint64_t)len * a.E + e] = RL_PAD;
             if (len > 0 && succ_prev == RL_CONTINUE) {
+                flags = 3;
                 a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
 #pragma unroll
                 for (int f = 0; f < EnvT::MAXF; ++f)
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(typename EnvT::Params p, R
             }
         }
         a.lane_len[e] = len;
+        a.lane_flags[e] = (uint8_t)flags;
         st.v[ST_STORED_STEPS] = (double)len;
         st.v[ST_STORED_EPS] = eps;
         nz.finish(a.noise, e);
@@ -412,18 +417,24 @@ __global__ void __launch_bounds__(128) rollout_cartpole_coop_kernel(CartPoleEnv:
     }
     if (valid) {
         uint32_t len = i;
+        uint32_t flags = 0;
         double eps = st.v[ST_EPS];
         if (i > 0 && succ_last == RL_CONTINUE) {
             len = i - 1;
+            flags = 1;
             // same thread as the in-loop store of these addresses, so program order applies
             if (sub == 7) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
             if (len > 0 && succ_prev == RL_CONTINUE) {
+                flags = 3;
                 if (sub == 7) a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
                 if (sub < F) a.next_obs[((uint64_t)(len - 1) * F + sub) * a.E + e] = pick5(last_obs, sub);
                 eps += 1.0;
             }
         }
-        if (sub == 0) a.lane_len[e] = len;
+        if (sub == 0) {
+            a.lane_len[e] = len;
+            a.lane_flags[e] = (uint8_t)flags;
+        }
         st.v[ST_STORED_STEPS] = (double)len;
         st.v[ST_STORED_EPS] = eps;
         if (sub == 0) nz.finish(a.noise, e);
@@ -508,6 +519,7 @@ rl_status rl_traj_create(rl_env *env, uint64_t step_capacity, rl_traj **out) {
     alloc((void **)&t->action, TE);
     alloc((void **)&t->succ, TE);
     alloc((void **)&t->lane_len, t->E * sizeof(uint32_t));
+    alloc((void **)&t->lane_flags, t->E);
     alloc((void **)&t->counts_dev, 8 * sizeof(double));
     if (e != cudaSuccess) {
         rl_traj_destroy(t);
@@ -516,6 +528,7 @@ rl_status rl_traj_create(rl_env *env, uint64_t step_capacity, rl_traj **out) {
     }
     cudaMemsetAsync(t->succ, RL_PAD, TE, ctx->stream);
     cudaMemsetAsync(t->lane_len, 0, t->E * sizeof(uint32_t), ctx->stream);
+    cudaMemsetAsync(t->lane_flags, 0, t->E, ctx->stream);
     cudaMemsetAsync(t->counts_dev, 0, 8 * sizeof(double), ctx->stream);
     *out = t;
     return RL_OK;
@@ -526,7 +539,7 @@ rl_status rl_traj_destroy(rl_traj *t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     cudaFree(t->obs); cudaFree(t->next_obs); cudaFree(t->reward); cudaFree(t->action); cudaFree(t->succ);
-    cudaFree(t->lane_len); cudaFree(t->counts_dev);
+    cudaFree(t->lane_len); cudaFree(t->lane_flags); cudaFree(t->counts_dev);
     delete t;
     return RL_OK;
 }
@@ -589,6 +602,7 @@ rl_status rl_traj_load(rl_traj *t, uint64_t steps, const float *obs_dev, const u
     const unsigned block = 128, grid = rl_grid_for(t->E, block);
     double *partials;
     RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    RL_CUDA(ctx, cudaMemsetAsync(t->lane_flags, 0, t->E, ctx->stream));  // loaded histories are already finalised
     RL_LAUNCH(ctx, traj_index_kernel, grid, block, 0, t->succ, steps, t->E, t->lane_len, partials + ST_COUNT);
     RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, partials + ST_COUNT, (int)grid, partials, t->counts_dev);
     t->used_T = steps;
@@ -623,6 +637,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     a.min_steps = (uint32_t)bound.min_steps; a.slack = (uint32_t)bound.slack_steps;
     a.obs = traj->obs; a.reward = traj->reward; a.next_obs = traj->next_obs; a.action = traj->action; a.succ = traj->succ;
     a.lane_len = traj->lane_len;
+    a.lane_flags = traj->lane_flags;
     a.actor_kind = actor->kind;
     a.net = rl_mlp_view(net);
     a.actions = actor->actions_dev;

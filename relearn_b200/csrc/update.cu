@@ -980,4 +980,63 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
     return RL_OK;
 }
 
+rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cfg *cfg, rl_opt_stats *stats) {
+    if (!rb || !q || !adam || !cfg)
+        return rl_fail(q ? q->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_dqn_update: NULL argument");
+    rl_ctx *ctx = rl_replay_ctx(rb);
+    constexpr int F = 5, A = 2, UPL = 4;
+    RL_REQUIRE(ctx, q->ctx == ctx, "rl_dqn_update: network belongs to another context");
+    RL_REQUIRE(ctx, adam->mlp == q, "rl_dqn_update: optimizer belongs to another module");
+    RL_REQUIRE(ctx, cfg->opt_steps_per_update >= 0 && cfg->opt_steps_per_update <= 100000,
+               "rl_dqn_update: opt_steps_per_update out of range");
+    if (!(rl_replay_num_features(rb) == F && q->in_dim == F && q->out_dim == A && q->hidden == 32 * UPL &&
+          q->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_dqn_update: built for a %d->%d->%d ReLU action-value network (got %d->%d->%d)",
+                       F, 32 * UPL, A, q->in_dim, q->hidden, q->out_dim);
+    const int P = (int)q->n_params;
+    const int n_steps = cfg->opt_steps_per_update;
+    // the minibatch planes hold at most minibatch_steps + one ring of columns; the plan is sized once
+    rl_minibatch_dev mb{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
+    PassPlan plan{};
+    double *losses = nullptr;
+    for (int s = 0; s < n_steps; ++s) {
+        // sample_minibatch (dqn.rs:280-314): episodes, features and targets (no_grad) of this step
+        RL_TRY(rl_replay_sample_enqueue(rb, cfg->minibatch_steps, cfg->sample_seed, rl_replay_next_draw_index(rb),
+                                        cfg->target_one_step_td, cfg->discount_factor, q, &mb));
+        if (s == 0) RL_TRY(make_plan(ctx, P, mb.capacity, &plan, (size_t)(n_steps + 1) * sizeof(double), (void **)&losses));
+        PassArgs pa{};
+        pa.obs = mb.obs; pa.action = mb.action; pa.succ = mb.succ; pa.T = 1; pa.E = mb.capacity;
+        pa.theta = q->params; pa.target = mb.target;
+        // loss_fn + backward_step (dqn.rs:316-336, coptimizer.rs:13-27)
+        RL_TRY((launch_pass<F, A, UPL, PASS_QLOSS>(ctx, plan, pa)));
+        adam->step += 1;
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, P, q->params, adam->m, adam->v, ac, adam->step,
+                  losses + s);
+    }
+    uint64_t m_last = 0;
+    if (n_steps > 0) RL_TRY(rl_replay_sample_finish(rb, &m_last, nullptr));
+    if (stats) {
+        RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+        double *host;
+        RL_TRY(rl_ctx_pinned(ctx, (size_t)(n_steps + 4) * sizeof(double), (void **)&host));
+        if (n_steps > 0) RL_CUDA(ctx, cudaMemcpyAsync(host, losses, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        stats->loss_first = n_steps > 0 ? host[0] : 0.0;
+        stats->loss_last = n_steps > 0 ? host[n_steps - 1] : 0.0;
+        stats->num_steps = m_last;
+        stats->opt_steps = (uint64_t)n_steps;
+        cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return RL_OK;
+}
+
 }  // extern "C"

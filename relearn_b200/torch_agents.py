@@ -221,3 +221,151 @@ class ActorCriticAgent:
         status = self.policy.update(traj, adv, logger)
         self.critic.update(traj, logger)
         return status
+
+
+# ------------------------------------------------------------------------------------------------
+# DQN (src/torch/agents/dqn.rs, schedules.rs; src/agents/buffers/replay.rs)
+# ------------------------------------------------------------------------------------------------
+class ReplayBuffer:
+    """One ReplayBuffer (replay.rs:11-126) per lane, resident in HBM."""
+
+    def __init__(self, env: BatchedEnv, capacity_per_lane: int):
+        self.env, self.ctx, self._lib = env, env.ctx, env.ctx._lib
+        self.capacity = int(capacity_per_lane)
+        h = C.c_void_p()
+        L.check(self._lib.rl_replay_create(env.handle, self.capacity, C.byref(h)), self.ctx.handle)
+        self.handle = h
+
+    def close(self):
+        if self.handle and self.ctx.handle:
+            self._lib.rl_replay_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def write_experience(self, traj: Trajectory):
+        """WriteExperience::write_experience of every lane (raises RL_ERR_BUFFER_FULL like
+        WriteExperienceError::Full)."""
+        L.check(self._lib.rl_replay_append(self.handle, traj.handle), self.ctx.handle)
+
+    def stats(self) -> L.ReplayStats:
+        s = L.ReplayStats()
+        L.check(self._lib.rl_replay_stats_of(self.handle, C.byref(s)), self.ctx.handle)
+        return s
+
+    def total_step_count(self) -> int:
+        return int(self.stats().total_step_count)
+
+    def read_lane(self, lane: int) -> dict:
+        """Stored steps of one lane, oldest first, and its episode lengths (parity read-back)."""
+        F, n = self.env.num_features, self.capacity
+        obs, nobs = np.zeros((n, F), np.float32), np.zeros((n, F), np.float32)
+        act, succ = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        rew = np.zeros(n, np.float32)
+        eps = np.zeros(n, np.uint64)
+        s = L.ReplayStats()
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.check(self._lib.rl_replay_read_lane(self.handle, lane, n, p(obs), p(act), p(rew), p(succ), p(nobs), p(eps),
+                                              C.byref(s)), self.ctx.handle)
+        k = int(s.num_steps)
+        return {"obs": obs[:k], "next_obs": nobs[:k], "action": act[:k], "reward": rew[:k], "succ": succ[:k],
+                "episode_len": eps[:int(s.num_episodes)].astype(np.int64), "total_step_count": int(s.total_step_count)}
+
+    def sample(self, cfg: "L.DqnCfg", q: Mlp | None, draw_index: int) -> dict:
+        """One sample_minibatch (dqn.rs:280-314), read back to the host."""
+        v = L.MinibatchView()
+        L.check(self._lib.rl_replay_sample(self.handle, C.byref(cfg), q.handle if q is not None else None, draw_index,
+                                           C.byref(v)), self.ctx.handle)
+        M, cap, F = int(v.num_steps), int(v.capacity), self.env.num_features
+        rd = self.ctx.read
+        return {"num_steps": M, "num_episodes": int(v.num_episodes),
+                "obs": rd(v.obs, (F, cap), np.float32)[:, :M].T.copy(), "action": rd(v.action, (cap,), np.uint8)[:M],
+                "target": rd(v.target, (cap,), np.float32)[:M], "succ": rd(v.succ, (cap,), np.uint8)}
+
+
+@dataclass
+class ExplorationRateSchedule:
+    """schedules.rs:7-45 (LinearAnnealed; a constant schedule has start == end)."""
+
+    start: float = 1.0
+    end: float = 0.1
+    period: int = 10_000_000
+
+    def exploration_rate(self, global_steps: int, training: bool = True) -> float:
+        return float(L.lib().rl_exploration_rate(self.start, self.end, self.period, global_steps, 1 if training else 0))
+
+
+@dataclass
+class DataCollectionSchedule:
+    """schedules.rs:51-68: FirstRest{first, rest}; Constant is first == rest."""
+
+    first: int = 1_000_000
+    rest: int = 100_000
+
+    def update_size(self, global_steps: int) -> HistoryDataBound:
+        return HistoryDataBound.with_default_slack(self.first if global_steps < self.first else self.rest)
+
+
+@dataclass
+class DqnConfig:
+    """dqn.rs:26-72"""
+
+    action_value_fn_config: MlpConfig = field(default_factory=MlpConfig)
+    optimizer_config: AdamConfig = field(default_factory=AdamConfig)
+    target_one_step_td: bool = False          # StepValueTarget::RewardToGo is the default
+    exploration_rate: ExplorationRateSchedule = field(default_factory=ExplorationRateSchedule)
+    minibatch_steps: int = 100_000
+    opt_steps_per_update: int = 50
+    buffer_capacity: int = 10_000_000         # per buffer (= per lane)
+    update_size: DataCollectionSchedule = field(default_factory=DataCollectionSchedule)
+    sample_seed: int = 0
+
+    def build_agent(self, env: BatchedEnv) -> "DqnAgent":
+        return DqnAgent(env, self)
+
+
+class DqnAgent:
+    """Agent + BatchUpdate (dqn.rs:186-337) over a batched env on one GPU; every lane is one worker with
+    its own ReplayBuffer."""
+
+    def __init__(self, env: BatchedEnv, cfg: DqnConfig):
+        self.env, self.cfg, self.ctx, self._lib = env, cfg, env.ctx, env.ctx._lib
+        self.action_value_fn = cfg.action_value_fn_config.build_module(env.ctx, env.num_features, env.num_actions)
+        self.optimizer = Adam(self.action_value_fn, cfg.optimizer_config)
+        self.discount_factor = np.float32(env.discount_factor)  # dqn.rs:178
+        self.global_steps = 0
+
+    def actor(self, training: bool = True) -> ActorSpec:
+        """Agent::actor(mode): epsilon is fixed from global_steps at actor creation (dqn.rs:202-212)."""
+        eps = self.cfg.exploration_rate.exploration_rate(self.global_steps, training)
+        return ActorSpec(kind=L.RL_ACTOR_EPS_GREEDY_Q, net=self.action_value_fn, exploration_rate=eps, training=training)
+
+    def buffer(self) -> ReplayBuffer:
+        return ReplayBuffer(self.env, self.cfg.buffer_capacity)
+
+    def min_update_size(self) -> HistoryDataBound:
+        return self.cfg.update_size.update_size(self.global_steps)
+
+    def c_cfg(self, minibatch_steps: int | None = None) -> L.DqnCfg:
+        world = max(self.ctx.world_size, 1)
+        mb = minibatch_steps if minibatch_steps is not None else -(-self.cfg.minibatch_steps // world)
+        return L.DqnCfg(mb, self.cfg.opt_steps_per_update, 1 if self.cfg.target_one_step_td else 0,
+                        float(self.discount_factor), self.cfg.sample_seed)
+
+    def batch_update(self, buffer: ReplayBuffer, logger: dict | None = None):
+        """dqn.rs:263-337"""
+        if logger is not None:
+            logger["exploration_rate"] = self.cfg.exploration_rate.exploration_rate(self.global_steps, True)
+        self.global_steps = buffer.total_step_count()
+        stats = L.OptStats()
+        cfg = self.c_cfg()
+        L.check(self._lib.rl_dqn_update(buffer.handle, self.action_value_fn.handle, self.optimizer.handle, C.byref(cfg),
+                                        C.byref(stats)), self.ctx.handle)
+        if logger is not None:
+            logger.update({"loss": stats.loss_last, "loss_first": stats.loss_first, "minibatch_steps": stats.num_steps,
+                           "agent_update/time": stats.update_ms * 1e-3})
+        return stats
