@@ -14,6 +14,8 @@
 //                                      lanes to fill the GPU with one thread each (E = 4096).
 #include "handles.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 enum { ST_STEPS = 0, ST_R, ST_R2, ST_EPS, ST_ER, ST_ER2, ST_EL, ST_EL2, ST_STORED_STEPS, ST_STORED_EPS, ST_COUNT };
@@ -69,7 +71,7 @@ __device__ __forceinline__ double warp_sum(double x) {
 }
 
 // Deterministic block reduction of the per-lane statistics into partials[blockIdx.x][*].
-__device__ void block_reduce_stats(const LaneStats &st, bool contributes, double *partials) {
+__device__ __forceinline__ void block_reduce_stats(const LaneStats &st, bool contributes, double *partials) {
     __shared__ double red[32][ST_COUNT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
 #pragma unroll
@@ -442,6 +444,284 @@ __global__ void __launch_bounds__(128) rollout_cartpole_coop_kernel(CartPoleEnv:
     block_reduce_stats(st, valid && sub == 0, a.partials);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K2c: CartPole + 5->128->2 ReLU network, LANES threads per env (LANES = 1 .. 32), 32 / LANES envs per warp.
+//
+// The step chain  policy -> sample -> f64 physics -> observe  is strictly sequential per env, so the
+// kernel is shaped by two costs: the physics (~the same instruction count per WARP however many envs
+// the warp carries) and the 128-unit hidden layer (per env).  Packing 32 / LANES envs into a warp
+// amortises the physics; splitting the hidden layer over LANES threads keeps enough warps in flight
+// when envs are scarce (E = 4096: LANES = 8 -> 1024 warps, one wave over 148 SMs).
+//
+// Hidden units are processed as PAIRS with packed FP32 (FFMA2): pair q = units (q, q + 64).  Weights
+// live in shared memory as four float4 planes [4][64] so that the LANES threads of a group read
+// LANES consecutive 16-byte words (conflict-free) and the 32 / LANES groups read the same words
+// (broadcast): 4 LDS.128 + 7 FFMA2 + 2 FMNMX per pair.
+//   plane 0: w1[q][0] w1[q+64][0] w1[q][1] w1[q+64][1]     plane 2: w1[.][4] pair, b1 pair
+//   plane 1: w1[.][2] pair, w1[.][3] pair                  plane 3: w2[0][.] pair, w2[1][.] pair
+// ------------------------------------------------------------------------------------------------
+constexpr int GK_H = 128, GK_PAIRS = 64;
+
+__device__ __forceinline__ void stage_pair_weights(const MlpView &m, float4 *sw4, float *tail, const CartPoleEnv::Params &p,
+                                                   int rem_entries) {
+    const int F = m.in_dim;
+    const float *w1 = m.w1(), *b1 = m.b1(), *w2 = m.w2();
+    for (int i = threadIdx.x; i < 4 * GK_PAIRS; i += blockDim.x) {
+        const int c = i / GK_PAIRS, q = i - c * GK_PAIRS, j0 = q, j1 = q + GK_PAIRS;
+        auto W1 = [&](int j, int f) { return f < F ? w1[j * F + f] : 0.0f; };
+        float4 v;
+        if (c == 0) v = make_float4(W1(j0, 0), W1(j1, 0), W1(j0, 1), W1(j1, 1));
+        else if (c == 1) v = make_float4(W1(j0, 2), W1(j1, 2), W1(j0, 3), W1(j1, 3));
+        else if (c == 2) v = make_float4(W1(j0, 4), W1(j1, 4), b1[j0], b1[j1]);
+        else v = make_float4(w2[j0], w2[j1], w2[GK_H + j0], w2[GK_H + j1]);
+        sw4[i] = v;
+    }
+    if (threadIdx.x < 2) tail[threadIdx.x] = m.b2()[threadIdx.x];
+    // StepLimitObs::remaining = steps_remaining as f64 / max_steps as f64, then `as f32` (step_limit.rs:194-200,
+    // interval.rs:114): exact table instead of an f64 division per step
+    for (int i = threadIdx.x; i < rem_entries; i += blockDim.x)
+        tail[2 + i] = (float)__ddiv_rn((double)i, (double)p.max_steps);
+}
+
+constexpr int GK_REM_TABLE_MAX = 2048;
+
+template <int LANES, bool REPLAY, int AK>
+__global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv::Params p, RolloutArgs a) {
+    using EnvT = CartPoleEnv;
+    constexpr int PPL = GK_PAIRS / LANES;  // pairs per thread
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    float4 *sw4 = reinterpret_cast<float4 *>(gk_smem);
+    float *tail = reinterpret_cast<float *>(sw4 + 4 * GK_PAIRS);
+    const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
+    stage_pair_weights(a.net, sw4, tail, p, rem_table ? (int)p.max_steps + 1 : 0);
+    __syncthreads();
+    const float b2a = tail[0], b2b = tail[1];
+    const float *rem = tail + 2;
+
+    const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t e = gtid / LANES;
+    const int sub = (int)(gtid % LANES);
+    const bool valid = e < a.E;
+    const int F = a.F;
+    const bool needs_logits = AK == RL_ACTOR_CATEGORICAL_POLICY || a.eps < 1.0;
+    constexpr bool REGW = PPL <= 8;  // LANES >= 8: at most 128 weight registers per thread
+    float4 wA[REGW ? PPL : 1], wB[REGW ? PPL : 1], wC[REGW ? PPL : 1], wD[REGW ? PPL : 1];
+    if constexpr (REGW) {
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int q = sub + LANES * u;
+            wA[u] = sw4[q]; wB[u] = sw4[GK_PAIRS + q]; wC[u] = sw4[2 * GK_PAIRS + q]; wD[u] = sw4[3 * GK_PAIRS + q];
+        }
+    }
+
+    auto observe = [&](const EnvT::State &s, float *obs) {
+        obs[0] = (float)s.x; obs[1] = (float)s.xd; obs[2] = (float)s.th; obs[3] = (float)s.thd;
+        const uint32_t r = s.meta & 0x7FFFFFFFu;
+        obs[4] = p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
+    };
+
+    LaneNoise<REPLAY> nz;
+    const uint64_t e_safe = valid ? e : 0;  // out-of-range threads shadow lane 0 without storing anything
+    nz.init(a.noise, a.lane_offset + e_safe, e_safe);
+    const uint32_t t0 = a.noise.step_counter;
+    EnvT::State s;
+    float obs[5] = {0, 0, 0, 0, 0}, last_obs[5] = {0, 0, 0, 0, 0};
+    uint32_t n = (valid && a.min_steps) ? a.min_steps + a.slack : 0;
+    uint32_t i = 0;
+    int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+    s.x = s.xd = s.th = s.thd = 0.0;
+    s.meta = 0x80000000u | p.max_steps;
+    if (n > 0) {
+        nz.set_step(t0);
+        EnvT::reset<REPLAY>(p, s, nz);
+        observe(s, obs);
+    }
+    // Column k of the step record (obs 0..4, action, reward, succ) is stored by thread k % LANES of the group.
+    bool owns[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) owns[k] = valid && sub == k % LANES && (k >= 5 || k < F);
+    const uint64_t FE = (uint64_t)F * a.E;
+    uint64_t io = e_safe, is = e_safe;  // running offsets: obs planes advance by F*E per step, the others by E
+    // OnlineStepsSummary::push (summary.rs:198-216) as raw f64 sums, branch-free
+    // (CartPole's reward is the constant 1.0, cartpole.rs:140: step sums follow from the step count and an
+    // episode's return equals its length; both are exact in f64)
+    double n_eps = 0.0, sum_el = 0.0, sum_el2 = 0.0;
+    uint32_t cur_len = 0;
+    uint32_t shared_word = 0;  // Philox: this thread's actor word for step (i rounded down to LANES) + sub
+
+    // The step loop is warp-uniform (all threads take part in the logit shuffles until the warp's last env is
+    // done; threads whose env finished earlier keep stepping a dead state with every side effect masked) and,
+    // apart from the rare Interrupt and reset paths, one basic block -- so the compiler interleaves the Philox
+    // draw, the stores and the statistics with the dependent policy -> sample -> physics chain.
+    while (__any_sync(0xffffffffu, n > 0)) {
+        const bool active = n > 0;
+        if (!REPLAY) nz.set_step(t0 + i);
+        float z0 = 0.0f, z1 = 0.0f;
+        if (needs_logits) {
+            const float2 o0 = make_float2(obs[0], obs[0]), o1 = make_float2(obs[1], obs[1]), o2 = make_float2(obs[2], obs[2]);
+            const float2 o3 = make_float2(obs[3], obs[3]), o4 = make_float2(obs[4], obs[4]);
+            float2 za = make_float2(0.0f, 0.0f), zb = make_float2(0.0f, 0.0f);
+            if constexpr (REGW) {
+                // this thread's pairs live in registers for the whole rollout: no shared-memory latency on the chain
+                float2 pre[PPL];
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].x, wA[u].y), o0, make_float2(wC[u].z, wC[u].w));
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].z, wA[u].w), o1, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].x, wB[u].y), o2, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].z, wB[u].w), o3, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wC[u].x, wC[u].y), o4, pre[u]);
+                float2 zc = make_float2(0.0f, 0.0f), zd = make_float2(0.0f, 0.0f);  // second accumulator pair: shorter chains
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) {
+                    const float2 h = make_float2(fmaxf(pre[u].x, 0.0f), fmaxf(pre[u].y, 0.0f));
+                    if (u & 1) {
+                        zc = __ffma2_rn(make_float2(wD[u].x, wD[u].y), h, zc);
+                        zd = __ffma2_rn(make_float2(wD[u].z, wD[u].w), h, zd);
+                    } else {
+                        za = __ffma2_rn(make_float2(wD[u].x, wD[u].y), h, za);
+                        zb = __ffma2_rn(make_float2(wD[u].z, wD[u].w), h, zb);
+                    }
+                }
+                za = __fadd2_rn(za, zc);
+                zb = __fadd2_rn(zb, zd);
+            } else {
+#pragma unroll(PPL < 8 ? PPL : 8)
+                for (int u = 0; u < PPL; ++u) {
+                    const int q = sub + LANES * u;
+                    const float4 A = sw4[q], B = sw4[GK_PAIRS + q], Cw = sw4[2 * GK_PAIRS + q], D = sw4[3 * GK_PAIRS + q];
+                    float2 pre = make_float2(Cw.z, Cw.w);
+                    pre = __ffma2_rn(make_float2(A.x, A.y), o0, pre);
+                    pre = __ffma2_rn(make_float2(A.z, A.w), o1, pre);
+                    pre = __ffma2_rn(make_float2(B.x, B.y), o2, pre);
+                    pre = __ffma2_rn(make_float2(B.z, B.w), o3, pre);
+                    pre = __ffma2_rn(make_float2(Cw.x, Cw.y), o4, pre);
+                    const float2 h = make_float2(fmaxf(pre.x, 0.0f), fmaxf(pre.y, 0.0f));
+                    za = __ffma2_rn(make_float2(D.x, D.y), h, za);
+                    zb = __ffma2_rn(make_float2(D.z, D.w), h, zb);
+                }
+            }
+            z0 = za.x + za.y;
+            z1 = zb.x + zb.y;
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) {
+                z0 += __shfl_xor_sync(0xffffffffu, z0, o);
+                z1 += __shfl_xor_sync(0xffffffffu, z1, o);
+            }
+            z0 += b2a;
+            z1 += b2b;
+        }
+        uint32_t action = 0;
+        if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
+            // policies/actor.rs:42-55; Categorical::new + sample (categorical.rs:29-33,52-54) as inverse CDF over
+            // exp(log_softmax(z)): action 0 iff u < p0 (the last category takes the rest)
+            uint32_t w = 0;
+            if constexpr (REPLAY) {
+                if (active) w = nz.template next_u32<RL_STREAM_ACTOR>();
+            } else if constexpr (LANES == 1) {
+                w = nz.template next_u32<RL_STREAM_ACTOR>();
+            } else {
+                // The LANES threads of a group would all compute the same Philox block; instead thread `sub`
+                // computes the word of step (i rounded down to a multiple of LANES) + sub once every LANES
+                // steps and the group picks the current one by shuffle (same words, 1/LANES of the work).
+                // Valid because a warp's active envs advance in lockstep (i is warp-uniform among them).
+                const uint32_t phase = i & (LANES - 1);
+                if (__any_sync(0xffffffffu, active && phase == 0))
+                    shared_word = (uint32_t)rl_philox_slot_impl(nz.seed, nz.lane, t0 + i - phase + sub, RL_STREAM_ACTOR, 0);
+                w = __shfl_sync(0xffffffffu, shared_word, (threadIdx.x & 31 & ~(LANES - 1)) + phase);
+            }
+            const float u = rl_u32_to_f32(w);
+            const float m = fmaxf(z0, z1);
+            const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
+            action = u < expf(z0 - lse) ? 0u : 1u;
+        } else if (active) {  // dqn.rs:360-379
+            if (rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps)) action = rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, 2u);
+            else action = z1 > z0 ? 1u : 0u;
+        }
+        if (active) {
+            if (owns[0]) a.obs[io] = obs[0];
+            if (owns[1]) a.obs[io + a.E] = obs[1];
+            if (owns[2]) a.obs[io + 2 * a.E] = obs[2];
+            if (owns[3]) a.obs[io + 3 * a.E] = obs[3];
+            if (owns[4]) a.obs[io + 4 * a.E] = obs[4];
+            if (owns[5]) a.action[is] = (uint8_t)action;
+        }
+#pragma unroll
+        for (int f = 0; f < 5; ++f) last_obs[f] = active ? obs[f] : last_obs[f];
+        const int sc = EnvT::step_fast(p, s, action);
+        const float r = 1.0f;  // cartpole.rs:140
+        if (active) {
+            if (owns[6]) a.reward[is] = r;
+            if (owns[7]) a.succ[is] = (uint8_t)sc;
+        }
+        if (sc == RL_INTERRUPT && active) {  // rare: once per max_steps
+            observe(s, obs);
+            if (sub == 0) {
+#pragma unroll
+                for (int f = 0; f < 5; ++f)
+                    if (f < F) a.next_obs[io + (uint64_t)f * a.E] = obs[f];
+            }
+        }
+        cur_len += active ? 1u : 0u;
+        if (sc != RL_CONTINUE && active) {  // steps.rs:116-124: the next call starts a new episode
+            nz.set_step(t0 + i + 1);
+            EnvT::reset<REPLAY>(p, s, nz);
+            const double ld = (double)cur_len;
+            n_eps += 1.0;
+            sum_el += ld;
+            sum_el2 = fma(ld, ld, sum_el2);
+            cur_len = 0;
+        }
+        observe(s, obs);
+        if (active) {
+            succ_prev = succ_last;
+            succ_last = sc;
+            i += 1;
+            n -= 1;
+            if (sc != RL_CONTINUE && n <= a.slack) n = 0;  // take_steps.rs:83-88
+            io += FE;
+            is += a.E;
+        }
+    }
+    LaneStats st;
+    st.init();
+    st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
+    st.v[ST_EPS] = n_eps; st.v[ST_ER] = st.v[ST_EL] = sum_el; st.v[ST_ER2] = st.v[ST_EL2] = sum_el2;
+    if (valid) {
+        uint32_t len = i;
+        uint32_t flags = 0;
+        double eps = n_eps;
+        if (i > 0 && succ_last == RL_CONTINUE) {
+            len = i - 1;
+            flags = 1;
+            // same thread as the in-loop store of these addresses, so program order applies
+            if (sub == (7 % LANES)) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (len > 0 && succ_prev == RL_CONTINUE) {
+                flags = 3;
+                if (sub == (7 % LANES)) a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+                if (sub == 0) {
+#pragma unroll
+                    for (int f = 0; f < 5; ++f)
+                        if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
+                }
+                eps += 1.0;
+            }
+        }
+        if (sub == 0) {
+            a.lane_len[e] = len;
+            a.lane_flags[e] = (uint8_t)flags;
+            nz.finish(a.noise, e);
+        }
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = eps;
+    }
+    block_reduce_stats(st, valid && sub == 0, a.partials);
+}
+
 // Sum the per-block partials in block order (deterministic) and publish the summary.
 __global__ void rollout_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ out,
                                         double *__restrict__ traj_counts) {
@@ -494,6 +774,32 @@ rl_status launch_coop(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a,
         RL_LAUNCH(ctx, (rollout_cartpole_coop_kernel<LANES, false>), grid, block, 0, p, a);
     }
     return RL_OK;
+}
+
+
+template <int LANES, int AK>
+rl_status launch_group_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
+    // one warp per CTA while CTAs are scarce, so that the warps spread evenly over the SM sub-partitions
+    const unsigned block = a.E * LANES < (uint64_t)ctx->sm_count * 4 * 128 ? 32 : 128;
+    const unsigned grid = rl_grid_for(a.E * LANES, block);
+    const size_t smem = 4 * GK_PAIRS * sizeof(float4) + (2 + GK_REM_TABLE_MAX) * sizeof(float);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    if (replay) {
+        RL_LAUNCH(ctx, (rollout_cartpole_group_kernel<LANES, true, AK>), grid, block, smem, p, a);
+    } else {
+        RL_LAUNCH(ctx, (rollout_cartpole_group_kernel<LANES, false, AK>), grid, block, smem, p, a);
+    }
+    return RL_OK;
+}
+
+template <int LANES>
+rl_status launch_group(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
+    if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
+        return launch_group_ak<LANES, RL_ACTOR_CATEGORICAL_POLICY>(ctx, p, a, replay, nblocks_out);
+    return launch_group_ak<LANES, RL_ACTOR_EPS_GREEDY_Q>(ctx, p, a, replay, nblocks_out);
 }
 
 }  // namespace
@@ -652,24 +958,39 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     switch (env->kind) {
     case RL_ENV_CARTPOLE: {
         int lanes = actor->lanes_per_env;
-        const bool coop_ok = net && net->hidden == 128 && es.num_actions == 2;
-        if (lanes == 0) {
-            // auto: fill ~8 warps per SM sub-partition's worth of threads when lanes are scarce
-            lanes = 1;
-            if (coop_ok) {
-                const uint64_t target_threads = (uint64_t)ctx->sm_count * 1024;
-                while (lanes < 32 && env->E * (uint64_t)lanes * 2 <= target_threads) lanes *= 2;
-                if (lanes > 1 && lanes < 8) lanes = 8;
+        // K2c serves the two network actors on the reference's default module (MlpConfig: one hidden layer of
+        // 128, ReLU); anything else takes the generic thread-per-env kernel K2a.
+        const bool group_ok = net && net->hidden == GK_H && net->act == RL_ACT_RELU && es.num_actions == 2 &&
+                              (es.num_features == 5 || es.num_features == 4) && env->cartpole.max_angle <= 0.5;
+        static const bool legacy = getenv("RL_ROLLOUT_LEGACY") != nullptr;
+        if (!group_ok || legacy) {
+            const bool coop_ok = net && net->hidden == 128 && es.num_actions == 2;
+            if (lanes == 0) lanes = 1;
+            if (lanes > 1 && !coop_ok)
+                return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env > 1 needs a 128-unit MLP on CartPole");
+            switch (lanes) {
+            case 1: RL_TRY((launch_rollout<CartPoleEnv>(ctx, env->cartpole, a, net, replay, &nblocks))); break;
+            case 8: RL_TRY((launch_coop<8>(ctx, env->cartpole, a, replay, &nblocks))); break;
+            case 16: RL_TRY((launch_coop<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
+            case 32: RL_TRY((launch_coop<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
+            default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 8, 16 or 32");
             }
+            break;
         }
-        if (lanes > 1 && !coop_ok)
-            return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env > 1 needs a 128-unit MLP on CartPole");
+        if (lanes == 0) {
+            // auto, from the B200 sweep in profiles/r1_rollout_sweep.md: with few envs the step chain of a
+            // single warp is the bound, so the hidden layer is split over 8 threads (weights in registers);
+            // as envs grow the redundant per-warp physics costs more than the latency it hides.
+            lanes = env->E <= 6144 ? 8 : env->E <= 12288 ? 4 : env->E <= 24576 ? 2 : 1;
+        }
         switch (lanes) {
-        case 1: RL_TRY((launch_rollout<CartPoleEnv>(ctx, env->cartpole, a, net, replay, &nblocks))); break;
-        case 8: RL_TRY((launch_coop<8>(ctx, env->cartpole, a, replay, &nblocks))); break;
-        case 16: RL_TRY((launch_coop<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
-        case 32: RL_TRY((launch_coop<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
-        default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 8, 16 or 32");
+        case 1: RL_TRY((launch_group<1>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 2: RL_TRY((launch_group<2>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 4: RL_TRY((launch_group<4>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 8: RL_TRY((launch_group<8>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 16: RL_TRY((launch_group<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        case 32: RL_TRY((launch_group<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
+        default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
         }
         break;
     }

@@ -19,7 +19,7 @@ for E in Es:
     T = 256 if E <= 65536 else (64 if E <= (1 << 20) else 16)
     env = R.build_env(ctx, cfg, E, seed=1)
     traj = R.Trajectory(env, T)
-    for lanes in (1, 8, 16, 32):
+    for lanes in (1, 2, 4, 8, 16, 32):
         if E * lanes > (1 << 25):
             continue
         spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes)

@@ -148,7 +148,7 @@ def test_philox_slot_matches_oracle():
         assert lib.rl_philox_slot(seed, lane, t, stream, draw) == olib.ro_philox_slot(seed, lane, t, stream, draw)
 
 
-@pytest.mark.parametrize("lanes", [1, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
 def test_fused_rollout_policy_cartpole_consistent(ctx, lanes):
     """Categorical policy inside the step kernel: every action is the inverse-CDF choice for the recorded
     observation (near-ties within 2e-6 of a CDF edge are tolerated and counted), and the dynamics given those
