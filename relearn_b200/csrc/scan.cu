@@ -108,6 +108,67 @@ __global__ void __launch_bounds__(256) value_forward_kernel(MlpView m, const flo
     if (intr) v_next[n] = zn;
 }
 
+
+// Same map for the default critic (5 -> 128 -> 1 ReLU, MlpConfig defaults): thread per slot, hidden units as
+// pairs (q, q + 64) with packed FP32, weights in shared memory as float4 planes read by warp-wide broadcast:
+//   plane 0: w1[.][0] pair, w1[.][1] pair   plane 1: w1[.][2] pair, w1[.][3] pair
+//   plane 2: w1[.][4] pair, b1 pair         plane 3: w2 pair, 0, 0
+// 4 LDS.128 + 6 FFMA2 + 2 FMNMX per pair instead of ~40 scalar instructions in the generic kernel.
+__global__ void __launch_bounds__(256) value_forward_pairs_kernel(MlpView m, const float *__restrict__ obs,
+                                                                 const float *__restrict__ next_obs,
+                                                                 const uint8_t *__restrict__ succ, uint64_t T, uint64_t E,
+                                                                 float *__restrict__ v, float *__restrict__ v_next) {
+    constexpr int H = 128, NPAIR = 64;
+    __shared__ float4 sw4[4 * NPAIR];
+    __shared__ float sb2;
+    const int F = m.in_dim;
+    const float *w1 = m.w1(), *b1 = m.b1(), *w2 = m.w2();
+    for (int i = threadIdx.x; i < 4 * NPAIR; i += blockDim.x) {
+        const int c = i / NPAIR, q = i - c * NPAIR, j0 = q, j1 = q + NPAIR;
+        auto W1 = [&](int j, int f) { return f < F ? w1[j * F + f] : 0.0f; };
+        float4 val;
+        if (c == 0) val = make_float4(W1(j0, 0), W1(j1, 0), W1(j0, 1), W1(j1, 1));
+        else if (c == 1) val = make_float4(W1(j0, 2), W1(j1, 2), W1(j0, 3), W1(j1, 3));
+        else if (c == 2) val = make_float4(W1(j0, 4), W1(j1, 4), b1[j0], b1[j1]);
+        else val = make_float4(w2[j0], w2[j1], 0.0f, 0.0f);
+        sw4[i] = val;
+    }
+    if (threadIdx.x == 0) sb2 = m.b2()[0];
+    __syncthreads();
+    const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= T * E) return;
+    const uint8_t sc = succ[n];
+    if (sc == RL_PAD) {
+        v[n] = 0.0f;
+        return;
+    }
+    const uint64_t t = n / E, e = n - t * E;
+    auto forward = [&](const float *src) {
+        float x[5];
+#pragma unroll
+        for (int f = 0; f < 5; ++f) x[f] = f < F ? __ldg(src + (t * F + f) * E + e) : 0.0f;
+        const float2 o0 = make_float2(x[0], x[0]), o1 = make_float2(x[1], x[1]), o2 = make_float2(x[2], x[2]);
+        const float2 o3 = make_float2(x[3], x[3]), o4 = make_float2(x[4], x[4]);
+        float2 za = make_float2(0.0f, 0.0f), zb = make_float2(0.0f, 0.0f);
+#pragma unroll 8
+        for (int q = 0; q < NPAIR; ++q) {
+            const float4 A = sw4[q], B = sw4[NPAIR + q], Cw = sw4[2 * NPAIR + q], D = sw4[3 * NPAIR + q];
+            float2 pre = make_float2(Cw.z, Cw.w);
+            pre = __ffma2_rn(make_float2(A.x, A.y), o0, pre);
+            pre = __ffma2_rn(make_float2(A.z, A.w), o1, pre);
+            pre = __ffma2_rn(make_float2(B.x, B.y), o2, pre);
+            pre = __ffma2_rn(make_float2(B.z, B.w), o3, pre);
+            pre = __ffma2_rn(make_float2(Cw.x, Cw.y), o4, pre);
+            const float2 h = make_float2(fmaxf(pre.x, 0.0f), fmaxf(pre.y, 0.0f));
+            if (q & 1) zb = __ffma2_rn(make_float2(D.x, D.y), h, zb);
+            else za = __ffma2_rn(make_float2(D.x, D.y), h, za);
+        }
+        return (za.x + za.y) + (zb.x + zb.y) + sb2;
+    };
+    v[n] = forward(obs);
+    if (sc == RL_INTERRUPT) v_next[n] = forward(next_obs);
+}
+
 // temporal_differences + gae + reward_to_go in one backward pass per lane
 // (critics/mod.rs:101-105,158-199).  delta = (r + gamma * V_next) - V, f32, unfused.
 template <bool HAS_V>
@@ -215,10 +276,15 @@ rl_status rl_gae(rl_traj *traj, rl_mlp *value_fn, float gamma, float lambda, flo
         float *v;
         RL_TRY(rl_ctx_scratch(ctx, 2 * T * E * sizeof(float), (void **)&v));
         float *v_next = v + T * E;
-        const size_t smem = value_fn->n_params * sizeof(float);
-        RL_CUDA(ctx, cudaFuncSetAttribute(value_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, value_forward_kernel, rl_grid_for(T * E, 256), 256, smem, rl_mlp_view(value_fn), traj->obs,
-                  traj->next_obs, traj->succ, T, E, v, v_next);
+        if (value_fn->hidden == 128 && value_fn->in_dim <= 5 && value_fn->act == RL_ACT_RELU) {
+            RL_LAUNCH(ctx, value_forward_pairs_kernel, rl_grid_for(T * E, 256), 256, 0, rl_mlp_view(value_fn), traj->obs,
+                      traj->next_obs, traj->succ, T, E, v, v_next);
+        } else {
+            const size_t smem = value_fn->n_params * sizeof(float);
+            RL_CUDA(ctx, cudaFuncSetAttribute(value_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RL_LAUNCH(ctx, value_forward_kernel, rl_grid_for(T * E, 256), 256, smem, rl_mlp_view(value_fn), traj->obs,
+                      traj->next_obs, traj->succ, T, E, v, v_next);
+        }
         RL_LAUNCH(ctx, gae_scan_kernel<true>, grid, block, 0, traj->reward, v, v_next, traj->succ, T, E, gamma, gl,
                   adv_dev, rtg_dev);
     } else {

@@ -683,6 +683,62 @@ __global__ void __launch_bounds__(VEC_THREADS)
     if (threadIdx.x == 0 && loss_out) *loss_out = sums[P + SC_LOSS] / N;
 }
 
+
+// reduce_rows_kernel + adam_step_kernel in one launch (single-GPU loops: no all-reduce sits between them).
+// Every block reduces its 32 columns exactly as reduce_rows_kernel does, plus the sample-count column, and
+// applies libtorch's Adam::step to its own parameters; block 0 also publishes the loss.
+__global__ void __launch_bounds__(256)
+    reduce_rows_adam_kernel(const double *__restrict__ rows, int B, int W, int P, double *__restrict__ sums, float *theta,
+                            float *m, float *v, AdamArgs c, uint64_t step, double *loss_out) {
+    __shared__ double part[8][32];
+    __shared__ double cnt_part[8], loss_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    double s = 0.0;
+    if (col < W) {
+#pragma unroll 8
+        for (int b = warp; b < B; b += 8) s += rows[(size_t)b * W + col];
+    }
+    part[warp][lane] = s;
+    // the scalar columns, summed in the same order as the owning block does
+    double cn = 0.0, ls = 0.0;
+    if (lane == 0) {
+        for (int b = warp; b < B; b += 8) {
+            cn += rows[(size_t)b * W + P + SC_COUNT];
+            ls += rows[(size_t)b * W + P + SC_LOSS];
+        }
+        cnt_part[warp] = cn;
+        loss_part[warp] = ls;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0, N = 0.0, lsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            t += part[w][lane];
+            N += cnt_part[w];
+            lsum += loss_part[w];
+        }
+        if (col < W) sums[col] = t;
+        if (col < P) {
+            const float beta1 = (float)c.beta1, beta2 = (float)c.beta2;
+            const float omb1 = (float)(1.0 - c.beta1), omb2 = (float)(1.0 - c.beta2);
+            const double bc1 = 1.0 - pow(c.beta1, (double)step), bc2 = 1.0 - pow(c.beta2, (double)step);
+            const float step_size = (float)(c.lr / bc1), bc2_sqrt = (float)sqrt(bc2), eps = (float)c.eps;
+            float g = (float)(t / N);
+            const float th = theta[col];
+            if (c.weight_decay != 0.0) g = __fadd_rn(g, __fmul_rn((float)c.weight_decay, th));
+            const float mi = __fadd_rn(__fmul_rn(m[col], beta1), __fmul_rn(omb1, g));
+            const float vi = __fadd_rn(__fmul_rn(v[col], beta2), __fmul_rn(__fmul_rn(omb2, g), g));
+            m[col] = mi;
+            v[col] = vi;
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+            theta[col] = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+        }
+        if (blockIdx.x == 0 && lane == 0 && loss_out) *loss_out = lsum / N;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -700,7 +756,7 @@ size_t pass_smem_bytes() {
 }
 
 template <int F, int A, int UPL, int MODE, int CH, int MINB>
-rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
+rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
     const size_t smem = pass_smem_bytes<F, A, UPL>();
     static bool configured = false;
     if (!configured) {
@@ -710,6 +766,7 @@ rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args) 
     }
     args.partials = plan.partials;
     RL_LAUNCH(ctx, (mlp_pass_kernel<F, A, UPL, MODE, CH, MINB>), plan.grid, PASS_THREADS, smem, args);
+    if (!reduce) return RL_OK;
     RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.sums,
               args.skip_flag);
     if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
@@ -729,16 +786,34 @@ int pass_variant() {
 // forward-only passes fit 2 CTAs/SM at CH=8; the critic pass is fastest at CH=4 with 2 CTAs/SM; the
 // gradient / Fisher-vector passes need the registers of 1 CTA/SM.  RL_PASS_VARIANT overrides (experiments).
 template <int F, int A, int UPL, int MODE>
-rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args) {
+rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
     switch (pass_variant()) {
-    case 1: return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args);
-    case 2: return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args);
-    case 3: return launch_pass_variant<F, A, UPL, MODE, 4, 1>(ctx, plan, args);
+    case 1: return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args, reduce);
+    case 2: return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args, reduce);
+    case 3: return launch_pass_variant<F, A, UPL, MODE, 4, 1>(ctx, plan, args, reduce);
     default:
-        if (MODE == PASS_VALUE || MODE == PASS_QLOSS) return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args);
-        if (MODE == PASS_STATS || MODE == PASS_EVAL) return launch_pass_variant<F, A, UPL, MODE, 8, 2>(ctx, plan, args);
-        return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args);
+        if (MODE == PASS_VALUE || MODE == PASS_QLOSS) return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args, reduce);
+        if (MODE == PASS_STATS || MODE == PASS_EVAL) return launch_pass_variant<F, A, UPL, MODE, 8, 2>(ctx, plan, args, reduce);
+        return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args, reduce);
     }
+}
+
+// One optimizer step on the sums of the pass just launched: pass -> [reduce -> all-reduce] -> Adam
+// (n_backward_steps: zero_grad, backward, step; torch/agents/mod.rs:50-55, coptimizer.rs:13-27).
+template <int F, int A, int UPL, int MODE>
+rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac,
+                        double *loss_out) {
+    adam->step += 1;
+    if (ctx->world > 1) {
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa)));
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
+                  loss_out);
+    } else {
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.P,
+                  plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
+    }
+    return RL_OK;
 }
 
 rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extra_bytes, void **extra) {
@@ -957,10 +1032,7 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
     AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
     for (int s = 0; s < n_steps; ++s) {
         // n_backward_steps: loss -> zero_grad -> backward -> step (torch/agents/mod.rs:50-55, coptimizer.rs:13-27)
-        RL_TRY((launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa)));
-        adam->step += 1;
-        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, P, value_fn->params, adam->m, adam->v, ac,
-                  adam->step, losses + s);
+        RL_TRY((pass_and_adam<F, A, UPL, PASS_VALUE>(ctx, plan, pa, value_fn, adam, ac, losses + s)));
     }
     if (stats) {
         RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -1015,10 +1087,7 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
         pa.obs = mb.obs; pa.action = mb.action; pa.succ = mb.succ; pa.T = 1; pa.E = mb.capacity;
         pa.theta = q->params; pa.target = mb.target;
         // loss_fn + backward_step (dqn.rs:316-336, coptimizer.rs:13-27)
-        RL_TRY((launch_pass<F, A, UPL, PASS_QLOSS>(ctx, plan, pa)));
-        adam->step += 1;
-        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, P, q->params, adam->m, adam->v, ac, adam->step,
-                  losses + s);
+        RL_TRY((pass_and_adam<F, A, UPL, PASS_QLOSS>(ctx, plan, pa, q, adam, ac, losses + s)));
     }
     uint64_t m_last = 0;
     if (n_steps > 0) RL_TRY(rl_replay_sample_finish(rb, &m_last, nullptr));
