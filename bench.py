@@ -184,7 +184,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -325,7 +325,7 @@ def run_ours(args):
                                 "sample": f"{periods} periods of {E} lanes x {T} steps ({cpu_s:.1f} s wall) of the same "
                                           f"workload, C oracle port of Steps::step + PolicyActor::act, {cores} threads"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -407,7 +407,26 @@ def kernel_rooflines(ctx, R, L, hbm_peak):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Route everything libraries write to fd 1 (e.g. NCCL's version banner) to stderr; the one JSON line
+    of the contract goes to the original stdout through emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
