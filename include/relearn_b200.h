@@ -62,6 +62,7 @@ typedef struct rl_adam rl_adam;
 typedef struct rl_traj rl_traj;
 typedef struct rl_tabq rl_tabq;
 typedef struct rl_replay rl_replay;
+typedef struct rl_grunet rl_grunet;
 
 /* ------------------------------------------------------------------------------------------ */
 /* Context                                                                                     */
@@ -213,6 +214,22 @@ rl_status rl_mlp_get_weights(rl_mlp *mlp, float *host, uint64_t n);
 rl_status rl_mlp_forward(rl_mlp *mlp, const float *x_dev, uint64_t n, float *out_dev);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Recurrent module Chain<Gru, Linear> (src/torch/modules/chain.rs:12-186, seq/rnn/gru.rs,      */
+/* seq/rnn/mod.rs:166-280, ff/linear.rs): one GRU layer in_dim -> hidden, activation, Linear     */
+/* hidden -> out_dim.  Parameters are flat f32 in Module::variables() order: w_ih[3H,in],         */
+/* w_hh[3H,H], b_ih[3H], b_hh[3H] (gate order r, z, n as libtorch), then kernel[out,H], bias.     */
+/* ------------------------------------------------------------------------------------------ */
+rl_status rl_grunet_create(rl_ctx *ctx, int32_t in_dim, int32_t hidden, int32_t out_dim, rl_activation activation,
+                           rl_grunet **out);
+rl_status rl_grunet_destroy(rl_grunet *net);
+rl_status rl_grunet_num_params(rl_grunet *net, uint64_t *n);
+rl_status rl_grunet_set_weights(rl_grunet *net, const float *host, uint64_t n);
+rl_status rl_grunet_get_weights(rl_grunet *net, float *host, uint64_t n);
+/* SeqPacked::seq_packed over the stored episodes of a trajectory (hidden state zero at the first step of
+ * every episode, gru.rs:23-28,72-102).  out_dev: f32 [T][out_dim][E], zeros in unused slots. */
+rl_status rl_grunet_seq_forward(rl_grunet *net, rl_traj *traj, float *out_dev);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Rollout = Agent::actor + Steps + TakeAlignedSteps + write_experience + OnlineStepsSummary     */
 /* (src/simulation/steps.rs:113-168, take_steps.rs:18-89, agents/buffers/vec.rs:113-141,        */
 /*  buffers/mod.rs:237-261, simulation/summary.rs:198-216, train.rs:98-158)                     */
@@ -236,6 +253,7 @@ typedef struct rl_actor_cfg {
     double exploration_rate;      /* EPS_GREEDY_Q / TABULAR_EPS_GREEDY */
     int32_t training;             /* ActorMode::Training (src/agents/mod.rs:144) */
     int32_t lanes_per_env;        /* 0 = auto; threads cooperating on one env's MLP (1,2,4,8,16,32) */
+    rl_grunet *seq_net;           /* CATEGORICAL_POLICY with a recurrent module (Chain<Gru, Linear>) instead of `net` */
 } rl_actor_cfg;
 
 /* HistoryDataBound (src/agents/buffers/mod.rs:25-113), per lane */

@@ -375,3 +375,53 @@ def dqn_update(flat_params, n_in, hidden, n_out, minibatches, discount, one_step
         opt.step(torch.autograd.grad(loss, params))
         losses.append(float(loss.detach()))
     return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses
+
+
+# ------------------------------------------------------------------------------------------------
+# Chain<Gru, Linear> (src/torch/modules/chain.rs:145-186, seq/rnn/gru.rs:30-39,72-102, ff/linear.rs:118-123)
+# ------------------------------------------------------------------------------------------------
+def unflatten_gru_linear(flat, n_in, hidden, n_out):
+    """Module::variables() order: w_ih[3H,in], w_hh[3H,H], b_ih[3H], b_hh[3H], kernel[out,H], bias[out]."""
+    flat = torch.as_tensor(np.asarray(flat))
+    sizes = [(3 * hidden, n_in), (3 * hidden, hidden), (3 * hidden,), (3 * hidden,), (n_out, hidden), (n_out,)]
+    out, off = [], 0
+    for sh in sizes:
+        n = int(np.prod(sh))
+        out.append(flat[off:off + n].reshape(sh))
+        off += n
+    assert off == flat.numel()
+    return out
+
+
+def gru_linear_episode(flat, n_in, hidden, n_out, obs, activation="relu", dtype=torch.float32):
+    """SeqIterative::step over one episode (rnn/mod.rs:166-184 -> gru.rs:30-39 gru_cell, chain.rs:176-186):
+    h0 = 0, per step h = gru_cell(x, h), logits = Linear(act(h)).  obs [L, F] -> logits [L, out]."""
+    w_ih, w_hh, b_ih, b_hh, lw, lb = [t.to(dtype) for t in unflatten_gru_linear(flat, n_in, hidden, n_out)]
+    x = torch.tensor(np.asarray(obs), dtype=dtype)
+    h = torch.zeros(1, hidden, dtype=dtype)
+    outs = []
+    act = {"relu": torch.relu, "identity": lambda t: t, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[activation]
+    for t in range(x.shape[0]):
+        h = torch.gru_cell(x[t:t + 1], h, w_ih, w_hh, b_ih, b_hh)
+        outs.append(torch.nn.functional.linear(act(h), lw, lb)[0])
+    return torch.stack(outs).numpy() if outs else np.zeros((0, n_out), np.float32)
+
+
+def gru_packed_episodes(flat, n_in, hidden, n_out, episodes, activation="relu", dtype=torch.float32):
+    """SeqPacked::seq_packed (gru.rs:72-102: Tensor::gru_data on the packed sequence) for a list of episodes
+    [L_i, F]; returns the per-episode logits (unpacked again) so that packed == iterated can be checked
+    (modules/testing.rs:124-157)."""
+    w_ih, w_hh, b_ih, b_hh, lw, lb = [t.to(dtype) for t in unflatten_gru_linear(flat, n_in, hidden, n_out)]
+    order = sorted(range(len(episodes)), key=lambda i: -len(episodes[i]))
+    seqs = [torch.tensor(np.asarray(episodes[i]), dtype=dtype) for i in order]
+    packed = torch.nn.utils.rnn.pack_sequence(seqs, enforce_sorted=True)
+    h0 = torch.zeros(1, len(seqs), hidden, dtype=dtype)
+    out, _ = torch._VF.gru(packed.data, packed.batch_sizes, h0, [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, True, False)
+    act = {"relu": torch.relu, "identity": lambda t: t, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[activation]
+    logits = torch.nn.functional.linear(act(out), lw, lb)
+    unpacked, lens = torch.nn.utils.rnn.pad_packed_sequence(
+        torch.nn.utils.rnn.PackedSequence(logits, packed.batch_sizes), batch_first=True)
+    res = [None] * len(episodes)
+    for k, i in enumerate(order):
+        res[i] = unpacked[k, :int(lens[k])].numpy()
+    return res

@@ -57,7 +57,8 @@ class StepOut(C.Structure):
 
 class ActorCfg(C.Structure):
     _fields_ = [("kind", C.c_int32), ("net", vp), ("actions_dev", vp), ("table", vp),
-                ("exploration_rate", C.c_double), ("training", C.c_int32), ("lanes_per_env", C.c_int32)]
+                ("exploration_rate", C.c_double), ("training", C.c_int32), ("lanes_per_env", C.c_int32),
+                ("seq_net", vp)]
 
 
 class Bound(C.Structure):
@@ -168,6 +169,12 @@ SIGNATURES = {
     "rl_mlp_set_weights": (st, [vp, vp, C.c_uint64]),
     "rl_mlp_get_weights": (st, [vp, vp, C.c_uint64]),
     "rl_mlp_forward": (st, [vp, vp, C.c_uint64, vp]),
+    "rl_grunet_create": (st, [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P(vp)]),
+    "rl_grunet_destroy": (st, [vp]),
+    "rl_grunet_num_params": (st, [vp, P(C.c_uint64)]),
+    "rl_grunet_set_weights": (st, [vp, vp, C.c_uint64]),
+    "rl_grunet_get_weights": (st, [vp, vp, C.c_uint64]),
+    "rl_grunet_seq_forward": (st, [vp, vp, vp]),
     "rl_traj_create": (st, [vp, C.c_uint64, P(vp)]),
     "rl_traj_destroy": (st, [vp]),
     "rl_traj_view_of": (st, [vp, P(TrajView)]),

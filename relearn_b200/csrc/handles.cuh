@@ -67,6 +67,9 @@ uint32_t rl_replay_next_draw_index(rl_replay *rb);
 rl_ctx *rl_replay_ctx(rl_replay *rb);
 int rl_replay_num_features(rl_replay *rb);
 
+// gru.cu: fused rollout with a recurrent policy; *totals_out receives the device pointer of the ST_COUNT sums
+rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *traj, double **totals_out);
+
 struct rl_tabq {
     rl_ctx *ctx = nullptr;
     uint64_t R = 0;

@@ -923,7 +923,8 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     RL_REQUIRE(ctx, cap <= traj->T, "rl_rollout: min_steps + slack_steps exceeds the trajectory capacity");
     const rl_env_structure &es = env->structure;
     rl_mlp *net = actor->net;
-    const bool needs_net = actor->kind == RL_ACTOR_CATEGORICAL_POLICY || actor->kind == RL_ACTOR_EPS_GREEDY_Q;
+    const bool seq_policy = actor->kind == RL_ACTOR_CATEGORICAL_POLICY && actor->seq_net != nullptr;
+    const bool needs_net = !seq_policy && (actor->kind == RL_ACTOR_CATEGORICAL_POLICY || actor->kind == RL_ACTOR_EPS_GREEDY_Q);
     if (needs_net) {
         RL_REQUIRE(ctx, net != nullptr, "rl_rollout: actor needs a network");
         RL_REQUIRE(ctx, net->in_dim == es.num_features && net->out_dim == es.num_actions,
@@ -955,6 +956,10 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     RL_CUDA(ctx, cudaMemsetAsync(traj->succ, RL_PAD, (size_t)traj->T * traj->E, ctx->stream));
     const bool replay = env->noise.mode == RL_NOISE_REPLAY;
     int nblocks = 0;
+    double *totals = nullptr;
+    if (seq_policy) {
+        RL_TRY(rl_rollout_seq(env, actor->seq_net, bound, traj, &totals));
+    } else {
     switch (env->kind) {
     case RL_ENV_CARTPOLE: {
         int lanes = actor->lanes_per_env;
@@ -998,8 +1003,9 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     case RL_ENV_MEMORY_GAME: RL_TRY((launch_rollout<MemoryEnv>(ctx, env->memory, a, net, replay, &nblocks))); break;
     case RL_ENV_BANDIT_META: RL_TRY((launch_rollout<BanditMetaEnv>(ctx, env->bandit, a, net, replay, &nblocks))); break;
     }
-    double *totals = a.partials - ST_COUNT;
+    totals = a.partials - ST_COUNT;
     RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, a.partials, nblocks, totals, traj->counts_dev);
+    }
     env->noise.step_counter += (uint32_t)cap + 1;  // fresh noise for the next period
     traj->used_T = cap;
     if (summary) {

@@ -44,6 +44,7 @@ class ActorSpec:
     exploration_rate: float = 0.0
     training: bool = True
     lanes_per_env: int = 0
+    seq_net: object = None             # modules.GruLinear (recurrent CATEGORICAL_POLICY)
 
 
 class Trajectory:
@@ -121,6 +122,7 @@ def rollout(env: BatchedEnv, actor: ActorSpec, bound: HistoryDataBound, traj: Tr
     cfg.exploration_rate = actor.exploration_rate
     cfg.training = 1 if actor.training else 0
     cfg.lanes_per_env = actor.lanes_per_env
+    cfg.seq_net = actor.seq_net.handle if actor.seq_net is not None else None
     summ = L.StepsSummary() if want_summary else None
     L.check(lib.rl_rollout(env.handle, C.byref(cfg), L.Bound(bound.min_steps, bound.slack_steps), traj.handle,
                            C.byref(summ) if want_summary else None), env.ctx.handle)

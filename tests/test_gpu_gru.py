@@ -1,0 +1,110 @@
+"""GPU parity: Chain<Gru, Linear> policy (config 4: bandit meta-env with a GRU policy) vs the torch oracle.
+
+Tolerance: f32 gru_cell with a different summation order than libtorch's GEMV -- logits within 1e-5 relative
+(2e-6 absolute), sampled actions identical except where the uniform lies within 2e-6 of a CDF edge."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import tensor_oracle as TO
+import relearn_b200 as R
+from relearn_b200 import _lib as L
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _episodes_of_lane(host, e):
+    n = int(host["lane_len"][e])
+    ends = np.flatnonzero(host["succ"][:n, e] != L.RL_CONTINUE)
+    starts = np.concatenate([[0], ends[:-1] + 1]) if len(ends) else np.zeros(0, int)
+    return [(int(a), int(b) + 1) for a, b in zip(starts, ends)]
+
+
+def _check_actions(host, logits, awords, atol=2e-6):
+    """Every action is the inverse-CDF choice of exp(log_softmax(logits)) for the replayed uniform."""
+    T, E, A = logits.shape
+    near = 0
+    for e in range(E):
+        n = int(host["lane_len"][e])
+        z = logits[:n, e].astype(np.float32)
+        m = z.max(axis=1, keepdims=True)
+        p = np.exp(z - (m + np.log(np.exp(z - m).sum(axis=1, keepdims=True))))
+        cdf = np.cumsum(p, axis=1)
+        u = (awords[e, :n] >> 8).astype(np.float32) * np.float32(2.0**-24)
+        expect = (u[:, None] >= cdf).sum(axis=1).clip(max=A - 1)
+        for i in np.flatnonzero(expect != host["action"][:n, e]):
+            assert np.min(np.abs(cdf[i] - u[i])) < atol, (e, i, host["action"][i, e], expect[i], u[i], cdf[i])
+            near += 1
+    return near
+
+
+@pytest.mark.parametrize("hidden,arms,episodes", [(4, 2, 10), (4, 5, 6), (24, 3, 8), (128, 10, 4)])
+def test_gru_policy_rollout_bandit_meta(ctx, hidden, arms, episodes):
+    rng = np.random.default_rng(hidden + arms)
+    cfg = R.MetaEnv(R.UniformBernoulliBandits(arms), episodes)
+    E = 96 if hidden < 128 else 40
+    T = 2 * (2 * episodes - 1) + 3  # two trials and a bit: exercises the hidden-state reset and the dangling step
+    env = R.build_env(ctx, cfg, E, seed=3)
+    nwords = 8 * T + 64 * arms
+    ewords, awords = P.random_words(rng, E, nwords), P.random_words(rng, E, nwords)
+    env.set_noise_replay(ewords, awords)
+    F, A = env.num_features, env.num_actions
+    params = R.init_gru_linear_params(rng, F, hidden, A)
+    params[3 * hidden * F + 3 * hidden * hidden:3 * hidden * F + 3 * hidden * hidden + 6 * hidden] = rng.normal(size=6 * hidden) * 0.3
+    net = R.GruLinear(ctx, F, hidden, A)
+    net.set_weights(params)
+    np.testing.assert_array_equal(net.get_weights(), params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(T, 0), traj)
+    host = traj.to_host()
+    # (i) the dynamics given the kernel's own actions match the oracle bit for bit
+    ref = P.oracle_rollout(cfg, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), env_words=ewords)
+    P.compare_traj(host, ref, what="gru bandit meta")
+    # (ii) logits of the stored episodes: SeqPacked on the device vs SeqIterative in torch
+    got = net.seq_packed(traj)
+    want = np.zeros_like(got)
+    for e in range(E):
+        n = int(host["lane_len"][e])
+        pos = 0
+        for a, b in _episodes_of_lane(host, e):
+            want[a:b, e] = TO.gru_linear_episode(params, F, hidden, A, host["obs"][a:b, e])
+            pos = b
+        assert pos == n
+    valid = host["succ"] != L.RL_PAD
+    np.testing.assert_allclose(got[valid], want[valid], rtol=1e-5, atol=2e-6)
+    assert (got[~valid] == 0).all()
+    # (iii) the actions sampled inside the rollout are consistent with those logits.  The dropped dangling step
+    # also consumed a uniform, but it is the last one of the lane, so indices line up.
+    near = _check_actions(host, want, awords)
+    assert near <= 3
+    # hidden state is reset between trials: the first step of a later episode sees h0 = 0
+    e = 0
+    eps = _episodes_of_lane(host, e)
+    assert len(eps) >= 2
+    a, b = eps[1]
+    np.testing.assert_allclose(got[a, e], TO.gru_linear_episode(params, F, hidden, A, host["obs"][a:a + 1, e])[0], rtol=1e-5, atol=2e-6)
+
+
+def test_gru_policy_rollout_cartpole_philox(ctx):
+    """Production noise, CartPole, hidden 8: runs, stores consistent trajectories, and sharding by lane offset does
+    not change them."""
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(50))
+    rng = np.random.default_rng(1)
+    params = R.init_gru_linear_params(rng, 5, 8, 2)
+    def run(n, off):
+        env = R.build_env(ctx, cfg, n, seed=9, lane_offset=off)
+        net = R.GruLinear(ctx, 5, 8, 2)
+        net.set_weights(params)
+        traj = R.Trajectory(env, 120)
+        summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(120, 0), traj)
+        return traj.to_host(), summ
+    full, summ = run(64, 0)
+    a, _ = run(32, 0)
+    b, _ = run(32, 32)
+    for k in ("obs", "action", "reward", "succ"):
+        np.testing.assert_array_equal(full[k][:, :32], a[k])
+        np.testing.assert_array_equal(full[k][:, 32:], b[k])
+    assert summ.step_reward.count == 64 * 120 and summ.episode_length.count > 64

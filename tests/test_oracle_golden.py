@@ -632,3 +632,23 @@ def test_tabular_q_learns_deterministic_bandit():
         a = int(rng.integers(0, 2))
         O.lib().ro_tabq_step_update(C.byref(t), 0, a, 1.0 if a == 1 else 0.0, 0, 0)
     assert O.lib().ro_argmax_f64(q[0].ctypes.data_as(C.POINTER(C.c_double)), 2) == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Chain<Gru, Linear>: packed == iterated steps (src/torch/modules/testing.rs:124-157)
+# ------------------------------------------------------------------------------------------------
+def test_gru_linear_packed_matches_iterated_steps():
+    from oracle import tensor_oracle as TO
+
+    rng = np.random.default_rng(5)
+    F, H, A = 6, 4, 2
+    n = 3 * H * F + 3 * H * H + 6 * H + A * H + A
+    flat = (rng.normal(size=n) * 0.5).astype(np.float32)
+    eps = [rng.normal(size=(L, F)).astype(np.float32) for L in (5, 3, 7, 1)]
+    iterated = [TO.gru_linear_episode(flat, F, H, A, e) for e in eps]
+    packed = TO.gru_packed_episodes(flat, F, H, A, eps)
+    for a, b in zip(iterated, packed):
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-6)
+    # identical inputs in different episodes give identical outputs (modules/testing.rs:80-122)
+    same = TO.gru_packed_episodes(flat, F, H, A, [eps[0], eps[0][:3]])
+    np.testing.assert_allclose(same[0][:3], same[1], rtol=0, atol=1e-6)
