@@ -404,6 +404,67 @@ def kernel_rooflines(ctx, R, L, hbm_peak):
                 "env_steps_per_s": E3 * T3 / (ms * 1e-3),
                 "trajectory_write_gbs": B_PER_STEP_ROLLOUT * E3 * T3 / (ms * 1e-3) / 1e9,
                 "policy_tflops": FLOP_PER_STEP_POLICY * E3 * T3 / (ms * 1e-3) / 1e12})
+    out += other_configs(ctx, R, L, hbm_peak)
+    return out
+
+
+def other_configs(ctx, R, L, hbm_peak):
+    """BASELINE configs 3 and 4 at their per-GPU sizes (timed alone, CUDA events): DQN collection + replay append +
+    update at 65 536 envs, and the bandit meta-env with the rnn.rs-sized GRU policy at 131 072 envs."""
+    out = []
+    rng = np.random.default_rng(3)
+    # ---- config 3: cartpole-dqn, 65 536 envs ----
+    E, cfg = 65536, R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    env = R.build_env(ctx, cfg, E, seed=5)
+    agent = R.DqnConfig(buffer_capacity=762).build_agent(env)  # 50 M steps of replay per GPU (examples/cartpole-dqn.rs:34-42)
+    agent.action_value_fn.set_weights(R.init_params(rng, 5, 128, 2))
+    rb = agent.buffer()
+    bound = R.HistoryDataBound(16, 5)  # first update: 1 M steps over 65 536 lanes
+    traj = R.Trajectory(env, bound.min_steps + bound.slack_steps)
+    times = {"rollout_ms": [], "append_ms": [], "update_ms": []}
+    for it in range(4):
+        e0 = ctx.event().record()
+        R.rollout(env, agent.actor(), bound, traj, want_summary=False)
+        e1 = ctx.event().record()
+        rb.write_experience(traj)
+        e2 = ctx.event().record()
+        stats = agent.batch_update(rb)
+        if it > 0:
+            times["rollout_ms"].append(e0.elapsed_ms(e1))
+            times["append_ms"].append(e1.elapsed_ms(e2))
+            times["update_ms"].append(stats.update_ms)
+    st = rb.stats()
+    steps = traj.view().num_steps
+    app_ms = float(np.mean(times["append_ms"]))
+    out.append({"kernel": "config 3 cartpole-dqn: eps-greedy rollout + replay append + 50 x (sample 100k, Q loss, Adam)",
+                "envs": E, "steps_per_period": int(steps), "rollout_ms": float(np.mean(times["rollout_ms"])),
+                "append_ms": app_ms, "append_gbs": 2 * 26 * steps / (app_ms * 1e-3) / 1e9,
+                "dqn_update_50_steps_ms": float(np.mean(times["update_ms"])), "replay_steps": int(st.num_steps),
+                "replay_episodes": int(st.num_episodes)})
+    traj.close(); rb.close(); env.close()
+    # ---- config 4: bandit meta-env (k = 2 arms, n = 10 episodes per trial) + GRU(6 -> 4) -> Linear(4 -> 2) ----
+    E4, trials = 131072, 10
+    mcfg = R.MetaEnv(R.UniformBernoulliBandits(2), 10)
+    env4 = R.build_env(ctx, mcfg, E4, seed=6)
+    net = R.GruLinear(ctx, env4.num_features, 4, env4.num_actions)
+    net.set_weights(R.init_gru_linear_params(rng, env4.num_features, 4, env4.num_actions))
+    T4 = trials * 19
+    traj4 = R.Trajectory(env4, T4)
+    spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net)
+    for _ in range(2):
+        R.rollout(env4, spec, R.HistoryDataBound(T4, 0), traj4, want_summary=False)
+    reps = 5
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        R.rollout(env4, spec, R.HistoryDataBound(T4, 0), traj4, want_summary=False)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    bytes_per_step = 4 * env4.num_features + 6  # obs planes + action + reward + succ
+    out.append({"kernel": "config 4 bandit meta-env + GRU(6->4)->Linear policy, fused rollout (thread per env)", "envs": E4,
+                "horizon": T4, "ms": ms, "env_steps_per_s": E4 * T4 / (ms * 1e-3), "bytes_per_step": bytes_per_step,
+                "trajectory_write_gbs": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9 / hbm_peak})
+    traj4.close(); env4.close()
     return out
 
 

@@ -246,12 +246,17 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
     }
 }
 
-__global__ void seq_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ out,
-                                    double *__restrict__ traj_counts) {
-    const int i = threadIdx.x;
-    if (i < SQ_COUNT) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * SQ_COUNT + i];
+__global__ void __launch_bounds__(32 * SQ_COUNT) seq_finalize_kernel(const double *__restrict__ partials, int nblocks,
+                                                                    double *__restrict__ out, double *__restrict__ traj_counts) {
+    // one warp per statistic, fixed summation order (see rollout_finalize_kernel)
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (i >= SQ_COUNT) return;
+    double s = 0.0;
+#pragma unroll 4
+    for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * SQ_COUNT + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
         out[i] = s;
         if (i == SQ_STORED_STEPS) traj_counts[0] = s;
         if (i == SQ_STORED_EPS) traj_counts[1] = s;
@@ -353,7 +358,7 @@ rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *t
     case RL_ENV_MEMORY_GAME: RL_TRY((launch_seq<MemoryEnv>(ctx, env->memory, a, replay, smem, grid))); break;
     default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: sequence policies are built for the bandit meta-env, MemoryGame and CartPole");
     }
-    RL_LAUNCH(ctx, seq_finalize_kernel, 1, 32, 0, a.partials, (int)grid, partials, traj->counts_dev);
+    RL_LAUNCH(ctx, seq_finalize_kernel, 1, 32 * SQ_COUNT, 0, a.partials, (int)grid, partials, traj->counts_dev);
     *totals_out = partials;
     return RL_OK;
 }

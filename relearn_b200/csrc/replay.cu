@@ -220,47 +220,65 @@ __global__ void __launch_bounds__(256)
 
 // Exclusive scan of the episode lengths in draw order; episodes are taken while the running total is
 // below minibatch_steps (take_while, dqn.rs:286-291: the episode that crosses the bound is included).
+// One block walks the draws in chunks of 4096 (coalesced uint4 loads, warp + block scan, running carry) and
+// stops at the first chunk that starts at or beyond the bound: offsets past the cut are never read.
 __global__ void __launch_bounds__(1024)
     sample_scan_kernel(const uint32_t *__restrict__ sel_len, uint64_t J, uint64_t minibatch_steps,
                        unsigned long long *__restrict__ sel_off, SampleMeta *meta) {
     __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t per = (J + blockDim.x - 1) / blockDim.x;
-    const uint64_t lo = (uint64_t)tid * per, hi = lo + per < J ? lo + per : J;
-    unsigned long long mine = 0;
-    for (uint64_t j = lo; j < hi; ++j) mine += sel_len[j];
-    unsigned long long incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
+    if (tid == 0) carry_s = 0;
     __syncthreads();
-    if (warp == 0) {
-        unsigned long long w = warp_tot[lane], wi = w;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o) wi += v;
-        }
-        warp_tot[lane] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    unsigned long long run = warp_tot[warp] + incl - mine;
     unsigned int taken = 0;
     unsigned long long last_end = 0;
-    for (uint64_t j = lo; j < hi; ++j) {
-        sel_off[j] = run;
-        if (run < minibatch_steps) {
-            taken += 1;
-            last_end = run + sel_len[j];
+    for (uint64_t base = 0; base < J; base += 4096) {
+        const unsigned long long carry = carry_s;
+        if (carry >= minibatch_steps) break;  // uniform: every thread reads the same shared value
+        const uint64_t j0 = base + (uint64_t)tid * 4;
+        uint32_t l[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) l[k] = j0 + k < J ? sel_len[j0 + k] : 0u;
+        const unsigned long long mine = (unsigned long long)l[0] + l[1] + l[2] + l[3];
+        unsigned long long incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        run += sel_len[j];
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = warp_tot[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += v;
+            }
+            warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
+            if (lane == 31) carry_s = carry + wi;
+        }
+        __syncthreads();
+        unsigned long long run = carry + warp_tot[warp] + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (j0 + k < J) {
+                sel_off[j0 + k] = run;
+                if (run < minibatch_steps) {
+                    taken += 1;
+                    last_end = run + l[k];
+                }
+                run += l[k];
+            }
+        }
+        __syncthreads();  // warp_tot / carry_s are rewritten by the next chunk
     }
     // the taken draws are a prefix, so the counts add up and the largest end is M
-    atomicAdd(&meta->num_episodes, taken);
-    atomicMax(&meta->num_steps, last_end);
+    if (taken) {
+        atomicAdd(&meta->num_episodes, taken);
+        atomicMax(&meta->num_steps, last_end);
+    }
 }
 
 struct MinibatchPtrs {

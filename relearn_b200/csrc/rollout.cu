@@ -722,13 +722,18 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
     block_reduce_stats(st, valid && sub == 0, a.partials);
 }
 
-// Sum the per-block partials in block order (deterministic) and publish the summary.
-__global__ void rollout_finalize_kernel(const double *__restrict__ partials, int nblocks, double *__restrict__ out,
-                                        double *__restrict__ traj_counts) {
-    const int i = threadIdx.x;
-    if (i < ST_COUNT) {
-        double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * ST_COUNT + i];
+// Sum the per-block partials in a fixed order (deterministic) and publish the summary: one warp per statistic,
+// lane l adds rows l, l + 32, ... (independent coalesced-by-row loads), then a shuffle tree combines the lanes.
+__global__ void __launch_bounds__(32 * ST_COUNT) rollout_finalize_kernel(const double *__restrict__ partials, int nblocks,
+                                                                        double *__restrict__ out,
+                                                                        double *__restrict__ traj_counts) {
+    const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (i >= ST_COUNT) return;
+    double s = 0.0;
+#pragma unroll 4
+    for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * ST_COUNT + i];
+    s = warp_sum(s);
+    if (lane == 0) {
         out[i] = s;
         if (i == ST_STORED_STEPS) traj_counts[0] = s;
         if (i == ST_STORED_EPS) traj_counts[1] = s;
@@ -910,7 +915,7 @@ rl_status rl_traj_load(rl_traj *t, uint64_t steps, const float *obs_dev, const u
     RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
     RL_CUDA(ctx, cudaMemsetAsync(t->lane_flags, 0, t->E, ctx->stream));  // loaded histories are already finalised
     RL_LAUNCH(ctx, traj_index_kernel, grid, block, 0, t->succ, steps, t->E, t->lane_len, partials + ST_COUNT);
-    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, partials + ST_COUNT, (int)grid, partials, t->counts_dev);
+    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32 * ST_COUNT, 0, partials + ST_COUNT, (int)grid, partials, t->counts_dev);
     t->used_T = steps;
     return RL_OK;
 }
@@ -1004,7 +1009,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     case RL_ENV_BANDIT_META: RL_TRY((launch_rollout<BanditMetaEnv>(ctx, env->bandit, a, net, replay, &nblocks))); break;
     }
     totals = a.partials - ST_COUNT;
-    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32, 0, a.partials, nblocks, totals, traj->counts_dev);
+    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32 * ST_COUNT, 0, a.partials, nblocks, totals, traj->counts_dev);
     }
     env->noise.step_counter += (uint32_t)cap + 1;  // fresh noise for the next period
     traj->used_T = cap;

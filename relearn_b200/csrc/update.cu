@@ -700,13 +700,16 @@ __global__ void __launch_bounds__(256)
         for (int b = warp; b < B; b += 8) s += rows[(size_t)b * W + col];
     }
     part[warp][lane] = s;
-    // the scalar columns, summed in the same order as the owning block does
+    // the scalar columns every block needs (sample count; loss for block 0): rows spread over all 256 threads.
+    // The count is an integer, exact in any order; the loss order is fixed by this loop.
     double cn = 0.0, ls = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) {
+        cn += rows[(size_t)b * W + P + SC_COUNT];
+        ls += rows[(size_t)b * W + P + SC_LOSS];
+    }
+    cn = warp_sum_f64(cn);
+    ls = warp_sum_f64(ls);
     if (lane == 0) {
-        for (int b = warp; b < B; b += 8) {
-            cn += rows[(size_t)b * W + P + SC_COUNT];
-            ls += rows[(size_t)b * W + P + SC_LOSS];
-        }
         cnt_part[warp] = cn;
         loss_part[warp] = ls;
     }
