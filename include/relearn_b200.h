@@ -346,6 +346,28 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
                           rl_opt_stats *stats);
 
 /* ------------------------------------------------------------------------------------------ */
+/* PPO and REINFORCE policies (Policy::update src/torch/agents/policies/ppo.rs:97-147,          */
+/* reinforce.rs:64-89) -- same data path as TRPO with an Adam step in place of the CG step.     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct rl_ppo_cfg {
+    uint64_t opt_steps_per_update; /* 10 (ppo.rs:33-41) */
+    double clip_distance;          /* 0.2 */
+} rl_ppo_cfg;
+void rl_ppo_cfg_default(rl_ppo_cfg *cfg);
+typedef struct rl_policy_opt_stats {
+    double entropy;                /* logged "entropy" (ppo.rs:116-117, reinforce.rs:85-87) */
+    double loss_first, loss_last;
+    uint64_t num_steps, opt_steps;
+    float update_ms;
+} rl_policy_opt_stats;
+/* no_grad initial log-probs, then opt_steps x { clipped surrogate loss, backward, Adam } */
+rl_status rl_ppo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, const rl_ppo_cfg *cfg,
+                        rl_policy_opt_stats *stats);
+/* one backward_step on -(log_probs * advantages).mean() */
+rl_status rl_reinforce_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam,
+                              rl_policy_opt_stats *stats);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Tabular Q (BaseTabularQLearningAgent src/agents/tabular.rs:84-232)                           */
 /* One table per replica; a replica folds its own lane's steps in order (bit-exact f64/u64).     */
 /* ------------------------------------------------------------------------------------------ */

@@ -260,7 +260,7 @@ def policy_loss_kl_grad_fvp(flat_params, n_in, hidden, n_out, obs, actions, adva
     g = flatten_tensors(torch.autograd.grad(loss, params, retain_graph=True))
     hvp = HessianVectorProduct(kl, params, reg)
     hv = hvp.mat_vec_mul(torch.tensor(np.asarray(vector), dtype=dtype))
-    return float(loss), float(kl), entropy, g.detach().numpy(), hv.detach().numpy()
+    return float(loss.detach()), float(kl.detach()), entropy, g.detach().numpy(), hv.detach().numpy()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -425,3 +425,46 @@ def gru_packed_episodes(flat, n_in, hidden, n_out, episodes, activation="relu", 
     for k, i in enumerate(order):
         res[i] = unpacked[k, :int(lens[k])].numpy()
     return res
+
+
+# ------------------------------------------------------------------------------------------------
+# PPO / REINFORCE (src/torch/agents/policies/ppo.rs:97-147, reinforce.rs:64-89)
+# ------------------------------------------------------------------------------------------------
+def ppo_update(flat_params, n_in, hidden, n_out, obs, actions, advantages, opt_steps=10, clip_distance=0.2, lr=1e-3,
+               dtype=torch.float32):
+    """no_grad initial log-probs + entropy, then opt_steps x Adam on
+    -mean(min(ratio * adv, clip(ratio, 1 - eps, 1 + eps) * adv)).  Returns (new flat params, losses, entropy)."""
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    opt = Adam112(params, lr)
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    act_t = torch.tensor(np.asarray(actions), dtype=torch.int64)
+    adv_t = torch.tensor(np.asarray(advantages), dtype=dtype)
+    with torch.no_grad():
+        d0 = Categorical(mlp_forward(params, obs_t))
+        lp0 = d0.log_prob(act_t)
+        entropy = float(d0.entropy().mean())
+    losses = []
+    for _ in range(opt_steps):
+        lp = Categorical(mlp_forward(params, obs_t)).log_prob(act_t)
+        ratio = (lp - lp0).exp()
+        clipped = ratio.clip(1.0 - clip_distance, 1.0 + clip_distance)
+        loss = -torch.minimum(ratio * adv_t, clipped * adv_t).mean()
+        opt.step(torch.autograd.grad(loss, params))
+        losses.append(float(loss.detach()))
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses, entropy
+
+
+def reinforce_update(flat_params, n_in, hidden, n_out, obs, actions, advantages, lr=1e-3, dtype=torch.float32):
+    """One backward_step on -(log_probs * advantages).mean(); logs the mean entropy of that evaluation."""
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in unflatten_mlp(flat, n_in, hidden, n_out)]
+    opt = Adam112(params, lr)
+    obs_t = torch.tensor(np.asarray(obs), dtype=dtype)
+    act_t = torch.tensor(np.asarray(actions), dtype=torch.int64)
+    adv_t = torch.tensor(np.asarray(advantages), dtype=dtype)
+    dist = Categorical(mlp_forward(params, obs_t))
+    loss = -(dist.log_prob(act_t) * adv_t).mean()
+    entropy = float(dist.entropy().mean().detach())
+    opt.step(torch.autograd.grad(loss, params))
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), float(loss.detach()), entropy

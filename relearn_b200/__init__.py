@@ -14,5 +14,6 @@ __version__ = "0.1.0"
 from .agents import TabularQ  # noqa: F401,E402
 from .torch_agents import (ActorCriticAgent, ActorCriticConfig, Adam, AdamConfig,  # noqa: F401,E402
                            ConjugateGradientOptimizerConfig, DataCollectionSchedule, DqnAgent, DqnConfig,
-                           ExplorationRateSchedule, OptimizerStepError, ReplayBuffer, Trpo, TrpoConfig, ValuesOpt,
+                           ExplorationRateSchedule, OptimizerStepError, Ppo, PpoConfig, Reinforce, ReinforceConfig,
+                           ReplayBuffer, Trpo, TrpoConfig, ValuesOpt,
                            ValuesOptConfig)

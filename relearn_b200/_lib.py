@@ -105,6 +105,15 @@ class OptStats(C.Structure):
                 ("opt_steps", C.c_uint64), ("update_ms", C.c_float)]
 
 
+class PpoCfg(C.Structure):
+    _fields_ = [("opt_steps_per_update", C.c_uint64), ("clip_distance", C.c_double)]
+
+
+class PolicyOptStats(C.Structure):
+    _fields_ = [("entropy", C.c_double), ("loss_first", C.c_double), ("loss_last", C.c_double),
+                ("num_steps", C.c_uint64), ("opt_steps", C.c_uint64), ("update_ms", C.c_float)]
+
+
 class ReplayStats(C.Structure):
     _fields_ = [("num_steps", C.c_uint64), ("num_episodes", C.c_uint64), ("total_step_count", C.c_uint64)]
 
@@ -190,6 +199,9 @@ SIGNATURES = {
     "rl_adam_create": (st, [vp, P(AdamCfg), P(vp)]),
     "rl_adam_destroy": (st, [vp]),
     "rl_value_update": (st, [vp, vp, vp, vp, C.c_int32, P(OptStats)]),
+    "rl_ppo_cfg_default": (None, [P(PpoCfg)]),
+    "rl_ppo_update": (st, [vp, vp, vp, vp, P(PpoCfg), P(PolicyOptStats)]),
+    "rl_reinforce_update": (st, [vp, vp, vp, vp, P(PolicyOptStats)]),
     "rl_tabq_create": (st, [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_double, P(vp)]),
     "rl_tabq_destroy": (st, [vp]),
     "rl_tabq_update": (st, [vp, vp]),

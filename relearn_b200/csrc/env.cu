@@ -46,7 +46,18 @@ __global__ void __launch_bounds__(256)
     }
     const uint32_t action = actions[e];
     float r;
-    const int sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
+    int sc;
+    if constexpr (std::is_same<EnvT, CartPoleEnv>::value) {
+        // the branch-free step (polynomial sin/cos, inline Newton division) whenever its angle bound holds
+        if (p.max_angle <= 0.5) {
+            sc = CartPoleEnv::step_fast(p, s, action);
+            r = 1.0f;
+        } else {
+            sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
+        }
+    } else {
+        sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
+    }
     const int F = EnvT::num_features(p);
     float o[EnvT::MAXF];
     if (sc == RL_INTERRUPT) {  // steps.rs:155-157: Interrupt carries observe(next_state)

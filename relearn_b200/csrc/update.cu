@@ -32,7 +32,7 @@
 
 namespace {
 
-enum { PASS_STATS = 0, PASS_EVAL = 1, PASS_GRAD = 2, PASS_FVP = 3, PASS_VALUE = 4, PASS_QLOSS = 5 };
+enum { PASS_STATS = 0, PASS_EVAL = 1, PASS_GRAD = 2, PASS_FVP = 3, PASS_VALUE = 4, PASS_QLOSS = 5, PASS_PPO = 6, PASS_REINFORCE = 7 };
 enum { SC_LOSS = 0, SC_KL = 1, SC_ENTROPY = 2, SC_COUNT = 3, NSCALAR = 4 };
 constexpr float F32_LOWEST = -3.402823466e+38f;
 constexpr int PASS_THREADS = 256;
@@ -48,6 +48,7 @@ struct PassArgs {
     const float *target;  // f32 [T*E]
     double *partials;     // f64 [gridDim.x][P + NSCALAR]
     const int *skip_flag;
+    float clip_lo, clip_hi;  // PASS_PPO: 1 -+ clip_distance as f32 (ppo.rs:131-132)
 };
 
 template <int A>
@@ -120,8 +121,12 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
     constexpr int W = P + NSCALAR;
     constexpr int XS = 12;          // floats per staged sample: F duplicated pairs (x, x), padded to 3 x float4
     static_assert(2 * F <= XS, "sample stage too small");
-    constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS;
-    constexpr bool IS_POLICY = MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP;
+    constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS ||
+                              MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool IS_POLICY = MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP ||
+                               MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
     constexpr bool FVP = MODE == PASS_FVP;
     if (a.skip_flag && *a.skip_flag) return;
 
@@ -230,10 +235,10 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
 #pragma unroll
         for (int f = 0; f < F; ++f) st.x[f] = st.valid ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
         st.act = ((IS_POLICY || MODE == PASS_QLOSS) && st.valid) ? (int)__ldg(a.action + n) : 0;
-        st.adv = ((MODE == PASS_EVAL || MODE == PASS_GRAD) && st.valid) ? __ldg(a.adv + n) : 0.0f;
+        st.adv = (USES_ADV && st.valid) ? __ldg(a.adv + n) : 0.0f;
         st.tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && st.valid) ? __ldg(a.target + n) : 0.0f;
         st.lp0a = st.lp0b = 0.0f;
-        if ((MODE == PASS_EVAL || MODE == PASS_GRAD) && st.valid) {
+        if (USES_LP0 && st.valid) {
             const float2 l = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n);
             st.lp0a = l.x;
             st.lp0b = l.y;
@@ -315,8 +320,8 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
             const bool s_valid = (valid_mask >> owner) & 1u;
             const int act_s = (IS_POLICY || MODE == PASS_QLOSS) ? __shfl_sync(0xffffffffu, my_act, owner) : 0;
             float adv_s = 0.0f, tgt_s = 0.0f, lp0[2] = {0.0f, 0.0f};
-            if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
-                adv_s = __shfl_sync(0xffffffffu, my_adv, owner);
+            if (USES_ADV) adv_s = __shfl_sync(0xffffffffu, my_adv, owner);
+            if (USES_LP0) {
                 lp0[0] = __shfl_sync(0xffffffffu, my_lp0[0], owner);
                 lp0[1] = __shfl_sync(0xffffffffu, my_lp0[1], owner);
             }
@@ -353,6 +358,36 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
                         if (MODE == PASS_GRAD) {
 #pragma unroll
                             for (int k = 0; k < A; ++k) dz[k] = loss_s * ((act_s == k ? 1.0f : 0.0f) - p[k]);
+                        }
+                    }
+                    if (MODE == PASS_PPO) {
+                        // ppo.rs:124-138: -mean(min(ratio * adv, clip(ratio, 1 - eps, 1 + eps) * adv)).  Backward as
+                        // libtorch: clamp passes the gradient on [lo, hi] (inclusive), minimum splits it on ties, so
+                        // d/d ratio = adv when the ratio is inside the clip range or the unclipped term is the smaller.
+                        float lpa = lp[0], lp0a = lp0[0];
+#pragma unroll
+                        for (int k = 1; k < A; ++k)
+                            if (act_s == k) { lpa = lp[k]; lp0a = lp0[k]; }
+                        const float ratio = expf(lpa - lp0a);
+                        const float clipped = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+                        const float t1 = ratio * adv_s, t2 = clipped * adv_s;
+                        loss_s = -fminf(t1, t2);
+                        const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
+                        const float g = (inside || t1 < t2) ? -t1 : 0.0f;
+#pragma unroll
+                        for (int k = 0; k < A; ++k) dz[k] = g * ((act_s == k ? 1.0f : 0.0f) - p[k]);
+                    }
+                    if (MODE == PASS_REINFORCE) {
+                        // reinforce.rs:72-79: -(log_probs * advantages).mean(); entropy of the current policy is logged
+                        float lpa = lp[0];
+#pragma unroll
+                        for (int k = 1; k < A; ++k)
+                            if (act_s == k) lpa = lp[k];
+                        loss_s = -(lpa * adv_s);
+#pragma unroll
+                        for (int k = 0; k < A; ++k) {
+                            ent_s -= fmaxf(lp[k], F32_LOWEST) * p[k];
+                            dz[k] = -adv_s * ((act_s == k ? 1.0f : 0.0f) - p[k]);
                         }
                     }
                     if (FVP) {
@@ -1053,6 +1088,90 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
         cudaEventDestroy(ev1);
     }
     return RL_OK;
+}
+
+void rl_ppo_cfg_default(rl_ppo_cfg *c) {
+    // ppo.rs:33-41
+    c->opt_steps_per_update = 10;
+    c->clip_distance = 0.2;
+}
+
+// Ppo::update (ppo.rs:97-147) with opt_steps > 0 and a clip, Reinforce::update (reinforce.rs:64-89) with clip < 0.
+static rl_status policy_adam_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, int n_steps,
+                                    double clip_distance, bool ppo, rl_policy_opt_stats *stats, const char *what) {
+    if (!traj || !adv_dev || !policy || !adam)
+        return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "%s: NULL argument", what);
+    rl_ctx *ctx = traj->ctx;
+    constexpr int F = 5, A = 2, UPL = 4;
+    RL_REQUIRE(ctx, adam->mlp == policy, "policy update: optimizer belongs to another module");
+    RL_REQUIRE(ctx, n_steps >= 0 && n_steps <= 100000, "policy update: opt_steps_per_update out of range");
+    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
+          policy->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "%s: built for a %d->%d->%d ReLU policy (got %d->%d->%d)", what, F, 32 * UPL, A,
+                       policy->in_dim, policy->hidden, policy->out_dim);
+    const int P = (int)policy->n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
+    PassPlan plan;
+    const size_t loss_bytes = ((size_t)(n_steps + 2) * sizeof(double) + 255) / 256 * 256;
+    char *ex;
+    RL_TRY(make_plan(ctx, P, TE, &plan, loss_bytes + TE * 2 * sizeof(float), (void **)&ex));
+    double *losses = (double *)ex;
+    float *logp0 = (float *)(ex + loss_bytes);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    PassArgs pa{};
+    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
+    pa.theta = policy->params; pa.adv = adv_dev; pa.logp0 = logp0;
+    pa.clip_lo = (float)(1.0 - clip_distance); pa.clip_hi = (float)(1.0 + clip_distance);
+    AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
+    double *entropy_sum = losses + n_steps;  // [sum of entropies, N]
+    if (ppo) {
+        // initial log-probs and entropy under no_grad (ppo.rs:108-119)
+        RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
+        RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum, plan.sums + P + SC_ENTROPY, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum + 1, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        for (int s = 0; s < n_steps; ++s) RL_TRY((pass_and_adam<F, A, UPL, PASS_PPO>(ctx, plan, pa, policy, adam, ac, losses + s)));
+    } else {
+        for (int s = 0; s < n_steps; ++s) {
+            RL_TRY((pass_and_adam<F, A, UPL, PASS_REINFORCE>(ctx, plan, pa, policy, adam, ac, losses + s)));
+            if (s == 0) {  // entropies.get_or_insert_with: the distribution of the first loss evaluation (reinforce.rs:76)
+                RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum, plan.sums + P + SC_ENTROPY, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum + 1, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+    }
+    if (stats) {
+        RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+        double *host;
+        RL_TRY(rl_ctx_pinned(ctx, (size_t)(n_steps + 4) * sizeof(double), (void **)&host));
+        RL_CUDA(ctx, cudaMemcpyAsync(host, losses, (size_t)(n_steps + 2) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const bool have = ppo || n_steps > 0;
+        stats->loss_first = n_steps > 0 ? host[0] : 0.0;
+        stats->loss_last = n_steps > 0 ? host[n_steps - 1] : 0.0;
+        stats->num_steps = have ? (uint64_t)host[n_steps + 1] : 0;
+        stats->entropy = have && host[n_steps + 1] > 0 ? host[n_steps] / host[n_steps + 1] : 0.0;
+        stats->opt_steps = (uint64_t)n_steps;
+        cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return RL_OK;
+}
+
+rl_status rl_ppo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, const rl_ppo_cfg *cfg,
+                        rl_policy_opt_stats *stats) {
+    if (!cfg) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_ppo_update: NULL argument");
+    return policy_adam_update(traj, adv_dev, policy, adam, (int)cfg->opt_steps_per_update, cfg->clip_distance, true, stats,
+                              "rl_ppo_update");
+}
+
+rl_status rl_reinforce_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, rl_policy_opt_stats *stats) {
+    return policy_adam_update(traj, adv_dev, policy, adam, 1, 0.0, false, stats, "rl_reinforce_update");
 }
 
 rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cfg *cfg, rl_opt_stats *stats) {

@@ -136,6 +136,68 @@ class Trpo:
 
 
 @dataclass
+class PpoConfig:
+    """policies/ppo.rs:14-41"""
+
+    policy_fn_config: MlpConfig = field(default_factory=MlpConfig)
+    optimizer_config: AdamConfig = field(default_factory=AdamConfig)
+    opt_steps_per_update: int = 10
+    clip_distance: float = 0.2
+
+    def build_policy(self, ctx: Context, in_dim: int, out_dim: int) -> "Ppo":
+        return Ppo(self.policy_fn_config.build_module(ctx, in_dim, out_dim), self)
+
+
+class _AdamPolicy:
+    def __init__(self, policy_fn: Mlp, cfg):
+        self.policy_fn, self.cfg = policy_fn, cfg
+        self.ctx, self._lib = policy_fn.ctx, policy_fn.ctx._lib
+        self.optimizer = Adam(policy_fn, cfg.optimizer_config)
+
+    def actor(self, lanes_per_env: int = 0) -> ActorSpec:
+        return ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=self.policy_fn, lanes_per_env=lanes_per_env)
+
+    def _log(self, stats, logger):
+        if logger is not None:
+            logger.update({"entropy": stats.entropy, "loss_first": stats.loss_first, "loss_last": stats.loss_last,
+                           "num_steps": stats.num_steps, "policy/update_time": stats.update_ms * 1e-3, "status": L.RL_OK})
+
+
+class Ppo(_AdamPolicy):
+    """Policy with the clipped-surrogate PPO update (ppo.rs:97-147)."""
+
+    def update(self, traj: Trajectory, advantages: DeviceBuffer, logger: dict | None = None) -> int:
+        stats = L.PolicyOptStats()
+        cfg = L.PpoCfg(self.cfg.opt_steps_per_update, self.cfg.clip_distance)
+        L.check(self._lib.rl_ppo_update(traj.handle, advantages.c, self.policy_fn.handle, self.optimizer.handle, C.byref(cfg),
+                                        C.byref(stats)), self.ctx.handle)
+        self._log(stats, logger)
+        return L.RL_OK
+
+
+@dataclass
+class ReinforceConfig:
+    """policies/reinforce.rs:10-16"""
+
+    policy_fn_config: MlpConfig = field(default_factory=MlpConfig)
+    optimizer_config: AdamConfig = field(default_factory=AdamConfig)
+
+    def build_policy(self, ctx: Context, in_dim: int, out_dim: int) -> "Reinforce":
+        return Reinforce(self.policy_fn_config.build_module(ctx, in_dim, out_dim), self)
+
+
+class Reinforce(_AdamPolicy):
+    """Policy with the REINFORCE policy-gradient update (reinforce.rs:64-89)."""
+
+    def update(self, traj: Trajectory, advantages: DeviceBuffer, logger: dict | None = None) -> int:
+        stats = L.PolicyOptStats()
+        L.check(self._lib.rl_reinforce_update(traj.handle, advantages.c, self.policy_fn.handle, self.optimizer.handle,
+                                              C.byref(stats)), self.ctx.handle)
+        self._log(stats, logger)
+        return L.RL_OK
+
+
+@dataclass
 class ValuesOptConfig:
     """critics/opt.rs:14-50: GAE(lambda 0.95) advantages, reward-to-go targets, 80 Adam steps, gamma <= 0.99."""
 
@@ -190,7 +252,7 @@ class ValuesOpt:
 class ActorCriticConfig:
     """actor_critic.rs:20-46"""
 
-    policy_config: TrpoConfig = field(default_factory=TrpoConfig)
+    policy_config: object = field(default_factory=TrpoConfig)  # TrpoConfig | PpoConfig | ReinforceConfig
     critic_config: ValuesOptConfig = field(default_factory=ValuesOptConfig)
     min_batch_size: HistoryDataBound = field(default_factory=lambda: HistoryDataBound(10_000, 100))
 

@@ -175,3 +175,71 @@ def test_actor_critic_learns_cartpole(ctx):
         agent.batch_update(traj, {})
     print("mean episode length per period:", [round(x, 1) for x in lengths])
     assert lengths[-1] > 1.5 * lengths[0]
+
+
+def _policy_batch(ctx, seed, E, T):
+    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=seed, scale=1.5)
+    rng = np.random.default_rng(seed + 100)
+    adv = rng.normal(size=(T, E)).astype(np.float32)
+    return env, traj, net, params, host, valid, adv, ctx.to_device(adv)
+
+
+@pytest.mark.parametrize("seed,E,T,steps,clip", [(21, 64, 64, 10, 0.2), (22, 100, 90, 25, 0.05)])
+def test_ppo_update_matches_oracle(ctx, seed, E, T, steps, clip):
+    """Ppo::update (ppo.rs:97-147): opt_steps Adam steps on the clipped surrogate.  Parameter delta within
+    max(2e-4, 4x the torch-f32 run's own distance from the f64 run); the small clip makes the clipped branch and
+    its zero gradient active on many samples."""
+    env, traj, net, params, host, valid, adv, adv_d = _policy_batch(ctx, seed, E, T)
+    policy = R.Ppo(net, R.PpoConfig(opt_steps_per_update=steps, clip_distance=clip))
+    log = {}
+    policy.update(traj, adv_d, log)
+    new = net.get_weights()
+    obs, act, a = host["obs"][valid], host["action"][valid], adv[valid]
+    new64, l64, ent64 = TO.ppo_update(params, 5, 128, 2, obs, act, a, steps, clip, dtype=torch.float64)
+    new32, l32, ent32 = TO.ppo_update(params, 5, 128, 2, obs, act, a, steps, clip, dtype=torch.float32)
+    d, d64, d32 = new - params, new64 - params.astype(np.float64), new32 - params
+    print(f"ppo delta rel err vs f64: kernel {_rel(d, d64):.2e}, torch-f32 {_rel(d32, d64):.2e}; loss {log['loss_first']:.6f}->"
+          f"{log['loss_last']:.6f} vs {l64[0]:.6f}->{l64[-1]:.6f}")
+    assert log["num_steps"] == int(valid.sum())
+    np.testing.assert_allclose(log["entropy"], ent64, rtol=1e-5)
+    np.testing.assert_allclose(log["loss_first"], l64[0], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(log["loss_last"], l64[-1], rtol=1e-4, atol=1e-6)
+    assert _rel(d, d64) <= max(2e-4, 4 * _rel(d32, d64) + 1e-5)
+
+
+def test_reinforce_update_matches_oracle(ctx):
+    """Reinforce::update (reinforce.rs:64-89): one Adam step on -(log_probs * advantages).mean()."""
+    env, traj, net, params, host, valid, adv, adv_d = _policy_batch(ctx, 31, 80, 70)
+    policy = R.Reinforce(net, R.ReinforceConfig())
+    log = {}
+    policy.update(traj, adv_d, log)
+    new = net.get_weights()
+    obs, act, a = host["obs"][valid], host["action"][valid], adv[valid]
+    new64, l64, ent64 = TO.reinforce_update(params, 5, 128, 2, obs, act, a, dtype=torch.float64)
+    new32, l32, ent32 = TO.reinforce_update(params, 5, 128, 2, obs, act, a, dtype=torch.float32)
+    d, d64, d32 = new - params, new64 - params.astype(np.float64), new32 - params
+    print(f"reinforce delta rel err vs f64: kernel {_rel(d, d64):.2e}, torch-f32 {_rel(d32, d64):.2e}")
+    np.testing.assert_allclose(log["entropy"], ent64, rtol=1e-5)
+    np.testing.assert_allclose(log["loss_first"], l64, rtol=1e-5, atol=1e-7)
+    # the first Adam step moves every parameter by ~lr * sign(g): compare where the gradient is not ~0
+    assert _rel(d, d64) <= max(2e-3, 4 * _rel(d32, d64) + 1e-5)
+
+
+@pytest.mark.parametrize("policy_config", ["ppo", "reinforce"])
+def test_actor_critic_learns_cartpole_with_adam_policies(ctx, policy_config):
+    """agents/testing.rs-style behavioural check for the PPO / REINFORCE rows of actor_critic.rs:292-333."""
+    E, T = 512, 128
+    env = R.build_env(ctx, CARTPOLE, E, seed=5)
+    pc = R.PpoConfig() if policy_config == "ppo" else R.ReinforceConfig(optimizer_config=R.AdamConfig(learning_rate=0.01))
+    agent = R.ActorCriticConfig(policy_config=pc).build_agent(env)
+    rng = np.random.default_rng(0)
+    agent.policy.policy_fn.set_weights(R.init_params(rng, 5, 128, 2))
+    agent.critic.state_value_fn.set_weights(R.init_params(rng, 5, 128, 1))
+    traj = R.Trajectory(env, T)
+    lengths = []
+    for period in range(12):
+        summ = R.rollout(env, agent.actor(), R.HistoryDataBound(T, 0), traj)
+        lengths.append(summ.episode_length.mean)
+        agent.batch_update(traj, {})
+    print(policy_config, "mean episode length per period:", [round(x, 1) for x in lengths])
+    assert max(lengths[-3:]) > 1.3 * lengths[0]
