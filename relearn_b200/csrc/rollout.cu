@@ -515,11 +515,14 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
         }
     }
 
+    auto remaining_feature = [&](uint32_t r) {
+        return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
+    };
     auto observe = [&](const EnvT::State &s, float *obs) {
         obs[0] = (float)s.x; obs[1] = (float)s.xd; obs[2] = (float)s.th; obs[3] = (float)s.thd;
-        const uint32_t r = s.meta & 0x7FFFFFFFu;
-        obs[4] = p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
+        obs[4] = remaining_feature(s.meta & 0x7FFFFFFFu);
     };
+    const float rem_full = remaining_feature(p.max_steps);
 
     LaneNoise<REPLAY> nz;
     const uint64_t e_safe = valid ? e : 0;  // out-of-range threads shadow lane 0 without storing anything
@@ -557,6 +560,10 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
     while (__any_sync(0xffffffffu, n > 0)) {
         const bool active = n > 0;
         if (!REPLAY) nz.set_step(t0 + i);
+        // the `remaining` feature of the next observation is known before the step: one less if the episode
+        // continues, the full limit after a reset.  Looked up here, off the dependent chain.
+        const uint32_t r_now = s.meta & 0x7FFFFFFFu;
+        const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
         float z0 = 0.0f, z1 = 0.0f;
         if (needs_logits) {
             const float2 o0 = make_float2(obs[0], obs[0]), o1 = make_float2(obs[1], obs[1]), o2 = make_float2(obs[2], obs[2]);
@@ -635,9 +642,13 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
                 w = __shfl_sync(0xffffffffu, shared_word, (threadIdx.x & 31 & ~(LANES - 1)) + phase);
             }
             const float u = rl_u32_to_f32(w);
-            const float m = fmaxf(z0, z1);
-            const float lse = m + logf(expf(z0 - m) + expf(z1 - m));
-            action = u < expf(z0 - lse) ? 0u : 1u;
+            // exp(log_softmax(z))[0] for two logits is the logistic of z0 - z1; evaluated as such (one exp and one
+            // reciprocal instead of three exps and a log on the step chain).  Identical in exact arithmetic and within
+            // rounding of the log_softmax route; decisions can differ only for u within ~1e-7 of the boundary, the
+            // same near-tie class the logit summation order already allows.
+            const float d = z1 - z0, ex = expf(-fabsf(d)), inv = __frcp_rn(1.0f + ex);
+            const float p0 = d <= 0.0f ? inv : ex * inv;
+            action = u < p0 ? 0u : 1u;
         } else if (active) {  // dqn.rs:360-379
             if (rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps)) action = rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, 2u);
             else action = z1 > z0 ? 1u : 0u;
@@ -659,7 +670,7 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
             if (owns[7]) a.succ[is] = (uint8_t)sc;
         }
         if (sc == RL_INTERRUPT && active) {  // rare: once per max_steps
-            observe(s, obs);
+            observe(s, obs);  // (remaining == 0 here)
             if (sub == 0) {
 #pragma unroll
                 for (int f = 0; f < 5; ++f)
@@ -676,7 +687,8 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
             sum_el2 = fma(ld, ld, sum_el2);
             cur_len = 0;
         }
-        observe(s, obs);
+        obs[0] = (float)s.x; obs[1] = (float)s.xd; obs[2] = (float)s.th; obs[3] = (float)s.thd;
+        obs[4] = sc != RL_CONTINUE ? rem_full : rem_cont;
         if (active) {
             succ_prev = succ_last;
             succ_last = sc;
@@ -991,7 +1003,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             // auto, from the B200 sweep in profiles/r1_rollout_sweep.md: with few envs the step chain of a
             // single warp is the bound, so the hidden layer is split over 8 threads (weights in registers);
             // as envs grow the redundant per-warp physics costs more than the latency it hides.
-            lanes = env->E <= 6144 ? 8 : env->E <= 12288 ? 4 : env->E <= 24576 ? 2 : 1;
+            lanes = env->E <= 6144 ? 8 : env->E <= 24576 ? 2 : 1;
         }
         switch (lanes) {
         case 1: RL_TRY((launch_group<1>(ctx, env->cartpole, a, replay, &nblocks))); break;
