@@ -36,6 +36,11 @@ B_PER_STEP_ROLLOUT = 26      # obs 5 x f32 + action u8 + reward f32 + succ u8 (D
 B_PER_STEP_UNFUSED = 98      # K1 (f64 state)
 B_PER_STEP_SCAN = 17         # K3
 FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2c launch at E = 4096, T = 256 from the round-1
+# `ncu --set full` capture (profiles/r1_summary.md section 2): 36.1 KB + 2.6 KB.  The 27 MB trajectory of a
+# period stays in the 126 MB L2 while the kernel runs and drains afterwards, so the in-kernel DRAM traffic
+# is far BELOW the algorithmic 26 B/env-step, not above it.
+K2C_NCU_DRAM_BYTES_PER_LAUNCH = 38656
 
 
 def measured_peaks():
@@ -267,7 +272,9 @@ def run_ours(args):
     hbm_peak, peak_src = measured_peaks()
     achieved = B_PER_STEP_ROLLOUT * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "rollout_cartpole (fused step+policy+sample)",
+                "traffic": K2C_NCU_DRAM_BYTES_PER_LAUNCH if (E == 4096 and T == 256) else None,
+                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s2); trajectory is L2-resident during the kernel",
+                "peak_source": peak_src, "kernel": "rollout_cartpole (fused step+policy+sample)",
                 "note": "K2 is FP32-FMA/latency bound by design (26 B of trajectory writes per env-step); see fp32 and kernels[]"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -226,23 +226,29 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
         int act;
         bool valid;
     };
+    // All loads of a tile are issued together: the observation / target / advantage loads do not wait for the
+    // successor code (one memory latency per tile instead of two); slots that turn out to be padding are zeroed.
     auto load_tile = [&](uint64_t tile, Staged &st) {
         const uint64_t n = tile * 32 + lane;
         const bool in_range = tile < ntiles && n < TE;
-        const uint8_t sc_code = in_range ? __ldg(a.succ + n) : (uint8_t)RL_PAD;
-        st.valid = sc_code != RL_PAD;
         const uint64_t t = in_range ? n / a.E : 0, e = in_range ? n - t * a.E : 0;
+        const uint8_t sc_code = in_range ? __ldg(a.succ + n) : (uint8_t)RL_PAD;
+        float x[F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) st.x[f] = st.valid ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
-        st.act = ((IS_POLICY || MODE == PASS_QLOSS) && st.valid) ? (int)__ldg(a.action + n) : 0;
-        st.adv = (USES_ADV && st.valid) ? __ldg(a.adv + n) : 0.0f;
-        st.tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && st.valid) ? __ldg(a.target + n) : 0.0f;
-        st.lp0a = st.lp0b = 0.0f;
-        if (USES_LP0 && st.valid) {
-            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n);
-            st.lp0a = l.x;
-            st.lp0b = l.y;
-        }
+        for (int f = 0; f < F; ++f) x[f] = in_range ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
+        const int act = ((IS_POLICY || MODE == PASS_QLOSS) && in_range) ? (int)__ldg(a.action + n) : 0;
+        const float adv = (USES_ADV && in_range) ? __ldg(a.adv + n) : 0.0f;
+        const float tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && in_range) ? __ldg(a.target + n) : 0.0f;
+        float2 l = make_float2(0.0f, 0.0f);
+        if (USES_LP0 && in_range) l = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n);
+        st.valid = sc_code != RL_PAD;
+#pragma unroll
+        for (int f = 0; f < F; ++f) st.x[f] = st.valid ? x[f] : 0.0f;
+        st.act = st.valid ? act : 0;
+        st.adv = st.valid ? adv : 0.0f;
+        st.tgt = st.valid ? tgt : 0.0f;
+        st.lp0a = st.valid ? l.x : 0.0f;
+        st.lp0b = st.valid ? l.y : 0.0f;
     };
     Staged nxt;
     load_tile(warp_global, nxt);
@@ -829,6 +835,7 @@ rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool red
     case 1: return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args, reduce);
     case 2: return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args, reduce);
     case 3: return launch_pass_variant<F, A, UPL, MODE, 4, 1>(ctx, plan, args, reduce);
+    case 4: return launch_pass_variant<F, A, UPL, MODE, 4, 3>(ctx, plan, args, reduce);
     default:
         if (MODE == PASS_VALUE || MODE == PASS_QLOSS) return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args, reduce);
         if (MODE == PASS_STATS || MODE == PASS_EVAL) return launch_pass_variant<F, A, UPL, MODE, 8, 2>(ctx, plan, args, reduce);
