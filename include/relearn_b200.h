@@ -346,6 +346,22 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
                           rl_opt_stats *stats);
 
 /* ------------------------------------------------------------------------------------------ */
+/* The same updates for a recurrent module (Chain<Gru, Linear>; rl2-bandits.rs:379-430): TRPO with   */
+/* back-propagation through time and a forward-tangent + BPTT Fisher-vector product in place of the  */
+/* reference's autograd double backward, ValuesOpt with a GRU critic, GAE over SeqPacked values.     */
+/* Built for hidden <= 8, features <= 20, actions <= 16; RL_ERR_UNSUPPORTED otherwise.               */
+/* ------------------------------------------------------------------------------------------ */
+rl_status rl_trpo_update_seq(rl_traj *traj, const float *adv_dev, rl_grunet *policy, const rl_trpo_cfg *cfg,
+                             rl_trpo_stats *stats);
+rl_status rl_trpo_probe_seq(rl_traj *traj, const float *adv_dev, rl_grunet *policy, const float *vec_host,
+                            double hpv_reg_coeff, double *loss, double *kl, double *entropy, float *grad_host,
+                            float *fvp_host);
+rl_status rl_adam_create_seq(rl_grunet *net, const rl_adam_cfg *cfg, rl_adam **out);
+rl_status rl_value_update_seq(rl_traj *traj, const float *targets_dev, rl_grunet *value_fn, rl_adam *adam, int32_t n_steps,
+                              rl_opt_stats *stats);
+rl_status rl_gae_seq(rl_traj *traj, rl_grunet *value_fn, float gamma, float lambda, float *adv_dev, float *rtg_dev);
+
+/* ------------------------------------------------------------------------------------------ */
 /* PPO and REINFORCE policies (Policy::update src/torch/agents/policies/ppo.rs:97-147,          */
 /* reinforce.rs:64-89) -- same data path as TRPO with an Adam step in place of the CG step.     */
 /* ------------------------------------------------------------------------------------------ */

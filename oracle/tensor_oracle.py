@@ -468,3 +468,119 @@ def reinforce_update(flat_params, n_in, hidden, n_out, obs, actions, advantages,
     entropy = float(dist.entropy().mean().detach())
     opt.step(torch.autograd.grad(loss, params))
     return flatten_tensors([p.detach() for p in params]).numpy().copy(), float(loss.detach()), entropy
+
+
+# ------------------------------------------------------------------------------------------------
+# The same updates with a recurrent module (Chain<Gru, Linear>) in place of the MLP: Trpo::update
+# (trpo.rs:97-164; cuDNN disabled :104-108 so autograd differentiates the composed gru_cell twice),
+# ValuesOpt::update (opt.rs:100-127), eval_extended_state_values (critics/mod.rs:116-131).
+# The reference feeds PackedTensor batches through SeqPacked::seq_packed; the loss is a mean over all
+# steps, so episodes are padded to a common length here and the valid steps selected afterwards.
+# ------------------------------------------------------------------------------------------------
+class EpisodeBatch:
+    """episodes: list of [L_i, F] observation arrays.  `select(x[B, Lmax, ...])` returns the valid steps
+    episode-major (episode 0 steps 0..L0-1, episode 1 ...)."""
+
+    def __init__(self, episodes, dtype):
+        self.lens = [len(e) for e in episodes]
+        B, Lmax = len(episodes), max(self.lens) if episodes else 0
+        F = np.asarray(episodes[0]).shape[1]
+        obs = np.zeros((B, Lmax, F), np.float64)
+        for i, e in enumerate(episodes):
+            obs[i, :len(e)] = e
+        self.obs = torch.tensor(obs, dtype=dtype)
+        mask = np.zeros((B, Lmax), bool)
+        for i, n in enumerate(self.lens):
+            mask[i, :n] = True
+        self.mask = torch.tensor(mask)
+
+    def select(self, x):
+        return x[self.mask]
+
+
+def gru_linear_forward(params, batch: EpisodeBatch, activation="relu"):
+    """h0 = 0 per episode (gru.rs:23-28); h = gru_cell(x, h); out = Linear(act(h)) (chain.rs:157-168)."""
+    w_ih, w_hh, b_ih, b_hh, lw, lb = params
+    act = {"relu": torch.relu, "identity": lambda t: t, "tanh": torch.tanh, "sigmoid": torch.sigmoid}[activation]
+    B, Lmax, _ = batch.obs.shape
+    h = torch.zeros(B, w_hh.shape[1], dtype=batch.obs.dtype)
+    outs = []
+    for t in range(Lmax):
+        # composed gru_cell (what libtorch's CPU gru_cell computes, gate order [r, z, n])
+        gi = torch.nn.functional.linear(batch.obs[:, t], w_ih, b_ih)
+        gh = torch.nn.functional.linear(h, w_hh, b_hh)
+        i_r, i_z, i_n = gi.chunk(3, 1)
+        h_r, h_z, h_n = gh.chunk(3, 1)
+        r = torch.sigmoid(h_r + i_r)
+        z = torch.sigmoid(h_z + i_z)
+        n = torch.tanh(i_n + r * h_n)
+        h = (h - n) * z + n
+        outs.append(torch.nn.functional.linear(act(h), lw, lb))
+    return batch.select(torch.stack(outs, dim=1))
+
+
+def _seq_params(flat_params, n_in, hidden, n_out, dtype):
+    flat = torch.tensor(np.asarray(flat_params), dtype=dtype)
+    return [p.clone().requires_grad_(True) for p in unflatten_gru_linear(flat, n_in, hidden, n_out)]
+
+
+def _cat(xs, dtype):
+    return torch.tensor(np.concatenate([np.asarray(x) for x in xs]), dtype=dtype)
+
+
+def seq_policy_loss_kl_grad_fvp(flat_params, n_in, hidden, n_out, episodes, actions, advantages, vector, reg=0.0,
+                                dtype=torch.float64, activation="relu"):
+    """episodes / actions / advantages: per-episode arrays.  Returns loss, kl, entropy, grad, (H + reg I) v."""
+    params = _seq_params(flat_params, n_in, hidden, n_out, dtype)
+    batch = EpisodeBatch(episodes, dtype)
+    act_t, adv_t = _cat(actions, torch.int64), _cat(advantages, dtype)
+    with torch.no_grad():
+        dist0 = Categorical(gru_linear_forward(params, batch, activation))
+        logp0 = dist0.log_prob(act_t)
+        entropy = float(dist0.entropy().mean())
+    dist = Categorical(gru_linear_forward(params, batch, activation))
+    loss = -((dist.log_prob(act_t) - logp0).exp() * adv_t).mean()
+    kl = dist0.kl_divergence_from(dist).mean()
+    g = flatten_tensors(torch.autograd.grad(loss, params, retain_graph=True))
+    hv = HessianVectorProduct(kl, params, reg).mat_vec_mul(torch.tensor(np.asarray(vector), dtype=dtype))
+    return float(loss.detach()), float(kl.detach()), entropy, g.detach().numpy(), hv.detach().numpy()
+
+
+def seq_trpo_update(flat_params, n_in, hidden, n_out, episodes, actions, advantages, max_kl=0.01,
+                    cfg: CgConfig | None = None, dtype=torch.float32, activation="relu"):
+    cfg = cfg or CgConfig()
+    params = _seq_params(flat_params, n_in, hidden, n_out, dtype)
+    batch = EpisodeBatch(episodes, dtype)
+    act_t, adv_t = _cat(actions, torch.int64), _cat(advantages, dtype)
+    log = {}
+    with torch.no_grad():
+        dist0 = Categorical(gru_linear_forward(params, batch, activation))
+        logp0 = dist0.log_prob(act_t)
+        log["entropy"] = float(dist0.entropy().mean())
+
+    def loss_distance_fn():
+        dist = Categorical(gru_linear_forward(params, batch, activation))
+        loss = -((dist.log_prob(act_t) - logp0).exp() * adv_t).mean()
+        return loss, dist0.kl_divergence_from(dist).mean()
+
+    log["error"] = None
+    try:
+        trust_region_backward_step(params, loss_distance_fn, max_kl, cfg, log)
+    except OptimizerStepError as e:
+        log["error"] = e.kind
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), log
+
+
+def seq_value_update(flat_params, n_in, hidden, episodes, targets, n_steps=80, lr=1e-3, dtype=torch.float32,
+                     activation="relu"):
+    params = _seq_params(flat_params, n_in, hidden, 1, dtype)
+    opt = Adam112(params, lr)
+    batch = EpisodeBatch(episodes, dtype)
+    tgt_t = _cat(targets, dtype)
+    losses = []
+    for _ in range(n_steps):
+        v = gru_linear_forward(params, batch, activation).squeeze(-1)
+        loss = torch.nn.functional.mse_loss(v, tgt_t, reduction="mean")
+        opt.step(torch.autograd.grad(loss, params))
+        losses.append(float(loss.detach()))
+    return flatten_tensors([p.detach() for p in params]).numpy().copy(), losses

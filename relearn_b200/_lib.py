@@ -199,6 +199,11 @@ SIGNATURES = {
     "rl_adam_create": (st, [vp, P(AdamCfg), P(vp)]),
     "rl_adam_destroy": (st, [vp]),
     "rl_value_update": (st, [vp, vp, vp, vp, C.c_int32, P(OptStats)]),
+    "rl_trpo_update_seq": (st, [vp, vp, vp, P(TrpoCfg), P(TrpoStats)]),
+    "rl_trpo_probe_seq": (st, [vp, vp, vp, vp, C.c_double, P(C.c_double), P(C.c_double), P(C.c_double), vp, vp]),
+    "rl_adam_create_seq": (st, [vp, P(AdamCfg), P(vp)]),
+    "rl_value_update_seq": (st, [vp, vp, vp, vp, C.c_int32, P(OptStats)]),
+    "rl_gae_seq": (st, [vp, vp, C.c_float, C.c_float, vp, vp]),
     "rl_ppo_cfg_default": (None, [P(PpoCfg)]),
     "rl_ppo_update": (st, [vp, vp, vp, vp, P(PpoCfg), P(PolicyOptStats)]),
     "rl_reinforce_update": (st, [vp, vp, vp, vp, P(PolicyOptStats)]),

@@ -267,8 +267,9 @@ __global__ void __launch_bounds__(32 * SQ_COUNT) seq_finalize_kernel(const doubl
 // state zeroed at the first step of every episode.  out f32 [T][A][E]; PAD slots get zeros.
 template <int HMAX>
 __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_in_smem, const float *__restrict__ obs,
-                                                        const uint8_t *__restrict__ succ, uint64_t T, uint64_t E,
-                                                        float *__restrict__ out) {
+                                                        const float *__restrict__ next_obs, const uint8_t *__restrict__ succ,
+                                                        uint64_t T, uint64_t E, float *__restrict__ out,
+                                                        float *__restrict__ out_next) {
     extern __shared__ __align__(16) float sw[];
     if (weights_in_smem) {
         const uint64_t np = m.count();
@@ -294,6 +295,17 @@ __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_
         for (int f = 0; f < MAXF; ++f) x[f] = f < m.F ? obs[(t * m.F + f) * E + e] : 0.0f;
         grunet_step<HMAX, MAXF, MAXA>(m, w, x, h, z);
         for (int k = 0; k < m.A; ++k) out[(t * m.A + k) * E + e] = z[k];
+        if (sc == RL_INTERRUPT && out_next) {
+            // the extended observation of an interrupted episode (features.rs:139-185): one more step of the same
+            // sequence on the successor observation
+            float h2[HMAX];
+#pragma unroll
+            for (int j = 0; j < HMAX; ++j) h2[j] = h[j];
+#pragma unroll
+            for (int f = 0; f < MAXF; ++f) x[f] = f < m.F ? next_obs[(t * m.F + f) * E + e] : 0.0f;
+            grunet_step<HMAX, MAXF, MAXA>(m, w, x, h2, z);
+            for (int k = 0; k < m.A; ++k) out_next[(t * m.A + k) * E + e] = z[k];
+        }
         if (sc != RL_CONTINUE) {
 #pragma unroll
             for (int j = 0; j < HMAX; ++j) h[j] = 0.0f;
@@ -363,6 +375,34 @@ rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *t
     return RL_OK;
 }
 
+// SeqPacked forward over a trajectory; out_next (optional) receives the outputs on the successor observation of
+// interrupted steps (eval_extended_state_values, critics/mod.rs:116-131).
+rl_status rl_grunet_seq_enqueue(rl_grunet *g, rl_traj *traj, float *out_dev, float *out_next_dev) {
+    rl_ctx *ctx = g->ctx;
+    RL_REQUIRE(ctx, traj->ctx == ctx, "rl_grunet_seq_forward: trajectory belongs to another context");
+    RL_REQUIRE(ctx, (int)traj->F == g->in_dim, "rl_grunet_seq_forward: feature count mismatch");
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, E = traj->E;
+    const size_t wbytes = g->n_params * sizeof(float);
+    const int in_smem = wbytes <= SEQ_SMEM_LIMIT;
+    const size_t smem = in_smem ? wbytes : 16;
+    const unsigned grid = rl_grid_for(E, 128);
+    const GruView v = view_of(g);
+    if (g->hidden <= 8) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, grunet_seq_kernel<8>, grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
+                  out_next_dev);
+    } else {
+        RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, grunet_seq_kernel<128>, grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
+                  out_next_dev);
+    }
+    return RL_OK;
+}
+
+rl_grunet_view rl_grunet_view_of(rl_grunet *g) {
+    return rl_grunet_view{g->ctx, g->in_dim, g->hidden, g->out_dim, (int)g->act, g->n_params, g->params};
+}
+
 extern "C" {
 
 rl_status rl_grunet_create(rl_ctx *ctx, int32_t in_dim, int32_t hidden, int32_t out_dim, rl_activation activation,
@@ -418,23 +458,7 @@ rl_status rl_grunet_get_weights(rl_grunet *g, float *host, uint64_t n) {
 
 rl_status rl_grunet_seq_forward(rl_grunet *g, rl_traj *traj, float *out_dev) {
     if (!g || !traj || !out_dev) return rl_fail(g ? g->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_grunet_seq_forward: NULL argument");
-    rl_ctx *ctx = g->ctx;
-    RL_REQUIRE(ctx, traj->ctx == ctx, "rl_grunet_seq_forward: trajectory belongs to another context");
-    RL_REQUIRE(ctx, (int)traj->F == g->in_dim, "rl_grunet_seq_forward: feature count mismatch");
-    const uint64_t T = traj->used_T ? traj->used_T : traj->T, E = traj->E;
-    const size_t wbytes = g->n_params * sizeof(float);
-    const int in_smem = wbytes <= SEQ_SMEM_LIMIT;
-    const size_t smem = in_smem ? wbytes : 16;
-    const unsigned grid = rl_grid_for(E, 128);
-    const GruView v = view_of(g);
-    if (g->hidden <= 8) {
-        RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, grunet_seq_kernel<8>, grid, 128, smem, v, in_smem, traj->obs, traj->succ, T, E, out_dev);
-    } else {
-        RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, grunet_seq_kernel<128>, grid, 128, smem, v, in_smem, traj->obs, traj->succ, T, E, out_dev);
-    }
-    return RL_OK;
+    return rl_grunet_seq_enqueue(g, traj, out_dev, nullptr);
 }
 
 }  // extern "C"

@@ -32,7 +32,9 @@ struct rl_mlp {
 };
 
 struct rl_adam {
-    rl_mlp *mlp = nullptr;
+    rl_mlp *mlp = nullptr;      // owning module when it is an Mlp
+    void *owner = nullptr;      // the module handle this optimizer was built for (rl_mlp* or rl_grunet*)
+    rl_ctx *ctx = nullptr;
     rl_adam_cfg cfg{};
     float *m = nullptr, *v = nullptr;  // device, n_params each
     uint64_t step = 0;
@@ -66,6 +68,30 @@ rl_status rl_replay_sample_finish(rl_replay *rb, uint64_t *num_steps, uint64_t *
 uint32_t rl_replay_next_draw_index(rl_replay *rb);
 rl_ctx *rl_replay_ctx(rl_replay *rb);
 int rl_replay_num_features(rl_replay *rb);
+
+// Full-batch pass modes shared by the MLP passes (update.cu) and the recurrent passes (gru_update.cu)
+enum { RL_PASS_STATS = 0, RL_PASS_EVAL = 1, RL_PASS_GRAD = 2, RL_PASS_FVP = 3, RL_PASS_VALUE = 4, RL_PASS_QLOSS = 5,
+       RL_PASS_PPO = 6, RL_PASS_REINFORCE = 7 };
+
+// Arguments of one recurrent pass (gru_update.cu).  Scratch planes are [T][.][E] like the trajectory.
+struct rl_seq_pass_args {
+    const float *obs;
+    const uint8_t *action, *succ;
+    uint64_t T, E;
+    int F, H, A, act;
+    const float *theta, *vec, *adv, *target;
+    float *logp0;   // f32 [T][A][E]
+    float *hbuf;    // f32 [T][H][E]  hidden state before each step
+    float *dzbuf;   // f32 [T][A][E]  output cotangent of each step
+    double *partials;
+    const int *skip_flag;
+    float clip_lo, clip_hi;
+};
+rl_status rl_seq_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a, int grid);
+bool rl_seq_pass_supports(int F, int H, int A);
+struct rl_grunet_view { rl_ctx *ctx; int in_dim, hidden, out_dim, act; uint64_t n_params; float *params; };
+rl_grunet_view rl_grunet_view_of(rl_grunet *g);
+rl_status rl_grunet_seq_enqueue(rl_grunet *g, rl_traj *traj, float *out_dev, float *out_next_dev);
 
 // gru.cu: fused rollout with a recurrent policy; *totals_out receives the device pointer of the ST_COUNT sums
 rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *traj, double **totals_out);

@@ -294,4 +294,23 @@ rl_status rl_gae(rl_traj *traj, rl_mlp *value_fn, float gamma, float lambda, flo
     return RL_OK;
 }
 
+// Critic::advantages / reward_to_go with a recurrent state-value module (ValuesOpt<Chain<Gru, Linear>>,
+// rl2-bandits.rs:412-419): V from SeqPacked over the stored episodes, V(next) of interrupted steps from one more
+// step of the same sequence, then the same scan as rl_gae.
+rl_status rl_gae_seq(rl_traj *traj, rl_grunet *value_fn, float gamma, float lambda, float *adv_dev, float *rtg_dev) {
+    if (!traj || !value_fn) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_gae_seq: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    const rl_grunet_view net = rl_grunet_view_of(value_fn);
+    RL_REQUIRE(ctx, net.in_dim == (int)traj->F && net.out_dim == 1, "rl_gae_seq: value function must map num_features -> 1");
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, E = traj->E;
+    const float gl = lambda * gamma;
+    float *v;
+    RL_TRY(rl_ctx_scratch(ctx, 2 * T * E * sizeof(float), (void **)&v));
+    float *v_next = v + T * E;
+    RL_TRY(rl_grunet_seq_enqueue(value_fn, traj, v, v_next));
+    RL_LAUNCH(ctx, gae_scan_kernel<true>, rl_grid_for(E, 128), 128, 0, traj->reward, v, v_next, traj->succ, T, E, gamma, gl,
+              adv_dev, rtg_dev);
+    return RL_OK;
+}
+
 }  // extern "C"

@@ -28,11 +28,13 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <functional>
 #include <vector>
 
 namespace {
 
-enum { PASS_STATS = 0, PASS_EVAL = 1, PASS_GRAD = 2, PASS_FVP = 3, PASS_VALUE = 4, PASS_QLOSS = 5, PASS_PPO = 6, PASS_REINFORCE = 7 };
+enum { PASS_STATS = RL_PASS_STATS, PASS_EVAL = RL_PASS_EVAL, PASS_GRAD = RL_PASS_GRAD, PASS_FVP = RL_PASS_FVP, PASS_VALUE = RL_PASS_VALUE,
+       PASS_QLOSS = RL_PASS_QLOSS, PASS_PPO = RL_PASS_PPO, PASS_REINFORCE = RL_PASS_REINFORCE };
 enum { SC_LOSS = 0, SC_KL = 1, SC_ENTROPY = 2, SC_COUNT = 3, NSCALAR = 4 };
 constexpr float F32_LOWEST = -3.402823466e+38f;
 constexpr int PASS_THREADS = 256;
@@ -877,6 +879,116 @@ rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extr
     return RL_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Trust-region step, network-agnostic: `pass(mode, vec, skip_flag)` runs one full-batch pass of the policy
+// module (MLP: mlp_pass_kernel; GRU: gru_pass_kernel) and leaves the all-reduced f64 sums in plan.sums.
+// ------------------------------------------------------------------------------------------------
+using PassFn = std::function<rl_status(int mode, const float *vec, const int *skip_flag)>;
+
+size_t trpo_vector_bytes(int P) {
+    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
+    return 256 + 6 * vec_bytes;  // TrpoState + theta0, g, x, r, p, descent
+}
+
+rl_status trpo_update_generic(rl_ctx *ctx, int P, float *theta, const PassPlan &plan, char *ex, const PassFn &pass,
+                              const rl_trpo_cfg *cfg, rl_trpo_stats *stats) {
+    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
+    TrpoState *st = (TrpoState *)ex;
+    float *theta0 = (float *)(ex + 256), *g = (float *)(ex + 256 + vec_bytes), *x = (float *)(ex + 256 + 2 * vec_bytes);
+    float *r = (float *)(ex + 256 + 3 * vec_bytes), *p = (float *)(ex + 256 + 4 * vec_bytes);
+    float *descent = (float *)(ex + 256 + 5 * vec_bytes);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    const float reg = (float)cfg->hpv_reg_coeff;
+    // behaviour-policy statistics (no_grad block, trpo.rs:112-122)
+    RL_TRY(pass(PASS_STATS, nullptr, nullptr));
+    RL_LAUNCH(ctx, trpo_begin_kernel, 1, 32, 0, st, plan.sums, P);
+    // loss gradient at theta0 (conjugate_gradient.rs:121-143)
+    RL_TRY(pass(PASS_GRAD, nullptr, nullptr));
+    RL_LAUNCH(ctx, trpo_cg_init_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, g, x, r, p, theta, theta0);
+    // conjugate gradient on the Fisher matrix (conjugate_gradient.rs:371-403)
+    for (uint64_t it = 0; it < cfg->cg_iterations; ++it) {
+        RL_TRY(pass(PASS_FVP, p, &st->cg_done));
+        RL_LAUNCH(ctx, trpo_cg_step_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, r, p, reg, 1e-10);
+    }
+    RL_LAUNCH(ctx, trpo_nan_to_num_kernel, 1, VEC_THREADS, 0, st, x, P);
+    RL_TRY(pass(PASS_FVP, x, nullptr));
+    RL_LAUNCH(ctx, trpo_step_size_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, descent, reg, cfg->max_policy_step_kl);
+    // backtracking line search (conjugate_gradient.rs:183-254)
+    for (uint64_t i = 0; i < cfg->max_backtracks; ++i) {
+        const double ratio = std::pow(cfg->backtrack_ratio, (double)i);
+        RL_LAUNCH(ctx, trpo_ls_candidate_kernel, 1, VEC_THREADS, 0, st, theta, theta0, descent, (float)ratio, P);
+        RL_TRY(pass(PASS_EVAL, nullptr, &st->accepted));
+        RL_LAUNCH(ctx, trpo_ls_check_kernel, 1, 32, 0, st, plan.sums, P, cfg->max_policy_step_kl, (int)i, ratio);
+    }
+    RL_LAUNCH(ctx, trpo_ls_finish_kernel, 1, VEC_THREADS, 0, st, theta, theta0, P, cfg->max_policy_step_kl,
+              cfg->accept_violation);
+    TrpoState *host;
+    RL_TRY(rl_ctx_pinned(ctx, sizeof(TrpoState), (void **)&host));
+    RL_CUDA(ctx, cudaMemcpyAsync(host, st, sizeof(TrpoState), cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats) RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (stats) {
+        stats->entropy = host->entropy; stats->step_size = host->step_size; stats->loss_initial = host->loss0;
+        stats->loss_final = host->loss_final; stats->constraint_val_final = host->kl_final;
+        stats->step_scale = host->step_scale; stats->num_backtracks = host->num_backtracks;
+        stats->cg_iterations = host->cg_iters; stats->num_steps = (uint64_t)host->N;
+        cudaEventElapsedTime(&stats->policy_update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return (rl_status)host->status;
+}
+
+// Recurrent module: plan with one block of 128 lanes per partial row, scratch for hbuf / dzbuf / logp0.
+struct SeqScratch {
+    float *logp0, *hbuf, *dzbuf;
+    char *extra;
+};
+
+rl_status make_seq_plan(rl_ctx *ctx, const rl_grunet_view &net, uint64_t T, uint64_t E, size_t extra_bytes, PassPlan *plan,
+                        SeqScratch *sc) {
+    const int P = (int)net.n_params;
+    plan->P = P;
+    plan->W = P + NSCALAR;
+    plan->grid = (int)rl_div_up(E, 128);
+    const size_t rows = (size_t)plan->grid * plan->W * sizeof(double), sums = ((size_t)plan->W * sizeof(double) + 255) / 256 * 256;
+    const size_t TE = (size_t)T * E;
+    const size_t lp = (TE * net.out_dim * sizeof(float) + 255) / 256 * 256, hb = (TE * net.hidden * sizeof(float) + 255) / 256 * 256;
+    extra_bytes = (extra_bytes + 255) / 256 * 256;
+    char *buf;
+    RL_TRY(rl_ctx_scratch(ctx, ((rows + 255) / 256 * 256) + sums + extra_bytes + 2 * lp + hb + 256, (void **)&buf));
+    plan->partials = (double *)buf;
+    plan->sums = (double *)(buf + (rows + 255) / 256 * 256);
+    char *q = (char *)plan->sums + sums;
+    sc->extra = q;
+    sc->logp0 = (float *)(q + extra_bytes);
+    sc->dzbuf = (float *)(q + extra_bytes + lp);
+    sc->hbuf = (float *)(q + extra_bytes + 2 * lp);
+    return RL_OK;
+}
+
+rl_status seq_pass(rl_ctx *ctx, const PassPlan &plan, int mode, const rl_seq_pass_args &a) {
+    RL_TRY(rl_seq_pass_launch(ctx, mode, a, plan.grid));
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.sums, a.skip_flag);
+    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    return RL_OK;
+}
+
+rl_status seq_check(rl_ctx *ctx, rl_traj *traj, const rl_grunet_view &net, int out_dim_expected, const char *what) {
+    RL_REQUIRE(ctx, net.ctx == ctx, "recurrent update: module belongs to another context");
+    if ((int)traj->F != net.in_dim || (out_dim_expected > 0 && net.out_dim != out_dim_expected) ||
+        !rl_seq_pass_supports(net.in_dim, net.hidden, net.out_dim))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "%s: recurrent passes are built for hidden <= 8, features <= 20, outputs <= 16 "
+                       "(got %d -> %d -> %d on %d features)", what, net.in_dim, net.hidden, net.out_dim, (int)traj->F);
+    return RL_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -906,73 +1018,25 @@ rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, co
     const int P = (int)policy->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
-    // extra: state + 6 P-vectors + logp0
-    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
-    const size_t extra = 256 + 6 * vec_bytes + TE * 2 * sizeof(float);
+    const size_t extra = trpo_vector_bytes(P) + TE * 2 * sizeof(float);
     char *ex;
     RL_TRY(make_plan(ctx, P, TE, &plan, extra, (void **)&ex));
-    TrpoState *st = (TrpoState *)ex;
-    float *theta0 = (float *)(ex + 256), *g = (float *)(ex + 256 + vec_bytes), *x = (float *)(ex + 256 + 2 * vec_bytes);
-    float *r = (float *)(ex + 256 + 3 * vec_bytes), *p = (float *)(ex + 256 + 4 * vec_bytes);
-    float *descent = (float *)(ex + 256 + 5 * vec_bytes);
-    float *logp0 = (float *)(ex + 256 + 6 * vec_bytes);
-    float *theta = policy->params;
-
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
-        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
-    }
-    PassArgs pa{};
-    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
-    pa.theta = theta; pa.vec = nullptr; pa.adv = adv_dev; pa.logp0 = logp0; pa.target = nullptr; pa.skip_flag = nullptr;
-    const float reg = (float)cfg->hpv_reg_coeff;
-
-    // behaviour-policy statistics (no_grad block, trpo.rs:112-122)
-    RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
-    RL_LAUNCH(ctx, trpo_begin_kernel, 1, 32, 0, st, plan.sums, P);
-    // loss gradient at theta0 (conjugate_gradient.rs:121-143)
-    RL_TRY((launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa)));
-    RL_LAUNCH(ctx, trpo_cg_init_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, g, x, r, p, theta, theta0);
-    // conjugate gradient on the Fisher matrix (conjugate_gradient.rs:371-403)
-    pa.vec = p;
-    pa.skip_flag = &st->cg_done;
-    for (uint64_t it = 0; it < cfg->cg_iterations; ++it) {
-        RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
-        RL_LAUNCH(ctx, trpo_cg_step_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, r, p, reg, 1e-10);
-    }
-    RL_LAUNCH(ctx, trpo_nan_to_num_kernel, 1, VEC_THREADS, 0, st, x, P);
-    pa.vec = x;
-    pa.skip_flag = nullptr;
-    RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
-    RL_LAUNCH(ctx, trpo_step_size_kernel, 1, VEC_THREADS, 0, st, plan.sums, P, x, descent, reg, cfg->max_policy_step_kl);
-    // backtracking line search (conjugate_gradient.rs:183-254)
-    pa.vec = nullptr;
-    pa.skip_flag = &st->accepted;
-    for (uint64_t i = 0; i < cfg->max_backtracks; ++i) {
-        const double ratio = std::pow(cfg->backtrack_ratio, (double)i);
-        RL_LAUNCH(ctx, trpo_ls_candidate_kernel, 1, VEC_THREADS, 0, st, theta, theta0, descent, (float)ratio, P);
-        RL_TRY((launch_pass<F, A, UPL, PASS_EVAL>(ctx, plan, pa)));
-        RL_LAUNCH(ctx, trpo_ls_check_kernel, 1, 32, 0, st, plan.sums, P, cfg->max_policy_step_kl, (int)i, ratio);
-    }
-    RL_LAUNCH(ctx, trpo_ls_finish_kernel, 1, VEC_THREADS, 0, st, theta, theta0, P, cfg->max_policy_step_kl,
-              cfg->accept_violation);
-    TrpoState *host;
-    RL_TRY(rl_ctx_pinned(ctx, sizeof(TrpoState), (void **)&host));
-    RL_CUDA(ctx, cudaMemcpyAsync(host, st, sizeof(TrpoState), cudaMemcpyDeviceToHost, ctx->stream));
-    if (stats) RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
-    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (stats) {
-        stats->entropy = host->entropy; stats->step_size = host->step_size; stats->loss_initial = host->loss0;
-        stats->loss_final = host->loss_final; stats->constraint_val_final = host->kl_final;
-        stats->step_scale = host->step_scale; stats->num_backtracks = host->num_backtracks;
-        stats->cg_iterations = host->cg_iters; stats->num_steps = (uint64_t)host->N;
-        cudaEventElapsedTime(&stats->policy_update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
-    }
-    return (rl_status)host->status;
+    float *logp0 = (float *)(ex + trpo_vector_bytes(P));
+    PassArgs base{};
+    base.obs = traj->obs; base.action = traj->action; base.succ = traj->succ; base.T = T; base.E = traj->E;
+    base.theta = policy->params; base.adv = adv_dev; base.logp0 = logp0;
+    PassFn pass = [&](int mode, const float *vec, const int *skip_flag) -> rl_status {
+        PassArgs pa = base;
+        pa.vec = vec;
+        pa.skip_flag = skip_flag;
+        switch (mode) {
+        case PASS_STATS: return launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa);
+        case PASS_GRAD: return launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa);
+        case PASS_FVP: return launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa);
+        default: return launch_pass<F, A, UPL, PASS_EVAL>(ctx, plan, pa);
+        }
+    };
+    return trpo_update_generic(ctx, P, policy->params, plan, ex, pass, cfg, stats);
 }
 
 rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const float *vec_host, double hpv_reg_coeff,
@@ -1026,6 +1090,8 @@ rl_status rl_adam_create(rl_mlp *mlp, const rl_adam_cfg *cfg, rl_adam **out) {
     rl_adam *a = new (std::nothrow) rl_adam();
     if (!a) return rl_fail(ctx, RL_ERR_OOM, "rl_adam_create: host allocation failed");
     a->mlp = mlp;
+    a->owner = mlp;
+    a->ctx = ctx;
     a->cfg = *cfg;
     cudaError_t e = cudaMalloc((void **)&a->m, mlp->n_params * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&a->v, mlp->n_params * sizeof(float));
@@ -1041,8 +1107,8 @@ rl_status rl_adam_create(rl_mlp *mlp, const rl_adam_cfg *cfg, rl_adam **out) {
 
 rl_status rl_adam_destroy(rl_adam *a) {
     if (!a) return RL_OK;
-    cudaSetDevice(a->mlp->ctx->device);
-    cudaStreamSynchronize(a->mlp->ctx->stream);
+    cudaSetDevice(a->ctx->device);
+    cudaStreamSynchronize(a->ctx->stream);
     cudaFree(a->m); cudaFree(a->v);
     delete a;
     return RL_OK;
@@ -1179,6 +1245,154 @@ rl_status rl_ppo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_
 
 rl_status rl_reinforce_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, rl_policy_opt_stats *stats) {
     return policy_adam_update(traj, adv_dev, policy, adam, 1, 0.0, false, stats, "rl_reinforce_update");
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Recurrent modules (Chain<Gru, Linear>): the same updates with gru_pass_kernel as the full-batch pass
+// ------------------------------------------------------------------------------------------------
+static rl_seq_pass_args seq_base_args(rl_traj *traj, const rl_grunet_view &net, uint64_t T, const SeqScratch &sc,
+                                      const PassPlan &plan) {
+    rl_seq_pass_args a{};
+    a.obs = traj->obs; a.action = traj->action; a.succ = traj->succ; a.T = T; a.E = traj->E;
+    a.F = net.in_dim; a.H = net.hidden; a.A = net.out_dim; a.act = net.act;
+    a.theta = net.params; a.logp0 = sc.logp0; a.hbuf = sc.hbuf; a.dzbuf = sc.dzbuf; a.partials = plan.partials;
+    return a;
+}
+
+rl_status rl_trpo_update_seq(rl_traj *traj, const float *adv_dev, rl_grunet *policy, const rl_trpo_cfg *cfg,
+                             rl_trpo_stats *stats) {
+    if (!traj || !adv_dev || !policy || !cfg)
+        return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_update_seq: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    const rl_grunet_view net = rl_grunet_view_of(policy);
+    RL_TRY(seq_check(ctx, traj, net, 0, "rl_trpo_update_seq"));
+    const int P = (int)net.n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T;
+    PassPlan plan;
+    SeqScratch sc;
+    RL_TRY(make_seq_plan(ctx, net, T, traj->E, trpo_vector_bytes(P), &plan, &sc));
+    rl_seq_pass_args base = seq_base_args(traj, net, T, sc, plan);
+    base.adv = adv_dev;
+    PassFn pass = [&](int mode, const float *vec, const int *skip_flag) -> rl_status {
+        rl_seq_pass_args a = base;
+        a.vec = vec;
+        a.skip_flag = skip_flag;
+        return seq_pass(ctx, plan, mode, a);
+    };
+    return trpo_update_generic(ctx, P, net.params, plan, sc.extra, pass, cfg, stats);
+}
+
+rl_status rl_trpo_probe_seq(rl_traj *traj, const float *adv_dev, rl_grunet *policy, const float *vec_host,
+                            double hpv_reg_coeff, double *loss, double *kl, double *entropy, float *grad_host,
+                            float *fvp_host) {
+    if (!traj || !adv_dev || !policy) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_probe_seq: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    const rl_grunet_view net = rl_grunet_view_of(policy);
+    RL_TRY(seq_check(ctx, traj, net, 0, "rl_trpo_probe_seq"));
+    const int P = (int)net.n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T;
+    PassPlan plan;
+    SeqScratch sc;
+    const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
+    RL_TRY(make_seq_plan(ctx, net, T, traj->E, vec_bytes, &plan, &sc));
+    float *vec = (float *)sc.extra;
+    rl_seq_pass_args a = seq_base_args(traj, net, T, sc, plan);
+    a.adv = adv_dev;
+    std::vector<double> host((size_t)plan.W);
+    auto fetch = [&]() -> rl_status {
+        RL_CUDA(ctx, cudaMemcpyAsync(host.data(), plan.sums, (size_t)plan.W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return RL_OK;
+    };
+    RL_TRY(seq_pass(ctx, plan, PASS_STATS, a));
+    RL_TRY(fetch());
+    const double N = host[P + SC_COUNT];
+    if (entropy) *entropy = host[P + SC_ENTROPY] / N;
+    RL_TRY(seq_pass(ctx, plan, PASS_GRAD, a));
+    RL_TRY(fetch());
+    if (loss) *loss = host[P + SC_LOSS] / N;
+    if (kl) *kl = host[P + SC_KL] / N;
+    if (grad_host)
+        for (int i = 0; i < P; ++i) grad_host[i] = (float)(host[i] / N);
+    if (vec_host && fvp_host) {
+        RL_CUDA(ctx, cudaMemcpyAsync(vec, vec_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        a.vec = vec;
+        RL_TRY(seq_pass(ctx, plan, PASS_FVP, a));
+        RL_TRY(fetch());
+        for (int i = 0; i < P; ++i) fvp_host[i] = (float)(host[i] / N) + vec_host[i] * (float)hpv_reg_coeff;
+    }
+    return RL_OK;
+}
+
+rl_status rl_adam_create_seq(rl_grunet *net_h, const rl_adam_cfg *cfg, rl_adam **out) {
+    if (!net_h || !cfg || !out) return rl_fail(nullptr, RL_ERR_INVALID_ARG, "rl_adam_create_seq: NULL argument");
+    const rl_grunet_view net = rl_grunet_view_of(net_h);
+    rl_ctx *ctx = net.ctx;
+    RL_CUDA(ctx, cudaSetDevice(ctx->device));
+    rl_adam *a = new (std::nothrow) rl_adam();
+    if (!a) return rl_fail(ctx, RL_ERR_OOM, "rl_adam_create_seq: host allocation failed");
+    a->owner = net_h;
+    a->ctx = ctx;
+    a->cfg = *cfg;
+    cudaError_t e = cudaMalloc((void **)&a->m, net.n_params * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&a->v, net.n_params * sizeof(float));
+    if (e != cudaSuccess) {
+        rl_adam_destroy(a);
+        return rl_fail(ctx, RL_ERR_OOM, "rl_adam_create_seq: %s", cudaGetErrorString(e));
+    }
+    cudaMemsetAsync(a->m, 0, net.n_params * sizeof(float), ctx->stream);
+    cudaMemsetAsync(a->v, 0, net.n_params * sizeof(float), ctx->stream);
+    *out = a;
+    return RL_OK;
+}
+
+rl_status rl_value_update_seq(rl_traj *traj, const float *targets_dev, rl_grunet *value_fn, rl_adam *adam, int32_t n_steps,
+                              rl_opt_stats *stats) {
+    if (!traj || !targets_dev || !value_fn || !adam)
+        return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_value_update_seq: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    const rl_grunet_view net = rl_grunet_view_of(value_fn);
+    RL_TRY(seq_check(ctx, traj, net, 1, "rl_value_update_seq"));
+    RL_REQUIRE(ctx, adam->owner == (void *)value_fn, "rl_value_update_seq: optimizer belongs to another module");
+    RL_REQUIRE(ctx, n_steps >= 0 && n_steps <= 100000, "rl_value_update_seq: n_steps out of range");
+    const int P = (int)net.n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T;
+    PassPlan plan;
+    SeqScratch sc;
+    RL_TRY(make_seq_plan(ctx, net, T, traj->E, (size_t)(n_steps + 1) * sizeof(double), &plan, &sc));
+    double *losses = (double *)sc.extra;
+    rl_seq_pass_args a = seq_base_args(traj, net, T, sc, plan);
+    a.target = targets_dev;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (stats) {
+        RL_CUDA(ctx, cudaEventCreate(&ev0));
+        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
+    }
+    AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
+    for (int s = 0; s < n_steps; ++s) {
+        RL_TRY(seq_pass(ctx, plan, PASS_VALUE, a));
+        adam->step += 1;
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, P, net.params, adam->m, adam->v, ac, adam->step,
+                  losses + s);
+    }
+    if (stats) {
+        RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
+        double *host;
+        RL_TRY(rl_ctx_pinned(ctx, (size_t)(n_steps + 4) * sizeof(double), (void **)&host));
+        if (n_steps > 0) RL_CUDA(ctx, cudaMemcpyAsync(host, losses, (size_t)n_steps * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaMemcpyAsync(host + n_steps, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        stats->loss_first = n_steps > 0 ? host[0] : 0.0;
+        stats->loss_last = n_steps > 0 ? host[n_steps - 1] : 0.0;
+        stats->num_steps = n_steps > 0 ? (uint64_t)host[n_steps] : 0;
+        stats->opt_steps = (uint64_t)n_steps;
+        cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return RL_OK;
 }
 
 rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cfg *cfg, rl_opt_stats *stats) {

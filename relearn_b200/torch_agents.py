@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib as L
 from .envs import BatchedEnv
-from .modules import Mlp, MlpConfig
+from .modules import GruLinear, GruLinearConfig, Mlp, MlpConfig
 from .runtime import Context, DeviceBuffer
 from .simulation import ActorSpec, HistoryDataBound, Trajectory
 
@@ -58,7 +58,8 @@ class Adam:
         self.ctx, self._lib, self.mlp = mlp.ctx, mlp.ctx._lib, mlp
         c = L.AdamCfg(cfg.learning_rate, cfg.beta1, cfg.beta2, cfg.weight_decay, cfg.eps)
         h = C.c_void_p()
-        L.check(self._lib.rl_adam_create(mlp.handle, C.byref(c), C.byref(h)), self.ctx.handle)
+        create = self._lib.rl_adam_create_seq if isinstance(mlp, GruLinear) else self._lib.rl_adam_create
+        L.check(create(mlp.handle, C.byref(c), C.byref(h)), self.ctx.handle)
         self.handle = h
 
     def close(self):
@@ -77,7 +78,7 @@ class Adam:
 class TrpoConfig:
     """policies/trpo.rs:17-59"""
 
-    policy_fn_config: MlpConfig = field(default_factory=MlpConfig)
+    policy_fn_config: object = field(default_factory=MlpConfig)  # MlpConfig | GruLinearConfig
     optimizer_config: ConjugateGradientOptimizerConfig = field(default_factory=ConjugateGradientOptimizerConfig)
     max_policy_step_kl: float = 0.01
 
@@ -92,8 +93,14 @@ class Trpo:
         self.policy_fn, self.cfg = policy_fn, cfg
         self.ctx, self._lib = policy_fn.ctx, policy_fn.ctx._lib
 
+    @property
+    def recurrent(self) -> bool:
+        return isinstance(self.policy_fn, GruLinear)
+
     def actor(self, lanes_per_env: int = 0) -> ActorSpec:
         """Policy::actor -> PolicyActor (policies/actor.rs)."""
+        if self.recurrent:
+            return ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=self.policy_fn)
         return ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=self.policy_fn, lanes_per_env=lanes_per_env)
 
     def _c_cfg(self) -> L.TrpoCfg:
@@ -106,8 +113,8 @@ class Trpo:
         (trpo.rs:154-159); the others are warnings there and are returned here."""
         stats = L.TrpoStats()
         cfg = self._c_cfg()
-        status = L.check(self._lib.rl_trpo_update(traj.handle, advantages.c, self.policy_fn.handle, C.byref(cfg),
-                                                  C.byref(stats)), self.ctx.handle)
+        fn = self._lib.rl_trpo_update_seq if self.recurrent else self._lib.rl_trpo_update
+        status = L.check(fn(traj.handle, advantages.c, self.policy_fn.handle, C.byref(cfg), C.byref(stats)), self.ctx.handle)
         if logger is not None:
             logger.update({
                 "entropy": stats.entropy, "step_size": stats.step_size, "loss_initial": stats.loss_initial,
@@ -127,7 +134,8 @@ class Trpo:
         grad = np.zeros(P, np.float32)
         fvp = np.zeros(P, np.float32)
         vec = np.ascontiguousarray(vector, np.float32) if vector is not None else None
-        L.check(self._lib.rl_trpo_probe(traj.handle, advantages.c, self.policy_fn.handle,
+        fn = self._lib.rl_trpo_probe_seq if self.recurrent else self._lib.rl_trpo_probe
+        L.check(fn(traj.handle, advantages.c, self.policy_fn.handle,
                                         vec.ctypes.data_as(C.c_void_p) if vec is not None else None,
                                         self.cfg.optimizer_config.hpv_reg_coeff, C.byref(loss), C.byref(kl),
                                         C.byref(ent), grad.ctypes.data_as(C.c_void_p),
@@ -201,7 +209,7 @@ class Reinforce(_AdamPolicy):
 class ValuesOptConfig:
     """critics/opt.rs:14-50: GAE(lambda 0.95) advantages, reward-to-go targets, 80 Adam steps, gamma <= 0.99."""
 
-    state_value_fn_config: MlpConfig = field(default_factory=MlpConfig)
+    state_value_fn_config: object = field(default_factory=MlpConfig)  # MlpConfig | GruLinearConfig
     optimizer_config: AdamConfig = field(default_factory=AdamConfig)
     gae_lambda: float = 0.95          # AdvantageFn::Gae { lambda } (critics/mod.rs:78)
     opt_steps_per_update: int = 80
@@ -217,6 +225,7 @@ class ValuesOpt:
     def __init__(self, ctx: Context, cfg: ValuesOptConfig, in_dim: int, discount_factor: float):
         self.ctx, self._lib, self.cfg = ctx, ctx._lib, cfg
         self.state_value_fn = cfg.state_value_fn_config.build_module(ctx, in_dim, 1)
+        self.recurrent = isinstance(self.state_value_fn, GruLinear)
         self.optimizer = Adam(self.state_value_fn, cfg.optimizer_config)
         self.discount_factor = np.float32(min(cfg.max_discount_factor, discount_factor))  # opt.rs:73
         self._adv = self._rtg = None
@@ -230,8 +239,9 @@ class ValuesOpt:
     def advantages(self, traj: Trajectory) -> DeviceBuffer:
         """Critic::advantages: GAE; also leaves the reward-to-go targets of this batch in `self._rtg`."""
         adv, rtg = self._buffers(traj)
-        L.check(self._lib.rl_gae(traj.handle, self.state_value_fn.handle, self.discount_factor,
-                                 np.float32(self.cfg.gae_lambda), adv.c, rtg.c), self.ctx.handle)
+        gae = self._lib.rl_gae_seq if self.recurrent else self._lib.rl_gae
+        L.check(gae(traj.handle, self.state_value_fn.handle, self.discount_factor, np.float32(self.cfg.gae_lambda), adv.c,
+                    rtg.c), self.ctx.handle)
         return adv
 
     def update(self, traj: Trajectory, logger: dict | None = None):
@@ -240,8 +250,9 @@ class ValuesOpt:
         L.check(self._lib.rl_gae(traj.handle, None, self.discount_factor, np.float32(self.cfg.gae_lambda), None, rtg.c),
                 self.ctx.handle)
         stats = L.OptStats()
-        L.check(self._lib.rl_value_update(traj.handle, rtg.c, self.state_value_fn.handle, self.optimizer.handle,
-                                          self.cfg.opt_steps_per_update, C.byref(stats)), self.ctx.handle)
+        upd = self._lib.rl_value_update_seq if self.recurrent else self._lib.rl_value_update
+        L.check(upd(traj.handle, rtg.c, self.state_value_fn.handle, self.optimizer.handle, self.cfg.opt_steps_per_update,
+                    C.byref(stats)), self.ctx.handle)
         if logger is not None:
             logger.update({"critic/loss": stats.loss_last, "critic/loss_first": stats.loss_first,
                            "critic/update_time": stats.update_ms * 1e-3})
