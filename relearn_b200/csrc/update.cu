@@ -500,6 +500,8 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
     }
 }
 
+#include "pass_tc.cuh"
+
 // rows[B][W] -> out[W] in a fixed summation order.  A block owns 32 columns; warp w sums rows
 // w, w + 8, ... (independent coalesced 256 B loads), then the 8 partials are added in warp order.
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restrict__ rows, int B, int W,
@@ -790,6 +792,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 struct PassPlan {
     int P, W, grid;
+    int grid_tc;  // CTAs of the tcgen05 critic pass (value_pass_tc_kernel); the partial rows hold max(grid, grid_tc)
     size_t smem;
     double *partials, *sums;
 };
@@ -845,13 +848,47 @@ rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool red
     }
 }
 
+// The critic pass runs on the tensor cores (pass_tc.cuh) unless RL_VALUE_PASS=ffma asks for the FP32-pipe kernel.
+bool value_pass_on_tensor_cores() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RL_VALUE_PASS");
+        v = (e && (e[0] == 'f' || e[0] == '0')) ? 0 : 1;
+    }
+    return v == 1;
+}
+
+rl_status launch_value_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(value_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TC_SMEM));
+        configured = true;
+    }
+    args.partials = plan.partials;
+    RL_LAUNCH(ctx, value_pass_tc_kernel, plan.grid_tc, tc::TC_THREADS, tc::TC_SMEM, args);
+    if (!reduce) return RL_OK;
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.sums,
+              args.skip_flag);
+    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    return RL_OK;
+}
+
 // One optimizer step on the sums of the pass just launched: pass -> [reduce -> all-reduce] -> Adam
 // (n_backward_steps: zero_grad, backward, step; torch/agents/mod.rs:50-55, coptimizer.rs:13-27).
 template <int F, int A, int UPL, int MODE>
 rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac,
                         double *loss_out) {
     adam->step += 1;
-    if (ctx->world > 1) {
+    const bool on_tc = MODE == PASS_VALUE && F == 5 && A == 1 && UPL == 4 && value_pass_on_tensor_cores();
+    if (on_tc) {
+        RL_TRY(launch_value_pass_tc(ctx, plan, pa, ctx->world > 1));
+        if (ctx->world > 1)
+            RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
+                      loss_out);
+        else
+            RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.P,
+                      plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
+    } else if (ctx->world > 1) {
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa)));
         RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
                   loss_out);
@@ -870,7 +907,10 @@ rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extr
     const uint64_t want = (ntiles + (PASS_THREADS / 32) - 1) / (PASS_THREADS / 32);
     const uint64_t cap = (uint64_t)ctx->sm_count * 2;  // persistent: 2 CTAs per SM (the FVP pass fits 1 and runs 2 waves)
     plan->grid = (int)(want < cap ? (want ? want : 1) : cap);
-    const size_t rows = (size_t)plan->grid * plan->W * sizeof(double), sums = (size_t)plan->W * sizeof(double);
+    const uint64_t tiles_tc = (TE + tc::TC_THREADS - 1) / tc::TC_THREADS, cap_tc = (uint64_t)ctx->sm_count * tc::TC_CTAS_PER_SM;
+    plan->grid_tc = (int)(tiles_tc < cap_tc ? (tiles_tc ? tiles_tc : 1) : cap_tc);
+    const size_t rows = (size_t)(plan->grid > plan->grid_tc ? plan->grid : plan->grid_tc) * plan->W * sizeof(double),
+                 sums = (size_t)plan->W * sizeof(double);
     char *buf;
     RL_TRY(rl_ctx_scratch(ctx, rows + sums + extra_bytes + 256, (void **)&buf));
     plan->partials = (double *)buf;
@@ -1160,6 +1200,34 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
         cudaEventDestroy(ev0);
         cudaEventDestroy(ev1);
     }
+    return RL_OK;
+}
+
+rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_fn, int32_t kernel, double *loss,
+                         float *grad_host) {
+    if (!traj || !targets_dev || !value_fn) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_value_probe: NULL argument");
+    rl_ctx *ctx = traj->ctx;
+    constexpr int F = 5, A = 1, UPL = 4;
+    if (!((int)traj->F == F && value_fn->in_dim == F && value_fn->out_dim == A && value_fn->hidden == 32 * UPL &&
+          value_fn->act == RL_ACT_RELU))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_value_probe: built for a %d->%d->1 ReLU critic", F, 32 * UPL);
+    RL_REQUIRE(ctx, kernel == RL_VALUE_KERNEL_FFMA || kernel == RL_VALUE_KERNEL_TCGEN05, "rl_value_probe: unknown kernel");
+    const int P = (int)value_fn->n_params;
+    const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
+    PassPlan plan;
+    RL_TRY(make_plan(ctx, P, TE, &plan, 0, nullptr));
+    PassArgs pa{};
+    pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
+    pa.theta = value_fn->params; pa.target = targets_dev;
+    if (kernel == RL_VALUE_KERNEL_TCGEN05) RL_TRY(launch_value_pass_tc(ctx, plan, pa));
+    else RL_TRY((launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa)));
+    std::vector<double> host((size_t)plan.W);
+    RL_CUDA(ctx, cudaMemcpyAsync(host.data(), plan.sums, (size_t)plan.W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double N = host[P + SC_COUNT];
+    if (loss) *loss = host[P + SC_LOSS] / N;
+    if (grad_host)
+        for (int i = 0; i < P; ++i) grad_host[i] = (float)(host[i] / N);
     return RL_OK;
 }
 

@@ -244,6 +244,18 @@ class ValuesOpt:
                     rtg.c), self.ctx.handle)
         return adv
 
+    def probe(self, traj: Trajectory, kernel: int = L.RL_VALUE_KERNEL_TCGEN05) -> dict:
+        """One full-batch pass at the current parameters: mean MSE against the reward-to-go targets and its flat
+        gradient, by the tcgen05 kernel (what `update` runs) or the FP32-pipe kernel (diagnostics / parity)."""
+        adv, rtg = self._buffers(traj)
+        L.check(self._lib.rl_gae(traj.handle, None, self.discount_factor, np.float32(self.cfg.gae_lambda), None, rtg.c),
+                self.ctx.handle)
+        loss = C.c_double()
+        grad = np.zeros(self.state_value_fn.num_params, np.float32)
+        L.check(self._lib.rl_value_probe(traj.handle, rtg.c, self.state_value_fn.handle, kernel, C.byref(loss),
+                                         grad.ctypes.data_as(C.c_void_p)), self.ctx.handle)
+        return {"loss": loss.value, "grad": grad}
+
     def update(self, traj: Trajectory, logger: dict | None = None):
         """Critic::update: targets = reward-to-go (no_grad), then n Adam steps on the MSE."""
         adv, rtg = self._buffers(traj)

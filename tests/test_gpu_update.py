@@ -159,6 +159,45 @@ def test_value_update_matches_oracle(ctx):
     assert _rel(d, d64) <= max(2e-4, 4 * _rel(d32, d64) + 1e-5)
 
 
+def _value_grad_oracle(vparams, obs, tgt, dtype):
+    flat = torch.tensor(np.asarray(vparams), dtype=dtype)
+    params = [p.clone().requires_grad_(True) for p in TO.unflatten_mlp(flat, 5, 128, 1)]
+    loss = torch.nn.functional.mse_loss(TO.mlp_forward(params, torch.tensor(obs, dtype=dtype)).squeeze(-1),
+                                        torch.tensor(tgt, dtype=dtype), reduction="mean")
+    grads = torch.autograd.grad(loss, params)
+    return float(loss), TO.flatten_tensors(list(grads)).numpy().astype(np.float64)
+
+
+@pytest.mark.parametrize("seed,E,T,scale", [(31, 80, 64, 1.0), (32, 128, 3, 1.0), (33, 37, 301, 3.0), (34, 1024, 130, 0.3)])
+def test_value_pass_tcgen05_and_ffma_match_f64_gradient(ctx, seed, E, T, scale):
+    """The critic pass on the tensor cores (bf16-piece MMAs, gradient from the mask contraction) and on the FP32
+    pipe both give the f64 autograd gradient of mse_loss(V(obs), reward-to-go) to f32 accuracy: rtol 1e-5 of the
+    gradient norm, and neither is further from f64 than 4x torch's own f32 pass (+1e-6)."""
+    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=seed)
+    rng = np.random.default_rng(seed + 100)
+    vparams = (R.init_params(rng, 5, 128, 1) * scale).astype(np.float32)
+    critic = R.ValuesOpt(ctx, R.ValuesOptConfig(), 5, 0.99)
+    critic.state_value_fn.set_weights(vparams)
+    rtg = np.zeros((T, E), np.float32)
+    for e in range(E):
+        n = int(host["lane_len"][e])
+        rtg[:n, e] = O.discounted_cumsum_lane(host["reward"][:n, e], host["succ"][:n, e], np.float32(0.99))
+    obs, tgt = host["obs"][valid], rtg[valid]
+    loss64, g64 = _value_grad_oracle(vparams, obs, tgt, torch.float64)
+    _, g32 = _value_grad_oracle(vparams, obs, tgt, torch.float32)
+    tc = critic.probe(traj, L.RL_VALUE_KERNEL_TCGEN05)
+    ff = critic.probe(traj, L.RL_VALUE_KERNEL_FFMA)
+    e_tc, e_ff, e_32 = _rel(tc["grad"], g64), _rel(ff["grad"], g64), _rel(g32, g64)
+    print(f"value grad rel err vs f64: tcgen05 {e_tc:.2e}, ffma {e_ff:.2e}, torch-f32 {e_32:.2e}; "
+          f"max abs tc-ffma {np.abs(tc['grad'] - ff['grad']).max():.2e}")
+    np.testing.assert_allclose(tc["loss"], loss64, rtol=1e-5)
+    np.testing.assert_allclose(ff["loss"], loss64, rtol=1e-5)
+    assert e_tc <= max(1e-5, 4 * e_32 + 1e-6) and e_ff <= max(1e-5, 4 * e_32 + 1e-6)
+    # per-block agreement too (a wrong operand layout would scramble units, not just perturb the norm)
+    for lo, hi in ((0, 640), (640, 768), (768, 896), (896, 897)):
+        assert _rel(tc["grad"][lo:hi], g64[lo:hi]) <= 5e-5, (lo, hi)
+
+
 def test_actor_critic_learns_cartpole(ctx):
     """Behavioural check in the spirit of agents/testing.rs: a few TRPO periods raise the mean episode length."""
     E, T = 512, 128
