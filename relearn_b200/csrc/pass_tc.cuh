@@ -12,15 +12,22 @@
 //         the 48 K-slots hold the six piece products that matter to f32 accuracy for the 5 features and the
 //         bias:  hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi   (dropped: <= 2^-24 relative each).  bf16
 //         products are exact in the f32 accumulator, so pre is an f32-accurate W1 x + b1.
-//   epilogue (thread = sample): tcgen05.ld the 128 pre-activations of the sample, h = relu, V = w2 . h + b2
-//         thread-local (no shuffles), loss and dV = 2 (V - target); the 0/1 ReLU mask goes back to shared
-//         memory as bf16 (exact), the six values y = dV * [x, 1] as 3 x bf16 pieces.
-//   MMA2  G[128 units x 18] = Mask^T[128 x 128 samples] . Y[128 x 18]             (8 x tcgen05.mma K = 16)
-//         exact 0/1 times bf16 pieces, f32 accumulation over the 128 samples of a tile, then f64 across tiles.
+//   epilogue 1 (thread = sample): tcgen05.ld the 128 pre-activations of the sample; only their SIGNS are used:
+//         the 0/1 ReLU mask as bf16 (exact), two units per PRMT + LOP3, written back to shared memory.  One spare
+//         K-slot of MMA1 adds -2^-120 to every pre-activation so that an exact +0 (a zero-initialised unit)
+//         counts as inactive, like relu'(0) = 0 in libtorch.
+//   MMA3  Q[128 samples x 18] = Mask[128 x 128 units] . C[128 x 18],  c_jf = w2_j * [w1_j, b1_j]_f in bf16 pieces
+//         (8 x tcgen05.mma K = 16; the mask is the same bytes read K-major).  ReLU is piecewise linear, so
+//         V_s = w2 . relu(pre_s) + b2 = sum_f [x_s, 1]_f * sum_j mask_sj c_jf + b2:
+//         epilogue 3 needs 18 columns and 6 FMAs per sample instead of 128 max + 128 FMA.
+//   epilogue 3: loss, dV = 2 (V - target), the six values y = dV * [x, 1] as 3 x bf16 pieces to shared memory.
+//   MMA2  G[128 units x 18] = Mask^T[128 x 128 samples] . Y[128 x 18]              (8 x tcgen05.mma K = 16)
+//         exact 0/1 times bf16 pieces, accumulated in TMEM (f32) over TC_DRAIN tiles, then in f64.
 //
-// The gradient follows from G alone:  dW1[j][f] = w2_j G[j][f],  db1[j] = w2_j G[j][5],
-//   dW2[j] = sum_s dV_s relu(pre_sj) = sum_s dV_s mask_sj (b1_j + w1_j . x_s) = b1_j G[j][5] + sum_f w1_jf G[j][f]
-// (ReLU is piecewise linear), so no second cross-sample contraction is needed.
+// The gradient follows from G_jf = sum_s mask_sj y_sf alone:
+//   dW1[j][f] = w2_j G[j][f],  db1[j] = w2_j G[j][5],
+//   dW2[j] = sum_s dV_s relu(pre_sj) = sum_s dV_s mask_sj (b1_j + w1_j . x_s) = b1_j G[j][5] + sum_f w1_jf G[j][f],
+// so no further cross-sample contraction is needed.
 //
 // Shared-memory operand layout: the no-swizzle canonical UMMA layout, 8 x 16 B core matrices stored as
 // [chunk of 8 elements along the thread-private dimension][row = thread][16 B], so every operand store is one
@@ -31,10 +38,11 @@ namespace tc {
 
 constexpr int TC_THREADS = 128;
 constexpr int TC_CHUNK = 2048;  // bytes of one 8-element chunk over 128 rows
-constexpr int TC_A1 = 0, TC_B1 = 6 * TC_CHUNK, TC_A2 = 12 * TC_CHUNK, TC_B2 = 28 * TC_CHUNK, TC_W2 = 32 * TC_CHUNK;
-constexpr int TC_RED = TC_W2 + 512, TC_BAR = TC_RED + 128, TC_TPTR = TC_BAR + 16;
+constexpr int TC_A1 = 0, TC_B1 = 6 * TC_CHUNK, TC_A2 = 12 * TC_CHUNK, TC_B2 = 28 * TC_CHUNK, TC_B3 = 32 * TC_CHUNK;
+constexpr int TC_RED = 36 * TC_CHUNK, TC_BAR = TC_RED + 512, TC_TPTR = TC_BAR + 32;
 constexpr int TC_SMEM = TC_TPTR + 16;
-constexpr int TC_CTAS_PER_SM = 3;  // 66 KB of shared memory and 128 + 32 TMEM columns each
+constexpr int TC_CTAS_PER_SM = 3;  // 73 KB of shared memory and 128 + 32 TMEM columns each
+constexpr int TC_DRAIN = 8;        // tiles accumulated in TMEM between f64 drains
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -99,6 +107,14 @@ __device__ __forceinline__ void split3(float v, uint32_t &hi, uint32_t &mid, uin
 // two upper halves -> one bf16x2 word (first element in the low half)
 __device__ __forceinline__ uint32_t pack_hi16(uint32_t first, uint32_t second) { return __byte_perm(first, second, 0x7632); }
 
+// bf16 pair (1.0 where v > 0 else 0.0) from the sign bits of two f32 values that are never +0: PRMT in sign-replicate
+// mode spreads bit 31 of each value over a half word, one LOP3 turns "negative" into 0 and the rest into 0x3F80.
+__device__ __forceinline__ uint32_t relu_mask_bf16x2(uint32_t first, uint32_t second) {
+    uint32_t neg;
+    asm("prmt.b32 %0, %1, %2, 0xFFBB;" : "=r"(neg) : "r"(first), "r"(second));
+    return ~neg & 0x3F803F80u;
+}
+
 // Store e[0 .. 8 * NCHUNK) (upper-half bf16 patterns) as row `row` of an operand: chunk c at base + c * TC_CHUNK + row * 16.
 template <int NCHUNK>
 __device__ __forceinline__ void store_row(unsigned char *base, int row, const uint32_t *e) {
@@ -115,35 +131,48 @@ __device__ __forceinline__ void store_row(unsigned char *base, int row, const ui
 __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass_tc_kernel(PassArgs a) {
     using namespace tc;
     constexpr int F = 5, H = 128, P = H * F + H + H + 1, W = P + NSCALAR;
-    constexpr int NY = 3 * (F + 1);  // 18 meaningful columns of G
+    constexpr int NF = F + 1;   // features + the bias input
+    constexpr int NY = 3 * NF;  // 18 meaningful columns of Q and SY
     if (a.skip_flag && *a.skip_flag) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2;
-    float *w2s = reinterpret_cast<float *>(smem + TC_W2);
+    unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2, *sB3 = smem + TC_B3;
     double *red = reinterpret_cast<double *>(smem + TC_RED);
     uint32_t *tptr = reinterpret_cast<uint32_t *>(smem + TC_TPTR);
-    const uint32_t bar1 = smem_u32(smem + TC_BAR), bar2 = bar1 + 8;
+    const uint32_t bar1 = smem_u32(smem + TC_BAR), bar2 = bar1 + 8, bar3 = bar1 + 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- one-time setup: this thread's hidden unit -> row `tid` of the B operand of MMA1 ----
+    // ---- one-time setup: this thread's hidden unit -> row `tid` of the B operands of MMA1 and MMA3 ----
     const float *tw1 = a.theta, *tb1 = tw1 + H * F, *tw2 = tb1 + H, *tb2 = tw2 + H;
-    float wrow[F + 1];
+    float wrow[NF];
 #pragma unroll
     for (int f = 0; f < F; ++f) wrow[f] = tw1[tid * F + f];
     wrow[F] = tb1[tid];
     const float w2j = tw2[tid], b2 = tb2[0];
-    w2s[tid] = w2j;
     {
-        uint32_t hi[F + 1], mid[F + 1], lo[F + 1], e[48];
+        uint32_t hi[NF], mid[NF], lo[NF], e[48];
 #pragma unroll
-        for (int f = 0; f <= F; ++f) split3(wrow[f], hi[f], mid[f], lo[f]);
+        for (int f = 0; f < NF; ++f) split3(wrow[f], hi[f], mid[f], lo[f]);
 #pragma unroll
         for (int k = 0; k < 48; ++k) {
-            const int g = k / (F + 1), f = k % (F + 1);  // piece pairing: x [hi hi mid mid hi lo] . w [hi mid hi mid lo hi]
-            e[k] = k >= 6 * (F + 1) ? 0u : (g == 0 || g == 2 || g == 5) ? hi[f] : (g == 1 || g == 3) ? mid[f] : lo[f];
+            const int g = k / NF, f = k % NF;  // piece pairing: x [hi hi mid mid hi lo] . w [hi mid hi mid lo hi]
+            e[k] = k == 6 * NF ? 0x83800000u   // -2^-120 against the bias input: +0 pre-activations become negative
+                   : k > 6 * NF ? 0u : (g == 0 || g == 2 || g == 5) ? hi[f] : (g == 1 || g == 3) ? mid[f] : lo[f];
         }
         store_row<6>(sB1, tid, e);
     }
+    {
+        uint32_t hi[NF], mid[NF], lo[NF], e[32];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) split3(__fmul_rn(w2j, wrow[f]), hi[f], mid[f], lo[f]);
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            const int g = k / NF, f = k % NF;
+            e[k] = k >= NY ? 0u : g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
+        }
+        store_row<4>(sB3, tid, e);
+    }
+    // the zero tail of X's rows (K-slots 40..47) never changes
+    *reinterpret_cast<uint4 *>(sA1 + 5 * TC_CHUNK + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 0) {
         tmem_alloc(smem_u32(tptr), 128);
         tmem_alloc(smem_u32(tptr + 1), 32);
@@ -152,6 +181,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
     if (tid == 0) {
         mbar_init(bar1, 1);
         mbar_init(bar2, 1);
+        mbar_init(bar3, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     fence_async_smem();
@@ -163,62 +193,71 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
 
     constexpr uint32_t IDESC1 = make_idesc(128, 128, false, false);  // X (K-major) . W1e (K-major)
     constexpr uint32_t IDESC2 = make_idesc(128, 32, true, true);     // Mask^T (MN-major) . Y (MN-major)
-    const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), aA2 = smem_u32(sA2), aB2 = smem_u32(sB2);
+    constexpr uint32_t IDESC3 = make_idesc(128, 32, false, true);    // Mask (K-major) . C (MN-major)
+    const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), aA2 = smem_u32(sA2), aB2 = smem_u32(sB2), aB3 = smem_u32(sB3);
 
     const uint64_t TE = a.T * a.E, ntiles = (TE + 127) / 128;
-    double G[NY], loss_acc = 0.0, count_acc = 0.0, gb2_acc = 0.0;
+    double SY[NY], loss_acc = 0.0, count_acc = 0.0, gb2_acc = 0.0;
 #pragma unroll
-    for (int n = 0; n < NY; ++n) G[n] = 0.0;
+    for (int n = 0; n < NY; ++n) SY[n] = 0.0;
 
+    // position of this thread's sample, advanced by one grid stride per tile without divisions
+    const uint64_t stride = (uint64_t)gridDim.x * 128, stride_t = stride / a.E, stride_e = stride - stride_t * a.E;
+    uint64_t n_next = (uint64_t)blockIdx.x * 128 + tid, t_next = n_next / a.E, e_next = n_next - t_next * a.E;
     struct Staged {
         float x[F], tgt;
-        bool valid;
+        uint8_t code;
     };
-    auto load_tile = [&](uint64_t tile, Staged &st) {
-        const uint64_t n = tile * 128 + tid;
-        const bool in_range = tile < ntiles && n < TE;
-        const uint64_t t = in_range ? n / a.E : 0, e = in_range ? n - t * a.E : 0;
-        const uint8_t code = in_range ? __ldg(a.succ + n) : (uint8_t)RL_PAD;
-        float x[F];
+    auto load_next = [&](Staged &st) {  // raw loads only: nothing here waits for the data
+        const bool in_range = n_next < TE;
+        st.code = in_range ? __ldg(a.succ + n_next) : (uint8_t)RL_PAD;
 #pragma unroll
-        for (int f = 0; f < F; ++f) x[f] = in_range ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
-        const float tgt = in_range ? __ldg(a.target + n) : 0.0f;
-        st.valid = code != RL_PAD;
-#pragma unroll
-        for (int f = 0; f < F; ++f) st.x[f] = st.valid ? x[f] : 0.0f;
-        st.tgt = st.valid ? tgt : 0.0f;
+        for (int f = 0; f < F; ++f) st.x[f] = in_range ? __ldg(a.obs + (t_next * F + f) * a.E + e_next) : 0.0f;
+        st.tgt = in_range ? __ldg(a.target + n_next) : 0.0f;
+        n_next += stride;
+        t_next += stride_t;
+        e_next += stride_e;
+        if (e_next >= a.E) {
+            e_next -= a.E;
+            t_next += 1;
+        }
     };
-    auto drain_g = [&](uint32_t parity) {
-        // G of the previous tile: wait for MMA2, read this unit's 18 columns, add in f64
+    auto drain = [&](uint32_t parity) {
+        // SY of the tiles accumulated so far: wait for the last MMA2, read this unit's 18 columns, add in f64
         mbar_wait(bar2, parity);
         fence_after();
         uint32_t r[32];
         tmem_ld32(tmem_d2 + lane_off, r);
 #pragma unroll
-        for (int n = 0; n < NY; ++n) G[n] += (double)__uint_as_float(r[n]);
+        for (int n = 0; n < NY; ++n) SY[n] += (double)__uint_as_float(r[n]);
     };
 
     Staged nxt;
-    load_tile(blockIdx.x, nxt);
+    load_next(nxt);
     uint32_t it = 0;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const Staged cur = nxt;
-        if (it > 0) drain_g((it - 1) & 1u);
+        const bool valid = nxt.code != RL_PAD;
+        float x[F];
+#pragma unroll
+        for (int f = 0; f < F; ++f) x[f] = valid ? nxt.x[f] : 0.0f;
+        const float tgt = valid ? nxt.tgt : 0.0f;
+        const bool drained = it > 0 && it % TC_DRAIN == 0;
+        if (drained) drain((it - 1) & 1u);
 
         // ---- A operand of MMA1: this sample's row of X (pieces of the 5 features and of the bias input 1) ----
         {
-            uint32_t hi[F + 1], mid[F + 1], lo[F + 1], e[48];
+            uint32_t hi[NF], mid[NF], lo[NF], e[40];
 #pragma unroll
-            for (int f = 0; f < F; ++f) split3(cur.x[f], hi[f], mid[f], lo[f]);
-            hi[F] = cur.valid ? 0x3F800000u : 0u;
+            for (int f = 0; f < F; ++f) split3(x[f], hi[f], mid[f], lo[f]);
+            hi[F] = valid ? 0x3F800000u : 0u;
             mid[F] = 0u;
             lo[F] = 0u;
 #pragma unroll
-            for (int k = 0; k < 48; ++k) {
-                const int g = k / (F + 1), f = k % (F + 1);
-                e[k] = k >= 6 * (F + 1) ? 0u : (g == 0 || g == 1 || g == 4) ? hi[f] : (g == 2 || g == 3) ? mid[f] : lo[f];
+            for (int k = 0; k < 40; ++k) {
+                const int g = k / NF, f = k % NF;
+                e[k] = k == 6 * NF ? hi[F] : k > 6 * NF ? 0u : (g == 0 || g == 1 || g == 4) ? hi[f] : (g == 2 || g == 3) ? mid[f] : lo[f];
             }
-            store_row<6>(sA1, tid, e);
+            store_row<5>(sA1, tid, e);
         }
         fence_async_smem();
         fence_before();
@@ -231,50 +270,70 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
                           IDESC1, k > 0);
             umma_commit(bar1);
         }
-        load_tile(tile + gridDim.x, nxt);  // in flight during the MMA and the epilogue
+        load_next(nxt);  // in flight during the MMAs and the epilogues
 
-        // ---- epilogue of MMA1: relu, V, mask ----
+        // ---- epilogue 1: signs of the pre-activations -> 0/1 mask (bf16), chunk = 8 units, row = sample ----
         mbar_wait(bar1, it & 1u);
+        if (it > 0 && !drained) mbar_wait(bar2, (it - 1) & 1u);  // MMA2 of the previous tile has read the mask and Y
         fence_after();
-        float2 zacc = f2(0.0f, 0.0f);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t r[32];
             tmem_ld32(tmem_d1 + lane_off + c * 32, r);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 wa = *reinterpret_cast<const float4 *>(w2s + c * 32 + q * 8);
-                const float4 wb = *reinterpret_cast<const float4 *>(w2s + c * 32 + q * 8 + 4);
-                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
                 uint32_t m[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float p0 = __uint_as_float(r[q * 8 + 2 * i]), p1 = __uint_as_float(r[q * 8 + 2 * i + 1]);
-                    zacc = __ffma2_rn(f2(wv[2 * i], wv[2 * i + 1]), f2(fmaxf(p0, 0.0f), fmaxf(p1, 0.0f)), zacc);
-                    m[i] = (p0 > 0.0f ? 0x3F80u : 0u) | (p1 > 0.0f ? 0x3F800000u : 0u);  // bf16 1.0 / 0.0
-                }
-                // Mask^T, MN-major: chunk = 8 units, row = sample
+                for (int i = 0; i < 4; ++i) m[i] = relu_mask_bf16x2(r[q * 8 + 2 * i], r[q * 8 + 2 * i + 1]);
                 *reinterpret_cast<uint4 *>(sA2 + (c * 4 + q) * TC_CHUNK + tid * 16) = make_uint4(m[0], m[1], m[2], m[3]);
             }
         }
+        fence_async_smem();
+        fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)  // 16 units per instruction; Q lands in the first 32 columns of the (consumed) D1
+                umma_bf16(tmem_d1, make_desc(aA2 + k * 2 * TC_CHUNK, TC_CHUNK, 128), make_desc(aB3 + k * 256, 128, TC_CHUNK), IDESC3, k > 0);
+            umma_commit(bar3);
+        }
+
+        // ---- epilogue 3: V, loss, dV and the Y operand ----
+        mbar_wait(bar3, it & 1u);
+        fence_after();
+        float z;
+        {
+            uint32_t r[32];
+            tmem_ld32(tmem_d1 + lane_off, r);
+            // V = sum_f [x, 1]_f * (sum_j mask_sj c_jf) + b2
+            float q[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) q[f] = (__uint_as_float(r[f]) + __uint_as_float(r[NF + f])) + __uint_as_float(r[2 * NF + f]);
+            z = q[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) z = fmaf(x[f], q[f], z);
+            z += b2;
+        }
         // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
-        const float z = (zacc.x + zacc.y) + b2;
-        const float diff = z - cur.tgt;
+        const float diff = z - tgt;
         float dz = 0.0f;
-        if (cur.valid) {
+        if (valid) {
             loss_acc += (double)(diff * diff);
             count_acc += 1.0;
             dz = 2.0f * diff;
             gb2_acc += (double)dz;
         }
         {
-            uint32_t hi[F + 1], mid[F + 1], lo[F + 1], e[32];
+            uint32_t hi[NF], mid[NF], lo[NF], e[32];
 #pragma unroll
-            for (int f = 0; f < F; ++f) split3(dz * cur.x[f], hi[f], mid[f], lo[f]);
-            split3(dz, hi[F], mid[F], lo[F]);
+            for (int f = 0; f < NF; ++f) {
+                const float y = f < F ? dz * x[f < F ? f : 0] : dz;
+                split3(y, hi[f], mid[f], lo[f]);
+            }
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-                const int g = k / (F + 1), f = k % (F + 1);
+                const int g = k / NF, f = k % NF;
                 e[k] = k >= NY ? 0u : g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
             }
             store_row<4>(sB2, tid, e);
@@ -286,45 +345,40 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
             fence_after();
 #pragma unroll
             for (int k = 0; k < 8; ++k)  // 16 samples per instruction = two 8-sample groups of 128 B
-                umma_bf16(tmem_d2, make_desc(aA2 + k * 256, 128, TC_CHUNK), make_desc(aB2 + k * 256, 128, TC_CHUNK), IDESC2, k > 0);
+                umma_bf16(tmem_d2, make_desc(aA2 + k * 256, 128, TC_CHUNK), make_desc(aB2 + k * 256, 128, TC_CHUNK), IDESC2,
+                          (k > 0 || it % TC_DRAIN != 0) ? 1u : 0u);
             umma_commit(bar2);
         }
     }
-    if (it > 0) drain_g((it - 1) & 1u);
+    if (it > 0) drain((it - 1) & 1u);
 
     // ---- this CTA's partial row ----
-    double *row = a.partials + (size_t)blockIdx.x * W;
-    double Gf[F + 1];
-#pragma unroll
-    for (int f = 0; f <= F; ++f) Gf[f] = (G[f] + G[(F + 1) + f]) + G[2 * (F + 1) + f];
-    double gw2 = (double)wrow[F] * Gf[F];
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
-        row[tid * F + f] = (double)w2j * Gf[f];
-        gw2 += (double)wrow[f] * Gf[f];
-    }
-    row[H * F + tid] = (double)w2j * Gf[F];
-    row[H * F + H + tid] = gw2;
-    const double s0 = warp_sum_f64(loss_acc), s1 = warp_sum_f64(count_acc), s2 = warp_sum_f64(gb2_acc);
+    const double s_l = warp_sum_f64(loss_acc), s_n = warp_sum_f64(count_acc), s_g = warp_sum_f64(gb2_acc);
     if (lane == 0) {
-        red[warp * 4 + 0] = s0;
-        red[warp * 4 + 1] = s1;
-        red[warp * 4 + 2] = s2;
+        red[warp * 4 + 0] = s_l;
+        red[warp * 4 + 1] = s_n;
+        red[warp * 4 + 2] = s_g;
     }
     fence_before();
     __syncthreads();
+    double *row = a.partials + (size_t)blockIdx.x * W;
+    double G[NF];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) G[f] = (SY[f] + SY[NF + f]) + SY[2 * NF + f];
+    double gw2 = (double)wrow[F] * G[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        row[tid * F + f] = (double)w2j * G[f];
+        gw2 += (double)wrow[f] * G[f];
+    }
+    row[H * F + tid] = (double)w2j * G[F];
+    row[H * F + H + tid] = gw2;
     if (tid == 0) {
-        double l = 0.0, n = 0.0, g = 0.0;
-        for (int w = 0; w < TC_THREADS / 32; ++w) {
-            l += red[w * 4 + 0];
-            n += red[w * 4 + 1];
-            g += red[w * 4 + 2];
-        }
-        row[P - 1] = g;
-        row[P + SC_LOSS] = l;
+        row[P - 1] = ((red[2] + red[6]) + red[10]) + red[14];
+        row[P + SC_LOSS] = ((red[0] + red[4]) + red[8]) + red[12];
         row[P + SC_KL] = 0.0;
         row[P + SC_ENTROPY] = 0.0;
-        row[P + SC_COUNT] = n;
+        row[P + SC_COUNT] = ((red[1] + red[5]) + red[9]) + red[13];
     }
     if (warp == 0) {
         fence_after();
