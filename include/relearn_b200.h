@@ -345,11 +345,15 @@ typedef struct rl_opt_stats { double loss_first, loss_last; uint64_t num_steps; 
 rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value_fn, rl_adam *adam, int32_t n_steps,
                           rl_opt_stats *stats);
 
+/* Which kernel runs the full-batch passes of the default networks (5 -> 128 -> 1 critic, 5 -> 128 -> 2 policy):
+ * mlp_pass_tc_kernel (tcgen05 tensor cores + TMEM; the default) or mlp_pass_kernel (FP32 pipe; also selected by
+ * RL_PASS_KERNEL=ffma in the environment).  Process-wide; for diagnostics and for parity checks between the two. */
+enum { RL_PASS_KERNEL_FFMA = 0, RL_PASS_KERNEL_TCGEN05 = 1 };
+rl_status rl_pass_kernel_select(int32_t kernel);
+
 /* One full-batch pass of the critic for diagnostics and parity checks: mse_loss(V(obs), targets) (opt.rs:109-115)
- * and its flat gradient at the current parameters, computed by the named kernel.  rl_value_update runs the
- * tcgen05 kernel (value_pass_tc_kernel, tensor cores + TMEM); RL_VALUE_KERNEL_FFMA is the FP32-pipe kernel the
- * Q-loss and policy passes use.  grad_host: f32 [num_params]; either output may be NULL. */
-enum { RL_VALUE_KERNEL_FFMA = 0, RL_VALUE_KERNEL_TCGEN05 = 1 };
+ * and its flat gradient at the current parameters, computed by the named kernel (RL_PASS_KERNEL_*).
+ * grad_host: f32 [num_params]; either output may be NULL. */
 rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_fn, int32_t kernel, double *loss,
                          float *grad_host);
 

@@ -24,7 +24,7 @@ RL_ACT_IDENTITY, RL_ACT_RELU, RL_ACT_SIGMOID, RL_ACT_TANH = 0, 1, 2, 3
  RL_ACTOR_TABULAR_EPS_GREEDY) = range(5)
 RL_STREAM_ENV_STEP, RL_STREAM_ENV_RESET, RL_STREAM_ACTOR, RL_STREAM_SAMPLER = 0, 1, 2, 3
 RL_NCCL_UNIQUE_ID_BYTES = 128
-RL_VALUE_KERNEL_FFMA, RL_VALUE_KERNEL_TCGEN05 = 0, 1
+RL_PASS_KERNEL_FFMA, RL_PASS_KERNEL_TCGEN05 = 0, 1
 
 vp = C.c_void_p
 
@@ -201,6 +201,7 @@ SIGNATURES = {
     "rl_adam_destroy": (st, [vp]),
     "rl_value_update": (st, [vp, vp, vp, vp, C.c_int32, P(OptStats)]),
     "rl_value_probe": (st, [vp, vp, vp, C.c_int32, P(C.c_double), vp]),
+    "rl_pass_kernel_select": (st, [C.c_int32]),
     "rl_trpo_update_seq": (st, [vp, vp, vp, P(TrpoCfg), P(TrpoStats)]),
     "rl_trpo_probe_seq": (st, [vp, vp, vp, vp, C.c_double, P(C.c_double), P(C.c_double), P(C.c_double), vp, vp]),
     "rl_adam_create_seq": (st, [vp, P(AdamCfg), P(vp)]),

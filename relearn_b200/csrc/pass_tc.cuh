@@ -1,8 +1,12 @@
-// pass_tc.cuh -- the critic's full-batch pass (K6) on the 5th-generation tensor cores (tcgen05 + TMEM).
+// pass_tc.cuh -- the full-batch passes of the update (K5 policy, K6 critic) on the 5th-generation tensor cores
+// (tcgen05 + TMEM).
 //
-// Same contract as mlp_pass_kernel<5, 1, 4, PASS_VALUE>: one f64 partial row [P + NSCALAR] per CTA holding the
-// sums over this CTA's samples of the loss, the sample count and the gradient of
-// mse_loss(V(obs), targets) for the 5 -> 128 -> 1 ReLU critic (ValuesOpt::update, critics/opt.rs:100-127).
+// Same contract as mlp_pass_kernel<5, A, 4, MODE>: one f64 partial row [P + NSCALAR] per CTA holding the sums over
+// this CTA's samples of the loss / KL / entropy, the sample count and the gradient (or Fisher-vector product) for
+// the 5 -> 128 -> A ReLU networks of the reference's defaults: the critic (A = 1, mse_loss(V(obs), targets),
+// critics/opt.rs:100-127) and the two-action policy (A = 2: TRPO statistics / loss+KL / gradient / Fisher-vector
+// product, trpo.rs:112-144, conjugate_gradient.rs:312-338; PPO, ppo.rs:124-138; REINFORCE, reinforce.rs:72-79).
+// The description below is for the critic; the policy differences are listed after it.
 //
 // Why this maps to tensor cores although K = 5: a CTA owns tiles of 128 samples, one sample per thread and
 // per TMEM lane, and both batch-sized contractions become MMAs whose operands are built in shared memory:
@@ -29,6 +33,12 @@
 //   dW2[j] = sum_s dV_s relu(pre_sj) = sum_s dV_s mask_sj (b1_j + w1_j . x_s) = b1_j G[j][5] + sum_f w1_jf G[j][f],
 // so no further cross-sample contraction is needed.
 //
+// Two-action policy: MMA3 has one 18-column block per logit (z_k = sum_f [x,1]_f sum_j mask_sj w2_kj [w1_j,b1_j]_f), and
+// for the Fisher-vector product a third block for the difference of the tangent logits, whose matrix is
+// (v2_0 - v2_1)_j [w1_j,b1_j] + (w2_0 - w2_1)_j [v1_j,vb1_j] (forward tangent of a piecewise-linear net, same mask).
+// Every per-sample logit gradient of a softmax sums to zero over the actions, so with two actions dz_1 = -dz_0 and
+// ONE block Y = dz_0 [x,1] gives both: dW1[j] = (w2_0j - w2_1j) G[j], dW2[0][j] = -dW2[1][j] = b1_j G[j][5] + w1_j . G[j].
+//
 // Shared-memory operand layout: the no-swizzle canonical UMMA layout, 8 x 16 B core matrices stored as
 // [chunk of 8 elements along the thread-private dimension][row = thread][16 B], so every operand store is one
 // conflict-free 16 B store per thread (a warp writes 512 contiguous bytes).
@@ -38,10 +48,12 @@ namespace tc {
 
 constexpr int TC_THREADS = 128;
 constexpr int TC_CHUNK = 2048;  // bytes of one 8-element chunk over 128 rows
-constexpr int TC_A1 = 0, TC_B1 = 6 * TC_CHUNK, TC_A2 = 12 * TC_CHUNK, TC_B2 = 28 * TC_CHUNK, TC_B3 = 32 * TC_CHUNK;
-constexpr int TC_RED = 36 * TC_CHUNK, TC_BAR = TC_RED + 512, TC_TPTR = TC_BAR + 32;
-constexpr int TC_SMEM = TC_TPTR + 16;
-constexpr int TC_CTAS_PER_SM = 3;  // 73 KB of shared memory and 128 + 32 TMEM columns each
+// operand regions, in chunks: X 5, W1e 5, one zero chunk (K-slots 40..47 of both), mask 16, Y 4, C 4 or 6
+constexpr int TC_A1 = 0, TC_B1 = 5 * TC_CHUNK, TC_Z = 10 * TC_CHUNK, TC_A2 = 11 * TC_CHUNK, TC_B2 = 27 * TC_CHUNK, TC_B3 = 31 * TC_CHUNK;
+__host__ __device__ constexpr int tc_n3(int blocks) { return (18 * blocks + 15) / 16 * 16; }  // MMA3 N: 32 / 48
+__host__ __device__ constexpr int tc_red(int blocks) { return TC_B3 + tc_n3(blocks) / 8 * TC_CHUNK; }
+__host__ __device__ constexpr int tc_smem(int blocks) { return tc_red(blocks) + 512 + 32 + 16; }
+constexpr int TC_CTAS_PER_SM = 3;  // 70.6 KB (critic) / 74.5 KB (policy) of shared memory and 128 + 32 TMEM columns each
 constexpr int TC_DRAIN = 8;        // tiles accumulated in TMEM between f64 drains
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -95,6 +107,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
                  : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                 "tcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
 // v = hi + mid + lo exactly, each piece a bf16 (returned as the upper 16 bits of an f32 pattern); truncation keeps
 // every remainder representable, so the two subtractions are exact.
 __device__ __forceinline__ void split3(float v, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
@@ -127,55 +147,98 @@ __device__ __forceinline__ void store_row(unsigned char *base, int row, const ui
 
 }  // namespace tc
 
-// One launch = one full-batch pass; grid <= TC_CTAS_PER_SM * SMs, block = 128, dynamic smem = tc::TC_SMEM.
-__global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass_tc_kernel(PassArgs a) {
+// One launch = one full-batch pass; grid <= TC_CTAS_PER_SM * SMs, block = 128, dynamic smem = tc::tc_smem(blocks).
+template <int A, int MODE>
+struct TcPass {
+    static constexpr bool FVP = MODE == PASS_FVP;
+    static constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_PPO ||
+                                     MODE == PASS_REINFORCE;
+    static constexpr bool IS_POLICY = MODE != PASS_VALUE;
+    static constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    static constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
+    static constexpr int BLOCKS = A;  // 18-column blocks of MMA3: one per logit; FVP: z_0 - z_1 and its tangent
+    static constexpr int N3 = tc::tc_n3(BLOCKS);
+    static constexpr int SMEM = tc::tc_smem(BLOCKS);
+    static_assert((A == 1 && MODE == PASS_VALUE) || (A == 2 && MODE != PASS_VALUE && MODE != PASS_QLOSS),
+                  "built for the critic and for the two-action policy");
+};
+
+template <int A, int MODE>
+__global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_tc_kernel(PassArgs a) {
     using namespace tc;
-    constexpr int F = 5, H = 128, P = H * F + H + H + 1, W = P + NSCALAR;
+    using K = TcPass<A, MODE>;
+    constexpr int F = 5, H = 128, P = H * F + H + A * H + A, W = P + NSCALAR;
     constexpr int NF = F + 1;   // features + the bias input
-    constexpr int NY = 3 * NF;  // 18 meaningful columns of Q and SY
+    constexpr int NY = 3 * NF;  // 18 columns per block: three bf16 pieces of six values
+    constexpr bool FVP = K::FVP, BACKWARD = K::BACKWARD, IS_POLICY = K::IS_POLICY;
+    constexpr int N3 = K::N3;
     if (a.skip_flag && *a.skip_flag) return;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2, *sB3 = smem + TC_B3;
-    double *red = reinterpret_cast<double *>(smem + TC_RED);
-    uint32_t *tptr = reinterpret_cast<uint32_t *>(smem + TC_TPTR);
-    const uint32_t bar1 = smem_u32(smem + TC_BAR), bar2 = bar1 + 8, bar3 = bar1 + 16;
+    double *red = reinterpret_cast<double *>(smem + tc_red(K::BLOCKS));
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(smem + tc_red(K::BLOCKS) + 512 + 32);
+    const uint32_t bar1 = smem_u32(smem + tc_red(K::BLOCKS) + 512), bar2 = bar1 + 8, bar3 = bar1 + 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup: this thread's hidden unit -> row `tid` of the B operands of MMA1 and MMA3 ----
-    const float *tw1 = a.theta, *tb1 = tw1 + H * F, *tw2 = tb1 + H, *tb2 = tw2 + H;
-    float wrow[NF];
+    const float *tw1 = a.theta, *tb1 = tw1 + H * F, *tw2 = tb1 + H, *tb2 = tw2 + A * H;
+    float wrow[NF], w2j[A], b2[A];
 #pragma unroll
     for (int f = 0; f < F; ++f) wrow[f] = tw1[tid * F + f];
     wrow[F] = tb1[tid];
-    const float w2j = tw2[tid], b2 = tb2[0];
+#pragma unroll
+    for (int k = 0; k < A; ++k) {
+        w2j[k] = tw2[k * H + tid];
+        b2[k] = tb2[k];
+    }
+    float vb2d = 0.0f;  // FVP: difference of the direction's output biases
     {
-        uint32_t hi[NF], mid[NF], lo[NF], e[48];
+        uint32_t hi[NF], mid[NF], lo[NF], e[40];
 #pragma unroll
         for (int f = 0; f < NF; ++f) split3(wrow[f], hi[f], mid[f], lo[f]);
 #pragma unroll
-        for (int k = 0; k < 48; ++k) {
+        for (int k = 0; k < 40; ++k) {
             const int g = k / NF, f = k % NF;  // piece pairing: x [hi hi mid mid hi lo] . w [hi mid hi mid lo hi]
             e[k] = k == 6 * NF ? 0x83800000u   // -2^-120 against the bias input: +0 pre-activations become negative
                    : k > 6 * NF ? 0u : (g == 0 || g == 2 || g == 5) ? hi[f] : (g == 1 || g == 3) ? mid[f] : lo[f];
         }
-        store_row<6>(sB1, tid, e);
+        store_row<5>(sB1, tid, e);
     }
     {
-        uint32_t hi[NF], mid[NF], lo[NF], e[32];
+        // C: block k holds w2_kj * [w1_j, b1_j] (logit k).  FVP: block 0 is z_0 - z_1 (all the softmax needs) and
+        // block 1 its tangent along `vec`: (v2_0 - v2_1)_j [w1_j, b1_j] + (w2_0 - w2_1)_j [v1_j, vb1_j].
+        uint32_t e[N3];
 #pragma unroll
-        for (int f = 0; f < NF; ++f) split3(__fmul_rn(w2j, wrow[f]), hi[f], mid[f], lo[f]);
+        for (int b = 0; b < K::BLOCKS; ++b) {
+            float c[NF];
+            if (!FVP) {
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-            const int g = k / NF, f = k % NF;
-            e[k] = k >= NY ? 0u : g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
+                for (int f = 0; f < NF; ++f) c[f] = __fmul_rn(w2j[b], wrow[f]);
+            } else {
+                const float w2d = w2j[0] - w2j[A > 1 ? 1 : 0];
+                if (b == 0) {
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) c[f] = __fmul_rn(w2d, wrow[f]);
+                } else {
+                    const float *pw1 = a.vec, *pb1 = pw1 + H * F, *pw2 = pb1 + H, *pb2 = pw2 + A * H;
+                    const float v2d = pw2[tid] - pw2[(A > 1 ? H : 0) + tid];
+                    vb2d = pb2[0] - pb2[A > 1 ? 1 : 0];
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) c[f] = fmaf(v2d, wrow[f], w2d * (f < F ? pw1[tid * F + (f < F ? f : 0)] : pb1[tid]));
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < NF; ++f) split3(c[f], e[b * NY + f], e[b * NY + NF + f], e[b * NY + 2 * NF + f]);
         }
-        store_row<4>(sB3, tid, e);
+#pragma unroll
+        for (int k = K::BLOCKS * NY; k < N3; ++k) e[k] = 0u;
+        store_row<N3 / 8>(sB3, tid, e);
     }
-    // the zero tail of X's rows (K-slots 40..47) never changes
-    *reinterpret_cast<uint4 *>(sA1 + 5 * TC_CHUNK + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    // K-slots 40..47 of both MMA1 operands are zero: one shared chunk
+    *reinterpret_cast<uint4 *>(smem + TC_Z + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 0) {
         tmem_alloc(smem_u32(tptr), 128);
-        tmem_alloc(smem_u32(tptr + 1), 32);
+        if (BACKWARD) tmem_alloc(smem_u32(tptr + 1), 32);
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -188,32 +251,39 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem_d1 = tptr[0], tmem_d2 = tptr[1];
+    const uint32_t tmem_d1 = tptr[0], tmem_d2 = BACKWARD ? tptr[1] : 0u;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
     constexpr uint32_t IDESC1 = make_idesc(128, 128, false, false);  // X (K-major) . W1e (K-major)
     constexpr uint32_t IDESC2 = make_idesc(128, 32, true, true);     // Mask^T (MN-major) . Y (MN-major)
-    constexpr uint32_t IDESC3 = make_idesc(128, 32, false, true);    // Mask (K-major) . C (MN-major)
+    constexpr uint32_t IDESC3 = make_idesc(128, N3, false, true);    // Mask (K-major) . C (MN-major)
     const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), aA2 = smem_u32(sA2), aB2 = smem_u32(sB2), aB3 = smem_u32(sB3);
 
     const uint64_t TE = a.T * a.E, ntiles = (TE + 127) / 128;
-    double SY[NY], loss_acc = 0.0, count_acc = 0.0, gb2_acc = 0.0;
+    double G[BACKWARD ? NY : 1], sc[NSCALAR], gb2_acc = 0.0;
 #pragma unroll
-    for (int n = 0; n < NY; ++n) SY[n] = 0.0;
+    for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSCALAR; ++k) sc[k] = 0.0;
 
     // position of this thread's sample, advanced by one grid stride per tile without divisions
     const uint64_t stride = (uint64_t)gridDim.x * 128, stride_t = stride / a.E, stride_e = stride - stride_t * a.E;
     uint64_t n_next = (uint64_t)blockIdx.x * 128 + tid, t_next = n_next / a.E, e_next = n_next - t_next * a.E;
     struct Staged {
-        float x[F], tgt;
-        uint8_t code;
+        float x[F], tgt, adv;
+        float2 lp0;
+        uint8_t code, act;
     };
     auto load_next = [&](Staged &st) {  // raw loads only: nothing here waits for the data
         const bool in_range = n_next < TE;
         st.code = in_range ? __ldg(a.succ + n_next) : (uint8_t)RL_PAD;
 #pragma unroll
         for (int f = 0; f < F; ++f) st.x[f] = in_range ? __ldg(a.obs + (t_next * F + f) * a.E + e_next) : 0.0f;
-        st.tgt = in_range ? __ldg(a.target + n_next) : 0.0f;
+        st.tgt = (MODE == PASS_VALUE && in_range) ? __ldg(a.target + n_next) : 0.0f;
+        st.act = (IS_POLICY && in_range) ? __ldg(a.action + n_next) : (uint8_t)0;
+        st.adv = (K::USES_ADV && in_range) ? __ldg(a.adv + n_next) : 0.0f;
+        st.lp0 = make_float2(0.0f, 0.0f);
+        if (K::USES_LP0 && in_range) st.lp0 = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n_next);
         n_next += stride;
         t_next += stride_t;
         e_next += stride_e;
@@ -223,13 +293,13 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
         }
     };
     auto drain = [&](uint32_t parity) {
-        // SY of the tiles accumulated so far: wait for the last MMA2, read this unit's 18 columns, add in f64
+        // G of the tiles accumulated so far: wait for the last MMA2, read this unit's 18 columns, add in f64
         mbar_wait(bar2, parity);
         fence_after();
         uint32_t r[32];
         tmem_ld32(tmem_d2 + lane_off, r);
 #pragma unroll
-        for (int n = 0; n < NY; ++n) SY[n] += (double)__uint_as_float(r[n]);
+        for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] += (double)__uint_as_float(r[n]);
     };
 
     Staged nxt;
@@ -240,8 +310,10 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
         float x[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) x[f] = valid ? nxt.x[f] : 0.0f;
-        const float tgt = valid ? nxt.tgt : 0.0f;
-        const bool drained = it > 0 && it % TC_DRAIN == 0;
+        const float tgt = valid ? nxt.tgt : 0.0f, adv_s = valid ? nxt.adv : 0.0f;
+        const float lp0[2] = {valid ? nxt.lp0.x : 0.0f, valid ? nxt.lp0.y : 0.0f};
+        const int act_s = valid ? (int)nxt.act : 0;
+        const bool drained = BACKWARD && it > 0 && it % TC_DRAIN == 0;
         if (drained) drain((it - 1) & 1u);
 
         // ---- A operand of MMA1: this sample's row of X (pieces of the 5 features and of the bias input 1) ----
@@ -265,16 +337,16 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
         if (tid == 0) {
             fence_after();
 #pragma unroll
-            for (int k = 0; k < 3; ++k)  // K = 16 per instruction = two 8-element chunks
-                umma_bf16(tmem_d1, make_desc(aA1 + k * 2 * TC_CHUNK, TC_CHUNK, 128), make_desc(aB1 + k * 2 * TC_CHUNK, TC_CHUNK, 128),
-                          IDESC1, k > 0);
+            for (int k = 0; k < 3; ++k)  // K = 16 per instruction = two 8-element chunks; the last pairs chunk 4 with the zero chunk
+                umma_bf16(tmem_d1, make_desc(aA1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TC_Z - TC_A1 - 4 * TC_CHUNK, 128),
+                          make_desc(aB1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TC_Z - TC_B1 - 4 * TC_CHUNK, 128), IDESC1, k > 0);
             umma_commit(bar1);
         }
         load_next(nxt);  // in flight during the MMAs and the epilogues
 
         // ---- epilogue 1: signs of the pre-activations -> 0/1 mask (bf16), chunk = 8 units, row = sample ----
         mbar_wait(bar1, it & 1u);
-        if (it > 0 && !drained) mbar_wait(bar2, (it - 1) & 1u);  // MMA2 of the previous tile has read the mask and Y
+        if (BACKWARD && it > 0 && !drained) mbar_wait(bar2, (it - 1) & 1u);  // MMA2 of the previous tile has read the mask and Y
         fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -294,41 +366,93 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
         if (tid == 0) {
             fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // 16 units per instruction; Q lands in the first 32 columns of the (consumed) D1
+            for (int k = 0; k < 8; ++k)  // 16 units per instruction; Q lands in the first N3 columns of the (consumed) D1
                 umma_bf16(tmem_d1, make_desc(aA2 + k * 2 * TC_CHUNK, TC_CHUNK, 128), make_desc(aB3 + k * 256, 128, TC_CHUNK), IDESC3, k > 0);
             umma_commit(bar3);
         }
 
-        // ---- epilogue 3: V, loss, dV and the Y operand ----
+        // ---- epilogue 3: the network outputs of this sample, then the per-sample algebra ----
         mbar_wait(bar3, it & 1u);
         fence_after();
-        float z;
+        float z[A], zdd = 0.0f;  // logits (or V); FVP: tangent of z_0 - z_1
         {
-            uint32_t r[32];
+            uint32_t r[N3];
             tmem_ld32(tmem_d1 + lane_off, r);
-            // V = sum_f [x, 1]_f * (sum_j mask_sj c_jf) + b2
-            float q[NF];
+            if (N3 > 32) tmem_ld16(tmem_d1 + lane_off + 32, r + 32);
 #pragma unroll
-            for (int f = 0; f < NF; ++f) q[f] = (__uint_as_float(r[f]) + __uint_as_float(r[NF + f])) + __uint_as_float(r[2 * NF + f]);
-            z = q[F];
+            for (int b = 0; b < K::BLOCKS; ++b) {
+                // sum_f [x, 1]_f * (sum_j mask_sj c_jf)
+                float acc = (__uint_as_float(r[b * NY + F]) + __uint_as_float(r[b * NY + NF + F])) + __uint_as_float(r[b * NY + 2 * NF + F]);
 #pragma unroll
-            for (int f = 0; f < F; ++f) z = fmaf(x[f], q[f], z);
-            z += b2;
+                for (int f = 0; f < F; ++f)
+                    acc = fmaf(x[f], (__uint_as_float(r[b * NY + f]) + __uint_as_float(r[b * NY + NF + f])) + __uint_as_float(r[b * NY + 2 * NF + f]), acc);
+                if (!FVP) z[b] = acc + b2[b];
+                else if (b == 0) z[0] = acc + (b2[0] - b2[A > 1 ? 1 : 0]);  // softmax([z_0 - z_1, 0]) = softmax(z)
+                else zdd = acc + vb2d;
+            }
+            if (FVP && A > 1) z[A > 1 ? 1 : 0] = 0.0f;
         }
-        // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
-        const float diff = z - tgt;
-        float dz = 0.0f;
+        float dz0 = 0.0f;  // d loss / d z_0 (two actions: d loss / d z_1 = -dz0)
         if (valid) {
-            loss_acc += (double)(diff * diff);
-            count_acc += 1.0;
-            dz = 2.0f * diff;
-            gb2_acc += (double)dz;
+            float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
+            if (IS_POLICY) {
+                float lp[A], p[A];
+                log_softmax<A>(z, lp);
+#pragma unroll
+                for (int k = 0; k < A; ++k) p[k] = expf(lp[k]);
+                const float onehot0 = act_s == 0 ? 1.0f : 0.0f;
+                if (MODE == PASS_STATS) {
+                    // trpo.rs:112-122: log-probs of the behaviour policy and its entropy (categorical.rs:62-68)
+#pragma unroll
+                    for (int k = 0; k < A; ++k) ent_s -= fmaxf(lp[k], F32_LOWEST) * p[k];
+                    reinterpret_cast<float2 *>(a.logp0)[tile * 128 + tid] = make_float2(lp[0], lp[A > 1 ? 1 : 0]);
+                }
+                if (MODE == PASS_EVAL || MODE == PASS_GRAD) {
+                    // trpo.rs:129-144: ratio = exp(logp - logp0); loss = -mean(ratio * adv); KL(p0 || p)
+                    const float lpa = act_s == 0 ? lp[0] : lp[A > 1 ? 1 : 0], lp0a = act_s == 0 ? lp0[0] : lp0[1];
+                    const float ratio = expf(lpa - lp0a);
+                    loss_s = -(ratio * adv_s);
+#pragma unroll
+                    for (int k = 0; k < A; ++k) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
+                    if (MODE == PASS_GRAD) dz0 = loss_s * (onehot0 - p[0]);
+                }
+                if (MODE == PASS_PPO) {
+                    // ppo.rs:124-138, backward as libtorch (see mlp_pass_kernel)
+                    const float lpa = act_s == 0 ? lp[0] : lp[A > 1 ? 1 : 0], lp0a = act_s == 0 ? lp0[0] : lp0[1];
+                    const float ratio = expf(lpa - lp0a);
+                    const float clipped = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+                    const float t1 = ratio * adv_s, t2 = clipped * adv_s;
+                    loss_s = -fminf(t1, t2);
+                    const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
+                    const float g = (inside || t1 < t2) ? -t1 : 0.0f;
+                    dz0 = g * (onehot0 - p[0]);
+                }
+                if (MODE == PASS_REINFORCE) {
+                    // reinforce.rs:72-79
+                    const float lpa = act_s == 0 ? lp[0] : lp[A > 1 ? 1 : 0];
+                    loss_s = -(lpa * adv_s);
+#pragma unroll
+                    for (int k = 0; k < A; ++k) ent_s -= fmaxf(lp[k], F32_LOWEST) * p[k];
+                    dz0 = -adv_s * (onehot0 - p[0]);
+                }
+                if (FVP) dz0 = p[0] * (p[A > 1 ? 1 : 0] * zdd);  // u = (diag p - p p^T) zdot with p_0 + p_1 = 1
+            } else {
+                // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
+                const float diff = z[0] - tgt;
+                loss_s = diff * diff;
+                dz0 = 2.0f * diff;
+            }
+            sc[SC_COUNT] += 1.0;
+            sc[SC_LOSS] += (double)loss_s;
+            sc[SC_KL] += (double)kl_s;
+            sc[SC_ENTROPY] += (double)ent_s;
+            gb2_acc += (double)dz0;
         }
-        {
+        if (BACKWARD) {
             uint32_t hi[NF], mid[NF], lo[NF], e[32];
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const float y = f < F ? dz * x[f < F ? f : 0] : dz;
+                const float y = f < F ? dz0 * x[f < F ? f : 0] : dz0;
                 split3(y, hi[f], mid[f], lo[f]);
             }
 #pragma unroll
@@ -337,52 +461,67 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) value_pass
                 e[k] = k >= NY ? 0u : g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
             }
             store_row<4>(sB2, tid, e);
-        }
-        fence_async_smem();
-        fence_before();
-        __syncthreads();
-        if (tid == 0) {
-            fence_after();
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; ++k)  // 16 samples per instruction = two 8-sample groups of 128 B
-                umma_bf16(tmem_d2, make_desc(aA2 + k * 256, 128, TC_CHUNK), make_desc(aB2 + k * 256, 128, TC_CHUNK), IDESC2,
-                          (k > 0 || it % TC_DRAIN != 0) ? 1u : 0u);
-            umma_commit(bar2);
+                for (int k = 0; k < 8; ++k)  // 16 samples per instruction = two 8-sample groups of 128 B
+                    umma_bf16(tmem_d2, make_desc(aA2 + k * 256, 128, TC_CHUNK), make_desc(aB2 + k * 256, 128, TC_CHUNK), IDESC2,
+                              (k > 0 || it % TC_DRAIN != 0) ? 1u : 0u);
+                umma_commit(bar2);
+            }
+        } else {
+            fence_before();
+            __syncthreads();  // every thread has read Q before the next tile's MMA1 overwrites D1
         }
     }
-    if (it > 0) drain((it - 1) & 1u);
+    if (BACKWARD && it > 0) drain((it - 1) & 1u);
 
     // ---- this CTA's partial row ----
-    const double s_l = warp_sum_f64(loss_acc), s_n = warp_sum_f64(count_acc), s_g = warp_sum_f64(gb2_acc);
+    double s_sc[NSCALAR];
+#pragma unroll
+    for (int k = 0; k < NSCALAR; ++k) s_sc[k] = warp_sum_f64(sc[k]);
+    const double s_g = warp_sum_f64(gb2_acc);
     if (lane == 0) {
-        red[warp * 4 + 0] = s_l;
-        red[warp * 4 + 1] = s_n;
-        red[warp * 4 + 2] = s_g;
+#pragma unroll
+        for (int k = 0; k < NSCALAR; ++k) red[warp * 8 + k] = s_sc[k];
+        red[warp * 8 + NSCALAR] = s_g;
     }
     fence_before();
     __syncthreads();
     double *row = a.partials + (size_t)blockIdx.x * W;
-    double G[NF];
+    if (BACKWARD) {
+        double Gf[NF];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) G[f] = (SY[f] + SY[NF + f]) + SY[2 * NF + f];
-    double gw2 = (double)wrow[F] * G[F];
+        for (int f = 0; f < NF; ++f) Gf[f] = (G[f] + G[NF + f]) + G[2 * NF + f];
+        // d/dz_1 = -d/dz_0 (A = 2): hidden-layer gradients see w2_0 - w2_1, the two output rows are opposite
+        const double wd = A > 1 ? (double)w2j[0] - (double)w2j[A > 1 ? 1 : 0] : (double)w2j[0];
+        double gw2 = (double)wrow[F] * Gf[F];
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-        row[tid * F + f] = (double)w2j * G[f];
-        gw2 += (double)wrow[f] * G[f];
+        for (int f = 0; f < F; ++f) {
+            row[tid * F + f] = wd * Gf[f];
+            gw2 += (double)wrow[f] * Gf[f];
+        }
+        row[H * F + tid] = wd * Gf[F];
+        row[H * F + H + tid] = gw2;
+        if (A > 1) row[H * F + H + H + tid] = -gw2;
+    } else {
+        for (int i = tid; i < P; i += TC_THREADS) row[i] = 0.0;
     }
-    row[H * F + tid] = (double)w2j * G[F];
-    row[H * F + H + tid] = gw2;
     if (tid == 0) {
-        row[P - 1] = ((red[2] + red[6]) + red[10]) + red[14];
-        row[P + SC_LOSS] = ((red[0] + red[4]) + red[8]) + red[12];
-        row[P + SC_KL] = 0.0;
-        row[P + SC_ENTROPY] = 0.0;
-        row[P + SC_COUNT] = ((red[1] + red[5]) + red[9]) + red[13];
+        if (BACKWARD) {
+            const double g = ((red[NSCALAR] + red[8 + NSCALAR]) + red[16 + NSCALAR]) + red[24 + NSCALAR];
+            row[P - A] = g;
+            if (A > 1) row[P - 1] = -g;
+        }
+#pragma unroll
+        for (int k = 0; k < NSCALAR; ++k) row[P + k] = ((red[k] + red[8 + k]) + red[16 + k]) + red[24 + k];
     }
     if (warp == 0) {
         fence_after();
         tmem_dealloc(tmem_d1, 128);
-        tmem_dealloc(tmem_d2, 32);
+        if (BACKWARD) tmem_dealloc(tmem_d2, 32);
     }
 }

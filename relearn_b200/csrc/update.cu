@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(256)
 // ------------------------------------------------------------------------------------------------
 struct PassPlan {
     int P, W, grid;
-    int grid_tc;  // CTAs of the tcgen05 critic pass (value_pass_tc_kernel); the partial rows hold max(grid, grid_tc)
+    int grid_tc;  // CTAs of the tcgen05 passes (mlp_pass_tc_kernel); the partial rows hold max(grid, grid_tc)
     size_t smem;
     double *partials, *sums;
 };
@@ -822,6 +822,50 @@ rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args, 
     return RL_OK;
 }
 
+// Passes of the reference's default networks (5 -> 128 -> 1 critic, 5 -> 128 -> 2 policy) run on the tensor cores
+// (pass_tc.cuh); the Q-loss pass and RL_PASS_KERNEL=ffma / rl_pass_kernel_select(RL_PASS_KERNEL_FFMA) use the FP32-pipe
+// kernel above.
+int g_pass_kernel = -1;
+int pass_kernel() {
+    if (g_pass_kernel < 0) {
+        const char *e = getenv("RL_PASS_KERNEL");
+        g_pass_kernel = (e && (e[0] == 'f' || e[0] == '0')) ? RL_PASS_KERNEL_FFMA : RL_PASS_KERNEL_TCGEN05;
+    }
+    return g_pass_kernel;
+}
+template <int F, int A, int UPL, int MODE>
+constexpr bool tc_built() {
+    return F == 5 && UPL == 4 &&
+           ((A == 1 && MODE == PASS_VALUE) || (A == 2 && (MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD ||
+                                                          MODE == PASS_FVP || MODE == PASS_PPO || MODE == PASS_REINFORCE)));
+}
+template <int F, int A, int UPL, int MODE>
+bool pass_on_tensor_cores() {
+    return tc_built<F, A, UPL, MODE>() && pass_kernel() == RL_PASS_KERNEL_TCGEN05;
+}
+// rows of plan.partials the pass writes
+template <int F, int A, int UPL, int MODE>
+int pass_rows(const PassPlan &plan) {
+    return pass_on_tensor_cores<F, A, UPL, MODE>() ? plan.grid_tc : plan.grid;
+}
+
+template <int A, int MODE>
+rl_status launch_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce) {
+    constexpr int smem = TcPass<A, MODE>::SMEM;
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_pass_tc_kernel<A, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    args.partials = plan.partials;
+    RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), plan.grid_tc, tc::TC_THREADS, smem, args);
+    if (!reduce) return RL_OK;
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.sums,
+              args.skip_flag);
+    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    return RL_OK;
+}
+
 int pass_variant() {
     static int v = -1;
     if (v < 0) {
@@ -836,6 +880,9 @@ int pass_variant() {
 // gradient / Fisher-vector passes need the registers of 1 CTA/SM.  RL_PASS_VARIANT overrides (experiments).
 template <int F, int A, int UPL, int MODE>
 rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
+    if constexpr (tc_built<F, A, UPL, MODE>()) {
+        if (pass_on_tensor_cores<F, A, UPL, MODE>()) return launch_pass_tc<A, MODE>(ctx, plan, args, reduce);
+    }
     switch (pass_variant()) {
     case 1: return launch_pass_variant<F, A, UPL, MODE, 8, 1>(ctx, plan, args, reduce);
     case 2: return launch_pass_variant<F, A, UPL, MODE, 4, 2>(ctx, plan, args, reduce);
@@ -848,54 +895,20 @@ rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool red
     }
 }
 
-// The critic pass runs on the tensor cores (pass_tc.cuh) unless RL_VALUE_PASS=ffma asks for the FP32-pipe kernel.
-bool value_pass_on_tensor_cores() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("RL_VALUE_PASS");
-        v = (e && (e[0] == 'f' || e[0] == '0')) ? 0 : 1;
-    }
-    return v == 1;
-}
-
-rl_status launch_value_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
-    static bool configured = false;
-    if (!configured) {
-        RL_CUDA(ctx, cudaFuncSetAttribute(value_pass_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::TC_SMEM));
-        configured = true;
-    }
-    args.partials = plan.partials;
-    RL_LAUNCH(ctx, value_pass_tc_kernel, plan.grid_tc, tc::TC_THREADS, tc::TC_SMEM, args);
-    if (!reduce) return RL_OK;
-    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.sums,
-              args.skip_flag);
-    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
-    return RL_OK;
-}
-
 // One optimizer step on the sums of the pass just launched: pass -> [reduce -> all-reduce] -> Adam
 // (n_backward_steps: zero_grad, backward, step; torch/agents/mod.rs:50-55, coptimizer.rs:13-27).
 template <int F, int A, int UPL, int MODE>
 rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac,
                         double *loss_out) {
     adam->step += 1;
-    const bool on_tc = MODE == PASS_VALUE && F == 5 && A == 1 && UPL == 4 && value_pass_on_tensor_cores();
-    if (on_tc) {
-        RL_TRY(launch_value_pass_tc(ctx, plan, pa, ctx->world > 1));
-        if (ctx->world > 1)
-            RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
-                      loss_out);
-        else
-            RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.P,
-                      plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
-    } else if (ctx->world > 1) {
+    if (ctx->world > 1) {
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa)));
         RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
                   loss_out);
     } else {
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
-        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.P,
-                  plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(plan)),
+                  plan.W, plan.P, plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
     }
     return RL_OK;
 }
@@ -1211,7 +1224,7 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
     if (!((int)traj->F == F && value_fn->in_dim == F && value_fn->out_dim == A && value_fn->hidden == 32 * UPL &&
           value_fn->act == RL_ACT_RELU))
         return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_value_probe: built for a %d->%d->1 ReLU critic", F, 32 * UPL);
-    RL_REQUIRE(ctx, kernel == RL_VALUE_KERNEL_FFMA || kernel == RL_VALUE_KERNEL_TCGEN05, "rl_value_probe: unknown kernel");
+    RL_REQUIRE(ctx, kernel == RL_PASS_KERNEL_FFMA || kernel == RL_PASS_KERNEL_TCGEN05, "rl_value_probe: unknown kernel");
     const int P = (int)value_fn->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
@@ -1219,8 +1232,11 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
     PassArgs pa{};
     pa.obs = traj->obs; pa.action = traj->action; pa.succ = traj->succ; pa.T = T; pa.E = traj->E;
     pa.theta = value_fn->params; pa.target = targets_dev;
-    if (kernel == RL_VALUE_KERNEL_TCGEN05) RL_TRY(launch_value_pass_tc(ctx, plan, pa));
-    else RL_TRY((launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa)));
+    const int selected = pass_kernel();
+    g_pass_kernel = kernel;
+    const rl_status launched = launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa);
+    g_pass_kernel = selected;
+    RL_TRY(launched);
     std::vector<double> host((size_t)plan.W);
     RL_CUDA(ctx, cudaMemcpyAsync(host.data(), plan.sums, (size_t)plan.W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1228,6 +1244,12 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
     if (loss) *loss = host[P + SC_LOSS] / N;
     if (grad_host)
         for (int i = 0; i < P; ++i) grad_host[i] = (float)(host[i] / N);
+    return RL_OK;
+}
+
+rl_status rl_pass_kernel_select(int32_t kernel) {
+    if (kernel != RL_PASS_KERNEL_FFMA && kernel != RL_PASS_KERNEL_TCGEN05) return RL_ERR_INVALID_ARG;
+    g_pass_kernel = kernel;
     return RL_OK;
 }
 

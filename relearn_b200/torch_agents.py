@@ -244,7 +244,7 @@ class ValuesOpt:
                     rtg.c), self.ctx.handle)
         return adv
 
-    def probe(self, traj: Trajectory, kernel: int = L.RL_VALUE_KERNEL_TCGEN05) -> dict:
+    def probe(self, traj: Trajectory, kernel: int = L.RL_PASS_KERNEL_TCGEN05) -> dict:
         """One full-batch pass at the current parameters: mean MSE against the reward-to-go targets and its flat
         gradient, by the tcgen05 kernel (what `update` runs) or the FP32-pipe kernel (diagnostics / parity)."""
         adv, rtg = self._buffers(traj)

@@ -22,6 +22,15 @@ torch = pytest.importorskip("torch")
 CARTPOLE = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
 
 
+@pytest.fixture(params=["tcgen05", "ffma"])
+def pass_kernel(request):
+    """Run a test once per full-batch pass kernel: tensor cores (the default) and the FP32-pipe kernel."""
+    k = L.RL_PASS_KERNEL_TCGEN05 if request.param == "tcgen05" else L.RL_PASS_KERNEL_FFMA
+    L.check(L.lib().rl_pass_kernel_select(k))
+    yield request.param
+    L.check(L.lib().rl_pass_kernel_select(L.RL_PASS_KERNEL_TCGEN05))
+
+
 def _collect(ctx, E, T, seed, scale=1.0):
     """Roll a random-init policy on CartPole and return (env, traj, params, flattened valid batch)."""
     rng = np.random.default_rng(seed)
@@ -41,9 +50,9 @@ def _rel(a, b):
                  max(np.linalg.norm(np.asarray(b, np.float64)), 1e-300))
 
 
-def test_trpo_probe_loss_grad_fvp(ctx):
-    E, T = 96, 80
-    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=1, scale=2.0)
+@pytest.mark.parametrize("E,T,seed,scale", [(96, 80, 1, 2.0), (1000, 33, 2, 1.0), (130, 257, 3, 4.0)])
+def test_trpo_probe_loss_grad_fvp(ctx, pass_kernel, E, T, seed, scale):
+    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=seed, scale=scale)
     rng = np.random.default_rng(2)
     adv = rng.normal(size=(T, E)).astype(np.float32)
     adv_d = ctx.to_device(adv)
@@ -86,7 +95,7 @@ def _run_trpo(ctx, seed, E, T, reg):
 
 
 @pytest.mark.parametrize("seed,E,T,reg", [(3, 64, 64, 0.1), (6, 128, 96, 0.1), (7, 40, 300, 0.3)])
-def test_trpo_update_well_conditioned_matches_f64(ctx, seed, E, T, reg):
+def test_trpo_update_well_conditioned_matches_f64(ctx, pass_kernel, seed, E, T, reg):
     """With a regulariser that makes 10 CG iterations numerically stable, the whole step (CG, step size,
     line search) reproduces the f64 run of the reference algorithm: parameter delta within 2e-5 relative (or
     within 1.25x of what the reference-style torch f32 run itself achieves, capped at 1e-4)."""
@@ -102,7 +111,7 @@ def test_trpo_update_well_conditioned_matches_f64(ctx, seed, E, T, reg):
 
 
 @pytest.mark.parametrize("seed,E,T", [(3, 64, 64), (4, 200, 100), (5, 33, 257)])
-def test_trpo_update_default_config(ctx, seed, E, T):
+def test_trpo_update_default_config(ctx, pass_kernel, seed, E, T):
     """Reference defaults (hpv_reg_coeff 1e-5): ten f32 CG iterations on a near-singular Fisher matrix are not
     numerically stable -- the reference-style f32 run itself lands 20-60% away from its own f64 run.  The kernel
     must (i) make the same accept/backtrack decision as the f32 run or the f64 run, (ii) be no further from the
@@ -116,7 +125,7 @@ def test_trpo_update_default_config(ctx, seed, E, T):
     assert _rel(d, d64) <= 1.5 * _rel(d32, d64) + 1e-5
 
 
-def test_trpo_update_rejects_and_restores(ctx):
+def test_trpo_update_rejects_and_restores(ctx, pass_kernel):
     """LossNotImproving: with all-zero advantages the loss cannot decrease; parameters must be restored
     (conjugate_gradient.rs:228-251)."""
     E, T = 64, 32
@@ -133,7 +142,7 @@ def test_trpo_update_rejects_and_restores(ctx):
     assert log32["error"] == "LossNotImproving"
 
 
-def test_value_update_matches_oracle(ctx):
+def test_value_update_matches_oracle(ctx, pass_kernel):
     E, T, steps = 80, 64, 20
     env, traj, net, params, host, valid = _collect(ctx, E, T, seed=11)
     rng = np.random.default_rng(12)
@@ -185,8 +194,8 @@ def test_value_pass_tcgen05_and_ffma_match_f64_gradient(ctx, seed, E, T, scale):
     obs, tgt = host["obs"][valid], rtg[valid]
     loss64, g64 = _value_grad_oracle(vparams, obs, tgt, torch.float64)
     _, g32 = _value_grad_oracle(vparams, obs, tgt, torch.float32)
-    tc = critic.probe(traj, L.RL_VALUE_KERNEL_TCGEN05)
-    ff = critic.probe(traj, L.RL_VALUE_KERNEL_FFMA)
+    tc = critic.probe(traj, L.RL_PASS_KERNEL_TCGEN05)
+    ff = critic.probe(traj, L.RL_PASS_KERNEL_FFMA)
     e_tc, e_ff, e_32 = _rel(tc["grad"], g64), _rel(ff["grad"], g64), _rel(g32, g64)
     print(f"value grad rel err vs f64: tcgen05 {e_tc:.2e}, ffma {e_ff:.2e}, torch-f32 {e_32:.2e}; "
           f"max abs tc-ffma {np.abs(tc['grad'] - ff['grad']).max():.2e}")
@@ -224,7 +233,7 @@ def _policy_batch(ctx, seed, E, T):
 
 
 @pytest.mark.parametrize("seed,E,T,steps,clip", [(21, 64, 64, 10, 0.2), (22, 100, 90, 25, 0.05)])
-def test_ppo_update_matches_oracle(ctx, seed, E, T, steps, clip):
+def test_ppo_update_matches_oracle(ctx, pass_kernel, seed, E, T, steps, clip):
     """Ppo::update (ppo.rs:97-147): opt_steps Adam steps on the clipped surrogate.  Parameter delta within
     max(2e-4, 4x the torch-f32 run's own distance from the f64 run); the small clip makes the clipped branch and
     its zero gradient active on many samples."""
@@ -246,7 +255,7 @@ def test_ppo_update_matches_oracle(ctx, seed, E, T, steps, clip):
     assert _rel(d, d64) <= max(2e-4, 4 * _rel(d32, d64) + 1e-5)
 
 
-def test_reinforce_update_matches_oracle(ctx):
+def test_reinforce_update_matches_oracle(ctx, pass_kernel):
     """Reinforce::update (reinforce.rs:64-89): one Adam step on -(log_probs * advantages).mean()."""
     env, traj, net, params, host, valid, adv, adv_d = _policy_batch(ctx, 31, 80, 70)
     policy = R.Reinforce(net, R.ReinforceConfig())
