@@ -115,6 +115,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
                  : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+// the first 18 (one block) or 36 (two blocks) columns of this thread's lane: TMEM reads are 64 B/clk per SM, so
+// the padding columns are not fetched
+template <int BLOCKS>
+__device__ __forceinline__ void tmem_ld_blocks(uint32_t taddr, uint32_t *r) {
+    if (BLOCKS == 1) {
+        tmem_ld16(taddr, r);
+        tmem_ld2(taddr + 16, r + 16);
+    } else {
+        tmem_ld32(taddr, r);
+        tmem_ld4(taddr + 32, r + 32);
+    }
+}
+
 // v = hi + mid + lo exactly, each piece a bf16 (returned as the upper 16 bits of an f32 pattern); truncation keeps
 // every remainder representable, so the two subtractions are exact.
 __device__ __forceinline__ void split3(float v, uint32_t &hi, uint32_t &mid, uint32_t &lo) {
@@ -296,8 +317,8 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         // G of the tiles accumulated so far: wait for the last MMA2, read this unit's 18 columns, add in f64
         mbar_wait(bar2, parity);
         fence_after();
-        uint32_t r[32];
-        tmem_ld32(tmem_d2 + lane_off, r);
+        uint32_t r[NY];
+        tmem_ld_blocks<1>(tmem_d2 + lane_off, r);
 #pragma unroll
         for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] += (double)__uint_as_float(r[n]);
     };
@@ -376,9 +397,8 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         fence_after();
         float z[A], zdd = 0.0f;  // logits (or V); FVP: tangent of z_0 - z_1
         {
-            uint32_t r[N3];
-            tmem_ld32(tmem_d1 + lane_off, r);
-            if (N3 > 32) tmem_ld16(tmem_d1 + lane_off + 32, r + 32);
+            uint32_t r[K::BLOCKS * NY];
+            tmem_ld_blocks<K::BLOCKS>(tmem_d1 + lane_off, r);
 #pragma unroll
             for (int b = 0; b < K::BLOCKS; ++b) {
                 // sum_f [x, 1]_f * (sum_j mask_sj c_jf)
