@@ -36,6 +36,11 @@ B_PER_STEP_ROLLOUT = 26      # obs 5 x f32 + action u8 + reward f32 + succ u8 (D
 B_PER_STEP_UNFUSED = 98      # K1 (f64 state)
 B_PER_STEP_SCAN = 17         # K3
 FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
+# K6 critic pass: forward 1536 + backward 3072 FLOP per sample per Adam iteration (the network's own
+# arithmetic).  What the tcgen05 kernel issues per 128-sample tile is larger (bf16-piece operands, padded N):
+# MMA1 128x128x48, MMA3 128x32x128, MMA2 128x32x128  =>  2 * (786432 + 524288 + 524288) / 128 = 28672 FLOP per sample.
+FLOP_PER_SAMPLE_CRITIC = 4608
+FLOP_ISSUED_PER_SAMPLE_CRITIC_TC = 28672
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2c launch at E = 4096, T = 256 from the round-1
 # `ncu --set full` capture (profiles/r1_summary.md section 2): 36.1 KB + 2.6 KB.  The 27 MB trajectory of a
 # period stays in the 126 MB L2 while the kernel runs and drains afterwards, so the in-kernel DRAM traffic
@@ -50,6 +55,40 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure (the critic pass runs 80 times back to back inside a long step)."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+    return 1500.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_update_baseline(n_steps: int, seed: int = 0):
+    """The reference's update on the host: torch-CPU restatement of Trpo::update + ValuesOpt::update (oracle/
+    tensor_oracle.py, all host threads) on a bounded sample of the same batch distribution."""
+    import torch
+
+    from oracle import tensor_oracle as TO
+    from relearn_b200.modules import init_params
+
+    rng = np.random.default_rng(seed)
+    obs = rng.uniform(-1, 1, size=(n_steps, 5)).astype(np.float32)
+    act = rng.integers(0, 2, n_steps)
+    adv = rng.normal(size=n_steps).astype(np.float32)
+    tgt = rng.uniform(0, 50, size=n_steps).astype(np.float32)
+    pp, vp = init_params(rng, 5, 128, 2), init_params(rng, 5, 128, 1)
+    t0 = time.perf_counter()
+    TO.trpo_update(pp, 5, 128, 2, obs, act, adv)
+    t1 = time.perf_counter()
+    TO.value_update(vp, 5, 128, obs, tgt, n_steps=80)
+    t2 = time.perf_counter()
+    return {"batch_steps": n_steps, "trpo_policy_ms": (t1 - t0) * 1e3, "critic_80_adam_ms": (t2 - t1) * 1e3,
+            "threads": torch.get_num_threads(), "kind": "port (torch-CPU autograd restatement, f32)"}
 
 
 class ClockSampler:
@@ -311,11 +350,24 @@ def run_ours(args):
                 upd["policy_ms"].append(log["policy/update_time"] * 1e3)
                 upd["critic_ms"].append(cstats.update_ms)
                 upd["status"].append(int(status))
+        adv_ms = float(np.mean(upd["adv_est_ms"]))
+        pol_ms = max_over_ranks(dist, local, float(np.mean(upd["policy_ms"])))
+        cri_ms = max_over_ranks(dist, local, float(np.mean(upd["critic_ms"])))
+        tpeak, tpeak_src = measured_tensor_peak()
+        fp32_peak = line.get("fp32", {}).get("measured_fma_peak_tflops")
+        alg = FLOP_PER_SAMPLE_CRITIC * steps_per_period * 80 / (cri_ms * 1e-3) / 1e12
+        issued = FLOP_ISSUED_PER_SAMPLE_CRITIC_TC * steps_per_period * 80 / (cri_ms * 1e-3) / 1e12
         line["update"] = {
-            "batch_steps_per_gpu": steps_per_period, "adv_est_ms": float(np.mean(upd["adv_est_ms"])),
-            "trpo_policy_ms": max_over_ranks(dist, local, float(np.mean(upd["policy_ms"]))),
-            "critic_80_adam_ms": max_over_ranks(dist, local, float(np.mean(upd["critic_ms"]))), "status": upd["status"],
+            "batch_steps_per_gpu": steps_per_period, "adv_est_ms": adv_ms, "trpo_policy_ms": pol_ms,
+            "critic_80_adam_ms": cri_ms, "total_ms": adv_ms + pol_ms + cri_ms, "status": upd["status"],
+            "pass_kernel": os.environ.get("RL_PASS_KERNEL", "tcgen05"),
             "all_reduce": "nccl f64 sum of grad/FVP/scalars" if world > 1 else "none (1 GPU)",
+            # the critic's 80 passes + Adam steps as one region: the network's own FLOPs per second (compare with the
+            # FP32 FMA peak, which bounds any non-tensor implementation) and the bf16 FLOPs the MMAs issue
+            "critic_roofline": {"bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak,
+                                "peak_source": tpeak_src, "algorithmic_tflops": alg, "fp32_fma_peak_tflops": fp32_peak,
+                                "note": "achieved = bf16 FLOPs issued by the three MMAs per tile (pieces + padding, 28 672 per "
+                                        "sample); algorithmic_tflops = 4608 FLOP per sample per iteration of the f32 network"},
         }
     # ---- per-kernel rooflines for the HBM-bound kernels (rank 0, 1 GPU only) ----
     if rank == 0 and world == 1 and not args.quick:
@@ -331,6 +383,11 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": periods * E * T / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{periods} periods of {E} lanes x {T} steps ({cpu_s:.1f} s wall) of the same "
                                           f"workload, C oracle port of Steps::step + PolicyActor::act, {cores} threads"}
+        if not args.no_update:
+            try:
+                line["update"]["cpu_baseline"] = cpu_update_baseline(1 << 16)
+            except Exception as exc:  # torch missing on the box: report, do not fail the bench
+                line["update"]["cpu_baseline"] = {"unavailable": repr(exc)[:200]}
     if rank == 0:
         emit(line)
     if dist is not None:
