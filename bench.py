@@ -361,7 +361,9 @@ def run_ours(args):
             "batch_steps_per_gpu": steps_per_period, "adv_est_ms": adv_ms, "trpo_policy_ms": pol_ms,
             "critic_80_adam_ms": cri_ms, "total_ms": adv_ms + pol_ms + cri_ms, "status": upd["status"],
             "pass_kernel": os.environ.get("RL_PASS_KERNEL", "tcgen05"),
-            "all_reduce": "nccl f64 sum of grad/FVP/scalars" if world > 1 else "none (1 GPU)",
+            "all_reduce": ("none (1 GPU)" if world == 1 else
+                           "fused row-reduction + NVLink peer-mailbox exchange (+ Adam), one kernel per pass"
+                           if ctx.comm_peer_info()["peer_mailboxes"] else "reduce + ncclAllReduce (f64 sums)"),
             # the critic's 80 passes + Adam steps as one region: the network's own FLOPs per second (compare with the
             # FP32 FMA peak, which bounds any non-tensor implementation) and the bf16 FLOPs the MMAs issue
             "critic_roofline": {"bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak,

@@ -107,6 +107,11 @@ rl_status rl_free_host(rl_ctx *ctx, void *host);
 rl_status rl_nccl_unique_id(void *out_id128);
 rl_status rl_ctx_comm_init(rl_ctx *ctx, const void *unique_id128, int32_t rank, int32_t world_size);
 rl_status rl_ctx_comm_info(rl_ctx *ctx, int32_t *rank, int32_t *world_size);
+/* Whether the update's reductions run as ONE kernel per pass that sums the partial rows and exchanges the sums
+ * with every peer through CUDA-IPC-mapped mailboxes over NVLink (peer_mailboxes = 1; set up by rl_ctx_comm_init
+ * on a single node, RL_XREDUCE=nccl disables it) or as reduce + ncclAllReduce (0), and whether any wait for a peer
+ * timed out (then the results of that update are invalid).  Synchronises the context stream. */
+rl_status rl_ctx_comm_peer_info(rl_ctx *ctx, int32_t *peer_mailboxes, int32_t *timed_out);
 /* In-place sum all-reduce of `n` f64 on the context stream (used by the update kernels; exposed
  * for tests). */
 rl_status rl_ctx_allreduce_f64(rl_ctx *ctx, double *buf_dev, size_t n);

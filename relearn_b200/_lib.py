@@ -158,6 +158,7 @@ SIGNATURES = {
     "rl_nccl_unique_id": (st, [vp]),
     "rl_ctx_comm_init": (st, [vp, vp, C.c_int32, C.c_int32]),
     "rl_ctx_comm_info": (st, [vp, P(C.c_int32), P(C.c_int32)]),
+    "rl_ctx_comm_peer_info": (st, [vp, P(C.c_int32), P(C.c_int32)]),
     "rl_ctx_allreduce_f64": (st, [vp, vp, C.c_size_t]),
     "rl_cartpole_cfg_default": (None, [P(CartPoleCfg), C.c_uint64]),
     "rl_chain_cfg_default": (None, [P(ChainCfg)]),

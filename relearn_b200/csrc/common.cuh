@@ -12,6 +12,18 @@
 
 #include "../../include/relearn_b200.h"
 
+// Peer mailboxes for the fused row-reduction + all-reduce (update.cu reduce_rows_x_kernel): every rank owns one
+// mailbox in its own HBM, mapped into every peer of the node through CUDA IPC (NVLink / NVSwitch peer memory).
+constexpr int RL_X_MAX_RANKS = 8;     // one node
+constexpr int RL_X_BLOCKS = 64;       // 32-column blocks per message set: W <= 2048
+constexpr int RL_X_SLOT = 40;         // doubles per (source rank, block): 32 column sums, count, loss, padding
+struct rl_xpeer {
+    double *data[RL_X_MAX_RANKS];               // data[owner]: [2 parity][world][RL_X_BLOCKS][RL_X_SLOT]
+    unsigned long long *flag[RL_X_MAX_RANKS];   // flag[owner]: [2 parity][world][RL_X_BLOCKS] sequence numbers
+    int rank, world;
+    int *error;                                 // set when a wait timed out (a peer never arrived)
+};
+
 struct rl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -24,6 +36,12 @@ struct rl_ctx {
     // NCCL data-parallel group (nccl.cu)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // peer mailboxes (nccl.cu sets them up after the communicator; x_ok false => NCCL all-reduce)
+    bool x_ok = false;
+    rl_xpeer x{};
+    void *x_local = nullptr;               // this rank's mailbox allocation
+    void *x_remote[RL_X_MAX_RANKS] = {};   // IPC mappings of the peers' mailboxes
+    unsigned long long x_seq = 0;          // collectives issued so far (identical on every rank)
     // scratch for small reductions (lazily grown)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;

@@ -787,6 +787,120 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Row reduction fused with the cross-GPU sum (and, for the optimizer loops, with Adam): the multi-GPU form of
+// reduce_rows_kernel / reduce_rows_adam_kernel.  Block b reduces its 32 columns over this rank's partial rows, PUSHES
+// the 32 sums (+ this rank's sample count and loss) into slot [parity][rank][b] of every peer's mailbox over NVLink,
+// publishes the collective's sequence number in the matching flag, then waits on its OWN mailbox for the same slot
+// of every source rank and adds the slots in rank order -- the same order on every rank, so all ranks hold
+// bit-identical sums and no broadcast is needed.  One launch replaces reduce + ncclAllReduce (+ Adam); the data
+// path is 7 KB of peer stores per rank and the waits are local polls.
+//   Slot reuse: collective k uses parity k & 1.  A rank can reach collective k + 2 only after it completed k + 1,
+// i.e. after every peer posted k + 1, which a peer does (stream order) after it finished reading k.  Skipped passes
+// (device-side skip flag, identical on every rank) still run the exchange so that parities stay aligned.
+struct XAdam {
+    float *theta, *m, *v;
+    AdamArgs c;
+    uint64_t step;
+    double *loss_out;
+    int P;
+};
+template <bool ADAM>
+__global__ void __launch_bounds__(256)
+    reduce_rows_x_kernel(const double *__restrict__ rows, int B, int W, int P, double *__restrict__ sums, rl_xpeer x,
+                         unsigned long long seq, const int *skip_flag, XAdam ad) {
+    __shared__ double part[8][32];
+    __shared__ double cnt_part[8], loss_part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const bool skip = skip_flag && *skip_flag;
+    double s = 0.0;
+    if (col < W && !skip) {
+#pragma unroll 8
+        for (int b = warp; b < B; b += 8) s += rows[(size_t)b * W + col];
+    }
+    part[warp][lane] = s;
+    double cn = 0.0, ls = 0.0;
+    if (ADAM && !skip) {
+        for (int b = threadIdx.x; b < B; b += 256) {
+            cn += rows[(size_t)b * W + P + SC_COUNT];
+            ls += rows[(size_t)b * W + P + SC_LOSS];
+        }
+        cn = warp_sum_f64(cn);
+        ls = warp_sum_f64(ls);
+    }
+    if (lane == 0) {
+        cnt_part[warp] = cn;
+        loss_part[warp] = ls;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    double t = 0.0, N = 0.0, lsum = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        t += part[w][lane];
+        N += cnt_part[w];
+        lsum += loss_part[w];
+    }
+    // ---- push this block's message to every rank (own mailbox included) ----
+    const size_t par = (size_t)(seq & 1ull);
+    const size_t slot_out = (par * x.world + x.rank) * RL_X_BLOCKS + blockIdx.x;
+    for (int p = 0; p < x.world; ++p) {
+        double *dst = x.data[p] + slot_out * RL_X_SLOT;
+        dst[lane] = t;
+        if (lane == 0) {
+            dst[32] = N;
+            dst[33] = lsum;
+        }
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < x.world) {
+        volatile unsigned long long *f = x.flag[lane] + slot_out;
+        *f = seq;
+    }
+    // ---- wait for every source rank's message in the own mailbox ----
+    if (lane < x.world) {
+        const volatile unsigned long long *f = x.flag[x.rank] + (par * x.world + lane) * RL_X_BLOCKS + blockIdx.x;
+        const long long t0 = clock64();
+        while (*f != seq) {
+            if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer never arrived
+                atomicExch(x.error, 1);
+                break;
+            }
+        }
+    }
+    __syncwarp();
+    __threadfence_system();
+    double tot = 0.0, Ntot = 0.0, ltot = 0.0;
+    for (int src = 0; src < x.world; ++src) {
+        const volatile double *msg = x.data[x.rank] + ((par * x.world + src) * RL_X_BLOCKS + blockIdx.x) * RL_X_SLOT;
+        tot += msg[lane];
+        Ntot += msg[32];
+        ltot += msg[33];
+    }
+    if (skip) return;
+    if (col < W) sums[col] = tot;
+    if (ADAM) {
+        if (col < ad.P) {
+            const AdamArgs &c = ad.c;
+            const float beta1 = (float)c.beta1, beta2 = (float)c.beta2;
+            const float omb1 = (float)(1.0 - c.beta1), omb2 = (float)(1.0 - c.beta2);
+            const double bc1 = 1.0 - pow(c.beta1, (double)ad.step), bc2 = 1.0 - pow(c.beta2, (double)ad.step);
+            const float step_size = (float)(c.lr / bc1), bc2_sqrt = (float)sqrt(bc2), eps = (float)c.eps;
+            float g = (float)(tot / Ntot);
+            const float th = ad.theta[col];
+            if (c.weight_decay != 0.0) g = __fadd_rn(g, __fmul_rn((float)c.weight_decay, th));
+            const float mi = __fadd_rn(__fmul_rn(ad.m[col], beta1), __fmul_rn(omb1, g));
+            const float vi = __fadd_rn(__fmul_rn(ad.v[col], beta2), __fmul_rn(__fmul_rn(omb2, g), g));
+            ad.m[col] = mi;
+            ad.v[col] = vi;
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+            ad.theta[col] = __fadd_rn(th, __fmul_rn(-step_size, __fdiv_rn(mi, denom)));
+        }
+        if (blockIdx.x == 0 && lane == 0 && ad.loss_out) *ad.loss_out = ltot / Ntot;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------------
@@ -804,6 +918,20 @@ size_t pass_smem_bytes() {
     return (size_t)nwarps * P * sizeof(double) + (size_t)nwarps * 32 * 12 * sizeof(float);
 }
 
+// rows of plan.partials -> plan.sums, summed over the data-parallel group: one fused kernel over the peer
+// mailboxes when they are mapped (common.cuh rl_xpeer), else reduce_rows_kernel + ncclAllReduce.
+rl_status reduce_over_group(rl_ctx *ctx, const PassPlan &plan, int rows, const int *skip_flag) {
+    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
+        ctx->x_seq += 1;
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<false>, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
+                  ctx->x, ctx->x_seq, skip_flag, XAdam{});
+        return RL_OK;
+    }
+    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.sums, skip_flag);
+    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    return RL_OK;
+}
+
 template <int F, int A, int UPL, int MODE, int CH, int MINB>
 rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce = true) {
     const size_t smem = pass_smem_bytes<F, A, UPL>();
@@ -816,10 +944,7 @@ rl_status launch_pass_variant(rl_ctx *ctx, const PassPlan &plan, PassArgs args, 
     args.partials = plan.partials;
     RL_LAUNCH(ctx, (mlp_pass_kernel<F, A, UPL, MODE, CH, MINB>), plan.grid, PASS_THREADS, smem, args);
     if (!reduce) return RL_OK;
-    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.sums,
-              args.skip_flag);
-    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
-    return RL_OK;
+    return reduce_over_group(ctx, plan, plan.grid, args.skip_flag);
 }
 
 // Passes of the reference's default networks (5 -> 128 -> 1 critic, 5 -> 128 -> 2 policy) run on the tensor cores
@@ -860,10 +985,7 @@ rl_status launch_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool 
     args.partials = plan.partials;
     RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), plan.grid_tc, tc::TC_THREADS, smem, args);
     if (!reduce) return RL_OK;
-    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid_tc, plan.W, plan.sums,
-              args.skip_flag);
-    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
-    return RL_OK;
+    return reduce_over_group(ctx, plan, plan.grid_tc, args.skip_flag);
 }
 
 int pass_variant() {
@@ -901,7 +1023,14 @@ template <int F, int A, int UPL, int MODE>
 rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac,
                         double *loss_out) {
     adam->step += 1;
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
+        // pass -> ONE kernel: row reduction + peer exchange + Adam
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
+        ctx->x_seq += 1;
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(plan)),
+                  plan.W, plan.P, plan.sums, ctx->x, ctx->x_seq, (const int *)nullptr,
+                  (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
+    } else if (ctx->world > 1) {
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa)));
         RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
                   loss_out);
@@ -1028,8 +1157,7 @@ rl_status make_seq_plan(rl_ctx *ctx, const rl_grunet_view &net, uint64_t T, uint
 
 rl_status seq_pass(rl_ctx *ctx, const PassPlan &plan, int mode, const rl_seq_pass_args &a) {
     RL_TRY(rl_seq_pass_launch(ctx, mode, a, plan.grid));
-    RL_LAUNCH(ctx, reduce_rows_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, plan.grid, plan.W, plan.sums, a.skip_flag);
-    if (ctx->world > 1) RL_TRY(rl_allreduce_f64_inplace(ctx, plan.sums, (size_t)plan.W));
+    RL_TRY(reduce_over_group(ctx, plan, plan.grid, a.skip_flag));
     return RL_OK;
 }
 

@@ -60,6 +60,13 @@ class Context:
         L.check(self._lib.rl_ctx_comm_init(self.handle, buf, rank, world_size), self.handle)
         self.rank, self.world_size = rank, world_size
 
+    def comm_peer_info(self) -> dict:
+        """Whether the update's reductions use the NVLink peer mailboxes (one fused kernel per pass) and whether a
+        wait for a peer ever timed out.  Synchronises the stream."""
+        on, bad = C.c_int32(), C.c_int32()
+        L.check(self._lib.rl_ctx_comm_peer_info(self.handle, C.byref(on), C.byref(bad)), self.handle)
+        return {"peer_mailboxes": bool(on.value), "timed_out": bool(bad.value)}
+
     @staticmethod
     def nccl_unique_id() -> bytes:
         buf = C.create_string_buffer(L.RL_NCCL_UNIQUE_ID_BYTES)

@@ -67,6 +67,12 @@ def main():
               flush=True)
         ok = (log_s["num_steps"] == log_f["num_steps"] and st_s == st_f and log_s["num_backtracks"] == log_f["num_backtracks"]
               and dp < 1e-4 and dv < 1e-4)
+    peer = ctx.comm_peer_info()
+    want_peer = os.environ.get("RL_XREDUCE", "")[:1] not in ("n", "0")
+    if rank == 0:
+        print("update reductions:", "fused row-reduction + NVLink peer exchange" if peer["peer_mailboxes"] else "reduce + ncclAllReduce",
+              flush=True)
+    ok = ok and not peer["timed_out"] and (peer["peer_mailboxes"] or not want_peer)
     # every rank must hold identical parameters afterwards (no broadcast is needed by construction)
     t = torch.tensor(np.concatenate([p_s, v_s]), device="cuda")
     ref = t.clone()
