@@ -15,5 +15,12 @@ $NCU -k "regex:env_step_kernel" -s 2 -c 1 -o $O/${R}_k1_step python scripts/prof
 $NCU -k "regex:gae_scan_kernel|value_forward_pairs_kernel" -s 1 -c 3 -o $O/${R}_k3_scan python scripts/profile_kernels.py scan >> $O/ncu.log 2>&1
 $NCU -k "regex:replay_copy_kernel<float, \(int\)8>|sample_gather_kernel|sample_scan_kernel|replay_book_kernel" -s 4 -c 4 -o $O/${R}_k4_replay python scripts/profile_extra.py dqn >> $O/ncu.log 2>&1
 $NCU -k "regex:rollout_seq_kernel" -s 1 -c 1 -o $O/${R}_k8_gru python scripts/profile_extra.py gru >> $O/ncu.log 2>&1
+# gpurun copies back at most 64 MiB: summarise every report here, keep only the reports of the two tensor-core kernels
+for rep in $O/${R}_*.ncu-rep; do
+  python scripts/ncu_summary.py $rep 16 > ${rep%.ncu-rep}.md 2>/dev/null
+done
 ls -la $O/*.ncu-rep | awk '{print $5, $9}'
+for rep in $O/${R}_*.ncu-rep; do
+  case $rep in *_tc.ncu-rep) ;; *) rm -f $rep ;; esac
+done
 tail -3 $O/ncu.log

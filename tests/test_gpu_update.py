@@ -207,6 +207,60 @@ def test_value_pass_tcgen05_and_ffma_match_f64_gradient(ctx, seed, E, T, scale):
         assert _rel(tc["grad"][lo:hi], g64[lo:hi]) <= 5e-5, (lo, hi)
 
 
+def test_value_pass_dead_and_zero_units(ctx, pass_kernel):
+    """relu'(0) = 0 (libtorch): hidden units whose weights and bias are exactly zero have pre-activation +0 on every
+    sample and must get a zero gradient (the tensor-core kernel derives the ReLU mask from a sign bit, so +0 has to
+    count as inactive); units that are negative on every sample likewise; the rest must still match f64."""
+    E, T = 96, 70
+    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=41)
+    rng = np.random.default_rng(42)
+    vparams = R.init_params(rng, 5, 128, 1).astype(np.float32)
+    w1 = vparams[:640].reshape(128, 5)
+    b1 = vparams[640:768]
+    w1[:16] = 0.0
+    b1[:16] = 0.0          # units 0..15: exactly zero pre-activation
+    w1[16:24] = 0.0
+    b1[16:24] = -1.0       # units 16..23: always negative
+    w1[24:32] = 0.0
+    b1[24:32] = 0.5        # units 24..31: always active, constant
+    critic = R.ValuesOpt(ctx, R.ValuesOptConfig(), 5, 0.99)
+    critic.state_value_fn.set_weights(vparams)
+    rtg = np.zeros((T, E), np.float32)
+    for e in range(E):
+        n = int(host["lane_len"][e])
+        rtg[:n, e] = O.discounted_cumsum_lane(host["reward"][:n, e], host["succ"][:n, e], np.float32(0.99))
+    obs, tgt = host["obs"][valid], rtg[valid]
+    loss64, g64 = _value_grad_oracle(vparams, obs, tgt, torch.float64)
+    k = L.RL_PASS_KERNEL_TCGEN05 if pass_kernel == "tcgen05" else L.RL_PASS_KERNEL_FFMA
+    got = critic.probe(traj, k)
+    gw1, gb1, gw2 = got["grad"][:640].reshape(128, 5), got["grad"][640:768], got["grad"][768:896]
+    assert np.all(gw1[:24] == 0.0) and np.all(gb1[:24] == 0.0) and np.all(gw2[:24] == 0.0)
+    assert np.all(g64[:120] == 0.0) and np.all(g64[640:664] == 0.0)
+    np.testing.assert_allclose(got["loss"], loss64, rtol=1e-5)
+    assert _rel(got["grad"], g64) <= 1e-5
+
+
+def test_policy_pass_large_logits_and_padding(ctx, pass_kernel):
+    """Saturated softmax (weights x 30: log-probs down to -1e2) and a batch whose last tile is mostly padding
+    (E * T = 7 * 19 = 133 = 128 + 5): loss, gradient and Fisher-vector product against f64."""
+    E, T = 7, 19
+    env, traj, net, params, host, valid = _collect(ctx, E, T, seed=43, scale=30.0)
+    rng = np.random.default_rng(44)
+    adv = rng.normal(size=(T, E)).astype(np.float32)
+    policy = R.Trpo(net, R.TrpoConfig())
+    vec = rng.normal(size=net.num_params).astype(np.float32)
+    got = policy.probe(traj, ctx.to_device(adv), vec)
+    obs, act, a = host["obs"][valid], host["action"][valid], adv[valid]
+    loss64, kl64, ent64, g64, hv64 = TO.policy_loss_kl_grad_fvp(params, 5, 128, 2, obs, act, a, vec, 1e-5, torch.float64)
+    _, _, _, g32, hv32 = TO.policy_loss_kl_grad_fvp(params, 5, 128, 2, obs, act, a, vec, 1e-5, torch.float32)
+    print(f"N={valid.sum()} saturated: grad rel err kernel {_rel(got['grad'], g64):.2e} torch-f32 {_rel(g32, g64):.2e}; "
+          f"fvp kernel {_rel(got['fvp'], hv64):.2e} torch-f32 {_rel(hv32, hv64):.2e}")
+    assert abs(got["loss"] - loss64) <= 1e-5 * max(1.0, abs(loss64))
+    assert abs(got["entropy"] - ent64) <= 1e-6
+    assert _rel(got["grad"], g64) <= max(1e-5, 4 * _rel(g32, g64))
+    assert _rel(got["fvp"], hv64) <= max(1e-5, 4 * _rel(hv32, hv64))
+
+
 def test_actor_critic_learns_cartpole(ctx):
     """Behavioural check in the spirit of agents/testing.rs: a few TRPO periods raise the mean episode length."""
     E, T = 512, 128
