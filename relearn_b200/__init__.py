@@ -17,3 +17,4 @@ from .torch_agents import (ActorCriticAgent, ActorCriticConfig, Adam, AdamConfig
                            ExplorationRateSchedule, OptimizerStepError, Ppo, PpoConfig, Reinforce, ReinforceConfig,
                            ReplayBuffer, Trpo, TrpoConfig, ValuesOpt,
                            ValuesOptConfig)
+from .serialize import load_actor, save_actor  # noqa: F401,E402
