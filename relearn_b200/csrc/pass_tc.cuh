@@ -20,10 +20,10 @@
 //         the 0/1 ReLU mask as bf16 (exact), two units per PRMT + LOP3, written back to shared memory.  One spare
 //         K-slot of MMA1 adds -2^-120 to every pre-activation so that an exact +0 (a zero-initialised unit)
 //         counts as inactive, like relu'(0) = 0 in libtorch.
-//   MMA3  Q[128 samples x 18] = Mask[128 x 128 units] . C[128 x 18],  c_jf = w2_j * [w1_j, b1_j]_f in bf16 pieces
+//   MMA3  Q[128 samples x 24] = Mask[128 x 128 units] . C[128 x 24],  c_jf = w2_j * [w1_j, b1_j]_f in four bf16 pieces
 //         (8 x tcgen05.mma K = 16; the mask is the same bytes read K-major).  ReLU is piecewise linear, so
 //         V_s = w2 . relu(pre_s) + b2 = sum_f [x_s, 1]_f * sum_j mask_sj c_jf + b2:
-//         epilogue 3 needs 18 columns and 6 FMAs per sample instead of 128 max + 128 FMA.
+//         epilogue 3 needs 24 columns and 6 FMAs per sample instead of 128 max + 128 FMA.
 //   epilogue 3: loss, dV = 2 (V - target), the six values y = dV * [x, 1] as 3 x bf16 pieces to shared memory.
 //   MMA2  G[128 units x 18] = Mask^T[128 x 128 samples] . Y[128 x 18]              (8 x tcgen05.mma K = 16)
 //         exact 0/1 times bf16 pieces, accumulated in TMEM (f32) over TC_DRAIN tiles, then in f64.
@@ -33,7 +33,7 @@
 //   dW2[j] = sum_s dV_s relu(pre_sj) = sum_s dV_s mask_sj (b1_j + w1_j . x_s) = b1_j G[j][5] + sum_f w1_jf G[j][f],
 // so no further cross-sample contraction is needed.
 //
-// Two-action policy: MMA3 has one 18-column block per logit (z_k = sum_f [x,1]_f sum_j mask_sj w2_kj [w1_j,b1_j]_f), and
+// Two-action policy: MMA3 has one 24-column block per logit (z_k = sum_f [x,1]_f sum_j mask_sj w2_kj [w1_j,b1_j]_f), and
 // for the Fisher-vector product a third block for the difference of the tangent logits, whose matrix is
 // (v2_0 - v2_1)_j [w1_j,b1_j] + (w2_0 - w2_1)_j [v1_j,vb1_j] (forward tangent of a piecewise-linear net, same mask).
 // Every per-sample logit gradient of a softmax sums to zero over the actions, so with two actions dz_1 = -dz_0 and
@@ -50,7 +50,7 @@ constexpr int TC_THREADS = 128;
 constexpr int TC_CHUNK = 2048;  // bytes of one 8-element chunk over 128 rows
 // operand regions, in chunks: X 5, W1e 5, one zero chunk (K-slots 40..47 of both), mask 16, Y 4, C 4 or 6
 constexpr int TC_A1 = 0, TC_B1 = 5 * TC_CHUNK, TC_Z = 10 * TC_CHUNK, TC_A2 = 11 * TC_CHUNK, TC_B2 = 27 * TC_CHUNK, TC_B3 = 31 * TC_CHUNK;
-__host__ __device__ constexpr int tc_n3(int blocks) { return (18 * blocks + 15) / 16 * 16; }  // MMA3 N: 32 / 48
+__host__ __device__ constexpr int tc_n3(int blocks) { return (24 * blocks + 15) / 16 * 16; }  // MMA3 N: 32 / 48 (24 columns per block)
 __host__ __device__ constexpr int tc_red(int blocks) { return TC_B3 + tc_n3(blocks) / 8 * TC_CHUNK; }
 __host__ __device__ constexpr int tc_smem(int blocks) { return tc_red(blocks) + 512 + 32 + 16; }
 constexpr int TC_CTAS_PER_SM = 3;  // 70.6 KB (critic) / 74.5 KB (policy) of shared memory and 128 + 32 TMEM columns each
@@ -123,16 +123,24 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t *r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\ttcgen05.wait::ld.sync.aligned;"
                  : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
-// the first 18 (one block) or 36 (two blocks) columns of this thread's lane: TMEM reads are 64 B/clk per SM, so
-// the padding columns are not fetched
-template <int BLOCKS>
-__device__ __forceinline__ void tmem_ld_blocks(uint32_t taddr, uint32_t *r) {
-    if (BLOCKS == 1) {
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+// the first N meaningful columns of this thread's lane (padding columns are not fetched): 18 (G), 24 / 48 (Q)
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *r) {
+    static_assert(N == 18 || N == 24 || N == 48, "column counts of this kernel");
+    if (N == 18) {
         tmem_ld16(taddr, r);
         tmem_ld2(taddr + 16, r + 16);
+    } else if (N == 24) {
+        tmem_ld16(taddr, r);
+        tmem_ld8(taddr + 16, r + 16);
     } else {
         tmem_ld32(taddr, r);
-        tmem_ld4(taddr + 32, r + 32);
+        tmem_ld16(taddr + 32, r + 32);
     }
 }
 
@@ -177,7 +185,7 @@ struct TcPass {
     static constexpr bool IS_POLICY = MODE != PASS_VALUE;
     static constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
     static constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
-    static constexpr int BLOCKS = A;  // 18-column blocks of MMA3: one per logit; FVP: z_0 - z_1 and its tangent
+    static constexpr int BLOCKS = A;  // 24-column blocks of MMA3: one per logit; FVP: z_0 - z_1 and its tangent
     static constexpr int N3 = tc::tc_n3(BLOCKS);
     static constexpr int SMEM = tc::tc_smem(BLOCKS);
     static_assert((A == 1 && MODE == PASS_VALUE) || (A == 2 && MODE != PASS_VALUE && MODE != PASS_QLOSS),
@@ -190,7 +198,8 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     using K = TcPass<A, MODE>;
     constexpr int F = 5, H = 128, P = H * F + H + A * H + A, W = P + NSCALAR;
     constexpr int NF = F + 1;   // features + the bias input
-    constexpr int NY = 3 * NF;  // 18 columns per block: three bf16 pieces of six values
+    constexpr int NY = 3 * NF;  // 18 columns of Y / G: three bf16 pieces of six values
+    constexpr int NC = 4 * NF;  // 24 columns per block of C / Q: four pieces (see the setup of C)
     constexpr bool FVP = K::FVP, BACKWARD = K::BACKWARD, IS_POLICY = K::IS_POLICY;
     constexpr int N3 = K::N3;
     if (a.skip_flag && *a.skip_flag) return;
@@ -228,31 +237,41 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     {
         // C: block k holds w2_kj * [w1_j, b1_j] (logit k).  FVP: block 0 is z_0 - z_1 (all the softmax needs) and
         // block 1 its tangent along `vec`: (v2_0 - v2_1)_j [w1_j, b1_j] + (w2_0 - w2_1)_j [v1_j, vb1_j].
+        // Four bf16 pieces per value: three of the rounded product and one of its exact rounding residual
+        // (fma(a, b, -fl(a b))) -- the regrouped sum over units cancels more than w2 . relu(pre) does, so the
+        // products carry ~32 bits; the fourth piece is free (N stays 32 / 48).
         uint32_t e[N3];
 #pragma unroll
         for (int b = 0; b < K::BLOCKS; ++b) {
-            float c[NF];
-            if (!FVP) {
+            float c[NF], cr[NF];
+            if (!FVP || b == 0) {
+                const float w2b = !FVP ? w2j[b] : w2j[0] - w2j[A > 1 ? 1 : 0];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) c[f] = __fmul_rn(w2j[b], wrow[f]);
+                for (int f = 0; f < NF; ++f) {
+                    c[f] = __fmul_rn(w2b, wrow[f]);
+                    cr[f] = __fmaf_rn(w2b, wrow[f], -c[f]);
+                }
             } else {
-                const float w2d = w2j[0] - w2j[A > 1 ? 1 : 0];
-                if (b == 0) {
+                const float *pw1 = a.vec, *pb1 = pw1 + H * F, *pw2 = pb1 + H, *pb2 = pw2 + A * H;
+                const float v2d = pw2[tid] - pw2[(A > 1 ? H : 0) + tid], w2d = w2j[0] - w2j[A > 1 ? 1 : 0];
+                vb2d = pb2[0] - pb2[A > 1 ? 1 : 0];
 #pragma unroll
-                    for (int f = 0; f < NF; ++f) c[f] = __fmul_rn(w2d, wrow[f]);
-                } else {
-                    const float *pw1 = a.vec, *pb1 = pw1 + H * F, *pw2 = pb1 + H, *pb2 = pw2 + A * H;
-                    const float v2d = pw2[tid] - pw2[(A > 1 ? H : 0) + tid];
-                    vb2d = pb2[0] - pb2[A > 1 ? 1 : 0];
-#pragma unroll
-                    for (int f = 0; f < NF; ++f) c[f] = fmaf(v2d, wrow[f], w2d * (f < F ? pw1[tid * F + (f < F ? f : 0)] : pb1[tid]));
+                for (int f = 0; f < NF; ++f) {
+                    const double exact = (double)v2d * (double)wrow[f] + (double)w2d * (double)(f < F ? pw1[tid * F + (f < F ? f : 0)] : pb1[tid]);
+                    c[f] = (float)exact;
+                    cr[f] = (float)(exact - (double)c[f]);
                 }
             }
 #pragma unroll
-            for (int f = 0; f < NF; ++f) split3(c[f], e[b * NY + f], e[b * NY + NF + f], e[b * NY + 2 * NF + f]);
+            for (int f = 0; f < NF; ++f) {
+                uint32_t rh, rm, rl;
+                split3(c[f], e[b * NC + f], e[b * NC + NF + f], e[b * NC + 2 * NF + f]);
+                split3(cr[f], rh, rm, rl);
+                e[b * NC + 3 * NF + f] = rh;
+            }
         }
 #pragma unroll
-        for (int k = K::BLOCKS * NY; k < N3; ++k) e[k] = 0u;
+        for (int k = K::BLOCKS * NC; k < N3; ++k) e[k] = 0u;
         store_row<N3 / 8>(sB3, tid, e);
     }
     // K-slots 40..47 of both MMA1 operands are zero: one shared chunk
@@ -318,7 +337,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         mbar_wait(bar2, parity);
         fence_after();
         uint32_t r[NY];
-        tmem_ld_blocks<1>(tmem_d2 + lane_off, r);
+        tmem_ld_cols<NY>(tmem_d2 + lane_off, r);
 #pragma unroll
         for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] += (double)__uint_as_float(r[n]);
     };
@@ -397,15 +416,18 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         fence_after();
         float z[A], zdd = 0.0f;  // logits (or V); FVP: tangent of z_0 - z_1
         {
-            uint32_t r[K::BLOCKS * NY];
-            tmem_ld_blocks<K::BLOCKS>(tmem_d1 + lane_off, r);
+            uint32_t r[K::BLOCKS * NC];
+            tmem_ld_cols<K::BLOCKS * NC>(tmem_d1 + lane_off, r);
 #pragma unroll
             for (int b = 0; b < K::BLOCKS; ++b) {
-                // sum_f [x, 1]_f * (sum_j mask_sj c_jf)
-                float acc = (__uint_as_float(r[b * NY + F]) + __uint_as_float(r[b * NY + NF + F])) + __uint_as_float(r[b * NY + 2 * NF + F]);
+                // sum_f [x, 1]_f * (sum_j mask_sj c_jf); the four piece sums are added smallest first
+                auto q = [&](int f) {
+                    return ((__uint_as_float(r[b * NC + 3 * NF + f]) + __uint_as_float(r[b * NC + 2 * NF + f])) +
+                            __uint_as_float(r[b * NC + NF + f])) + __uint_as_float(r[b * NC + f]);
+                };
+                float acc = q(F);
 #pragma unroll
-                for (int f = 0; f < F; ++f)
-                    acc = fmaf(x[f], (__uint_as_float(r[b * NY + f]) + __uint_as_float(r[b * NY + NF + f])) + __uint_as_float(r[b * NY + 2 * NF + f]), acc);
+                for (int f = 0; f < F; ++f) acc = fmaf(x[f], q(f), acc);
                 if (!FVP) z[b] = acc + b2[b];
                 else if (b == 0) z[0] = acc + (b2[0] - b2[A > 1 ? 1 : 0]);  // softmax([z_0 - z_1, 0]) = softmax(z)
                 else zdd = acc + vb2d;
@@ -420,7 +442,8 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
                 log_softmax<A>(z, lp);
 #pragma unroll
                 for (int k = 0; k < A; ++k) p[k] = expf(lp[k]);
-                const float onehot0 = act_s == 0 ? 1.0f : 0.0f;
+                // onehot_0 - p_0 without the cancellation of 1 - p_0 near saturation: p_0 + p_1 = 1
+                const float d0 = act_s == 0 ? p[A > 1 ? 1 : 0] : -p[0];
                 if (MODE == PASS_STATS) {
                     // trpo.rs:112-122: log-probs of the behaviour policy and its entropy (categorical.rs:62-68)
 #pragma unroll
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
                     loss_s = -(ratio * adv_s);
 #pragma unroll
                     for (int k = 0; k < A; ++k) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
-                    if (MODE == PASS_GRAD) dz0 = loss_s * (onehot0 - p[0]);
+                    if (MODE == PASS_GRAD) dz0 = loss_s * d0;
                 }
                 if (MODE == PASS_PPO) {
                     // ppo.rs:124-138, backward as libtorch (see mlp_pass_kernel)
@@ -445,7 +468,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
                     loss_s = -fminf(t1, t2);
                     const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
                     const float g = (inside || t1 < t2) ? -t1 : 0.0f;
-                    dz0 = g * (onehot0 - p[0]);
+                    dz0 = g * d0;
                 }
                 if (MODE == PASS_REINFORCE) {
                     // reinforce.rs:72-79
@@ -453,7 +476,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
                     loss_s = -(lpa * adv_s);
 #pragma unroll
                     for (int k = 0; k < A; ++k) ent_s -= fmaxf(lp[k], F32_LOWEST) * p[k];
-                    dz0 = -adv_s * (onehot0 - p[0]);
+                    dz0 = -adv_s * d0;
                 }
                 if (FVP) dz0 = p[0] * (p[A > 1 ? 1 : 0] * zdd);  // u = (diag p - p p^T) zdot with p_0 + p_1 = 1
             } else {

@@ -222,3 +222,28 @@ def test_rollout_lane_sharding_invariance(ctx):
     for k in ("obs", "action", "reward", "succ"):
         np.testing.assert_array_equal(full[k][:, : E // 2], a[k])
         np.testing.assert_array_equal(full[k][:, E // 2 :], b[k])
+
+
+def test_actor_file_roundtrip_reproduces_rollout(ctx, tmp_path):
+    """A policy written in the reference's actor format (serde TensorDef in CBOR, examples/cartpole-trpo.rs:69-75) and
+    read back drives bit-identical rollouts."""
+    import relearn_b200 as R
+    from relearn_b200 import _lib as L
+
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    params = R.init_params(np.random.default_rng(5), 5, 128, 2)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    path = str(tmp_path / "actor.cbor")
+    R.save_actor(path, net.get_weights())
+    loaded = R.load_actor(path)
+    net2 = R.Mlp(ctx, loaded["in_dim"], loaded["hidden_sizes"], loaded["out_dim"])
+    net2.set_weights(loaded["params"])
+    hosts = []
+    for n in (net, net2):
+        env = R.build_env(ctx, cfg, 256, seed=9)
+        traj = R.Trajectory(env, 64)
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=n), R.HistoryDataBound(64, 0), traj)
+        hosts.append(traj.to_host())
+    for k in ("obs", "action", "reward", "succ"):
+        assert np.array_equal(hosts[0][k], hosts[1][k]), k
