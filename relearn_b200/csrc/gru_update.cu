@@ -22,8 +22,8 @@
 
 namespace {
 
-constexpr int GH = 8, GF = 20, GA = 16;
-constexpr int GP_MAX = 3 * GH * GF + 3 * GH * GH + 6 * GH + GA * GH + GA;
+constexpr int GH_MAX = 8, GF_MAX = 20, GA_MAX = 16;
+constexpr int GP_MAX_ALL = 3 * GH_MAX * GF_MAX + 3 * GH_MAX * GH_MAX + 6 * GH_MAX + GA_MAX * GH_MAX + GA_MAX;
 constexpr float F32_LOWEST_G = -3.402823466e+38f;
 
 __device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
@@ -43,13 +43,16 @@ __device__ __forceinline__ void gru_gates(const Dims &d, const float *__restrict
                                           float *u, float *n, float *ghn) {
     const int F = d.F, H = d.H;
     const float *w_ih = w, *w_hh = w + d.o_whh(), *b_ih = w + d.o_bih(), *b_hh = w + d.o_bhh();
+#pragma unroll
     for (int j = 0; j < H; ++j) {
         float gi[3], gh[3];
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
             const int row = g * H + j;
             float a = b_ih[row], b = b_hh[row];
+#pragma unroll
             for (int f = 0; f < F; ++f) a = fmaf(w_ih[row * F + f], x[f], a);
+#pragma unroll
             for (int k = 0; k < H; ++k) b = fmaf(w_hh[row * H + k], h[k], b);
             gi[g] = a;
             gh[g] = b;
@@ -71,8 +74,12 @@ __device__ __forceinline__ float act_grad(int act, float pre, float out) {
     }
 }
 
-template <int MODE>
+// TF / TH / TA > 0 fix the sizes at compile time (every loop unrolls, every per-thread array -- the 150-odd gradient
+// accumulators included -- lives in registers); 0 = sizes from the arguments, arrays of the maximum sizes in local memory.
+template <int MODE, int TF, int TH, int TA>
 __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
+    constexpr int GH = TH ? TH : GH_MAX, GF = TF ? TF : GF_MAX, GA = TA ? TA : GA_MAX;
+    constexpr int GP_MAX = 3 * GH * GF + 3 * GH * GH + 6 * GH + GA * GH + GA;
     constexpr bool BACKWARD = MODE == RL_PASS_GRAD || MODE == RL_PASS_FVP || MODE == RL_PASS_VALUE || MODE == RL_PASS_PPO ||
                               MODE == RL_PASS_REINFORCE;
     constexpr bool IS_POLICY = MODE != RL_PASS_VALUE;
@@ -80,11 +87,12 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     constexpr bool USES_ADV = MODE == RL_PASS_EVAL || MODE == RL_PASS_GRAD || MODE == RL_PASS_PPO || MODE == RL_PASS_REINFORCE;
     constexpr bool USES_LP0 = MODE == RL_PASS_EVAL || MODE == RL_PASS_GRAD || MODE == RL_PASS_PPO;
     if (a.skip_flag && *a.skip_flag) return;
-    const Dims d{a.F, a.H, a.A, a.act};
+    const Dims d{TF ? TF : a.F, TH ? TH : a.H, TA ? TA : a.A, a.act};
     const int F = d.F, H = d.H, A = d.A, P = d.P();
     extern __shared__ __align__(16) unsigned char gsm[];
     float *sw = reinterpret_cast<float *>(gsm);      // theta [P]
     float *sv = sw + P;                              // direction [P] (FVP)
+#pragma unroll
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         sw[i] = a.theta[i];
         if (FVP) sv[i] = a.vec[i];
@@ -101,6 +109,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     if (valid_lane) {
         // ---------------- forward ----------------
         float h[GH], hd[GH];
+#pragma unroll
         for (int j = 0; j < H; ++j) h[j] = hd[j] = 0.0f;
         uint64_t len = 0;
         for (uint64_t t = 0; t < a.T; ++t) {
@@ -108,6 +117,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
             if (sc == RL_PAD) break;
             len = t + 1;
             float x[GF];
+#pragma unroll
             for (int f = 0; f < F; ++f) x[f] = a.obs[(t * F + f) * E + e];
             if (BACKWARD)
                 for (int j = 0; j < H; ++j) a.hbuf[(t * H + j) * E + e] = h[j];
@@ -118,13 +128,16 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 // forward-mode tangents along v: gi' = V_ih x + v_bih ; gh' = V_hh h + W_hh h' + v_bhh
                 const float *v_ih = sv, *v_hh = sv + d.o_whh(), *vb_ih = sv + d.o_bih(), *vb_hh = sv + d.o_bhh();
                 const float *w_hh = sw + d.o_whh();
+#pragma unroll
                 for (int j = 0; j < H; ++j) {
                     float gid[3], ghd[3];
 #pragma unroll
                     for (int gg = 0; gg < 3; ++gg) {
                         const int row = gg * H + j;
                         float p = vb_ih[row], q = vb_hh[row];
+#pragma unroll
                         for (int f = 0; f < F; ++f) p = fmaf(v_ih[row * F + f], x[f], p);
+#pragma unroll
                         for (int k = 0; k < H; ++k) q = fmaf(v_hh[row * H + k], h[k], fmaf(w_hh[row * H + k], hd[k], q));
                         gid[gg] = p;
                         ghd[gg] = q;
@@ -135,12 +148,15 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                     hdnew[j] = ud * (h[j] - n[j]) + u[j] * hd[j] + (1.0f - u[j]) * nd;
                 }
             }
+#pragma unroll
             for (int j = 0; j < H; ++j) hnew[j] = __fadd_rn(__fmul_rn(__fsub_rn(h[j], n[j]), u[j]), n[j]);
             // Chain: activation, Linear
             const float *lw = sw + d.o_lw(), *lb = sw + d.o_lb();
             float z[GA], zd[GA];
+#pragma unroll
             for (int k = 0; k < A; ++k) {
                 float acc = lb[k], accd = FVP ? sv[d.o_lb() + k] : 0.0f;
+#pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float av = act_fwd(d.act, hnew[j]);
                     acc = fmaf(lw[k * H + j], av, acc);
@@ -151,16 +167,20 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
             }
             // ---- per-step algebra (same definitions as mlp_pass_kernel, update.cu) ----
             float dz[GA];
+#pragma unroll
             for (int k = 0; k < A; ++k) dz[k] = 0.0f;
             float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
             const uint64_t n_idx = t * E + e;
             if (IS_POLICY) {
                 float m = z[0];
+#pragma unroll
                 for (int k = 1; k < A; ++k) m = fmaxf(m, z[k]);
                 float sum = 0.0f;
+#pragma unroll
                 for (int k = 0; k < A; ++k) sum += expf(z[k] - m);
                 const float lse = m + logf(sum);
                 float lp[GA], p[GA];
+#pragma unroll
                 for (int k = 0; k < A; ++k) {
                     lp[k] = z[k] - lse;
                     p[k] = expf(lp[k]);
@@ -168,6 +188,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 const int act_s = (int)a.action[n_idx];
                 const float adv_s = USES_ADV ? a.adv[n_idx] : 0.0f;
                 if (MODE == RL_PASS_STATS) {
+#pragma unroll
                     for (int k = 0; k < A; ++k) {
                         ent_s -= fmaxf(lp[k], F32_LOWEST_G) * p[k];
                         a.logp0[(t * A + k) * E + e] = lp[k];
@@ -182,9 +203,11 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                         loss_s = -fminf(t1, t2);
                         const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
                         const float gg = (inside || t1 < t2) ? -t1 : 0.0f;
+#pragma unroll
                         for (int k = 0; k < A; ++k) dz[k] = gg * ((act_s == k ? 1.0f : 0.0f) - p[k]);
                     } else {
                         loss_s = -(ratio * adv_s);
+#pragma unroll
                         for (int k = 0; k < A; ++k) {
                             const float lp0k = a.logp0[(t * A + k) * E + e];
                             kl_s += fmaxf(lp0k - lp[k], F32_LOWEST_G) * expf(lp0k);
@@ -194,6 +217,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 }
                 if (MODE == RL_PASS_REINFORCE) {
                     loss_s = -(lp[act_s] * adv_s);
+#pragma unroll
                     for (int k = 0; k < A; ++k) {
                         ent_s -= fmaxf(lp[k], F32_LOWEST_G) * p[k];
                         dz[k] = -adv_s * ((act_s == k ? 1.0f : 0.0f) - p[k]);
@@ -201,7 +225,9 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 }
                 if (FVP) {
                     float pd = 0.0f;
+#pragma unroll
                     for (int k = 0; k < A; ++k) pd = fmaf(p[k], zd[k], pd);
+#pragma unroll
                     for (int k = 0; k < A; ++k) dz[k] = p[k] * (zd[k] - pd);
                 }
             } else {  // VALUE: mse(V(obs), targets)  (opt.rs:109-115)
@@ -217,6 +243,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 for (int k = 0; k < A; ++k) a.dzbuf[(t * A + k) * E + e] = dz[k];
             // next hidden state; a new episode starts from zeros (gru.rs:23-28)
             const bool done = sc != RL_CONTINUE;
+#pragma unroll
             for (int j = 0; j < H; ++j) {
                 h[j] = done ? 0.0f : hnew[j];
                 if (FVP) hd[j] = done ? 0.0f : hdnew[j];
@@ -225,6 +252,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
         // ---------------- backward (BPTT) ----------------
         if (BACKWARD) {
             float dh[GH];
+#pragma unroll
             for (int j = 0; j < H; ++j) dh[j] = 0.0f;
             const float *w_hh = sw + d.o_whh(), *lw = sw + d.o_lw();
             float *g_ih = g, *g_hh = g + d.o_whh(), *gb_ih = g + d.o_bih(), *gb_hh = g + d.o_bhh(), *g_lw = g + d.o_lw(),
@@ -234,16 +262,21 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                 if (sc != RL_CONTINUE)
                     for (int j = 0; j < H; ++j) dh[j] = 0.0f;  // last step of its episode: nothing flows back from t + 1
                 float x[GF], hp[GH], dz[GA];
+#pragma unroll
                 for (int f = 0; f < F; ++f) x[f] = a.obs[((uint64_t)t * F + f) * E + e];
+#pragma unroll
                 for (int j = 0; j < H; ++j) hp[j] = a.hbuf[((uint64_t)t * H + j) * E + e];
+#pragma unroll
                 for (int k = 0; k < A; ++k) dz[k] = a.dzbuf[((uint64_t)t * A + k) * E + e];
                 float r[GH], u[GH], n[GH], ghn[GH];
                 gru_gates(d, sw, x, hp, r, u, n, ghn);
                 float dgi[3 * GH], dgh[3 * GH], dhp[GH];
+#pragma unroll
                 for (int j = 0; j < H; ++j) {
                     const float hn = __fadd_rn(__fmul_rn(__fsub_rn(hp[j], n[j]), u[j]), n[j]);
                     const float av = act_fwd(d.act, hn);
                     float da = 0.0f;
+#pragma unroll
                     for (int k = 0; k < A; ++k) {
                         da = fmaf(lw[k * H + j], dz[k], da);
                         g_lw[k * H + j] = fmaf(dz[k], av, g_lw[k * H + j]);
@@ -259,17 +292,22 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                     dgi[j] = dpr; dgi[H + j] = dpu; dgi[2 * H + j] = dpn;
                     dgh[j] = dpr; dgh[H + j] = dpu; dgh[2 * H + j] = dpn * r[j];
                 }
+#pragma unroll
                 for (int k = 0; k < A; ++k) g_lb[k] += dz[k];
+#pragma unroll
                 for (int row = 0; row < 3 * H; ++row) {
                     const float a_i = dgi[row], a_h = dgh[row];
                     gb_ih[row] += a_i;
                     gb_hh[row] += a_h;
+#pragma unroll
                     for (int f = 0; f < F; ++f) g_ih[row * F + f] = fmaf(a_i, x[f], g_ih[row * F + f]);
+#pragma unroll
                     for (int k = 0; k < H; ++k) {
                         g_hh[row * H + k] = fmaf(a_h, hp[k], g_hh[row * H + k]);
                         dhp[k] = fmaf(w_hh[row * H + k], a_h, dhp[k]);
                     }
                 }
+#pragma unroll
                 for (int j = 0; j < H; ++j) dh[j] = dhp[j];
             }
         }
@@ -285,6 +323,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     };
     __syncthreads();
     if (BACKWARD) {
+#pragma unroll  // static indices keep g[] in registers when the sizes are compile-time
         for (int i = 0; i < P; ++i) {
             const double s = wsum(valid_lane ? (double)g[i] : 0.0);
             if (lane == 0) part[warp * W + i] = s;
@@ -303,18 +342,26 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     for (int i = threadIdx.x; i < W; i += blockDim.x) row[i] = part[i] + part[W + i] + part[2 * W + i] + part[3 * W + i];
 }
 
+template <int MODE, int TF, int TH, int TA>
+rl_status launch_sized(rl_ctx *ctx, const rl_seq_pass_args &a, int grid, size_t smem) {
+    RL_CUDA(ctx, cudaFuncSetAttribute(gru_pass_kernel<MODE, TF, TH, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RL_LAUNCH(ctx, (gru_pass_kernel<MODE, TF, TH, TA>), grid, 128, smem, a);
+    return RL_OK;
+}
+
+// BASELINE config 4 (2-armed bandit meta-env, rnn.rs-sized GRU): features 6, hidden 4, 2 logits (policy) or 1 (critic)
 template <int MODE>
 rl_status launch_mode(rl_ctx *ctx, const rl_seq_pass_args &a, int grid, size_t smem) {
-    RL_CUDA(ctx, cudaFuncSetAttribute(gru_pass_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RL_LAUNCH(ctx, gru_pass_kernel<MODE>, grid, 128, smem, a);
-    return RL_OK;
+    constexpr bool POLICY = MODE != RL_PASS_VALUE;
+    if (a.F == 6 && a.H == 4 && a.A == (POLICY ? 2 : 1)) return launch_sized<MODE, 6, 4, POLICY ? 2 : 1>(ctx, a, grid, smem);
+    return launch_sized<MODE, 0, 0, 0>(ctx, a, grid, smem);
 }
 
 }  // namespace
 
-int rl_seq_pass_max_params() { return GP_MAX; }
+int rl_seq_pass_max_params() { return GP_MAX_ALL; }
 
-bool rl_seq_pass_supports(int F, int H, int A) { return F >= 1 && F <= GF && H >= 1 && H <= GH && A >= 1 && A <= GA; }
+bool rl_seq_pass_supports(int F, int H, int A) { return F >= 1 && F <= GF_MAX && H >= 1 && H <= GH_MAX && A >= 1 && A <= GA_MAX; }
 
 // One pass; writes `grid` partial rows of P + 4 doubles (order: loss, kl, entropy, count as in update.cu).
 rl_status rl_seq_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a, int grid) {
