@@ -530,7 +530,29 @@ def other_configs(ctx, R, L, hbm_peak):
                 "horizon": T4, "ms": ms, "env_steps_per_s": E4 * T4 / (ms * 1e-3), "bytes_per_step": bytes_per_step,
                 "trajectory_write_gbs": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9 / hbm_peak})
-    traj4.close(); env4.close()
+    traj4.close()
+    # the update that consumes it: GAE + TRPO + 80-step critic through Chain<Gru, Linear> on one trial per lane (T = 19)
+    g = R.GruLinearConfig(hidden_dim=4)
+    agent4 = R.ActorCriticConfig(policy_config=R.TrpoConfig(policy_fn_config=g),
+                                 critic_config=R.ValuesOptConfig(state_value_fn_config=g)).build_agent(env4)
+    agent4.policy.policy_fn.set_weights(R.init_gru_linear_params(rng, env4.num_features, 4, env4.num_actions))
+    agent4.critic.state_value_fn.set_weights(R.init_gru_linear_params(rng, env4.num_features, 4, 1))
+    traj5 = R.Trajectory(env4, 19)
+    upd = []
+    for it in range(3):
+        R.rollout(env4, agent4.actor(), R.HistoryDataBound(19, 0), traj5, want_summary=False)
+        e0 = ctx.event().record()
+        adv = agent4.critic.advantages(traj5)
+        e1 = ctx.event().record()
+        log = {}
+        agent4.policy.update(traj5, adv, log)
+        cs = agent4.critic.update(traj5, log)
+        if it > 0:
+            upd.append((e0.elapsed_ms(e1), log["policy/update_time"] * 1e3, cs.update_ms))
+    out.append({"kernel": "config 4 update: GAE + TRPO + 80-step critic through GRU(6->4)->Linear (BPTT pass kernel)", "envs": E4,
+                "batch_steps": E4 * 19, "adv_est_ms": float(np.mean([u[0] for u in upd])),
+                "trpo_policy_ms": float(np.mean([u[1] for u in upd])), "critic_80_adam_ms": float(np.mean([u[2] for u in upd]))})
+    traj5.close(); env4.close()
     return out
 
 
