@@ -62,8 +62,11 @@ struct rl_minibatch_dev {
     const float *target;     // f32 [capacity]
     const uint8_t *succ;     // u8 [capacity]
 };
+// n_sets minibatches with consecutive draw indices; set s starts s * capacity columns (s * capacity * F for obs) after
+// set 0 in every plane
 rl_status rl_replay_sample_enqueue(rl_replay *rb, uint64_t minibatch_steps, uint64_t seed, uint32_t draw_index,
-                                   int one_step_td, float discount, rl_mlp *q, rl_minibatch_dev *out);
+                                   int one_step_td, float discount, rl_mlp *q, uint32_t n_sets, rl_minibatch_dev *out);
+uint32_t rl_replay_take_draw_indices(rl_replay *rb, uint32_t n);
 rl_status rl_replay_sample_finish(rl_replay *rb, uint64_t *num_steps, uint64_t *num_episodes);
 uint32_t rl_replay_next_draw_index(rl_replay *rb);
 rl_ctx *rl_replay_ctx(rl_replay *rb);

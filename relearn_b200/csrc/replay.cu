@@ -185,6 +185,12 @@ struct SampleMeta {
 __global__ void __launch_bounds__(256)
     sample_draw_kernel(ReplayPtrs rb, uint64_t J, uint64_t seed, uint32_t draw_index, uint32_t *__restrict__ sel_lane,
                        uint32_t *__restrict__ sel_start, uint32_t *__restrict__ sel_len, SampleMeta *meta) {
+    // blockIdx.y = minibatch of a batched sample (rl_replay_sample_enqueue with n_sets > 1): its own draw index and arrays
+    draw_index += blockIdx.y;
+    sel_lane += (uint64_t)blockIdx.y * J;
+    sel_start += (uint64_t)blockIdx.y * J;
+    sel_len += (uint64_t)blockIdx.y * J;
+    meta += blockIdx.y;
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
     const uint64_t lane = j % rb.E;
@@ -225,6 +231,9 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(1024)
     sample_scan_kernel(const uint32_t *__restrict__ sel_len, uint64_t J, uint64_t minibatch_steps,
                        unsigned long long *__restrict__ sel_off, SampleMeta *meta) {
+    sel_len += (uint64_t)blockIdx.x * J;  // one block per minibatch of a batched sample
+    sel_off += (uint64_t)blockIdx.x * J;
+    meta += blockIdx.x;
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -292,7 +301,13 @@ template <bool TD>
 __global__ void __launch_bounds__(256)
     sample_gather_kernel(ReplayPtrs rb, const uint32_t *__restrict__ sel_lane, const uint32_t *__restrict__ sel_start,
                          const uint32_t *__restrict__ sel_len, const unsigned long long *__restrict__ sel_off,
-                         const SampleMeta *__restrict__ meta, MinibatchPtrs mb, float discount) {
+                         const SampleMeta *__restrict__ meta, MinibatchPtrs mb, float discount, uint64_t J) {
+    {   // blockIdx.y = minibatch of a batched sample: planes of set s start s * cap columns (s * cap * F for obs) further on
+        const uint64_t s = blockIdx.y;
+        sel_lane += s * J; sel_start += s * J; sel_len += s * J; sel_off += s * J; meta += s;
+        mb.obs += s * mb.cap * rb.F; mb.action += s * mb.cap; mb.succ += s * mb.cap; mb.target += s * mb.cap;
+        if (TD) { mb.nobs += s * mb.cap * rb.F; mb.reward += s * mb.cap; mb.code += s * mb.cap; }
+    }
     const int lane_id = threadIdx.x & 31;
     const uint64_t warp_global = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t total_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -413,10 +428,13 @@ struct rl_replay {
     unsigned long long *stats = nullptr;
     // sampler state
     uint64_t mb_minibatch = 0;
+    uint32_t mb_sets = 0;  // minibatches the sampler arrays hold (batched sampling of a whole update)
     MinibatchPtrs mb{};
     uint32_t *sel_lane = nullptr, *sel_start = nullptr, *sel_len = nullptr;
     unsigned long long *sel_off = nullptr;
-    SampleMeta *meta = nullptr;
+    SampleMeta *meta = nullptr;        // single-sample meta (rl_replay_create)
+    SampleMeta *meta_sets = nullptr;   // [mb_sets] for batched samples
+    uint32_t last_sets = 1;            // minibatches of the last enqueue (rl_replay_sample_finish reads the last one)
     uint32_t draw_counter = 0;
 };
 
@@ -431,79 +449,94 @@ void free_sampler(rl_replay *rb) {
     rb->sel_lane = rb->sel_start = rb->sel_len = nullptr;
     rb->sel_off = nullptr;
     rb->mb_minibatch = 0;
+    rb->mb_sets = 0;
+    cudaFree(rb->meta_sets);
+    rb->meta_sets = nullptr;
 }
 
-rl_status ensure_sampler(rl_replay *rb, uint64_t minibatch_steps) {
+rl_status ensure_sampler(rl_replay *rb, uint64_t minibatch_steps, uint32_t sets, bool td) {
     rl_ctx *ctx = rb->ctx;
-    if (rb->mb_minibatch == minibatch_steps && rb->mb.obs) return RL_OK;
+    if (rb->mb_minibatch == minibatch_steps && rb->mb.obs && rb->mb_sets >= sets && (!td || rb->mb.nobs)) return RL_OK;
     RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     free_sampler(rb);
     // the last episode taken may overshoot the bound by at most one ring of steps
     const uint64_t cap = ((minibatch_steps + rb->p.C + 1 + 31) / 32) * 32;
-    const size_t F = (size_t)rb->p.F;
+    const size_t F = (size_t)rb->p.F, S = sets;
     cudaError_t e = cudaSuccess;
     auto alloc = [&](void **p, size_t bytes) {
         if (e == cudaSuccess) e = cudaMalloc(p, bytes);
     };
-    alloc((void **)&rb->mb.obs, cap * F * sizeof(float));
-    alloc((void **)&rb->mb.nobs, cap * F * sizeof(float));
-    alloc((void **)&rb->mb.reward, cap * sizeof(float));
-    alloc((void **)&rb->mb.target, cap * sizeof(float));
-    alloc((void **)&rb->mb.qmax, cap * sizeof(float));
-    alloc((void **)&rb->mb.qmax_next, cap * sizeof(float));
-    alloc((void **)&rb->mb.action, cap);
-    alloc((void **)&rb->mb.succ, cap);
-    alloc((void **)&rb->mb.code, cap);
-    alloc((void **)&rb->sel_lane, minibatch_steps * sizeof(uint32_t));
-    alloc((void **)&rb->sel_start, minibatch_steps * sizeof(uint32_t));
-    alloc((void **)&rb->sel_len, minibatch_steps * sizeof(uint32_t));
-    alloc((void **)&rb->sel_off, minibatch_steps * sizeof(unsigned long long));
+    alloc((void **)&rb->mb.obs, S * cap * F * sizeof(float));
+    alloc((void **)&rb->mb.target, S * cap * sizeof(float));
+    alloc((void **)&rb->mb.action, S * cap);
+    alloc((void **)&rb->mb.succ, S * cap);
+    if (td) {  // OneStepTd targets only (sampled one minibatch at a time: they depend on the current parameters)
+        alloc((void **)&rb->mb.nobs, cap * F * sizeof(float));
+        alloc((void **)&rb->mb.reward, cap * sizeof(float));
+        alloc((void **)&rb->mb.qmax, cap * sizeof(float));
+        alloc((void **)&rb->mb.qmax_next, cap * sizeof(float));
+        alloc((void **)&rb->mb.code, cap);
+    }
+    alloc((void **)&rb->sel_lane, S * minibatch_steps * sizeof(uint32_t));
+    alloc((void **)&rb->sel_start, S * minibatch_steps * sizeof(uint32_t));
+    alloc((void **)&rb->sel_len, S * minibatch_steps * sizeof(uint32_t));
+    alloc((void **)&rb->sel_off, S * minibatch_steps * sizeof(unsigned long long));
+    alloc((void **)&rb->meta_sets, S * sizeof(SampleMeta));
     if (e != cudaSuccess) {
         free_sampler(rb);
         return rl_fail(ctx, RL_ERR_OOM, "replay sampler: %s", cudaGetErrorString(e));
     }
     rb->mb.cap = cap;
     rb->mb_minibatch = minibatch_steps;
+    rb->mb_sets = sets;
     return RL_OK;
 }
 
 }  // namespace
 
-// Enqueue one sample_minibatch (dqn.rs:280-314) on the context stream; no host synchronisation.
+// Enqueue `n_sets` sample_minibatch calls (dqn.rs:280-314) with draw indices draw_index .. draw_index + n_sets - 1 on
+// the context stream; no host synchronisation.  The ring does not change during an update and reward-to-go targets
+// do not depend on the parameters, so the minibatches of all optimizer steps of one update are drawn, cut and
+// gathered by three launches (grid.y = minibatch) -- large enough to run at HBM speed -- and come out exactly as
+// n_sets separate calls would produce them.  Set s starts s * capacity columns after set 0 in every plane.
+// OneStepTd targets need the parameters of their step: n_sets must be 1.
 rl_status rl_replay_sample_enqueue(rl_replay *rb, uint64_t minibatch_steps, uint64_t seed, uint32_t draw_index,
-                                   int one_step_td, float discount, rl_mlp *q, rl_minibatch_dev *out) {
+                                   int one_step_td, float discount, rl_mlp *q, uint32_t n_sets, rl_minibatch_dev *out) {
     rl_ctx *ctx = rb->ctx;
     RL_REQUIRE(ctx, minibatch_steps > 0 && minibatch_steps < (1ull << 31), "replay sample: minibatch_steps out of range");
-    RL_TRY(ensure_sampler(rb, minibatch_steps));
+    RL_REQUIRE(ctx, n_sets >= 1 && n_sets <= 65535 && (!one_step_td || n_sets == 1), "replay sample: bad number of minibatches");
+    RL_TRY(ensure_sampler(rb, minibatch_steps, n_sets, one_step_td != 0));
+    SampleMeta *meta = rb->meta_sets;
     if (one_step_td) {
         RL_REQUIRE(ctx, q != nullptr, "replay sample: OneStepTd targets need the action-value network");
         RL_REQUIRE(ctx, q->in_dim == rb->p.F, "replay sample: network input does not match the observation features");
         RL_REQUIRE(ctx, q->in_dim <= 36 && q->out_dim <= 32, "replay sample: network too large");
     }
     const uint64_t J = minibatch_steps;  // every episode has at least one step
-    RL_CUDA(ctx, cudaMemsetAsync(rb->meta, 0, sizeof(SampleMeta), ctx->stream));
-    RL_CUDA(ctx, cudaMemsetAsync(rb->mb.succ, RL_PAD, rb->mb.cap, ctx->stream));
-    RL_LAUNCH(ctx, sample_draw_kernel, rl_grid_for(J, 256), 256, 0, rb->p, J, seed, draw_index, rb->sel_lane,
-              rb->sel_start, rb->sel_len, rb->meta);
-    RL_LAUNCH(ctx, sample_scan_kernel, 1, 1024, 0, rb->sel_len, J, minibatch_steps, rb->sel_off, rb->meta);
-    const unsigned gather_grid = (unsigned)ctx->sm_count * 4;
+    RL_CUDA(ctx, cudaMemsetAsync(meta, 0, (size_t)n_sets * sizeof(SampleMeta), ctx->stream));
+    RL_CUDA(ctx, cudaMemsetAsync(rb->mb.succ, RL_PAD, (size_t)n_sets * rb->mb.cap, ctx->stream));
+    RL_LAUNCH(ctx, sample_draw_kernel, dim3(rl_grid_for(J, 256), n_sets), 256, 0, rb->p, J, seed, draw_index, rb->sel_lane,
+              rb->sel_start, rb->sel_len, meta);
+    RL_LAUNCH(ctx, sample_scan_kernel, n_sets, 1024, 0, rb->sel_len, J, minibatch_steps, rb->sel_off, meta);
+    const dim3 gather_grid(n_sets > 1 ? (unsigned)ctx->sm_count : (unsigned)ctx->sm_count * 4, n_sets);
     if (one_step_td) {
         RL_LAUNCH(ctx, sample_gather_kernel<true>, gather_grid, 256, 0, rb->p, rb->sel_lane, rb->sel_start, rb->sel_len,
-                  rb->sel_off, rb->meta, rb->mb, discount);
+                  rb->sel_off, meta, rb->mb, discount, J);
         const size_t smem = q->n_params * sizeof(float);
         const unsigned grid = rl_grid_for(rb->mb.cap, 256);
         if (q->in_dim <= 8 && q->out_dim <= 2) {
             RL_CUDA(ctx, cudaFuncSetAttribute(q_values_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RL_LAUNCH(ctx, (q_values_kernel<8, 2>), grid, 256, smem, rl_mlp_view(q), rb->mb, rb->meta);
+            RL_LAUNCH(ctx, (q_values_kernel<8, 2>), grid, 256, smem, rl_mlp_view(q), rb->mb, meta);
         } else {
             RL_CUDA(ctx, cudaFuncSetAttribute(q_values_kernel<36, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            RL_LAUNCH(ctx, (q_values_kernel<36, 32>), grid, 256, smem, rl_mlp_view(q), rb->mb, rb->meta);
+            RL_LAUNCH(ctx, (q_values_kernel<36, 32>), grid, 256, smem, rl_mlp_view(q), rb->mb, meta);
         }
-        RL_LAUNCH(ctx, td_target_kernel, grid, 256, 0, rb->mb, rb->meta, discount);
+        RL_LAUNCH(ctx, td_target_kernel, grid, 256, 0, rb->mb, meta, discount);
     } else {
         RL_LAUNCH(ctx, sample_gather_kernel<false>, gather_grid, 256, 0, rb->p, rb->sel_lane, rb->sel_start, rb->sel_len,
-                  rb->sel_off, rb->meta, rb->mb, discount);
+                  rb->sel_off, meta, rb->mb, discount, J);
     }
+    rb->last_sets = n_sets;
     out->capacity = rb->mb.cap;
     out->obs = rb->mb.obs;
     out->action = rb->mb.action;
@@ -516,17 +549,25 @@ rl_status rl_replay_sample_enqueue(rl_replay *rb, uint64_t minibatch_steps, uint
 rl_status rl_replay_sample_finish(rl_replay *rb, uint64_t *num_steps, uint64_t *num_episodes) {
     rl_ctx *ctx = rb->ctx;
     SampleMeta *host;
-    RL_TRY(rl_ctx_pinned(ctx, sizeof(SampleMeta), (void **)&host));
-    RL_CUDA(ctx, cudaMemcpyAsync(host, rb->meta, sizeof(SampleMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    const uint32_t sets = rb->last_sets ? rb->last_sets : 1;
+    RL_REQUIRE(ctx, rb->meta_sets != nullptr, "replay sample: nothing was sampled");
+    RL_TRY(rl_ctx_pinned(ctx, (size_t)sets * sizeof(SampleMeta), (void **)&host));
+    RL_CUDA(ctx, cudaMemcpyAsync(host, rb->meta_sets, (size_t)sets * sizeof(SampleMeta), cudaMemcpyDeviceToHost, ctx->stream));
     RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (host->error == RB_ERR_NO_EPISODES)
-        return rl_fail(ctx, RL_ERR_INVALID_ARG, "replay sample: a lane has no stored episode (Uniform::new(0, 0))");
-    if (num_steps) *num_steps = host->num_steps;
-    if (num_episodes) *num_episodes = host->num_episodes;
+    for (uint32_t i = 0; i < sets; ++i)
+        if (host[i].error == RB_ERR_NO_EPISODES)
+            return rl_fail(ctx, RL_ERR_INVALID_ARG, "replay sample: a lane has no stored episode (Uniform::new(0, 0))");
+    if (num_steps) *num_steps = host[sets - 1].num_steps;
+    if (num_episodes) *num_episodes = host[sets - 1].num_episodes;
     return RL_OK;
 }
 
 uint32_t rl_replay_next_draw_index(rl_replay *rb) { return rb->draw_counter++; }
+uint32_t rl_replay_take_draw_indices(rl_replay *rb, uint32_t n) {
+    const uint32_t first = rb->draw_counter;
+    rb->draw_counter += n;
+    return first;
+}
 rl_ctx *rl_replay_ctx(rl_replay *rb) { return rb->ctx; }
 int rl_replay_num_features(rl_replay *rb) { return rb->p.F; }
 
@@ -704,7 +745,7 @@ rl_status rl_replay_sample(rl_replay *rb, const rl_dqn_cfg *cfg, rl_mlp *q, uint
     if (!rb || !cfg || !out) return rl_fail(rb ? rb->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_replay_sample: NULL argument");
     rl_minibatch_dev dev{};
     RL_TRY(rl_replay_sample_enqueue(rb, cfg->minibatch_steps, cfg->sample_seed, draw_index, cfg->target_one_step_td,
-                                    cfg->discount_factor, q, &dev));
+                                    cfg->discount_factor, q, 1, &dev));
     uint64_t m = 0, eps = 0;
     RL_TRY(rl_replay_sample_finish(rb, &m, &eps));
     out->num_steps = m;

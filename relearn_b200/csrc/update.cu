@@ -1639,14 +1639,24 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
     AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
     PassPlan plan{};
     double *losses = nullptr;
+    // sample_minibatch (dqn.rs:280-314): episodes, features and targets (no_grad) of every step.  Reward-to-go targets
+    // do not depend on the parameters and the ring does not change during the update, so all n_steps minibatches are
+    // sampled up front by three launches (identical to sampling them one by one); OneStepTd targets need the
+    // parameters of their step and are sampled inside the loop.
+    const bool batched = !cfg->target_one_step_td && n_steps > 1;
+    if (batched)
+        RL_TRY(rl_replay_sample_enqueue(rb, cfg->minibatch_steps, cfg->sample_seed, rl_replay_take_draw_indices(rb, (uint32_t)n_steps),
+                                        0, cfg->discount_factor, q, (uint32_t)n_steps, &mb));
     for (int s = 0; s < n_steps; ++s) {
-        // sample_minibatch (dqn.rs:280-314): episodes, features and targets (no_grad) of this step
-        RL_TRY(rl_replay_sample_enqueue(rb, cfg->minibatch_steps, cfg->sample_seed, rl_replay_next_draw_index(rb),
-                                        cfg->target_one_step_td, cfg->discount_factor, q, &mb));
+        if (!batched)
+            RL_TRY(rl_replay_sample_enqueue(rb, cfg->minibatch_steps, cfg->sample_seed, rl_replay_next_draw_index(rb),
+                                            cfg->target_one_step_td, cfg->discount_factor, q, 1, &mb));
         if (s == 0) RL_TRY(make_plan(ctx, P, mb.capacity, &plan, (size_t)(n_steps + 1) * sizeof(double), (void **)&losses));
+        const size_t set = batched ? (size_t)s : 0;
         PassArgs pa{};
-        pa.obs = mb.obs; pa.action = mb.action; pa.succ = mb.succ; pa.T = 1; pa.E = mb.capacity;
-        pa.theta = q->params; pa.target = mb.target;
+        pa.obs = mb.obs + set * mb.capacity * F; pa.action = mb.action + set * mb.capacity; pa.succ = mb.succ + set * mb.capacity;
+        pa.T = 1; pa.E = mb.capacity;
+        pa.theta = q->params; pa.target = mb.target + set * mb.capacity;
         // loss_fn + backward_step (dqn.rs:316-336, coptimizer.rs:13-27)
         RL_TRY((pass_and_adam<F, A, UPL, PASS_QLOSS>(ctx, plan, pa, q, adam, ac, losses + s)));
     }
