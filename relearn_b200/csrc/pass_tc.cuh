@@ -48,11 +48,13 @@ namespace tc {
 
 constexpr int TC_THREADS = 128;
 constexpr int TC_CHUNK = 2048;  // bytes of one 8-element chunk over 128 rows
-// operand regions, in chunks: X 5, W1e 5, one zero chunk (K-slots 40..47 of both), mask 16, Y 4, C 4 or 6
-constexpr int TC_A1 = 0, TC_B1 = 5 * TC_CHUNK, TC_Z = 10 * TC_CHUNK, TC_A2 = 11 * TC_CHUNK, TC_B2 = 27 * TC_CHUNK, TC_B3 = 31 * TC_CHUNK;
+// operand regions, in chunks: X 5, W1e 5, one zero chunk (K-slots 40..47 of both), mask 16, Y 4 (Q-loss: 6), C 4 or 6
+constexpr int TC_A1 = 0, TC_B1 = 5 * TC_CHUNK, TC_Z = 10 * TC_CHUNK, TC_A2 = 11 * TC_CHUNK, TC_B2 = 27 * TC_CHUNK;
 __host__ __device__ constexpr int tc_n3(int blocks) { return (24 * blocks + 15) / 16 * 16; }  // MMA3 N: 32 / 48 (24 columns per block)
-__host__ __device__ constexpr int tc_red(int blocks) { return TC_B3 + tc_n3(blocks) / 8 * TC_CHUNK; }
-__host__ __device__ constexpr int tc_smem(int blocks) { return tc_red(blocks) + 512 + 32 + 16; }
+__host__ __device__ constexpr int tc_n2(int yblocks) { return (18 * yblocks + 15) / 16 * 16; }  // MMA2 N: 32 / 48
+__host__ __device__ constexpr int tc_b3(int yblocks) { return TC_B2 + tc_n2(yblocks) / 8 * TC_CHUNK; }  // C follows Y
+__host__ __device__ constexpr int tc_red(int blocks, int yblocks) { return tc_b3(yblocks) + tc_n3(blocks) / 8 * TC_CHUNK; }
+__host__ __device__ constexpr int tc_smem(int blocks, int yblocks) { return tc_red(blocks, yblocks) + 512 + 32 + 16; }
 constexpr int TC_CTAS_PER_SM = 3;  // 70.6 KB (critic) / 74.5 KB (policy) of shared memory and 128 + 32 TMEM columns each
 constexpr int TC_DRAIN = 8;        // tiles accumulated in TMEM between f64 drains
 
@@ -131,10 +133,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t *r) {
 // the first N meaningful columns of this thread's lane (padding columns are not fetched): 18 (G), 24 / 48 (Q)
 template <int N>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t *r) {
-    static_assert(N == 18 || N == 24 || N == 48, "column counts of this kernel");
+    static_assert(N == 18 || N == 24 || N == 36 || N == 48, "column counts of this kernel");
     if (N == 18) {
         tmem_ld16(taddr, r);
         tmem_ld2(taddr + 16, r + 16);
+    } else if (N == 36) {
+        tmem_ld32(taddr, r);
+        tmem_ld4(taddr + 32, r + 32);
     } else if (N == 24) {
         tmem_ld16(taddr, r);
         tmem_ld8(taddr + 16, r + 16);
@@ -181,19 +186,25 @@ template <int A, int MODE>
 struct TcPass {
     static constexpr bool FVP = MODE == PASS_FVP;
     static constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_PPO ||
-                                     MODE == PASS_REINFORCE;
-    static constexpr bool IS_POLICY = MODE != PASS_VALUE;
+                                     MODE == PASS_REINFORCE || MODE == PASS_QLOSS;
+    static constexpr bool IS_POLICY = MODE != PASS_VALUE && MODE != PASS_QLOSS;
+    // Y blocks of MMA2: one, except for the Q-loss, whose logit gradients do not sum to zero (only the taken action's
+    // output has one): block k holds y where action == k
+    static constexpr int YBLOCKS = MODE == PASS_QLOSS ? 2 : 1;
+    static constexpr int N2 = tc::tc_n2(YBLOCKS);
+    static constexpr int D2_COLS = N2 <= 32 ? 32 : 64;
+    static constexpr int CTAS_PER_SM = YBLOCKS == 1 ? tc::TC_CTAS_PER_SM : 2;  // 128 + 64 TMEM columns, 80 KB of shared memory
     static constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
     static constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
     static constexpr int BLOCKS = A;  // 24-column blocks of MMA3: one per logit; FVP: z_0 - z_1 and its tangent
     static constexpr int N3 = tc::tc_n3(BLOCKS);
-    static constexpr int SMEM = tc::tc_smem(BLOCKS);
-    static_assert((A == 1 && MODE == PASS_VALUE) || (A == 2 && MODE != PASS_VALUE && MODE != PASS_QLOSS),
-                  "built for the critic and for the two-action policy");
+    static constexpr int SMEM = tc::tc_smem(BLOCKS, YBLOCKS);
+    static_assert((A == 1 && MODE == PASS_VALUE) || (A == 2 && MODE != PASS_VALUE),
+                  "built for the critic and for the two-action policy / action-value network");
 };
 
 template <int A, int MODE>
-__global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_tc_kernel(PassArgs a) {
+__global__ void __launch_bounds__(tc::TC_THREADS, TcPass<A, MODE>::CTAS_PER_SM) mlp_pass_tc_kernel(PassArgs a) {
     using namespace tc;
     using K = TcPass<A, MODE>;
     constexpr int F = 5, H = 128, P = H * F + H + A * H + A, W = P + NSCALAR;
@@ -201,13 +212,14 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     constexpr int NY = 3 * NF;  // 18 columns of Y / G: three bf16 pieces of six values
     constexpr int NC = 4 * NF;  // 24 columns per block of C / Q: four pieces (see the setup of C)
     constexpr bool FVP = K::FVP, BACKWARD = K::BACKWARD, IS_POLICY = K::IS_POLICY;
-    constexpr int N3 = K::N3;
+    constexpr int N3 = K::N3, YB = K::YBLOCKS, N2 = K::N2;
+    constexpr int RED = tc_red(K::BLOCKS, YB);
     if (a.skip_flag && *a.skip_flag) return;
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2, *sB3 = smem + TC_B3;
-    double *red = reinterpret_cast<double *>(smem + tc_red(K::BLOCKS));
-    uint32_t *tptr = reinterpret_cast<uint32_t *>(smem + tc_red(K::BLOCKS) + 512 + 32);
-    const uint32_t bar1 = smem_u32(smem + tc_red(K::BLOCKS) + 512), bar2 = bar1 + 8, bar3 = bar1 + 16;
+    unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2, *sB3 = smem + tc_b3(YB);
+    double *red = reinterpret_cast<double *>(smem + RED);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(smem + RED + 512 + 32);
+    const uint32_t bar1 = smem_u32(smem + RED + 512), bar2 = bar1 + 8, bar3 = bar1 + 16;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time setup: this thread's hidden unit -> row `tid` of the B operands of MMA1 and MMA3 ----
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     *reinterpret_cast<uint4 *>(smem + TC_Z + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     if (warp == 0) {
         tmem_alloc(smem_u32(tptr), 128);
-        if (BACKWARD) tmem_alloc(smem_u32(tptr + 1), 32);
+        if (BACKWARD) tmem_alloc(smem_u32(tptr + 1), K::D2_COLS);
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
@@ -295,14 +307,16 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
 
     constexpr uint32_t IDESC1 = make_idesc(128, 128, false, false);  // X (K-major) . W1e (K-major)
-    constexpr uint32_t IDESC2 = make_idesc(128, 32, true, true);     // Mask^T (MN-major) . Y (MN-major)
+    constexpr uint32_t IDESC2 = make_idesc(128, N2, true, true);     // Mask^T (MN-major) . Y (MN-major)
     constexpr uint32_t IDESC3 = make_idesc(128, N3, false, true);    // Mask (K-major) . C (MN-major)
     const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), aA2 = smem_u32(sA2), aB2 = smem_u32(sB2), aB3 = smem_u32(sB3);
 
     const uint64_t TE = a.T * a.E, ntiles = (TE + 127) / 128;
-    double G[BACKWARD ? NY : 1], sc[NSCALAR], gb2_acc = 0.0;
+    double G[BACKWARD ? YB * NY : 1], sc[NSCALAR], gb2_acc[YB];
 #pragma unroll
-    for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] = 0.0;
+    for (int n = 0; n < (BACKWARD ? YB * NY : 1); ++n) G[n] = 0.0;
+#pragma unroll
+    for (int k = 0; k < YB; ++k) gb2_acc[k] = 0.0;
 #pragma unroll
     for (int k = 0; k < NSCALAR; ++k) sc[k] = 0.0;
 
@@ -319,8 +333,8 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         st.code = in_range ? __ldg(a.succ + n_next) : (uint8_t)RL_PAD;
 #pragma unroll
         for (int f = 0; f < F; ++f) st.x[f] = in_range ? __ldg(a.obs + (t_next * F + f) * a.E + e_next) : 0.0f;
-        st.tgt = (MODE == PASS_VALUE && in_range) ? __ldg(a.target + n_next) : 0.0f;
-        st.act = (IS_POLICY && in_range) ? __ldg(a.action + n_next) : (uint8_t)0;
+        st.tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && in_range) ? __ldg(a.target + n_next) : 0.0f;
+        st.act = ((IS_POLICY || MODE == PASS_QLOSS) && in_range) ? __ldg(a.action + n_next) : (uint8_t)0;
         st.adv = (K::USES_ADV && in_range) ? __ldg(a.adv + n_next) : 0.0f;
         st.lp0 = make_float2(0.0f, 0.0f);
         if (K::USES_LP0 && in_range) st.lp0 = __ldg(reinterpret_cast<const float2 *>(a.logp0) + n_next);
@@ -336,10 +350,10 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         // G of the tiles accumulated so far: wait for the last MMA2, read this unit's 18 columns, add in f64
         mbar_wait(bar2, parity);
         fence_after();
-        uint32_t r[NY];
-        tmem_ld_cols<NY>(tmem_d2 + lane_off, r);
+        uint32_t r[YB * NY];
+        tmem_ld_cols<YB * NY>(tmem_d2 + lane_off, r);
 #pragma unroll
-        for (int n = 0; n < (BACKWARD ? NY : 1); ++n) G[n] += (double)__uint_as_float(r[n]);
+        for (int n = 0; n < (BACKWARD ? YB * NY : 1); ++n) G[n] += (double)__uint_as_float(r[n]);
     };
 
     Staged nxt;
@@ -479,6 +493,11 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
                     dz0 = -adv_s * d0;
                 }
                 if (FVP) dz0 = p[0] * (p[A > 1 ? 1 : 0] * zdd);  // u = (diag p - p p^T) zdot with p_0 + p_1 = 1
+            } else if (MODE == PASS_QLOSS) {
+                // dqn.rs:316-326: mse(Q(obs).gather(action), targets); dz0 is the gradient w.r.t. the TAKEN action's output
+                const float diff = (act_s == 0 ? z[0] : z[A > 1 ? 1 : 0]) - tgt;
+                loss_s = diff * diff;
+                dz0 = 2.0f * diff;
             } else {
                 // opt.rs:109-115: mse_loss(V(obs), targets, Mean)
                 const float diff = z[0] - tgt;
@@ -489,21 +508,23 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
             sc[SC_LOSS] += (double)loss_s;
             sc[SC_KL] += (double)kl_s;
             sc[SC_ENTROPY] += (double)ent_s;
-            gb2_acc += (double)dz0;
+#pragma unroll
+            for (int k = 0; k < YB; ++k) gb2_acc[k] += (YB == 1 || (act_s == 0) == (k == 0)) ? (double)dz0 : 0.0;
         }
         if (BACKWARD) {
-            uint32_t hi[NF], mid[NF], lo[NF], e[32];
+            uint32_t hi[NF], mid[NF], lo[NF], e[N2];
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
                 const float y = f < F ? dz0 * x[f < F ? f : 0] : dz0;
                 split3(y, hi[f], mid[f], lo[f]);
             }
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int g = k / NF, f = k % NF;
-                e[k] = k >= NY ? 0u : g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
+            for (int k = 0; k < N2; ++k) {
+                const int blk = k / NY, g = (k % NY) / NF, f = k % NF;
+                const uint32_t piece = g == 0 ? hi[f] : g == 1 ? mid[f] : lo[f];
+                e[k] = k >= YB * NY ? 0u : (YB == 1 || (act_s == 0) == (blk == 0)) ? piece : 0u;  // Q-loss: block of the taken action
             }
-            store_row<4>(sB2, tid, e);
+            store_row<N2 / 8>(sB2, tid, e);
             fence_async_smem();
             fence_before();
             __syncthreads();
@@ -526,16 +547,19 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     double s_sc[NSCALAR];
 #pragma unroll
     for (int k = 0; k < NSCALAR; ++k) s_sc[k] = warp_sum_f64(sc[k]);
-    const double s_g = warp_sum_f64(gb2_acc);
+    double s_g[YB];
+#pragma unroll
+    for (int k = 0; k < YB; ++k) s_g[k] = warp_sum_f64(gb2_acc[k]);
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < NSCALAR; ++k) red[warp * 8 + k] = s_sc[k];
-        red[warp * 8 + NSCALAR] = s_g;
+#pragma unroll
+        for (int k = 0; k < YB; ++k) red[warp * 8 + NSCALAR + k] = s_g[k];
     }
     fence_before();
     __syncthreads();
     double *row = a.partials + (size_t)blockIdx.x * W;
-    if (BACKWARD) {
+    if (BACKWARD && YB == 1) {
         double Gf[NF];
 #pragma unroll
         for (int f = 0; f < NF; ++f) Gf[f] = (G[f] + G[NF + f]) + G[2 * NF + f];
@@ -550,14 +574,37 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
         row[H * F + tid] = wd * Gf[F];
         row[H * F + H + tid] = gw2;
         if (A > 1) row[H * F + H + H + tid] = -gw2;
+    } else if (BACKWARD) {
+        // Q-loss: one G per output, dW1[j] = sum_k w2_kj G^k[j], dW2[k][j] = b1_j G^k[j][5] + w1_j . G^k[j]
+        double gw1[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) gw1[f] = 0.0;
+#pragma unroll
+        for (int k = 0; k < YB; ++k) {
+            double Gf[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) Gf[f] = (G[k * NY + f] + G[k * NY + NF + f]) + G[k * NY + 2 * NF + f];
+            double gw2 = (double)wrow[F] * Gf[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) gw2 += (double)wrow[f] * Gf[f];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) gw1[f] += (double)w2j[k < A ? k : 0] * Gf[f];
+            row[H * F + H + k * H + tid] = gw2;
+        }
+#pragma unroll
+        for (int f = 0; f < F; ++f) row[tid * F + f] = gw1[f];
+        row[H * F + tid] = gw1[F];
     } else {
         for (int i = tid; i < P; i += TC_THREADS) row[i] = 0.0;
     }
     if (tid == 0) {
         if (BACKWARD) {
-            const double g = ((red[NSCALAR] + red[8 + NSCALAR]) + red[16 + NSCALAR]) + red[24 + NSCALAR];
-            row[P - A] = g;
-            if (A > 1) row[P - 1] = -g;
+#pragma unroll
+            for (int k = 0; k < YB; ++k) {
+                const double g = ((red[NSCALAR + k] + red[8 + NSCALAR + k]) + red[16 + NSCALAR + k]) + red[24 + NSCALAR + k];
+                row[P - A + k] = g;
+                if (YB == 1 && A > 1) row[P - 1] = -g;
+            }
         }
 #pragma unroll
         for (int k = 0; k < NSCALAR; ++k) row[P + k] = ((red[k] + red[8 + k]) + red[16 + k]) + red[24 + k];
@@ -565,6 +612,6 @@ __global__ void __launch_bounds__(tc::TC_THREADS, tc::TC_CTAS_PER_SM) mlp_pass_t
     if (warp == 0) {
         fence_after();
         tmem_dealloc(tmem_d1, 128);
-        if (BACKWARD) tmem_dealloc(tmem_d2, 32);
+        if (BACKWARD) tmem_dealloc(tmem_d2, K::D2_COLS);
     }
 }

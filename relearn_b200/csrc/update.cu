@@ -961,17 +961,27 @@ int pass_kernel() {
 template <int F, int A, int UPL, int MODE>
 constexpr bool tc_built() {
     return F == 5 && UPL == 4 &&
-           ((A == 1 && MODE == PASS_VALUE) || (A == 2 && (MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD ||
-                                                          MODE == PASS_FVP || MODE == PASS_PPO || MODE == PASS_REINFORCE)));
+           ((A == 1 && MODE == PASS_VALUE) ||
+            (A == 2 && (MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_PPO ||
+                        MODE == PASS_REINFORCE || MODE == PASS_QLOSS)));
 }
 template <int F, int A, int UPL, int MODE>
 bool pass_on_tensor_cores() {
     return tc_built<F, A, UPL, MODE>() && pass_kernel() == RL_PASS_KERNEL_TCGEN05;
 }
+// CTAs of a tensor-core pass: the plan's count (3 per SM) capped at what the mode keeps resident per SM
+template <int A, int MODE>
+int tc_grid(const rl_ctx *ctx, const PassPlan &plan) {
+    const int cap = ctx->sm_count * TcPass<A, MODE>::CTAS_PER_SM;
+    return plan.grid_tc < cap ? plan.grid_tc : cap;
+}
 // rows of plan.partials the pass writes
 template <int F, int A, int UPL, int MODE>
-int pass_rows(const PassPlan &plan) {
-    return pass_on_tensor_cores<F, A, UPL, MODE>() ? plan.grid_tc : plan.grid;
+int pass_rows(const rl_ctx *ctx, const PassPlan &plan) {
+    if constexpr (tc_built<F, A, UPL, MODE>()) {
+        if (pass_on_tensor_cores<F, A, UPL, MODE>()) return tc_grid<A, MODE>(ctx, plan);
+    }
+    return plan.grid;
 }
 
 template <int A, int MODE>
@@ -983,9 +993,10 @@ rl_status launch_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool 
         configured = true;
     }
     args.partials = plan.partials;
-    RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), plan.grid_tc, tc::TC_THREADS, smem, args);
+    const int grid = tc_grid<A, MODE>(ctx, plan);
+    RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), grid, tc::TC_THREADS, smem, args);
     if (!reduce) return RL_OK;
-    return reduce_over_group(ctx, plan, plan.grid_tc, args.skip_flag);
+    return reduce_over_group(ctx, plan, grid, args.skip_flag);
 }
 
 int pass_variant() {
@@ -1027,7 +1038,7 @@ rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, r
         // pass -> ONE kernel: row reduction + peer exchange + Adam
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
         ctx->x_seq += 1;
-        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(plan)),
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(ctx, plan)),
                   plan.W, plan.P, plan.sums, ctx->x, ctx->x_seq, (const int *)nullptr,
                   (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
     } else if (ctx->world > 1) {
@@ -1036,7 +1047,7 @@ rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, r
                   loss_out);
     } else {
         RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
-        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(plan)),
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(ctx, plan)),
                   plan.W, plan.P, plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
     }
     return RL_OK;
