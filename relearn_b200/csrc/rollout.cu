@@ -564,6 +564,15 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
         // continues, the full limit after a reset.  Looked up here, off the dependent chain.
         const uint32_t r_now = s.meta & 0x7FFFFFFFu;
         const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
+        // Speculative dynamics (LANES >= 2): the threads of a group used to compute the same f64 step redundantly after
+        // the action was known.  Instead the lower half of the group steps a copy of the state with action 0 and the
+        // upper half with action 1 BEFORE the policy is evaluated -- the two instruction streams are independent, so
+        // the scheduler interleaves them -- and the sampled action only selects which half's result is taken (one
+        // round of shuffles).  Same operations on the same operands as before: results are bit-identical.
+        constexpr bool SPEC = LANES >= 2;
+        EnvT::State cand = s;
+        int cand_sc = RL_CONTINUE;
+        if constexpr (SPEC) cand_sc = EnvT::step_fast(p, cand, sub >= LANES / 2 ? 1u : 0u);
         float z0 = 0.0f, z1 = 0.0f;
         if (needs_logits) {
             const float2 o0 = make_float2(obs[0], obs[0]), o1 = make_float2(obs[1], obs[1]), o2 = make_float2(obs[2], obs[2]);
@@ -663,7 +672,18 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
         }
 #pragma unroll
         for (int f = 0; f < 5; ++f) last_obs[f] = active ? obs[f] : last_obs[f];
-        const int sc = EnvT::step_fast(p, s, action);
+        int sc;
+        if constexpr (SPEC) {
+            const int src = (threadIdx.x & 31 & ~(LANES - 1)) + (action ? LANES / 2 : 0);
+            s.x = __shfl_sync(0xffffffffu, cand.x, src);
+            s.xd = __shfl_sync(0xffffffffu, cand.xd, src);
+            s.th = __shfl_sync(0xffffffffu, cand.th, src);
+            s.thd = __shfl_sync(0xffffffffu, cand.thd, src);
+            s.meta = __shfl_sync(0xffffffffu, cand.meta, src);
+            sc = __shfl_sync(0xffffffffu, cand_sc, src);
+        } else {
+            sc = EnvT::step_fast(p, s, action);
+        }
         const float r = 1.0f;  // cartpole.rs:140
         if (active) {
             if (owns[6]) a.reward[is] = r;

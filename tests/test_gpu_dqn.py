@@ -216,7 +216,7 @@ def test_sample_one_step_td_targets(ctx, filled):
 
 
 @pytest.mark.parametrize("td", [False, True])
-def test_dqn_update_matches_oracle(ctx, filled, td):
+def test_dqn_update_matches_oracle(ctx, filled, pass_kernel, td):
     """opt_steps x {sample, mse(Q(obs)[a], target), backward, Adam} vs the torch restatement on the same sampled
     episodes: parameter delta within max(2e-4, 4x the torch-f32 run's own distance from the f64 run)."""
     env, rb, lanes = filled
@@ -237,7 +237,7 @@ def test_dqn_update_matches_oracle(ctx, filled, td):
     new32, losses32 = TO.dqn_update(params, 5, 128, 2, mbs, g, one_step_td=td, dtype=torch.float32)
     d, d64, d32 = new - params, new64 - params.astype(np.float64), new32 - params
     rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
-    print(f"dqn td={td} delta rel err vs f64: kernel {rel(d, d64):.2e}, torch-f32 {rel(d32, d64):.2e}; "
+    print(f"dqn {pass_kernel} td={td} delta rel err vs f64: kernel {rel(d, d64):.2e}, torch-f32 {rel(d32, d64):.2e}; "
           f"loss first/last {stats.loss_first:.6f}/{stats.loss_last:.6f} vs {losses64[0]:.6f}/{losses64[-1]:.6f}")
     assert stats.opt_steps == steps and stats.num_steps == sum(len(e["action"]) for e in mbs[-1])
     np.testing.assert_allclose(stats.loss_first, losses64[0], rtol=1e-5)

@@ -22,15 +22,6 @@ torch = pytest.importorskip("torch")
 CARTPOLE = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
 
 
-@pytest.fixture(params=["tcgen05", "ffma"])
-def pass_kernel(request):
-    """Run a test once per full-batch pass kernel: tensor cores (the default) and the FP32-pipe kernel."""
-    k = L.RL_PASS_KERNEL_TCGEN05 if request.param == "tcgen05" else L.RL_PASS_KERNEL_FFMA
-    L.check(L.lib().rl_pass_kernel_select(k))
-    yield request.param
-    L.check(L.lib().rl_pass_kernel_select(L.RL_PASS_KERNEL_TCGEN05))
-
-
 def _collect(ctx, E, T, seed, scale=1.0):
     """Roll a random-init policy on CartPole and return (env, traj, params, flattened valid batch)."""
     rng = np.random.default_rng(seed)
