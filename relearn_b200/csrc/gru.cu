@@ -19,6 +19,8 @@
 // trajectory write stream and the env arithmetic, like K2a.  The rl2-sized module (hidden 128, 1.1e5 FLOP per
 // env-step) is a dense [E, F+H] x [F+H, 3H] GEMM per step and belongs on tcgen05 tensor cores; that variant is
 // not built yet -- this FP32 kernel is the correct-but-slow path for it.
+#include <type_traits>
+
 #include "handles.cuh"
 
 struct rl_grunet {
@@ -40,9 +42,10 @@ struct GruView {
 __device__ __forceinline__ float sigmoidf_ref(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 // One gru_cell + activation + Linear for this thread's env.  `w` points at the parameters (shared or global).
-template <int HMAX, int MAXF, int MAXA>
+// EXACT: the sizes ARE (MAXF, HMAX, MAXA) -- no padded iterations, no predicates (BASELINE config 4: 6 / 4 / 2).
+template <int HMAX, int MAXF, int MAXA, bool EXACT = false>
 __device__ __forceinline__ void grunet_step(const GruView &m, const float *__restrict__ w, const float *x, float *h, float *z) {
-    const int F = m.F, H = m.H, A = m.A;
+    const int F = EXACT ? MAXF : m.F, H = EXACT ? HMAX : m.H, A = EXACT ? MAXA : m.A;
     const float *w_ih = w, *w_hh = w_ih + (size_t)3 * H * F, *b_ih = w_hh + (size_t)3 * H * H, *b_hh = b_ih + 3 * H;
     const float *lin_w = b_hh + 3 * H, *lin_b = lin_w + (size_t)A * H;
     // HMAX <= 8: everything unrolled, hidden state in registers.  Larger: plain loops over thread-local arrays.
@@ -123,8 +126,15 @@ struct SeqArgs {
     double *partials;  // f64 [gridDim.x][SQ_COUNT]
 };
 
-template <class EnvT, bool REPLAY, int HMAX>
+// XF / XA > 0: features / actions (and hidden = HMAX) fixed at compile time, see grunet_step<EXACT>.
+template <class EnvT, bool REPLAY, int HMAX, int XF = 0, int XA = 0>
 __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params p, SeqArgs a) {
+    constexpr bool EXACT = XF > 0;
+    constexpr int MF = EXACT ? XF : EnvT::MAXF, MA = EXACT ? XA : EnvT::MAXA;
+    auto observe = [&](const typename EnvT::State &st, float *o) {
+        if constexpr (EXACT) EnvT::template observe_arms<XA>(st, o);
+        else EnvT::observe(p, st, o);
+    };
     extern __shared__ __align__(16) float sw[];
     if (a.weights_in_smem) {
         const uint64_t np = a.net.count();
@@ -138,14 +148,14 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
 #pragma unroll
     for (int i = 0; i < SQ_COUNT; ++i) st[i] = 0.0;
     if (valid) {
-        const int F = a.F;
+        const int F = EXACT ? XF : a.F, A = EXACT ? XA : a.A;
         LaneNoise<REPLAY> nz;
         nz.init(a.noise, a.lane_offset + e, e);
         const uint32_t t0 = a.noise.step_counter;
         typename EnvT::State s;
-        float obs[EnvT::MAXF], last_obs[EnvT::MAXF], h[HMAX];
+        float obs[MF], last_obs[MF], h[HMAX];
 #pragma unroll
-        for (int f = 0; f < EnvT::MAXF; ++f) obs[f] = last_obs[f] = 0.0f;
+        for (int f = 0; f < MF; ++f) obs[f] = last_obs[f] = 0.0f;
 #pragma unroll
         for (int j = 0; j < HMAX; ++j) h[j] = 0.0f;  // SeqIterative::initial_state (gru.rs:23-28)
         uint32_t n = a.min_steps ? a.min_steps + a.slack : 0;  // take_steps.rs:20-31
@@ -155,16 +165,16 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
         if (n > 0) {  // train.rs:135: every period starts fresh episodes
             nz.set_step(t0);
             EnvT::template reset<REPLAY>(p, s, nz);
-            EnvT::observe(p, s, obs);
+            observe(s, obs);
         }
         while (n > 0) {
             nz.set_step(t0 + i);
-            float z[EnvT::MAXA];
-            grunet_step<HMAX, EnvT::MAXF, EnvT::MAXA>(a.net, w, obs, h, z);
+            float z[MA];
+            grunet_step<HMAX, MF, MA, EXACT>(a.net, w, obs, h, z);
             const float u = rl_u32_to_f32(nz.template next_u32<RL_STREAM_ACTOR>());
-            const uint32_t action = categorical_sample_seq<EnvT::MAXA>(z, a.A, u);
+            const uint32_t action = categorical_sample_seq<MA>(z, A, u);
 #pragma unroll
-            for (int f = 0; f < EnvT::MAXF; ++f)
+            for (int f = 0; f < MF; ++f)
                 if (f < F) {
                     a.obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
                     last_obs[f] = obs[f];
@@ -172,9 +182,9 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
             float r;
             const int sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
             if (sc == RL_INTERRUPT) {
-                EnvT::observe(p, s, obs);
+                observe(s, obs);
 #pragma unroll
-                for (int f = 0; f < EnvT::MAXF; ++f)
+                for (int f = 0; f < MF; ++f)
                     if (f < F) a.next_obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
             }
             if (sc != RL_CONTINUE) {
@@ -183,7 +193,7 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
 #pragma unroll
                 for (int j = 0; j < HMAX; ++j) h[j] = 0.0f;  // steps.rs:116-124: actor.initial_state for the new episode
             }
-            EnvT::observe(p, s, obs);
+            observe(s, obs);
             a.action[(uint64_t)i * a.E + e] = (uint8_t)action;
             a.reward[(uint64_t)i * a.E + e] = r;
             a.succ[(uint64_t)i * a.E + e] = (uint8_t)sc;
@@ -217,7 +227,7 @@ __global__ void __launch_bounds__(128) rollout_seq_kernel(typename EnvT::Params 
                 flags = 3;
                 a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
 #pragma unroll
-                for (int f = 0; f < EnvT::MAXF; ++f)
+                for (int f = 0; f < MF; ++f)
                     if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
                 eps += 1.0;
             }
@@ -333,9 +343,24 @@ rl_status launch_seq_h(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, 
     return RL_OK;
 }
 
+// BASELINE config 4: 2-armed bandit meta-env (6 features) with the rnn.rs-sized GRU (hidden 4)
+rl_status launch_seq_bandit_6_4_2(rl_ctx *ctx, const BanditMetaEnv::Params &p, SeqArgs &a, bool replay, size_t smem, unsigned grid) {
+    if (replay) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_kernel<BanditMetaEnv, true, 4, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_seq_kernel<BanditMetaEnv, true, 4, 6, 2>), grid, 128, smem, p, a);
+    } else {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_kernel<BanditMetaEnv, false, 4, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_seq_kernel<BanditMetaEnv, false, 4, 6, 2>), grid, 128, smem, p, a);
+    }
+    return RL_OK;
+}
+
 template <class EnvT>
 rl_status launch_seq(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bool replay, size_t smem, unsigned grid) {
     const int H = a.net.H;
+    if constexpr (std::is_same<EnvT, BanditMetaEnv>::value) {
+        if (H == 4 && a.F == 6 && a.A == 2 && p.num_arms == 2) return launch_seq_bandit_6_4_2(ctx, p, a, replay, smem, grid);
+    }
     if (H <= 8) return launch_seq_h<EnvT, 8>(ctx, p, a, replay, smem, grid);
     return launch_seq_h<EnvT, 128>(ctx, p, a, replay, smem, grid);
 }
