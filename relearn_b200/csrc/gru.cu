@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(32 * SQ_COUNT) seq_finalize_kernel(const doubl
 
 // SeqPacked::seq_packed (gru.rs:72-102 -> chain.rs:157-168) over a stored trajectory: thread per lane, hidden
 // state zeroed at the first step of every episode.  out f32 [T][A][E]; PAD slots get zeros.
-template <int HMAX>
+template <int HMAX, int XF = 0, int XA = 0>
 __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_in_smem, const float *__restrict__ obs,
                                                         const float *__restrict__ next_obs, const uint8_t *__restrict__ succ,
                                                         uint64_t T, uint64_t E, float *__restrict__ out,
@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_
     const float *w = weights_in_smem ? sw : m.params;
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
-    constexpr int MAXF = 36, MAXA = 32;
+    constexpr bool EXACT = XF > 0;  // sizes fixed at compile time (config 4: 6 features, hidden 4, 1 or 2 outputs)
+    constexpr int MAXF = EXACT ? XF : 36, MAXA = EXACT ? XA : 32;
+    const int nF = EXACT ? XF : m.F, nA = EXACT ? XA : m.A;
     float h[HMAX];
 #pragma unroll
     for (int j = 0; j < HMAX; ++j) h[j] = 0.0f;
@@ -297,14 +299,16 @@ __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_
         const uint8_t sc = succ[t * E + e];
         float z[MAXA];
         if (sc == RL_PAD) {
-            for (int k = 0; k < m.A; ++k) out[(t * m.A + k) * E + e] = 0.0f;
+            for (int k = 0; k < nA; ++k) out[(t * nA + k) * E + e] = 0.0f;
             continue;
         }
         float x[MAXF];
 #pragma unroll
-        for (int f = 0; f < MAXF; ++f) x[f] = f < m.F ? obs[(t * m.F + f) * E + e] : 0.0f;
-        grunet_step<HMAX, MAXF, MAXA>(m, w, x, h, z);
-        for (int k = 0; k < m.A; ++k) out[(t * m.A + k) * E + e] = z[k];
+        for (int f = 0; f < MAXF; ++f) x[f] = f < nF ? obs[(t * nF + f) * E + e] : 0.0f;
+        grunet_step<HMAX, MAXF, MAXA, EXACT>(m, w, x, h, z);
+        #pragma unroll
+        for (int k = 0; k < MAXA; ++k)
+            if (k < nA) out[(t * nA + k) * E + e] = z[k];
         if (sc == RL_INTERRUPT && out_next) {
             // the extended observation of an interrupted episode (features.rs:139-185): one more step of the same
             // sequence on the successor observation
@@ -312,9 +316,11 @@ __global__ void __launch_bounds__(128) grunet_seq_kernel(GruView m, int weights_
 #pragma unroll
             for (int j = 0; j < HMAX; ++j) h2[j] = h[j];
 #pragma unroll
-            for (int f = 0; f < MAXF; ++f) x[f] = f < m.F ? next_obs[(t * m.F + f) * E + e] : 0.0f;
-            grunet_step<HMAX, MAXF, MAXA>(m, w, x, h2, z);
-            for (int k = 0; k < m.A; ++k) out_next[(t * m.A + k) * E + e] = z[k];
+            for (int f = 0; f < MAXF; ++f) x[f] = f < nF ? next_obs[(t * nF + f) * E + e] : 0.0f;
+            grunet_step<HMAX, MAXF, MAXA, EXACT>(m, w, x, h2, z);
+            #pragma unroll
+            for (int k = 0; k < MAXA; ++k)
+                if (k < nA) out_next[(t * nA + k) * E + e] = z[k];
         }
         if (sc != RL_CONTINUE) {
 #pragma unroll
@@ -412,7 +418,17 @@ rl_status rl_grunet_seq_enqueue(rl_grunet *g, rl_traj *traj, float *out_dev, flo
     const size_t smem = in_smem ? wbytes : 16;
     const unsigned grid = rl_grid_for(E, 128);
     const GruView v = view_of(g);
-    if (g->hidden <= 8) {
+    if (g->hidden == 4 && g->in_dim == 6 && (g->out_dim == 1 || g->out_dim == 2)) {
+        if (g->out_dim == 1) {
+            RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<4, 6, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RL_LAUNCH(ctx, (grunet_seq_kernel<4, 6, 1>), grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
+                      out_next_dev);
+        } else {
+            RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<4, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            RL_LAUNCH(ctx, (grunet_seq_kernel<4, 6, 2>), grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
+                      out_next_dev);
+        }
+    } else if (g->hidden <= 8) {
         RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RL_LAUNCH(ctx, grunet_seq_kernel<8>, grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
                   out_next_dev);
