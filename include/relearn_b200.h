@@ -120,7 +120,7 @@ rl_status rl_ctx_allreduce_f64(rl_ctx *ctx, double *buf_dev, size_t n);
 /* Environments   (BuildEnv::build_env src/envs/builders.rs:17; Environment src/envs/mod.rs:76) */
 /* ------------------------------------------------------------------------------------------ */
 typedef enum {
-    RL_ENV_CARTPOLE = 0,    /* CartPole (+ VisibleStepLimit)  src/envs/cartpole.rs, wrappers/step_limit.rs */
+    RL_ENV_CARTPOLE = 0,    /* CartPole (+ Visible / LatentStepLimit)  src/envs/cartpole.rs, wrappers/step_limit.rs */
     RL_ENV_CHAIN = 1,       /* Chain                          src/envs/chain.rs */
     RL_ENV_MEMORY_GAME = 2, /* MemoryGame                     src/envs/memory.rs */
     RL_ENV_BANDIT_META = 3  /* MetaEnv<UniformBernoulliBandits> + TrialEpisodeLimit  src/envs/meta.rs, bandits.rs */
@@ -132,6 +132,9 @@ typedef struct rl_cartpole_cfg {
     double gravity, mass_cart, mass_pole, length_half_pole, friction_cart, friction_pole, time_step;
     double action_force, max_pos, max_angle, discount_factor;
     uint64_t max_steps_per_episode;
+    /* 1 = VisibleStepLimit (the observation gains the `remaining` feature, step_limit.rs:97-223);
+     * 0 = LatentStepLimit (same interruption, observation unchanged, step_limit.rs:13-90) */
+    uint64_t step_limit_visible;
 } rl_cartpole_cfg;
 /* Chain (chain.rs:21-45) */
 typedef struct rl_chain_cfg { uint64_t size; double discount_factor; } rl_chain_cfg;

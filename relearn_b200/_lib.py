@@ -32,7 +32,8 @@ vp = C.c_void_p
 class CartPoleCfg(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "gravity", "mass_cart", "mass_pole", "length_half_pole", "friction_cart", "friction_pole", "time_step",
-        "action_force", "max_pos", "max_angle", "discount_factor")] + [("max_steps_per_episode", C.c_uint64)]
+        "action_force", "max_pos", "max_angle", "discount_factor")] + [("max_steps_per_episode", C.c_uint64),
+                                                                        ("step_limit_visible", C.c_uint64)]
 
 
 class ChainCfg(C.Structure):

@@ -130,6 +130,7 @@ void rl_cartpole_cfg_default(rl_cartpole_cfg *c, uint64_t max_steps_per_episode)
     c->max_angle = 12.0 * (3.14159265358979323846264338327950288 / 180.0);
     c->discount_factor = 0.99;
     c->max_steps_per_episode = max_steps_per_episode;
+    c->step_limit_visible = 1;
 }
 
 void rl_chain_cfg_default(rl_chain_cfg *c) {
@@ -171,6 +172,7 @@ rl_status rl_env_create(rl_ctx *ctx, rl_env_kind kind, const void *cfg, uint64_t
         p.mass_length_pole = c->mass_pole * c->length_half_pole;
         uniform_inclusive(-0.05, 0.05, &p.reset_low, &p.reset_scale);  // cartpole.rs:105
         p.max_steps = (uint32_t)c->max_steps_per_episode;
+        p.visible = c->step_limit_visible != 0 ? 1u : 0u;
         st.num_features = CartPoleEnv::num_features(p);
         st.num_actions = 2;
         st.num_observations = 0;

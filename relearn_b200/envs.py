@@ -32,8 +32,16 @@ class VisibleStepLimit:
 
 
 @dataclass
+class LatentStepLimit:
+    """src/envs/wrappers/step_limit.rs:13-90: episodes are interrupted after the limit, the observation does not show it"""
+
+    max_steps_per_episode: int = 100
+
+
+@dataclass
 class CartPoleConfig:
-    """PhysicalConstants + EnvironmentParams (src/envs/cartpole.rs:157-216); `.wrap(VisibleStepLimit(n))`."""
+    """PhysicalConstants + EnvironmentParams (src/envs/cartpole.rs:157-216); `.wrap(VisibleStepLimit(n))` or
+    `.wrap(LatentStepLimit(n))`."""
 
     gravity: float = 9.8
     mass_cart: float = 1.0
@@ -47,12 +55,14 @@ class CartPoleConfig:
     max_angle: float = 12.0 * (math.pi / 180.0)
     discount_factor: float = 0.99
     max_steps_per_episode: int = 0
+    step_limit_visible: int = 1
 
     kind = L.RL_ENV_CARTPOLE
 
-    def wrap(self, limit: VisibleStepLimit) -> "CartPoleConfig":
+    def wrap(self, limit) -> "CartPoleConfig":
         out = CartPoleConfig(**{k: getattr(self, k) for k in self.__dataclass_fields__})
         out.max_steps_per_episode = limit.max_steps_per_episode
+        out.step_limit_visible = 0 if isinstance(limit, LatentStepLimit) else 1
         return out
 
     def c_cfg(self):

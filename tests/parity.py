@@ -17,6 +17,7 @@ def oracle_cfg_for(config) -> O.EnvCfg:
         for k in ("gravity", "mass_cart", "mass_pole", "length_half_pole", "friction_cart", "friction_pole",
                   "time_step", "action_force", "max_pos", "max_angle", "discount_factor"):
             setattr(c, k, getattr(config, k))
+        c.step_limit_visible = int(config.step_limit_visible)
         return c
     if isinstance(config, R.Chain):
         return O.chain_cfg(config.size, config.discount_factor)

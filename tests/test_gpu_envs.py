@@ -247,3 +247,49 @@ def test_actor_file_roundtrip_reproduces_rollout(ctx, tmp_path):
         hosts.append(traj.to_host())
     for k in ("obs", "action", "reward", "succ"):
         assert np.array_equal(hosts[0][k], hosts[1][k]), k
+
+
+LATENT = R.CartPoleConfig().wrap(R.LatentStepLimit(9))
+
+
+def test_latent_step_limit_unfused_and_fused(ctx):
+    """LatentStepLimit (step_limit.rs:13-90): same interruption after the limit as VisibleStepLimit, but the observation
+    keeps CartPole's four features.  Unfused steps and the fused replay rollout against the oracle (limit 9 so that
+    Interrupt, Terminate and resets all occur)."""
+    env = R.build_env(ctx, LATENT, 8, seed=1)
+    assert env.num_features == 4 and env.num_actions == 2
+    env.close()
+    _unfused_vs_oracle(ctx, LATENT, E=200, T=40, rng=np.random.default_rng(51), exact=False)
+    rng = np.random.default_rng(52)
+    E, T, slack = 193, 48, 5
+    env = R.build_env(ctx, LATENT, E, seed=3)
+    words = P.random_words(rng, E, 8 * (T + slack) + 64)
+    env.set_noise_replay(words, None)
+    actions = rng.integers(0, 2, size=(T + slack, E), dtype=np.uint8)
+    traj = R.Trajectory(env, T + slack)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_REPLAY_ACTIONS, actions=actions), R.HistoryDataBound(T, slack), traj)
+    ref = P.oracle_rollout(LATENT, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=actions, env_words=words)
+    host = traj.to_host()
+    assert host["obs"].shape[-1] == 4 and (host["succ"] == L.RL_INTERRUPT).any() and (host["succ"] == L.RL_TERMINATE).any()
+    P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what="fused cartpole latent limit")
+    P.compare_summary(summ, ref["summary"])
+
+
+@pytest.mark.parametrize("lanes", [1, 8])
+def test_latent_step_limit_policy_rollout(ctx, lanes):
+    """A 4-feature policy (MLP 4 -> 128 -> 2) inside the fused step kernel under the latent limit."""
+    rng = np.random.default_rng(60 + lanes)
+    E, T = 96, 40
+    env = R.build_env(ctx, LATENT, E, seed=3)
+    ewords, awords = P.random_words(rng, E, 8 * T + 64), P.random_words(rng, E, 8 * T + 64)
+    env.set_noise_replay(ewords, awords)
+    params = R.init_params(rng, 4, 128, 2) * 3.0
+    net = R.Mlp(ctx, 4, [128], 2)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes), R.HistoryDataBound(T, 0), traj)
+    host = traj.to_host()
+    checked, near = P.check_policy_consistency(host, params, 128, 2, awords)
+    assert checked > E * (T - 2) and near <= 3
+    ref = P.oracle_rollout(LATENT, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), env_words=ewords)
+    P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what=f"latent policy lanes={lanes}")
