@@ -26,7 +26,9 @@ constexpr int GH_MAX = 8, GF_MAX = 20, GA_MAX = 16;
 constexpr int GP_MAX_ALL = 3 * GH_MAX * GF_MAX + 3 * GH_MAX * GH_MAX + 6 * GH_MAX + GA_MAX * GH_MAX + GA_MAX;
 constexpr float F32_LOWEST_G = -3.402823466e+38f;
 
-__device__ __forceinline__ float sigm(float v) { return 1.0f / (1.0f + expf(-v)); }
+// 1 / (1 + e^-v) with the hardware reciprocal (MUFU.RCP, <= 1 ulp) instead of the ~10-instruction IEEE division:
+// 24 of these per step sit on the recurrence's dependency chain
+__device__ __forceinline__ float sigm(float v) { return __fdividef(1.0f, 1.0f + expf(-v)); }
 
 struct Dims {
     int F, H, A, act;
@@ -112,13 +114,29 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
 #pragma unroll
         for (int j = 0; j < H; ++j) h[j] = hd[j] = 0.0f;
         uint64_t len = 0;
+        // software pipeline: the loads of step t + 1 are in flight while step t is computed (a step is ~400 dependent
+        // instructions at 2 warps per scheduler: an exposed DRAM latency per step was 35 % of the stall cycles)
+        uint8_t sc_next = a.T ? a.succ[e] : (uint8_t)RL_PAD;
+        float x_next[GF], tgt_next = 0.0f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) x_next[f] = a.T ? a.obs[(uint64_t)f * E + e] : 0.0f;
+        if (MODE == RL_PASS_VALUE && a.T) tgt_next = a.target[e];
         for (uint64_t t = 0; t < a.T; ++t) {
-            const uint8_t sc = a.succ[t * E + e];
+            const uint8_t sc = sc_next;
             if (sc == RL_PAD) break;
             len = t + 1;
             float x[GF];
 #pragma unroll
-            for (int f = 0; f < F; ++f) x[f] = a.obs[(t * F + f) * E + e];
+            for (int f = 0; f < F; ++f) x[f] = x_next[f];
+            const float tgt_cur = tgt_next;
+            if (t + 1 < a.T) {
+                sc_next = a.succ[(t + 1) * E + e];
+#pragma unroll
+                for (int f = 0; f < F; ++f) x_next[f] = a.obs[((t + 1) * F + f) * E + e];
+                if (MODE == RL_PASS_VALUE) tgt_next = a.target[(t + 1) * E + e];
+            } else {
+                sc_next = RL_PAD;
+            }
             if (BACKWARD)
                 for (int j = 0; j < H; ++j) a.hbuf[(t * H + j) * E + e] = h[j];
             float r[GH], u[GH], n[GH], ghn[GH];
@@ -231,7 +249,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
                     for (int k = 0; k < A; ++k) dz[k] = p[k] * (zd[k] - pd);
                 }
             } else {  // VALUE: mse(V(obs), targets)  (opt.rs:109-115)
-                const float diff = z[0] - a.target[n_idx];
+                const float diff = z[0] - tgt_cur;
                 loss_s = diff * diff;
                 dz[0] = 2.0f * diff;
             }
@@ -257,17 +275,30 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
             const float *w_hh = sw + d.o_whh(), *lw = sw + d.o_lw();
             float *g_ih = g, *g_hh = g + d.o_whh(), *gb_ih = g + d.o_bih(), *gb_hh = g + d.o_bhh(), *g_lw = g + d.o_lw(),
                   *g_lb = g + d.o_lb();
+            uint8_t sc_prev = RL_PAD;
+            float x_prev[GF], hp_prev[GH], dz_prev[GA];
+            auto load_step = [&](uint64_t t) {
+                sc_prev = a.succ[t * E + e];
+#pragma unroll
+                for (int f = 0; f < F; ++f) x_prev[f] = a.obs[(t * F + f) * E + e];
+#pragma unroll
+                for (int j = 0; j < H; ++j) hp_prev[j] = a.hbuf[(t * H + j) * E + e];
+#pragma unroll
+                for (int k = 0; k < A; ++k) dz_prev[k] = a.dzbuf[(t * A + k) * E + e];
+            };
+            if (len > 0) load_step(len - 1);
             for (int64_t t = (int64_t)len - 1; t >= 0; --t) {
-                const uint8_t sc = a.succ[(uint64_t)t * E + e];
+                const uint8_t sc = sc_prev;
                 if (sc != RL_CONTINUE)
                     for (int j = 0; j < H; ++j) dh[j] = 0.0f;  // last step of its episode: nothing flows back from t + 1
                 float x[GF], hp[GH], dz[GA];
 #pragma unroll
-                for (int f = 0; f < F; ++f) x[f] = a.obs[((uint64_t)t * F + f) * E + e];
+                for (int f = 0; f < F; ++f) x[f] = x_prev[f];
 #pragma unroll
-                for (int j = 0; j < H; ++j) hp[j] = a.hbuf[((uint64_t)t * H + j) * E + e];
+                for (int j = 0; j < H; ++j) hp[j] = hp_prev[j];
 #pragma unroll
-                for (int k = 0; k < A; ++k) dz[k] = a.dzbuf[((uint64_t)t * A + k) * E + e];
+                for (int k = 0; k < A; ++k) dz[k] = dz_prev[k];
+                if (t > 0) load_step((uint64_t)t - 1);  // in flight during this step
                 float r[GH], u[GH], n[GH], ghn[GH];
                 gru_gates(d, sw, x, hp, r, u, n, ghn);
                 float dgi[3 * GH], dgh[3 * GH], dhp[GH];
