@@ -79,7 +79,7 @@ __device__ __forceinline__ float act_grad(int act, float pre, float out) {
 // TF / TH / TA > 0 fix the sizes at compile time (every loop unrolls, every per-thread array -- the 150-odd gradient
 // accumulators included -- lives in registers); 0 = sizes from the arguments, arrays of the maximum sizes in local memory.
 template <int MODE, int TF, int TH, int TA>
-__global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
+__global__ void __launch_bounds__(RL_SEQ_BLOCK) gru_pass_kernel(rl_seq_pass_args a) {
     constexpr int GH = TH ? TH : GH_MAX, GF = TF ? TF : GF_MAX, GA = TA ? TA : GA_MAX;
     constexpr int GP_MAX = 3 * GH * GF + 3 * GH * GH + 6 * GH + GA * GH + GA;
     constexpr bool BACKWARD = MODE == RL_PASS_GRAD || MODE == RL_PASS_FVP || MODE == RL_PASS_VALUE || MODE == RL_PASS_PPO ||
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     }
     // ---------------- block reduction into one partial row [P + 4] ----------------
     __syncthreads();
-    double *part = reinterpret_cast<double *>(gsm);  // reuse: [4 warps][P + 4]
+    double *part = reinterpret_cast<double *>(gsm);  // reuse: [warps][P + 4]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = P + 4;
     auto wsum = [](double v) {
 #pragma unroll
@@ -370,13 +370,18 @@ __global__ void __launch_bounds__(128) gru_pass_kernel(rl_seq_pass_args a) {
     }
     __syncthreads();
     double *row = a.partials + (size_t)blockIdx.x * W;
-    for (int i = threadIdx.x; i < W; i += blockDim.x) row[i] = part[i] + part[W + i] + part[2 * W + i] + part[3 * W + i];
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        double v = part[i];
+#pragma unroll
+        for (int w2 = 1; w2 < RL_SEQ_BLOCK / 32; ++w2) v += part[w2 * W + i];
+        row[i] = v;
+    }
 }
 
 template <int MODE, int TF, int TH, int TA>
 rl_status launch_sized(rl_ctx *ctx, const rl_seq_pass_args &a, int grid, size_t smem) {
     RL_CUDA(ctx, cudaFuncSetAttribute(gru_pass_kernel<MODE, TF, TH, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    RL_LAUNCH(ctx, (gru_pass_kernel<MODE, TF, TH, TA>), grid, 128, smem, a);
+    RL_LAUNCH(ctx, (gru_pass_kernel<MODE, TF, TH, TA>), grid, RL_SEQ_BLOCK, smem, a);
     return RL_OK;
 }
 
@@ -397,7 +402,7 @@ bool rl_seq_pass_supports(int F, int H, int A) { return F >= 1 && F <= GF_MAX &&
 // One pass; writes `grid` partial rows of P + 4 doubles (order: loss, kl, entropy, count as in update.cu).
 rl_status rl_seq_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a, int grid) {
     const int P = 3 * a.H * a.F + 3 * a.H * a.H + 6 * a.H + a.A * a.H + a.A;
-    const size_t smem_w = (size_t)2 * P * sizeof(float), smem_r = (size_t)4 * (P + 4) * sizeof(double);
+    const size_t smem_w = (size_t)2 * P * sizeof(float), smem_r = (size_t)(RL_SEQ_BLOCK / 32) * (P + 4) * sizeof(double);
     const size_t smem = smem_w > smem_r ? smem_w : smem_r;
     switch (mode) {
     case RL_PASS_STATS: return launch_mode<RL_PASS_STATS>(ctx, a, grid, smem);

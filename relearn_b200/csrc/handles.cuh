@@ -90,6 +90,8 @@ struct rl_seq_pass_args {
     const int *skip_flag;
     float clip_lo, clip_hi;
 };
+// lanes per block (= per partial row) of the recurrent passes: two warps, so that a block's warps finish close together
+constexpr int RL_SEQ_BLOCK = 64;
 rl_status rl_seq_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a, int grid);
 bool rl_seq_pass_supports(int F, int H, int A);
 struct rl_grunet_view { rl_ctx *ctx; int in_dim, hidden, out_dim, act; uint64_t n_params; float *params; };

@@ -1138,7 +1138,7 @@ rl_status trpo_update_generic(rl_ctx *ctx, int P, float *theta, const PassPlan &
     return (rl_status)host->status;
 }
 
-// Recurrent module: plan with one block of 128 lanes per partial row, scratch for hbuf / dzbuf / logp0.
+// Recurrent module: plan with one block of RL_SEQ_BLOCK lanes per partial row, scratch for hbuf / dzbuf / logp0.
 struct SeqScratch {
     float *logp0, *hbuf, *dzbuf;
     char *extra;
@@ -1149,7 +1149,7 @@ rl_status make_seq_plan(rl_ctx *ctx, const rl_grunet_view &net, uint64_t T, uint
     const int P = (int)net.n_params;
     plan->P = P;
     plan->W = P + NSCALAR;
-    plan->grid = (int)rl_div_up(E, 128);
+    plan->grid = (int)rl_div_up(E, RL_SEQ_BLOCK);
     const size_t rows = (size_t)plan->grid * plan->W * sizeof(double), sums = ((size_t)plan->W * sizeof(double) + 255) / 256 * 256;
     const size_t TE = (size_t)T * E;
     const size_t lp = (TE * net.out_dim * sizeof(float) + 255) / 256 * 256, hb = (TE * net.hidden * sizeof(float) + 255) / 256 * 256;
