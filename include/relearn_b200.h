@@ -142,7 +142,9 @@ typedef struct rl_chain_cfg { uint64_t size; double discount_factor; } rl_chain_
 typedef struct rl_memory_cfg { uint64_t num_actions, history_len; } rl_memory_cfg;
 /* MetaEnv<UniformBernoulliBandits{num_arms}>.wrap(TrialEpisodeLimit{episodes_per_trial})
  * (bandits.rs:128-181, meta.rs:49-203,541-617) */
-typedef struct rl_bandit_meta_cfg { uint64_t num_arms, episodes_per_trial; } rl_bandit_meta_cfg;
+/* distribution: 0 = UniformBernoulliBandits (means ~ U[0,1], Bernoulli rewards), 1 = OneHotBandits (one arm chosen
+ * uniformly pays 1, DeterministicBandit rewards; bandits.rs:187-243) */
+typedef struct rl_bandit_meta_cfg { uint64_t num_arms, episodes_per_trial, distribution; } rl_bandit_meta_cfg;
 
 void rl_cartpole_cfg_default(rl_cartpole_cfg *cfg, uint64_t max_steps_per_episode);
 void rl_chain_cfg_default(rl_chain_cfg *cfg);

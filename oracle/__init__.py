@@ -22,7 +22,7 @@ _SO = os.path.join(_HERE, "librelearn_oracle.so")
 CONTINUE, TERMINATE, INTERRUPT = 0, 1, 2
 STREAM_ENV_STEP, STREAM_ENV_RESET, STREAM_ACTOR = 0, 1, 2
 ENV_CARTPOLE, ENV_CHAIN, ENV_MEMORY, ENV_BANDIT_META = 0, 1, 2, 3
-BANDIT_UNIFORM_BERNOULLI, BANDIT_ROUND_ROBIN_DETERMINISTIC = 0, 1
+BANDIT_UNIFORM_BERNOULLI, BANDIT_ROUND_ROBIN_DETERMINISTIC, BANDIT_ONE_HOT = 0, 1, 2
 ACTOR_REPLAY, ACTOR_RANDOM, ACTOR_POLICY, ACTOR_EPS_GREEDY_Q, ACTOR_TABULAR = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
 MAX_ARMS = 32

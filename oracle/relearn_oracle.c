@@ -321,6 +321,9 @@ void ro_env_initial_state(ro_env *env, ro_state *s, ro_rng *rng) {
         if (c->bandit_dist == RO_BANDIT_UNIFORM_BERNOULLI) {
             for (uint64_t i = 0; i < c->num_arms; ++i)
                 s->means[i] = ro_uniform_sample(&env->mean_dist, rng, RO_STREAM_ENV_RESET);
+        } else if (c->bandit_dist == RO_BANDIT_ONE_HOT) {  /* OneHotBandits::sample_environment, bandits.rs:236-241 */
+            for (uint64_t i = 0; i < c->num_arms; ++i) s->means[i] = 0.0;
+            s->means[ro_gen_range(rng, RO_STREAM_ENV_RESET, c->num_arms)] = 1.0;
         } else {                               /* envs/testing.rs:147-160 */
             for (uint64_t i = 0; i < c->num_arms; ++i) s->means[i] = 0.0;
             s->means[env->rr_good_arm] = 1.0;

@@ -88,7 +88,7 @@ double ro_u64_to_f64(uint64_t w);
 /* Environments                                                        */
 /* ------------------------------------------------------------------ */
 enum { RO_ENV_CARTPOLE = 0, RO_ENV_CHAIN = 1, RO_ENV_MEMORY = 2, RO_ENV_BANDIT_META = 3 };
-enum { RO_BANDIT_UNIFORM_BERNOULLI = 0, RO_BANDIT_ROUND_ROBIN_DETERMINISTIC = 1 };
+enum { RO_BANDIT_UNIFORM_BERNOULLI = 0, RO_BANDIT_ROUND_ROBIN_DETERMINISTIC = 1, RO_BANDIT_ONE_HOT = 2 };
 #define RO_MAX_ARMS 32
 #define RO_MAX_FEATURES 64
 

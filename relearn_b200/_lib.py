@@ -45,7 +45,7 @@ class MemoryCfg(C.Structure):
 
 
 class BanditMetaCfg(C.Structure):
-    _fields_ = [("num_arms", C.c_uint64), ("episodes_per_trial", C.c_uint64)]
+    _fields_ = [("num_arms", C.c_uint64), ("episodes_per_trial", C.c_uint64), ("distribution", C.c_uint64)]
 
 
 class EnvStructure(C.Structure):

@@ -212,13 +212,14 @@ rl_status rl_env_create(rl_ctx *ctx, rl_env_kind kind, const void *cfg, uint64_t
     case RL_ENV_BANDIT_META: {
         const rl_bandit_meta_cfg *c = (const rl_bandit_meta_cfg *)cfg;
         if (c->num_arms < 1 || c->num_arms > (uint64_t)BanditMetaEnv::MAX_ARMS || c->episodes_per_trial < 1 ||
-            c->episodes_per_trial > 65535) {
+            c->episodes_per_trial > 65535 || c->distribution > 1) {
             delete env;
             return rl_fail(ctx, RL_ERR_UNSUPPORTED, "bandit meta: num_arms in [1,%d], episodes_per_trial in [1,65535]",
                            BanditMetaEnv::MAX_ARMS);
         }
         env->bandit.num_arms = (uint32_t)c->num_arms;
         env->bandit.episodes_per_trial = (uint32_t)c->episodes_per_trial;
+        env->bandit.one_hot = (uint32_t)c->distribution;
         uniform_inclusive(0.0, 1.0, &env->bandit.mean_low, &env->bandit.mean_scale);  // bandits.rs:100
         st.num_features = (int)c->num_arms + 4;  // meta.rs:357-363
         st.num_actions = (int)c->num_arms;

@@ -107,6 +107,13 @@ class UniformBernoulliBandits:
 
 
 @dataclass
+class OneHotBandits:
+    """src/envs/bandits.rs:187-243: deterministic bandits, one uniformly chosen arm pays 1"""
+
+    num_arms: int = 2
+
+
+@dataclass
 class TrialEpisodeLimit:
     """src/envs/meta.rs:541-566"""
 
@@ -115,7 +122,7 @@ class TrialEpisodeLimit:
 
 @dataclass
 class MetaEnv:
-    """MetaEnv<UniformBernoulliBandits>.wrap(TrialEpisodeLimit) (src/envs/meta.rs:49-203,568-617)."""
+    """MetaEnv<UniformBernoulliBandits | OneHotBandits>.wrap(TrialEpisodeLimit) (src/envs/meta.rs:49-203,568-617)."""
 
     env_distribution: UniformBernoulliBandits = field(default_factory=UniformBernoulliBandits)
     episodes_per_trial: int = 10
@@ -125,7 +132,8 @@ class MetaEnv:
         return MetaEnv(self.env_distribution, limit.episodes_per_trial)
 
     def c_cfg(self):
-        return L.BanditMetaCfg(self.env_distribution.num_arms, self.episodes_per_trial)
+        return L.BanditMetaCfg(self.env_distribution.num_arms, self.episodes_per_trial,
+                               1 if isinstance(self.env_distribution, OneHotBandits) else 0)
 
 
 class BatchedEnv:

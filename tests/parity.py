@@ -24,7 +24,8 @@ def oracle_cfg_for(config) -> O.EnvCfg:
     if isinstance(config, R.MemoryGame):
         return O.memory_cfg(config.num_actions, config.history_len)
     if isinstance(config, R.MetaEnv):
-        return O.bandit_meta_cfg(config.env_distribution.num_arms, config.episodes_per_trial)
+        dist = O.BANDIT_ONE_HOT if isinstance(config.env_distribution, R.OneHotBandits) else O.BANDIT_UNIFORM_BERNOULLI
+        return O.bandit_meta_cfg(config.env_distribution.num_arms, config.episodes_per_trial, dist)
     raise TypeError(config)
 
 

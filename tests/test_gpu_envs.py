@@ -17,6 +17,8 @@ INT_ENVS = [
     pytest.param(R.MemoryGame(4, 3), id="memory-4-3"),
     pytest.param(R.MetaEnv(R.UniformBernoulliBandits(2), 3), id="bandit-2x3"),
     pytest.param(R.MetaEnv(R.UniformBernoulliBandits(10), 7), id="bandit-10x7"),
+    pytest.param(R.MetaEnv(R.OneHotBandits(3), 4), id="onehot-3x4"),
+    pytest.param(R.MetaEnv(R.OneHotBandits(2), 10), id="onehot-2x10"),
 ]
 
 

@@ -159,6 +159,32 @@ def test_meta_env_expected_steps():
     np.testing.assert_array_equal(_meta_obs(env, st), _expect_meta(2, False, (0, 0.0), True))
 
 
+def test_one_hot_bandits_meta_env():
+    # OneHotBandits (bandits.rs:187-243): one gen_range draw per trial picks the arm that pays exactly 1;
+    # DeterministicBandit::step draws nothing (bandits.rs:116-126, rewards test bandits.rs:296-305)
+    k, n = 3, 4
+    cfg = O.bandit_meta_cfg(k, n, O.BANDIT_ONE_HOT)
+    env = O.make_env(cfg)
+    L = O.lib()
+    words = (np.arange(64, dtype=np.uint64) * 2654435761 % (1 << 32)).astype(np.uint32)
+    rng = O.ScriptRng(words)
+    st = O.State()
+    r = C.c_double()
+    for _trial in range(3):
+        L.ro_env_initial_state(C.byref(env), C.byref(st), rng.ref)
+        means = [st.means[i] for i in range(k)]
+        assert sorted(means) == [0.0] * (k - 1) + [1.0]
+        good = means.index(1.0)
+        for ep in range(n):
+            a = (ep + _trial) % k
+            code = L.ro_env_step(C.byref(env), C.byref(st), a, rng.ref, C.byref(r))
+            assert r.value == (1.0 if a == good else 0.0)
+            assert code == (INTR if ep == n - 1 else CONT)
+            np.testing.assert_array_equal(_meta_obs(env, st), _expect_meta(k, False, (a, r.value), True))
+            if ep < n - 1:
+                assert L.ro_env_step(C.byref(env), C.byref(st), 0, rng.ref, C.byref(r)) == CONT and r.value == 0.0
+
+
 def test_meta_trial_length_is_2n_minus_1():
     # a trial of n inner episodes is 2n-1 meta-steps
     for n in (1, 2, 10):
