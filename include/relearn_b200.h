@@ -255,6 +255,8 @@ typedef enum {
     RL_ACTOR_TABULAR_EPS_GREEDY = 4  /* BaseTabularQLearningActor::act (src/agents/tabular.rs:222-232) */
 } rl_actor_kind;
 
+/* rl_actor_cfg.lanes_per_env value selecting the tensor-core rollout kernel (CartPole + 5/4-128-2 ReLU network) */
+#define RL_LANES_TENSOR_CORE 128
 typedef struct rl_actor_cfg {
     int32_t kind;                 /* rl_actor_kind */
     rl_mlp *net;                  /* CATEGORICAL_POLICY / EPS_GREEDY_Q */
@@ -262,7 +264,8 @@ typedef struct rl_actor_cfg {
     rl_tabq *table;               /* TABULAR_EPS_GREEDY */
     double exploration_rate;      /* EPS_GREEDY_Q / TABULAR_EPS_GREEDY */
     int32_t training;             /* ActorMode::Training (src/agents/mod.rs:144) */
-    int32_t lanes_per_env;        /* 0 = auto; threads cooperating on one env's MLP (1,2,4,8,16,32) */
+    int32_t lanes_per_env;        /* 0 = auto; threads cooperating on one env's MLP (1,2,4,8,16,32), or
+                                   * RL_LANES_TENSOR_CORE: 128-env tiles, hidden layer on tcgen05 (K2t) */
     rl_grunet *seq_net;           /* CATEGORICAL_POLICY with a recurrent module (Chain<Gru, Linear>) instead of `net` */
 } rl_actor_cfg;
 

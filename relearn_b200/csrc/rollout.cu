@@ -13,6 +13,7 @@
 //                                      an xor-shuffle butterfly.  Used when there are too few
 //                                      lanes to fill the GPU with one thread each (E = 4096).
 #include "handles.cuh"
+#include "tcgen05.cuh"
 
 #include <cstdlib>
 
@@ -754,6 +755,255 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
     block_reduce_stats(st, valid && sub == 0, a.partials);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2t: CartPole + 5->128->2 ReLU network with the hidden layer on the tensor cores (tcgen05 + TMEM), for env counts
+// at which the actor GEMM is dense: a CTA owns 128 envs, one env per thread and per TMEM lane, and every step of the
+// rollout is one  pre[128 envs x 128 units] = X[128 x 48] . W1e[48 x 128]  (3 x tcgen05.mma, K = 16) whose operands
+// are the exact three-piece bf16 split of the f32 observations / weights (tcgen05.cuh, same K-slot pairing as the
+// update passes in pass_tc.cuh: hi.hi, hi.mid, mid.hi, mid.mid, hi.lo, lo.hi => pre is f32-accurate).  W1e is built
+// once and stays in shared memory for the whole rollout; per step a thread writes its env's 80-byte row of X, thread 0
+// issues the MMAs, and while they run every thread stores the observation, draws its Philox word and looks up the
+// step-limit feature.  The epilogue reads the env's 128 pre-activations from TMEM (tcgen05.ld, thread = env) and
+// folds them into the only quantity the two-action actor needs, z_1 - z_0 = sum_j (w2_1j - w2_0j) relu(pre_j) + (b2_1
+// - b2_0): 128 FMNMX + 64 FFMA2 against broadcast shared-memory weights instead of the 448 FFMA2 + 256 LDS.128 of
+// the FP32-pipe kernel (K2c, LANES = 1).  Sampling, the f64 step, resets, trajectory stores and statistics are K2c's.
+// ------------------------------------------------------------------------------------------------
+constexpr int TK_A1 = 0, TK_B1 = 5 * tc::TC_CHUNK, TK_Z = 10 * tc::TC_CHUNK, TK_W2D = 11 * tc::TC_CHUNK;
+constexpr int TK_REM = TK_W2D + GK_H * (int)sizeof(float);
+constexpr int TK_BAR = TK_REM + GK_REM_TABLE_MAX * (int)sizeof(float);
+constexpr int TK_SMEM = TK_BAR + 32;
+constexpr int TK_CTAS_PER_SM = 4;  // 4 x 128 TMEM columns = all 512
+
+template <bool REPLAY, int AK>
+__global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kernel(CartPoleEnv::Params p, RolloutArgs a) {
+    using namespace tc;
+    using EnvT = CartPoleEnv;
+    constexpr int NF = 6;  // 5 features + the bias input
+    extern __shared__ __align__(128) unsigned char tk_smem[];
+    unsigned char *sA1 = tk_smem + TK_A1, *sB1 = tk_smem + TK_B1;
+    float *w2d = reinterpret_cast<float *>(tk_smem + TK_W2D);
+    float *rem = reinterpret_cast<float *>(tk_smem + TK_REM);
+    uint32_t *tptr = reinterpret_cast<uint32_t *>(tk_smem + TK_BAR + 16);
+    const uint32_t bar1 = smem_u32(tk_smem + TK_BAR);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int F = a.F;
+    const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
+
+    // ---- one-time setup: hidden unit `tid` -> row `tid` of the B operand; output-layer difference weights ----
+    {
+        const float *w1 = a.net.w1(), *b1 = a.net.b1(), *w2 = a.net.w2();
+        uint32_t hi[NF], mid[NF], lo[NF], e[40];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            const float w = f == 5 ? b1[tid] : f < F ? w1[tid * F + f] : 0.0f;
+            split3(w, hi[f], mid[f], lo[f]);
+        }
+#pragma unroll
+        for (int k = 0; k < 40; ++k) {
+            const int g = k / NF, f = k % NF;  // piece pairing: x [hi hi mid mid hi lo] . w [hi mid hi mid lo hi]
+            e[k] = k >= 6 * NF ? 0u : (g == 0 || g == 2 || g == 5) ? hi[f] : (g == 1 || g == 3) ? mid[f] : lo[f];
+        }
+        store_row<5>(sB1, tid, e);
+        w2d[tid] = w2[GK_H + tid] - w2[tid];
+        *reinterpret_cast<uint4 *>(tk_smem + TK_Z + tid * 16) = make_uint4(0u, 0u, 0u, 0u);  // K-slots 40..47 of both operands
+        if (rem_table)
+            for (int i = tid; i <= (int)p.max_steps; i += 128) rem[i] = (float)__ddiv_rn((double)i, (double)p.max_steps);
+    }
+    const float b2d = a.net.b2()[1] - a.net.b2()[0];
+    if (warp == 0) {
+        tmem_alloc(smem_u32(tptr), 128);
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_d = tptr[0] + ((uint32_t)(warp * 32) << 16);
+    constexpr uint32_t IDESC1 = make_idesc(128, 128, false, false);  // X (K-major) . W1e (K-major)
+    const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1);
+
+    auto remaining_feature = [&](uint32_t r) {
+        return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
+    };
+    const float rem_full = remaining_feature(p.max_steps);
+
+    const uint64_t e = (uint64_t)blockIdx.x * 128 + tid;
+    const bool valid = e < a.E;
+    LaneNoise<REPLAY> nz;
+    const uint64_t e_safe = valid ? e : 0;  // out-of-range threads shadow lane 0 without storing anything
+    nz.init(a.noise, a.lane_offset + e_safe, e_safe);
+    const uint32_t t0 = a.noise.step_counter;
+    EnvT::State s;
+    float obs[5] = {0, 0, 0, 0, 0}, last_obs[5] = {0, 0, 0, 0, 0};
+    uint32_t n = (valid && a.min_steps) ? a.min_steps + a.slack : 0;
+    uint32_t i = 0;
+    int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+    s.x = s.xd = s.th = s.thd = 0.0;
+    s.meta = 0x80000000u | p.max_steps;
+    if (n > 0) {
+        nz.set_step(t0);
+        EnvT::reset<REPLAY>(p, s, nz);
+        obs[0] = (float)s.x; obs[1] = (float)s.xd; obs[2] = (float)s.th; obs[3] = (float)s.thd;
+        obs[4] = rem_full;
+    }
+    const uint64_t FE = (uint64_t)F * a.E;
+    uint64_t io = e_safe, is = e_safe;
+    double n_eps = 0.0, sum_el = 0.0, sum_el2 = 0.0;  // OnlineStepsSummary as raw sums (reward is the constant 1.0)
+    uint32_t cur_len = 0;
+
+    // CTA-uniform step loop: a thread whose env is done keeps stepping a dead state with every side effect masked
+    for (uint32_t it = 0;; ++it) {
+        const bool active = n > 0;
+        // ---- A operand: this env's row of X (pieces of the 5 features and of the bias input 1) ----
+        {
+            uint32_t hi[NF], mid[NF], lo[NF], ex[40];
+#pragma unroll
+            for (int f = 0; f < 5; ++f) split3(obs[f], hi[f], mid[f], lo[f]);
+            hi[5] = 0x3F800000u;
+            mid[5] = 0u;
+            lo[5] = 0u;
+#pragma unroll
+            for (int k = 0; k < 40; ++k) {
+                const int g = k / NF, f = k % NF;
+                ex[k] = k >= 6 * NF ? 0u : (g == 0 || g == 1 || g == 4) ? hi[f] : (g == 2 || g == 3) ? mid[f] : lo[f];
+            }
+            store_row<5>(sA1, tid, ex);
+        }
+        fence_async_smem();
+        fence_before();
+        if (!__syncthreads_or(active)) break;  // also: every thread has read the previous step's pre-activations
+        if (tid == 0) {
+            fence_after();
+#pragma unroll
+            for (int k = 0; k < 3; ++k)  // K = 16 per instruction = two 8-element chunks; the last pairs chunk 4 with the zero chunk
+                umma_bf16(tptr[0], make_desc(aA1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_A1 - 4 * TC_CHUNK, 128),
+                          make_desc(aB1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_B1 - 4 * TC_CHUNK, 128), IDESC1, k > 0);
+            umma_commit(bar1);
+        }
+        // ---- while the MMAs run: noise, the step-limit feature of the next observation, the observation stores ----
+        if (!REPLAY) nz.set_step(t0 + i);
+        const uint32_t r_now = s.meta & 0x7FFFFFFFu;
+        const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
+        uint32_t w = 0;
+        bool explore = false;
+        uint32_t explore_action = 0;
+        if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
+            if (!REPLAY || active) w = nz.template next_u32<RL_STREAM_ACTOR>();
+        } else if (active) {  // dqn.rs:360-379
+            explore = rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps);
+            if (explore) explore_action = rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, 2u);
+        }
+        if (active) {
+            a.obs[io] = obs[0];
+            a.obs[io + a.E] = obs[1];
+            a.obs[io + 2 * a.E] = obs[2];
+            a.obs[io + 3 * a.E] = obs[3];
+            if (F > 4) a.obs[io + 4 * a.E] = obs[4];
+        }
+#pragma unroll
+        for (int f = 0; f < 5; ++f) last_obs[f] = active ? obs[f] : last_obs[f];
+
+        // ---- epilogue: z_1 - z_0 from this env's 128 pre-activations ----
+        mbar_wait(bar1, it & 1u);
+        fence_after();
+        float2 acc0 = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_d + c * 32, r);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 wq = *reinterpret_cast<const float4 *>(w2d + c * 32 + q * 4);
+                const float2 h0 = make_float2(fmaxf(__uint_as_float(r[4 * q]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 1]), 0.0f));
+                const float2 h1 = make_float2(fmaxf(__uint_as_float(r[4 * q + 2]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 3]), 0.0f));
+                acc0 = __ffma2_rn(h0, make_float2(wq.x, wq.y), acc0);
+                acc1 = __ffma2_rn(h1, make_float2(wq.z, wq.w), acc1);
+            }
+        }
+        const float d = ((acc0.x + acc0.y) + (acc1.x + acc1.y)) + b2d;
+        uint32_t action;
+        if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
+            // policies/actor.rs:42-55; exp(log_softmax(z))[0] for two logits is the logistic of z_0 - z_1 (see K2c)
+            const float u = rl_u32_to_f32(w);
+            const float ex = expf(-fabsf(d)), inv = __frcp_rn(1.0f + ex);
+            const float p0 = d <= 0.0f ? inv : ex * inv;
+            action = u < p0 ? 0u : 1u;
+        } else {
+            action = explore ? explore_action : (d > 0.0f ? 1u : 0u);
+        }
+        if (active) a.action[is] = (uint8_t)action;
+        const int sc = EnvT::step_fast(p, s, action);
+        if (active) {
+            a.reward[is] = 1.0f;  // cartpole.rs:140
+            a.succ[is] = (uint8_t)sc;
+        }
+        if (sc == RL_INTERRUPT && active) {  // rare: once per max_steps (remaining == 0 here)
+            a.next_obs[io] = (float)s.x;
+            a.next_obs[io + a.E] = (float)s.xd;
+            a.next_obs[io + 2 * a.E] = (float)s.th;
+            a.next_obs[io + 3 * a.E] = (float)s.thd;
+            if (F > 4) a.next_obs[io + 4 * a.E] = remaining_feature(0);
+        }
+        cur_len += active ? 1u : 0u;
+        if (sc != RL_CONTINUE && active) {  // steps.rs:116-124: the next call starts a new episode
+            nz.set_step(t0 + i + 1);
+            EnvT::reset<REPLAY>(p, s, nz);
+            const double ld = (double)cur_len;
+            n_eps += 1.0;
+            sum_el += ld;
+            sum_el2 = fma(ld, ld, sum_el2);
+            cur_len = 0;
+        }
+        obs[0] = (float)s.x; obs[1] = (float)s.xd; obs[2] = (float)s.th; obs[3] = (float)s.thd;
+        obs[4] = sc != RL_CONTINUE ? rem_full : rem_cont;
+        if (active) {
+            succ_prev = succ_last;
+            succ_last = sc;
+            i += 1;
+            n -= 1;
+            if (sc != RL_CONTINUE && n <= a.slack) n = 0;  // take_steps.rs:83-88
+            io += FE;
+            is += a.E;
+        }
+    }
+    if (warp == 0) {
+        fence_after();
+        tmem_dealloc(tptr[0], 128);
+    }
+    LaneStats st;
+    st.init();
+    st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
+    st.v[ST_EPS] = n_eps; st.v[ST_ER] = st.v[ST_EL] = sum_el; st.v[ST_ER2] = st.v[ST_EL2] = sum_el2;
+    if (valid) {
+        uint32_t len = i;
+        uint32_t flags = 0;
+        double eps = n_eps;
+        if (i > 0 && succ_last == RL_CONTINUE) {  // buffers/mod.rs:237-261: the dangling last step is dropped
+            len = i - 1;
+            flags = 1;
+            a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (len > 0 && succ_prev == RL_CONTINUE) {
+                flags = 3;
+                a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+#pragma unroll
+                for (int f = 0; f < 5; ++f)
+                    if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
+                eps += 1.0;
+            }
+        }
+        a.lane_len[e] = len;
+        a.lane_flags[e] = (uint8_t)flags;
+        nz.finish(a.noise, e);
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = eps;
+    }
+    block_reduce_stats(st, valid, a.partials);
+}
+
 // Sum the per-block partials in a fixed order (deterministic) and publish the summary: one warp per statistic,
 // lane l adds rows l, l + 32, ... (independent coalesced-by-row loads), then a shuffle tree combines the lanes.
 __global__ void __launch_bounds__(32 * ST_COUNT) rollout_finalize_kernel(const double *__restrict__ partials, int nblocks,
@@ -830,6 +1080,31 @@ rl_status launch_group_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs
         RL_LAUNCH(ctx, (rollout_cartpole_group_kernel<LANES, false, AK>), grid, block, smem, p, a);
     }
     return RL_OK;
+}
+
+template <int AK>
+rl_status launch_tc_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
+    const unsigned block = 128, grid = rl_grid_for(a.E, block);
+    // the request is padded so that at most TK_CTAS_PER_SM CTAs (128 TMEM columns each) are resident per SM
+    const size_t smem = TK_SMEM > 56 * 1024 ? TK_SMEM : 56 * 1024;
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    if (replay) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_tc_kernel<true, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_cartpole_tc_kernel<true, AK>), grid, block, smem, p, a);
+    } else {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_tc_kernel<false, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_cartpole_tc_kernel<false, AK>), grid, block, smem, p, a);
+    }
+    return RL_OK;
+}
+
+rl_status launch_tc(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
+    if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
+        return launch_tc_ak<RL_ACTOR_CATEGORICAL_POLICY>(ctx, p, a, replay, nblocks_out);
+    return launch_tc_ak<RL_ACTOR_EPS_GREEDY_Q>(ctx, p, a, replay, nblocks_out);
 }
 
 template <int LANES>
@@ -1032,7 +1307,9 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
         case 8: RL_TRY((launch_group<8>(ctx, env->cartpole, a, replay, &nblocks))); break;
         case 16: RL_TRY((launch_group<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
         case 32: RL_TRY((launch_group<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
-        default: return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 2, 4, 8, 16 or 32");
+        case RL_LANES_TENSOR_CORE: RL_TRY(launch_tc(ctx, env->cartpole, a, replay, &nblocks)); break;
+        default:
+            return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 2, 4, 8, 16, 32 or RL_LANES_TENSOR_CORE");
         }
         break;
     }

@@ -14,13 +14,14 @@ cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
 net = R.Mlp(ctx, 5, [128], 2)
 net.set_weights(R.init_params(np.random.default_rng(0), 5, 128, 2))
 Es = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1024, 4096, 16384, 65536, 262144, 1 << 20]
+LANES = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [1, 2, 4, 8, 16, 32, L.RL_LANES_TENSOR_CORE]
 out = []
 for E in Es:
     T = 256 if E <= 65536 else (64 if E <= (1 << 20) else 16)
     env = R.build_env(ctx, cfg, E, seed=1)
     traj = R.Trajectory(env, T)
-    for lanes in (1, 2, 4, 8, 16, 32):
-        if E * lanes > (1 << 25):
+    for lanes in LANES:
+        if lanes != L.RL_LANES_TENSOR_CORE and E * lanes > (1 << 25):
             continue
         spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes)
         for _ in range(2):

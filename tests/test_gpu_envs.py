@@ -150,7 +150,7 @@ def test_philox_slot_matches_oracle():
         assert lib.rl_philox_slot(seed, lane, t, stream, draw) == olib.ro_philox_slot(seed, lane, t, stream, draw)
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32])
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 16, 32, L.RL_LANES_TENSOR_CORE])
 def test_fused_rollout_policy_cartpole_consistent(ctx, lanes):
     """Categorical policy inside the step kernel: every action is the inverse-CDF choice for the recorded
     observation (near-ties within 2e-6 of a CDF edge are tolerated and counted), and the dynamics given those
@@ -277,7 +277,7 @@ def test_latent_step_limit_unfused_and_fused(ctx):
     P.compare_summary(summ, ref["summary"])
 
 
-@pytest.mark.parametrize("lanes", [1, 8])
+@pytest.mark.parametrize("lanes", [1, 8, L.RL_LANES_TENSOR_CORE])
 def test_latent_step_limit_policy_rollout(ctx, lanes):
     """A 4-feature policy (MLP 4 -> 128 -> 2) inside the fused step kernel under the latent limit."""
     rng = np.random.default_rng(60 + lanes)
@@ -295,3 +295,100 @@ def test_latent_step_limit_policy_rollout(ctx, lanes):
     assert checked > E * (T - 2) and near <= 3
     ref = P.oracle_rollout(LATENT, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), env_words=ewords)
     P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what=f"latent policy lanes={lanes}")
+
+
+# ------------------------------------------------------------------------------------------------
+# K2t: the tensor-core rollout (hidden layer of the policy on tcgen05, 128-env tiles)
+# ------------------------------------------------------------------------------------------------
+SHORT = R.CartPoleConfig().wrap(R.VisibleStepLimit(23))
+
+
+@pytest.mark.parametrize("E,T,slack", [(300, 60, 7), (128, 31, 0), (1, 17, 3), (1031, 40, 5)])
+def test_tc_rollout_policy_replay_ragged(ctx, E, T, slack):
+    """K2t on env counts that do not fill its 128-env tiles, with slack (ragged lane lengths), Interrupts (limit 23),
+    Terminates and resets: actions are the inverse-CDF choices of the oracle's softmax for the recorded observations,
+    and the oracle reproduces the whole trajectory (dangling-step finalisation included) from those actions."""
+    rng = np.random.default_rng(70 + E)
+    env = R.build_env(ctx, SHORT, E, seed=3)
+    nw = 8 * (T + slack) + 64
+    ewords, awords = P.random_words(rng, E, nw), P.random_words(rng, E, nw)
+    env.set_noise_replay(ewords, awords)
+    params = R.init_params(rng, 5, 128, 2) * 3.0
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T + slack)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=L.RL_LANES_TENSOR_CORE),
+                     R.HistoryDataBound(T, slack), traj)
+    host = traj.to_host()
+    checked, near = P.check_policy_consistency(host, params, 128, 2, awords)
+    assert checked >= E * (T - 1) and near <= 3
+    # the action slot of a dropped dangling step keeps the action that was taken, so the oracle can replay it
+    acts = host["action"][: T + slack].copy()
+    ref = P.oracle_rollout(SHORT, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=acts, env_words=ewords)
+    P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what=f"K2t E={E}")
+    assert summ.num_stored_steps == int(host["lane_len"].sum())
+    assert E < 100 or ((host["succ"] == L.RL_INTERRUPT).any() and (host["succ"] == L.RL_TERMINATE).any())
+
+
+def test_tc_rollout_equals_fp32_rollout_philox(ctx):
+    """Production (Philox) noise: K2t and the FP32-pipe kernel (K2c, one thread per env) see the same noise and differ
+    only in the rounding of the logits, so lanes agree bit for bit except where a uniform fell within rounding of the
+    CDF edge -- and there the first difference must be that action, with identical observations up to it."""
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    E, T = 4096, 96
+    params = R.init_params(np.random.default_rng(81), 5, 128, 2) * 2.0
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    hosts, summs = [], []
+    for lanes in (1, L.RL_LANES_TENSOR_CORE):
+        env = R.build_env(ctx, cfg, E, seed=11, lane_offset=5000)
+        env.set_noise_philox(11, 3)
+        traj = R.Trajectory(env, T)
+        summs.append(R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes),
+                               R.HistoryDataBound(T, 0), traj))
+        hosts.append(traj.to_host())
+        env.close()
+    a, b = hosts
+    same = (a["action"] == b["action"]).all(axis=0) & (a["succ"] == b["succ"]).all(axis=0) & \
+        (a["obs"] == b["obs"]).all(axis=(0, 2))
+    assert same.mean() >= 0.995, same.mean()
+    for e in np.nonzero(~same)[0]:
+        t = int(np.argmax(a["action"][:, e] != b["action"][:, e]))
+        assert a["action"][t, e] != b["action"][t, e]
+        np.testing.assert_array_equal(a["obs"][: t + 1, e], b["obs"][: t + 1, e])
+    assert summs[0].step_reward.count == summs[1].step_reward.count == E * T
+    if same.all():
+        assert summs[0].episode_length.count == summs[1].episode_length.count
+
+
+def test_tc_rollout_eps_greedy_cartpole(ctx):
+    """DqnActor (dqn.rs:360-379) on K2t: exploration draws replayed, greedy choice = argmax of the oracle's Q values
+    unless the two values are within rounding of each other."""
+    rng = np.random.default_rng(90)
+    E, T, eps = 200, 40, 0.25
+    ewords, awords = P.random_words(rng, E, 8 * T + 64), P.random_words(rng, E, 8 * T + 64)
+    params = R.init_params(rng, 5, 128, 2) * 2.0
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    hosts = []
+    for lanes in (1, L.RL_LANES_TENSOR_CORE):
+        env = R.build_env(ctx, SHORT, E, seed=3)
+        env.set_noise_replay(ewords, awords)
+        traj = R.Trajectory(env, T)
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_EPS_GREEDY_Q, net=net, exploration_rate=eps, lanes_per_env=lanes),
+                  R.HistoryDataBound(T, 0), traj)
+        hosts.append(traj.to_host())
+    a, b = hosts
+    differing = 0
+    for e in range(E):
+        n = int(a["lane_len"][e])
+        if np.array_equal(a["action"][:n, e], b["action"][:n, e]) and b["lane_len"][e] == n:
+            np.testing.assert_array_equal(a["obs"][:n, e], b["obs"][:n, e])
+            continue
+        differing += 1
+        t = int(np.argmax(a["action"][:, e] != b["action"][:, e]))
+        q = O.mlp_forward(params, 5, 128, 2, b["obs"][t : t + 1, e])[0]
+        assert abs(q[1] - q[0]) < 1e-5 * max(1.0, abs(q).max()), (e, t, q)
+    assert differing <= 2
+    ref = P.oracle_rollout(SHORT, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=b["action"].copy(), env_words=ewords)
+    P.compare_traj(b, ref, obs_rtol=1e-6, obs_atol=1e-7, what="K2t eps-greedy")
