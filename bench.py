@@ -453,23 +453,29 @@ def kernel_rooflines(ctx, R, L, hbm_peak):
     gbs = 9 * T * E2 / (ms * 1e-3) / 1e9
     out.append({"kernel": "cumsum_kernel (discounted_cumsum_from_end)", "steps": T * E2, "bytes_per_step": 9, "ms": ms,
                 "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
-    # large-E fused rollout: thread-per-env regime (throughput ceiling of K2a)
+    # large-E fused rollout (config 5's throughput end): K2c with one thread per env on the FP32 pipe, and K2t with the
+    # policy's hidden layer on tcgen05 (what `lanes_per_env = 0` picks at this size)
     E3, T3 = 1 << 20, 64
     env3 = R.build_env(ctx, cfg, E3, seed=9)
     traj3 = R.Trajectory(env3, T3)
-    spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net)
-    for _ in range(2):
-        R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
-    reps = 5
-    e0 = ctx.event().record()
-    for _ in range(reps):
-        R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
-    e1 = ctx.event().record()
-    ms = e0.elapsed_ms(e1) / reps
-    out.append({"kernel": "rollout_kernel<CartPole> (fused, thread per env)", "envs": E3, "horizon": T3, "ms": ms,
-                "env_steps_per_s": E3 * T3 / (ms * 1e-3),
-                "trajectory_write_gbs": B_PER_STEP_ROLLOUT * E3 * T3 / (ms * 1e-3) / 1e9,
-                "policy_tflops": FLOP_PER_STEP_POLICY * E3 * T3 / (ms * 1e-3) / 1e12})
+    for lanes, name in ((1, "rollout_cartpole_group_kernel<1> K2c (fused, thread per env, FP32 pipe)"),
+                        (L.RL_LANES_TENSOR_CORE, "rollout_cartpole_tc_kernel K2t (fused, 128-env tiles, hidden layer on tcgen05)")):
+        spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes)
+        for _ in range(2):
+            R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
+        reps = 5
+        e0 = ctx.event().record()
+        for _ in range(reps):
+            R.rollout(env3, spec, R.HistoryDataBound(T3, 0), traj3, want_summary=False)
+        e1 = ctx.event().record()
+        ms = e0.elapsed_ms(e1) / reps
+        rec = {"kernel": name, "envs": E3, "horizon": T3, "ms": ms, "env_steps_per_s": E3 * T3 / (ms * 1e-3),
+               "trajectory_write_gbs": B_PER_STEP_ROLLOUT * E3 * T3 / (ms * 1e-3) / 1e9,
+               "policy_tflops": FLOP_PER_STEP_POLICY * E3 * T3 / (ms * 1e-3) / 1e12}
+        if lanes == L.RL_LANES_TENSOR_CORE:
+            # bf16 FLOPs the MMAs issue: [128 x 48] . [48 x 128] per 128 env-steps
+            rec["mma_bf16_tflops"] = 2 * 48 * 128 * E3 * T3 / (ms * 1e-3) / 1e12
+        out.append(rec)
     out += other_configs(ctx, R, L, hbm_peak)
     return out
 

@@ -15,6 +15,7 @@
 #include "handles.cuh"
 #include "tcgen05.cuh"
 
+#include <cstdio>
 #include <cstdlib>
 
 namespace {
@@ -774,8 +775,14 @@ constexpr int TK_BAR = TK_REM + GK_REM_TABLE_MAX * (int)sizeof(float);
 constexpr int TK_SMEM = TK_BAR + 32;
 constexpr int TK_CTAS_PER_SM = 4;  // 4 x 128 TMEM columns = all 512
 
-template <bool REPLAY, int AK>
-__global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kernel(CartPoleEnv::Params p, RolloutArgs a) {
+#ifdef TK_PROFILE
+#define TK_STAMP(k) do { const long long _c = clock64(); tk_ph[k] += _c - tk_last; tk_last = _c; } while (0)
+#else
+#define TK_STAMP(k) do { } while (0)
+#endif
+
+template <bool REPLAY, int AK, bool SPEC>
+__global__ void __launch_bounds__(128, SPEC ? 2 : TK_CTAS_PER_SM) rollout_cartpole_tc_kernel(CartPoleEnv::Params p, RolloutArgs a) {
     using namespace tc;
     using EnvT = CartPoleEnv;
     constexpr int NF = 6;  // 5 features + the bias input
@@ -822,9 +829,15 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
     fence_before();
     __syncthreads();
     fence_after();
-    const uint32_t tmem_d = tptr[0] + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem_d = tptr[0] + ((uint32_t)(warp * 32) << 16);  // this warp's 32 TMEM lanes
     constexpr uint32_t IDESC1 = make_idesc(128, 128, false, false);  // X (K-major) . W1e (K-major)
-    const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1);
+    const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), tmem_base = tptr[0];
+    uint64_t descA[3], descB[3];  // K = 16 per instruction = two 8-element chunks; the last pairs chunk 4 with the zero chunk
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        descA[k] = make_desc(aA1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_A1 - 4 * TC_CHUNK, 128);
+        descB[k] = make_desc(aB1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_B1 - 4 * TC_CHUNK, 128);
+    }
 
     auto remaining_feature = [&](uint32_t r) {
         return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
@@ -856,6 +869,9 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
     uint32_t cur_len = 0;
 
     // CTA-uniform step loop: a thread whose env is done keeps stepping a dead state with every side effect masked
+#ifdef TK_PROFILE
+    long long tk_ph[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk_last = clock64();
+#endif
     for (uint32_t it = 0;; ++it) {
         const bool active = n > 0;
         // ---- A operand: this env's row of X (pieces of the 5 features and of the bias input 1) ----
@@ -875,15 +891,16 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
         }
         fence_async_smem();
         fence_before();
+        TK_STAMP(0);
         if (!__syncthreads_or(active)) break;  // also: every thread has read the previous step's pre-activations
+        TK_STAMP(1);
         if (tid == 0) {
             fence_after();
 #pragma unroll
-            for (int k = 0; k < 3; ++k)  // K = 16 per instruction = two 8-element chunks; the last pairs chunk 4 with the zero chunk
-                umma_bf16(tptr[0], make_desc(aA1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_A1 - 4 * TC_CHUNK, 128),
-                          make_desc(aB1 + k * 2 * TC_CHUNK, k < 2 ? TC_CHUNK : TK_Z - TK_B1 - 4 * TC_CHUNK, 128), IDESC1, k > 0);
+            for (int k = 0; k < 3; ++k) umma_bf16(tmem_base, descA[k], descB[k], IDESC1, k > 0);
             umma_commit(bar1);
         }
+        TK_STAMP(2);
         // ---- while the MMAs run: noise, the step-limit feature of the next observation, the observation stores ----
         if (!REPLAY) nz.set_step(t0 + i);
         const uint32_t r_now = s.meta & 0x7FFFFFFFu;
@@ -907,24 +924,51 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
 #pragma unroll
         for (int f = 0; f < 5; ++f) last_obs[f] = active ? obs[f] : last_obs[f];
 
+        // Speculative dynamics (few CTAs: the step chain of one CTA is the bound, not throughput): both actions' f64
+        // steps are evaluated while the MMAs run and the sampled action selects one -- same operations on the same
+        // operands, bit-identical results.
+        EnvT::State cand0 = s, cand1 = s;
+        int sc0 = RL_CONTINUE, sc1 = RL_CONTINUE;
+        if constexpr (SPEC) {
+            sc0 = EnvT::step_fast(p, cand0, 0u);
+            sc1 = EnvT::step_fast(p, cand1, 1u);
+        }
+        // ... and, with counter-based noise, so is the state a reset at the end of this step would produce
+        EnvT::State fresh = s;
+        if constexpr (SPEC && !REPLAY) {
+            LaneNoise<REPLAY> nzr = nz;
+            nzr.set_step(t0 + i + 1);
+            EnvT::reset<REPLAY>(p, fresh, nzr);
+        }
+
+        TK_STAMP(3);
         // ---- epilogue: z_1 - z_0 from this env's 128 pre-activations ----
-        mbar_wait(bar1, it & 1u);
+        if constexpr (SPEC) mbar_wait_after(bar1, it & 1u, cand0.x, cand1.x, __dadd_rn(cand0.thd, cand1.thd), __dadd_rn(fresh.thd, fresh.x), w);
+        else mbar_wait(bar1, it & 1u);
         fence_after();
-        float2 acc0 = make_float2(0.0f, 0.0f), acc1 = make_float2(0.0f, 0.0f);
+        TK_STAMP(4);
+        float2 acc[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            uint32_t r[32];
-            tmem_ld32(tmem_d + c * 32, r);
+        for (int k = 0; k < 4; ++k) acc[k] = make_float2(0.0f, 0.0f);
+        constexpr int LDW = SPEC ? 64 : 32;  // columns per TMEM load: one wait per 64 when registers allow (2 CTAs per SM)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 wq = *reinterpret_cast<const float4 *>(w2d + c * 32 + q * 4);
+        for (int c = 0; c < GK_H / LDW; ++c) {
+            uint32_t r[LDW];
+            if constexpr (LDW == 64) tmem_ld64(tmem_d + c * LDW, r);
+            else tmem_ld32(tmem_d + c * LDW, r);
+#pragma unroll
+            for (int q = 0; q < LDW / 4; ++q) {
+                const float4 wq = *reinterpret_cast<const float4 *>(w2d + c * LDW + q * 4);
                 const float2 h0 = make_float2(fmaxf(__uint_as_float(r[4 * q]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 1]), 0.0f));
                 const float2 h1 = make_float2(fmaxf(__uint_as_float(r[4 * q + 2]), 0.0f), fmaxf(__uint_as_float(r[4 * q + 3]), 0.0f));
-                acc0 = __ffma2_rn(h0, make_float2(wq.x, wq.y), acc0);
-                acc1 = __ffma2_rn(h1, make_float2(wq.z, wq.w), acc1);
+                acc[(2 * q) & 3] = __ffma2_rn(h0, make_float2(wq.x, wq.y), acc[(2 * q) & 3]);
+                acc[(2 * q + 1) & 3] = __ffma2_rn(h1, make_float2(wq.z, wq.w), acc[(2 * q + 1) & 3]);
             }
         }
-        const float d = ((acc0.x + acc0.y) + (acc1.x + acc1.y)) + b2d;
+        acc[0] = __fadd2_rn(acc[0], acc[2]);
+        acc[1] = __fadd2_rn(acc[1], acc[3]);
+        const float d = ((acc[0].x + acc[0].y) + (acc[1].x + acc[1].y)) + b2d;
+        TK_STAMP(5);
         uint32_t action;
         if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
             // policies/actor.rs:42-55; exp(log_softmax(z))[0] for two logits is the logistic of z_0 - z_1 (see K2c)
@@ -936,7 +980,13 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
             action = explore ? explore_action : (d > 0.0f ? 1u : 0u);
         }
         if (active) a.action[is] = (uint8_t)action;
-        const int sc = EnvT::step_fast(p, s, action);
+        int sc;
+        if constexpr (SPEC) {
+            s = action ? cand1 : cand0;
+            sc = action ? sc1 : sc0;
+        } else {
+            sc = EnvT::step_fast(p, s, action);
+        }
         if (active) {
             a.reward[is] = 1.0f;  // cartpole.rs:140
             a.succ[is] = (uint8_t)sc;
@@ -948,10 +998,15 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
             a.next_obs[io + 3 * a.E] = (float)s.thd;
             if (F > 4) a.next_obs[io + 4 * a.E] = remaining_feature(0);
         }
+        TK_STAMP(6);
         cur_len += active ? 1u : 0u;
         if (sc != RL_CONTINUE && active) {  // steps.rs:116-124: the next call starts a new episode
-            nz.set_step(t0 + i + 1);
-            EnvT::reset<REPLAY>(p, s, nz);
+            if constexpr (SPEC && !REPLAY) {
+                s = fresh;
+            } else {
+                nz.set_step(t0 + i + 1);
+                EnvT::reset<REPLAY>(p, s, nz);
+            }
             const double ld = (double)cur_len;
             n_eps += 1.0;
             sum_el += ld;
@@ -969,10 +1024,17 @@ __global__ void __launch_bounds__(128, TK_CTAS_PER_SM) rollout_cartpole_tc_kerne
             io += FE;
             is += a.E;
         }
+        TK_STAMP(7);
     }
+#ifdef TK_PROFILE
+    if (blockIdx.x == 0 && (tid == 0 || tid == 77))
+        printf("K2t tid %d steps %u clk/step: xbuild %lld sync %lld mma_issue %lld overlap %lld mbar_wait %lld epilogue %lld sample+step %lld tail %lld\n",
+               tid, i, tk_ph[0] / (i ? i : 1), tk_ph[1] / (i ? i : 1), tk_ph[2] / (i ? i : 1), tk_ph[3] / (i ? i : 1), tk_ph[4] / (i ? i : 1),
+               tk_ph[5] / (i ? i : 1), tk_ph[6] / (i ? i : 1), tk_ph[7] / (i ? i : 1));
+#endif
     if (warp == 0) {
         fence_after();
-        tmem_dealloc(tptr[0], 128);
+        tmem_dealloc(tmem_base, 128);
     }
     LaneStats st;
     st.init();
@@ -1082,6 +1144,13 @@ rl_status launch_group_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs
     return RL_OK;
 }
 
+template <bool REPLAY, int AK, bool SPEC>
+rl_status launch_tc_variant(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, unsigned grid, size_t smem) {
+    RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_tc_kernel<REPLAY, AK, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RL_LAUNCH(ctx, (rollout_cartpole_tc_kernel<REPLAY, AK, SPEC>), grid, 128, smem, p, a);
+    return RL_OK;
+}
+
 template <int AK>
 rl_status launch_tc_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
     const unsigned block = 128, grid = rl_grid_for(a.E, block);
@@ -1091,14 +1160,10 @@ rl_status launch_tc_ak(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a
     RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
     a.partials = partials + ST_COUNT;
     *nblocks_out = (int)grid;
-    if (replay) {
-        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_tc_kernel<true, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, (rollout_cartpole_tc_kernel<true, AK>), grid, block, smem, p, a);
-    } else {
-        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_tc_kernel<false, AK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, (rollout_cartpole_tc_kernel<false, AK>), grid, block, smem, p, a);
-    }
-    return RL_OK;
+    static const char *spec_env = getenv("RL_TC_SPEC");  // 0 / 1 overrides the choice (measurements)
+    const bool spec = spec_env ? spec_env[0] == '1' : grid <= 2u * (unsigned)ctx->sm_count;
+    if (replay) return spec ? launch_tc_variant<true, AK, true>(ctx, p, a, grid, smem) : launch_tc_variant<true, AK, false>(ctx, p, a, grid, smem);
+    return spec ? launch_tc_variant<false, AK, true>(ctx, p, a, grid, smem) : launch_tc_variant<false, AK, false>(ctx, p, a, grid, smem);
 }
 
 rl_status launch_tc(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
@@ -1298,7 +1363,9 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             // auto, from the B200 sweep in profiles/r1_rollout_sweep.md: with few envs the step chain of a
             // single warp is the bound, so the hidden layer is split over 8 threads (weights in registers);
             // as envs grow the redundant per-warp physics costs more than the latency it hides.
-            lanes = env->E <= 6144 ? 8 : env->E <= 24576 ? 2 : 1;
+            // Above ~6 K envs the tensor-core kernel wins at every size measured (8 K: 0.33 ms per 256-step period vs
+            // 0.40 for LANES = 2; 1 M envs: 24 G env-steps/s vs 15.5 G for LANES = 1).
+            lanes = env->E <= 6144 ? 8 : RL_LANES_TENSOR_CORE;
         }
         switch (lanes) {
         case 1: RL_TRY((launch_group<1>(ctx, env->cartpole, a, replay, &nblocks))); break;
