@@ -6,7 +6,9 @@ O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on --kernel-name-base demangled"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $O/${R}_launches.csv python bench.py --steps 2 --warmup 3 > $O/${R}_bench_under_ncu.log 2>&1
 $NCU -k "regex:rollout_cartpole_group_kernel" -s 2 -c 1 -o $O/${R}_k2c_e4096 python scripts/profile_rollout_small.py 4096 256 0 > $O/ncu.log 2>&1
-$NCU -k "regex:rollout_cartpole_group_kernel" -s 2 -c 1 -o $O/${R}_k2c_e1m python scripts/profile_rollout_small.py 1048576 32 0 >> $O/ncu.log 2>&1
+$NCU -k "regex:rollout_cartpole_group_kernel" -s 2 -c 1 -o $O/${R}_k2c_e1m python scripts/profile_rollout_small.py 1048576 32 1 >> $O/ncu.log 2>&1
+$NCU -k "regex:rollout_cartpole_tc_kernel" -s 2 -c 1 -o $O/${R}_k2t_e1m python scripts/profile_rollout_small.py 1048576 32 128 >> $O/ncu.log 2>&1
+$NCU -k "regex:rollout_cartpole_tc_kernel" -s 2 -c 1 -o $O/${R}_k2t_e16k python scripts/profile_rollout_small.py 16384 256 128 >> $O/ncu.log 2>&1
 $NCU -k "regex:mlp_pass_tc_kernel<\(int\)1, \(int\)4>" -s 2 -c 1 -o $O/${R}_k6_value_tc python scripts/profile_kernels.py update >> $O/ncu.log 2>&1
 $NCU -k "regex:mlp_pass_tc_kernel<\(int\)2, \(int\)3>" -s 2 -c 1 -o $O/${R}_k5_fvp_tc python scripts/profile_kernels.py update >> $O/ncu.log 2>&1
 RL_PASS_KERNEL=ffma $NCU -k "regex:mlp_pass_kernel<\(int\)5, \(int\)1" -s 1 -c 1 -o $O/${R}_k6_value python scripts/profile_kernels.py update >> $O/ncu.log 2>&1
