@@ -35,9 +35,31 @@ def unflatten_mlp(flat: torch.Tensor, n_in: int, hidden: int, n_out: int):
     return out
 
 
+# hidden activation of mlp_forward (Activation enum, src/torch/modules/ff/activation.rs:11; MlpConfig default Relu,
+# mlp.rs:25-34); tests of non-default modules switch it with `with mlp_activation("tanh"):`
+_MLP_ACTIVATION = "relu"
+_ACTIVATIONS = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "identity": lambda t: t}
+
+
+class mlp_activation:
+    def __init__(self, name: str):
+        assert name in _ACTIVATIONS, name
+        self.name = name
+
+    def __enter__(self):
+        global _MLP_ACTIVATION
+        self.prev, _MLP_ACTIVATION = _MLP_ACTIVATION, self.name
+        return self
+
+    def __exit__(self, *exc):
+        global _MLP_ACTIVATION
+        _MLP_ACTIVATION = self.prev
+        return False
+
+
 def mlp_forward(params, x):
     w1, b1, w2, b2 = params
-    h = torch.relu(torch.nn.functional.linear(x, w1, b1))
+    h = _ACTIVATIONS[_MLP_ACTIVATION](torch.nn.functional.linear(x, w1, b1))
     return torch.nn.functional.linear(h, w2, b2)
 
 

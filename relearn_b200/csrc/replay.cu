@@ -528,6 +528,8 @@ rl_status rl_replay_sample_enqueue(rl_replay *rb, uint64_t minibatch_steps, uint
             RL_CUDA(ctx, cudaFuncSetAttribute(q_values_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             RL_LAUNCH(ctx, (q_values_kernel<8, 2>), grid, 256, smem, rl_mlp_view(q), rb->mb, meta);
         } else {
+            if (q->in_dim > 36 || q->out_dim > 32)
+                return rl_fail(ctx, RL_ERR_UNSUPPORTED, "replay sample: one-step TD targets are built for <= 36 features and <= 32 actions");
             RL_CUDA(ctx, cudaFuncSetAttribute(q_values_kernel<36, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             RL_LAUNCH(ctx, (q_values_kernel<36, 32>), grid, 256, smem, rl_mlp_view(q), rb->mb, meta);
         }

@@ -502,6 +502,282 @@ __global__ void __launch_bounds__(PASS_THREADS, MINB) mlp_pass_kernel(PassArgs a
 
 #include "pass_tc.cuh"
 
+// ------------------------------------------------------------------------------------------------
+// mlp_pass_any_kernel<MODE>: the same passes for ANY one-hidden-layer module of the reference's MlpConfig
+// (mlp.rs:21-61: run-time features F <= 64, hidden units H <= 1024, outputs A <= 16; ReLU / sigmoid / tanh /
+// identity), so that TRPO / PPO / REINFORCE / critic / DQN updates also serve Chain, MemoryGame, the bandit
+// meta-env and non-default CartPole networks.  Same contract as mlp_pass_kernel (one f64 partial row per CTA),
+// different shape of work: sizes are run-time values, so nothing is register-blocked -- a warp owns tiles of 32
+// samples and walks them one by one; lane l owns hidden units {l + 32 u}; parameters (W1 transposed to [F][H] so
+// that lanes read consecutive words) and the tile's observations sit in shared memory; logits are combined by an
+// xor-butterfly (bit-identical in every lane); the backward sweep recomputes a unit's pre-activation instead of
+// keeping it, and adds this lane's gradient entries straight into the warp's f64 totals in shared memory (each
+// entry has one owner lane: no atomics, fixed order).  Correctness-first fallback: ~5-10x slower per sample than the
+// tensor-core passes of the default networks.
+// ------------------------------------------------------------------------------------------------
+constexpr int ANY_MAXA = 16, ANY_MAXF = 64, ANY_MAXH = 1024, ANY_THREADS = 128;
+constexpr size_t ANY_SMEM_CAP = 200 * 1024;
+struct AnyShape {
+    int F, H, A, act;
+};
+
+__host__ __device__ inline size_t any_smem_bytes(const AnyShape &sh, int nwarps, bool backward, bool fvp) {
+    const size_t P = (size_t)sh.H * sh.F + sh.H + (size_t)sh.A * sh.H + sh.A;
+    return (backward ? (size_t)nwarps * P * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
+           P * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float);
+}
+
+__device__ __forceinline__ float any_act_grad(int act, float pre, float h) {
+    switch (act) {
+    case RL_ACT_RELU: return pre > 0.0f ? 1.0f : 0.0f;  // relu'(0) = 0 as in libtorch
+    case RL_ACT_SIGMOID: return h * (1.0f - h);
+    case RL_ACT_TANH: return 1.0f - h * h;
+    default: return 1.0f;
+    }
+}
+
+__device__ __forceinline__ float warp_allsum_f32(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, AnyShape sh) {
+    constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS ||
+                              MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool IS_POLICY = MODE == PASS_STATS || MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_FVP ||
+                               MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
+    constexpr bool FVP = MODE == PASS_FVP;
+    if (a.skip_flag && *a.skip_flag) return;
+    const int F = sh.F, H = sh.H, A = sh.A, act = sh.act;
+    const int P = H * F + H + A * H + A, W = P + NSCALAR;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+
+    extern __shared__ __align__(16) unsigned char any_smem[];
+    double *tot_all = reinterpret_cast<double *>(any_smem);                        // [nwarps][P], W1 part as [F][H]
+    double *red = tot_all + (BACKWARD ? (size_t)nwarps * P : 0);                   // [nwarps][NSCALAR + ANY_MAXA]
+    float *th = reinterpret_cast<float *>(red + (size_t)nwarps * (NSCALAR + ANY_MAXA));  // theta, W1 as [F][H]
+    float *tv = th + P;                                                            // FVP: the direction, same layout
+    float *xs_all = th + (FVP ? 2 : 1) * (size_t)P;
+    float *xs = xs_all + (size_t)warp * 32 * F;
+    double *tot = tot_all + (size_t)warp * P;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        int dst = i;
+        if (i < H * F) dst = (i % F) * H + i / F;  // W1[j][f] -> [f][j]
+        th[dst] = a.theta[i];
+        if (FVP) tv[dst] = a.vec[i];
+    }
+    if (BACKWARD)
+        for (int i = lane; i < P; i += 32) tot[i] = 0.0;
+    __syncthreads();
+    const float *w1t = th, *b1 = th + H * F, *w2 = b1 + H, *b2 = w2 + A * H;
+    const float *vw1t = tv, *vb1 = tv + H * F, *vw2 = vb1 + H, *vb2 = vw2 + A * H;
+
+    double gb2[ANY_MAXA], sc[NSCALAR];  // lane 0's copies are the ones reported (every lane computes the same values)
+#pragma unroll
+    for (int k = 0; k < ANY_MAXA; ++k) gb2[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NSCALAR; ++k) sc[k] = 0.0;
+
+    const uint64_t TE = a.T * a.E, ntiles = (TE + 31) / 32;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * nwarps + warp, total_warps = (uint64_t)gridDim.x * nwarps;
+    for (uint64_t tile = warp_global; tile < ntiles; tile += total_warps) {
+        const uint64_t n = tile * 32 + lane;
+        const bool in_range = n < TE;
+        const uint64_t t = in_range ? n / a.E : 0, e = in_range ? n - t * a.E : 0;
+        const bool valid = in_range && a.succ[n] != RL_PAD;
+        __syncwarp();
+        for (int f = 0; f < F; ++f) xs[lane * F + f] = valid ? __ldg(a.obs + (t * F + f) * a.E + e) : 0.0f;
+        const int my_act = ((IS_POLICY || MODE == PASS_QLOSS) && valid) ? (int)a.action[n] : 0;
+        const float my_adv = (USES_ADV && valid) ? a.adv[n] : 0.0f;
+        const float my_tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && valid) ? a.target[n] : 0.0f;
+        const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+        __syncwarp();
+        for (int s = 0; s < 32; ++s) {
+            if (!((valid_mask >> s) & 1u)) continue;  // warp-uniform
+            const float *x = xs + s * F;
+            const uint64_t ns = tile * 32 + s;
+            // ---- forward: this lane's units -> partial outputs (and their tangents along `vec`) ----
+            float pz[ANY_MAXA], pzd[FVP ? ANY_MAXA : 1];
+#pragma unroll
+            for (int k = 0; k < ANY_MAXA; ++k) {
+                pz[k] = 0.0f;
+                if (FVP) pzd[k] = 0.0f;
+            }
+            for (int j = lane; j < H; j += 32) {
+                float pre = b1[j];
+                for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
+                const float h = rl_activate(act, pre);
+                float dh = 0.0f;
+                if (FVP) {
+                    float dpre = vb1[j];
+                    for (int f = 0; f < F; ++f) dpre = fmaf(vw1t[f * H + j], x[f], dpre);
+                    dh = any_act_grad(act, pre, h) * dpre;
+                }
+#pragma unroll
+                for (int k = 0; k < ANY_MAXA; ++k)
+                    if (k < A) {
+                        pz[k] = fmaf(w2[k * H + j], h, pz[k]);
+                        if (FVP) pzd[k] = fmaf(vw2[k * H + j], h, fmaf(w2[k * H + j], dh, pzd[k]));
+                    }
+            }
+            float z[ANY_MAXA], zd[FVP ? ANY_MAXA : 1];
+#pragma unroll
+            for (int k = 0; k < ANY_MAXA; ++k) {
+                z[k] = k < A ? warp_allsum_f32(pz[k]) + b2[k] : 0.0f;
+                if (FVP) zd[k] = k < A ? warp_allsum_f32(pzd[k]) + vb2[k] : 0.0f;
+            }
+            const int act_s = __shfl_sync(0xffffffffu, my_act, s);
+            const float adv_s = __shfl_sync(0xffffffffu, my_adv, s), tgt_s = __shfl_sync(0xffffffffu, my_tgt, s);
+
+            // ---- per-sample algebra (every lane computes the same values) ----
+            float dz[ANY_MAXA];
+#pragma unroll
+            for (int k = 0; k < ANY_MAXA; ++k) dz[k] = 0.0f;
+            float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
+            if (IS_POLICY) {
+                // log_softmax over the A outputs
+                float m = z[0];
+#pragma unroll
+                for (int k = 1; k < ANY_MAXA; ++k)
+                    if (k < A) m = fmaxf(m, z[k]);
+                float sum = 0.0f;
+#pragma unroll
+                for (int k = 0; k < ANY_MAXA; ++k)
+                    if (k < A) sum += expf(z[k] - m);
+                const float lse = m + logf(sum);
+                float lp[ANY_MAXA], pr[ANY_MAXA], lp0[USES_LP0 ? ANY_MAXA : 1];
+                float lpa = 0.0f, lp0a = 0.0f;
+#pragma unroll
+                for (int k = 0; k < ANY_MAXA; ++k) {
+                    lp[k] = k < A ? z[k] - lse : 0.0f;
+                    pr[k] = k < A ? expf(lp[k]) : 0.0f;
+                    if (USES_LP0) lp0[k] = k < A ? a.logp0[ns * A + k] : 0.0f;
+                    if (k == act_s) {
+                        lpa = lp[k];
+                        if (USES_LP0) lp0a = lp0[k];
+                    }
+                }
+                if (MODE == PASS_STATS) {  // trpo.rs:112-122, categorical.rs:62-68
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) {
+                            ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
+                            if (lane == k) a.logp0[ns * A + k] = lp[k];
+                        }
+                }
+                if (MODE == PASS_EVAL || MODE == PASS_GRAD) {  // trpo.rs:129-144
+                    const float ratio = expf(lpa - lp0a);
+                    loss_s = -(ratio * adv_s);
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
+                    if (MODE == PASS_GRAD) {
+#pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) dz[k] = loss_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                    }
+                }
+                if (MODE == PASS_PPO) {  // ppo.rs:124-138 (backward as libtorch, see mlp_pass_kernel)
+                    const float ratio = expf(lpa - lp0a);
+                    const float clipped = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+                    const float t1 = ratio * adv_s, t2 = clipped * adv_s;
+                    loss_s = -fminf(t1, t2);
+                    const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
+                    const float g = (inside || t1 < t2) ? -t1 : 0.0f;
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) dz[k] = g * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                }
+                if (MODE == PASS_REINFORCE) {  // reinforce.rs:72-79
+                    loss_s = -(lpa * adv_s);
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) {
+                            ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
+                            dz[k] = -adv_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                        }
+                }
+                if (FVP) {  // u = (diag p - p p^T) zdot
+                    float pd = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) pd = fmaf(pr[k], zd[k], pd);
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) dz[k] = pr[k] * (zd[k] - pd);
+                }
+            } else if (MODE == PASS_VALUE) {  // opt.rs:109-115
+                const float diff = z[0] - tgt_s;
+                loss_s = diff * diff;
+                dz[0] = 2.0f * diff;
+            } else {  // PASS_QLOSS, dqn.rs:316-326
+                float qv = z[0];
+#pragma unroll
+                for (int k = 1; k < ANY_MAXA; ++k)
+                    if (k == act_s) qv = z[k];
+                const float diff = qv - tgt_s;
+                loss_s = diff * diff;
+#pragma unroll
+                for (int k = 0; k < ANY_MAXA; ++k) dz[k] = (k == act_s && k < A) ? 2.0f * diff : 0.0f;
+            }
+            sc[SC_COUNT] += 1.0;
+            sc[SC_LOSS] += (double)loss_s;
+            sc[SC_KL] += (double)kl_s;
+            sc[SC_ENTROPY] += (double)ent_s;
+#pragma unroll
+            for (int k = 0; k < ANY_MAXA; ++k) gb2[k] += (double)dz[k];
+
+            // ---- backward: this lane's units, straight into the warp's f64 totals ----
+            if (BACKWARD) {
+                for (int j = lane; j < H; j += 32) {
+                    float pre = b1[j];
+                    for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
+                    const float h = rl_activate(act, pre);
+                    float dh = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) {
+                            dh = fmaf(dz[k], w2[k * H + j], dh);
+                            tot[H * F + H + k * H + j] += (double)(dz[k] * h);
+                        }
+                    const float dp = dh * any_act_grad(act, pre, h);
+                    tot[H * F + j] += (double)dp;
+                    for (int f = 0; f < F; ++f) tot[f * H + j] += (double)(dp * x[f]);
+                }
+            }
+        }
+    }
+
+    // ---- block reduction into one partial row (parameter order of Module::variables) ----
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NSCALAR; ++k) red[warp * (NSCALAR + ANY_MAXA) + k] = sc[k];
+#pragma unroll
+        for (int k = 0; k < ANY_MAXA; ++k) red[warp * (NSCALAR + ANY_MAXA) + NSCALAR + k] = gb2[k];
+    }
+    __syncthreads();
+    double *row = a.partials + (size_t)blockIdx.x * W;
+    for (int i = threadIdx.x; i < W; i += blockDim.x) {
+        double s = 0.0;
+        if (i < P - A) {
+            const int src = i < H * F ? (i % F) * H + i / F : i;
+            if (BACKWARD)
+                for (int w = 0; w < nwarps; ++w) s += tot_all[(size_t)w * P + src];
+        } else if (i < P) {
+            if (BACKWARD)
+                for (int w = 0; w < nwarps; ++w) s += red[w * (NSCALAR + ANY_MAXA) + NSCALAR + (i - (P - A))];
+        } else {
+            for (int w = 0; w < nwarps; ++w) s += red[w * (NSCALAR + ANY_MAXA) + (i - P)];
+        }
+        row[i] = s;
+    }
+}
+
+
 // rows[B][W] -> out[W] in a fixed summation order.  A block owns 32 columns; warp w sums rows
 // w, w + 8, ... (independent coalesced 256 B loads), then the 8 partials are added in warp order.
 __global__ void __launch_bounds__(256) reduce_rows_kernel(const double *__restrict__ rows, int B, int W,
@@ -1072,6 +1348,110 @@ rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extr
     return RL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Run-time dispatch over module shapes: the reference's default networks (5 -> 128 -> 1 critic, 5 -> 128 -> 2 policy /
+// action-value network, ReLU) take the compile-time kernels above (tensor cores or FP32 pipe); every other
+// one-hidden-layer module takes mlp_pass_any_kernel.
+// ------------------------------------------------------------------------------------------------
+struct PassNet {
+    bool deflt;
+    AnyShape sh;
+};
+
+rl_status pass_net_for(rl_ctx *ctx, const rl_mlp *m, int F_data, const char *what, PassNet *out) {
+    if (m->in_dim != F_data)
+        return rl_fail(ctx, RL_ERR_INVALID_ARG, "%s: a %d->%d->%d module does not match observations of %d features", what,
+                       m->in_dim, m->hidden, m->out_dim, F_data);
+    out->sh = AnyShape{m->in_dim, m->hidden, m->out_dim, (int)m->act};
+    out->deflt = F_data == 5 && m->hidden == 128 && m->act == RL_ACT_RELU && (m->out_dim == 1 || m->out_dim == 2);
+    if (!out->deflt && !(m->in_dim >= 1 && m->in_dim <= ANY_MAXF && m->hidden >= 1 && m->hidden <= ANY_MAXH && m->out_dim >= 1 &&
+                         m->out_dim <= ANY_MAXA && any_smem_bytes(out->sh, 1, true, true) <= ANY_SMEM_CAP))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED,
+                       "%s: built for one-hidden-layer modules with <= %d features, <= %d units, <= %d outputs and "
+                       "<= ~12 K parameters (got %d->%d->%d)", what, ANY_MAXF, ANY_MAXH, ANY_MAXA, m->in_dim, m->hidden, m->out_dim);
+    return RL_OK;
+}
+
+template <int MODE>
+rl_status launch_pass_any_mode(rl_ctx *ctx, const PassPlan &plan, PassArgs args, const AnyShape &sh, bool reduce) {
+    constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS ||
+                              MODE == PASS_PPO || MODE == PASS_REINFORCE;
+    int nwarps = ANY_THREADS / 32;
+    while (nwarps > 1 && any_smem_bytes(sh, nwarps, BACKWARD, MODE == PASS_FVP) > ANY_SMEM_CAP) nwarps >>= 1;
+    const size_t smem = any_smem_bytes(sh, nwarps, BACKWARD, MODE == PASS_FVP);
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(mlp_pass_any_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ANY_SMEM_CAP));
+        configured = true;
+    }
+    args.partials = plan.partials;
+    RL_LAUNCH(ctx, (mlp_pass_any_kernel<MODE>), plan.grid, nwarps * 32, smem, args, sh);
+    if (!reduce) return RL_OK;
+    return reduce_over_group(ctx, plan, plan.grid, args.skip_flag);
+}
+
+// One full-batch pass of `pn` in `mode` by whichever kernel serves its shape; *rows = partial rows it wrote.
+rl_status launch_pass_rt(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, int mode, const PassNet &pn, bool reduce = true,
+                         int *rows = nullptr) {
+    constexpr int F = 5, UPL = 4;
+    if (pn.deflt && pn.sh.A == 1 && mode == PASS_VALUE) {
+        if (rows) *rows = pass_rows<F, 1, UPL, PASS_VALUE>(ctx, plan);
+        return launch_pass<F, 1, UPL, PASS_VALUE>(ctx, plan, pa, reduce);
+    }
+    if (pn.deflt && pn.sh.A == 2 && mode != PASS_VALUE) {
+#define RL_DEFAULT_CASE(M)                                          \
+    case M:                                                         \
+        if (rows) *rows = pass_rows<F, 2, UPL, M>(ctx, plan);       \
+        return launch_pass<F, 2, UPL, M>(ctx, plan, pa, reduce);
+        switch (mode) {
+            RL_DEFAULT_CASE(PASS_STATS)
+            RL_DEFAULT_CASE(PASS_EVAL)
+            RL_DEFAULT_CASE(PASS_GRAD)
+            RL_DEFAULT_CASE(PASS_FVP)
+            RL_DEFAULT_CASE(PASS_PPO)
+            RL_DEFAULT_CASE(PASS_REINFORCE)
+            RL_DEFAULT_CASE(PASS_QLOSS)
+        default: return rl_fail(ctx, RL_ERR_INVALID_ARG, "unknown pass mode %d", mode);
+        }
+#undef RL_DEFAULT_CASE
+    }
+    if (rows) *rows = plan.grid;
+    switch (mode) {
+    case PASS_STATS: return launch_pass_any_mode<PASS_STATS>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_EVAL: return launch_pass_any_mode<PASS_EVAL>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_GRAD: return launch_pass_any_mode<PASS_GRAD>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_FVP: return launch_pass_any_mode<PASS_FVP>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_PPO: return launch_pass_any_mode<PASS_PPO>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_REINFORCE: return launch_pass_any_mode<PASS_REINFORCE>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_QLOSS: return launch_pass_any_mode<PASS_QLOSS>(ctx, plan, pa, pn.sh, reduce);
+    case PASS_VALUE: return launch_pass_any_mode<PASS_VALUE>(ctx, plan, pa, pn.sh, reduce);
+    default: return rl_fail(ctx, RL_ERR_INVALID_ARG, "unknown pass mode %d", mode);
+    }
+}
+
+// pass_and_adam over launch_pass_rt
+rl_status pass_and_adam_rt(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, int mode, const PassNet &pn, rl_mlp *net,
+                           rl_adam *adam, const AdamArgs &ac, double *loss_out) {
+    adam->step += 1;
+    int rows = plan.grid;
+    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn, false, &rows));
+        ctx->x_seq += 1;
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
+                  ctx->x, ctx->x_seq, (const int *)nullptr, (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
+    } else if (ctx->world > 1) {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn));
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
+                  loss_out);
+    } else {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn, false, &rows));
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
+                  net->params, adam->m, adam->v, ac, adam->step, loss_out);
+    }
+    return RL_OK;
+}
+
+
 
 // ------------------------------------------------------------------------------------------------
 // Trust-region step, network-agnostic: `pass(mode, vec, skip_flag)` runs one full-batch pass of the policy
@@ -1201,16 +1581,12 @@ rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, co
     if (!traj || !adv_dev || !policy || !cfg)
         return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_update: NULL argument");
     rl_ctx *ctx = traj->ctx;
-    constexpr int F = 5, A = 2, UPL = 4;
-    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
-          policy->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED,
-                       "rl_trpo_update: built for a %d->%d->%d ReLU policy (got %d->%d->%d)", F, 32 * UPL, A,
-                       policy->in_dim, policy->hidden, policy->out_dim);
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, policy, (int)traj->F, "rl_trpo_update", &pn));
     const int P = (int)policy->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
-    const size_t extra = trpo_vector_bytes(P) + TE * 2 * sizeof(float);
+    const size_t extra = trpo_vector_bytes(P) + TE * (size_t)pn.sh.A * sizeof(float);
     char *ex;
     RL_TRY(make_plan(ctx, P, TE, &plan, extra, (void **)&ex));
     float *logp0 = (float *)(ex + trpo_vector_bytes(P));
@@ -1221,12 +1597,7 @@ rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, co
         PassArgs pa = base;
         pa.vec = vec;
         pa.skip_flag = skip_flag;
-        switch (mode) {
-        case PASS_STATS: return launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa);
-        case PASS_GRAD: return launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa);
-        case PASS_FVP: return launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa);
-        default: return launch_pass<F, A, UPL, PASS_EVAL>(ctx, plan, pa);
-        }
+        return launch_pass_rt(ctx, plan, pa, mode == PASS_STATS || mode == PASS_GRAD || mode == PASS_FVP ? mode : PASS_EVAL, pn);
     };
     return trpo_update_generic(ctx, P, policy->params, plan, ex, pass, cfg, stats);
 }
@@ -1235,16 +1606,14 @@ rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, con
                         double *loss, double *kl, double *entropy, float *grad_host, float *fvp_host) {
     if (!traj || !adv_dev || !policy) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_trpo_probe: NULL argument");
     rl_ctx *ctx = traj->ctx;
-    constexpr int F = 5, A = 2, UPL = 4;
-    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
-          policy->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_trpo_probe: built for a %d->%d->%d ReLU policy", F, 32 * UPL, A);
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, policy, (int)traj->F, "rl_trpo_probe", &pn));
     const int P = (int)policy->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
     const size_t vec_bytes = ((size_t)P * sizeof(float) + 255) / 256 * 256;
     char *ex;
-    RL_TRY(make_plan(ctx, P, TE, &plan, vec_bytes + TE * 2 * sizeof(float), (void **)&ex));
+    RL_TRY(make_plan(ctx, P, TE, &plan, vec_bytes + TE * (size_t)pn.sh.A * sizeof(float), (void **)&ex));
     float *vec = (float *)ex, *logp0 = (float *)(ex + vec_bytes);
     std::vector<double> host((size_t)plan.W);
     PassArgs pa{};
@@ -1255,11 +1624,11 @@ rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, con
         RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return RL_OK;
     };
-    RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
+    RL_TRY(launch_pass_rt(ctx, plan, pa, PASS_STATS, pn));
     RL_TRY(fetch());
     const double N = host[P + SC_COUNT];
     if (entropy) *entropy = host[P + SC_ENTROPY] / N;
-    RL_TRY((launch_pass<F, A, UPL, PASS_GRAD>(ctx, plan, pa)));
+    RL_TRY(launch_pass_rt(ctx, plan, pa, PASS_GRAD, pn));
     RL_TRY(fetch());
     if (loss) *loss = host[P + SC_LOSS] / N;
     if (kl) *kl = host[P + SC_KL] / N;
@@ -1268,7 +1637,7 @@ rl_status rl_trpo_probe(rl_traj *traj, const float *adv_dev, rl_mlp *policy, con
     if (vec_host && fvp_host) {
         RL_CUDA(ctx, cudaMemcpyAsync(vec, vec_host, (size_t)P * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         pa.vec = vec;
-        RL_TRY((launch_pass<F, A, UPL, PASS_FVP>(ctx, plan, pa)));
+        RL_TRY(launch_pass_rt(ctx, plan, pa, PASS_FVP, pn));
         RL_TRY(fetch());
         for (int i = 0; i < P; ++i) fvp_host[i] = (float)(host[i] / N) + vec_host[i] * (float)hpv_reg_coeff;
     }
@@ -1311,13 +1680,11 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
     if (!traj || !targets_dev || !value_fn || !adam)
         return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_value_update: NULL argument");
     rl_ctx *ctx = traj->ctx;
-    constexpr int F = 5, A = 1, UPL = 4;
     RL_REQUIRE(ctx, adam->mlp == value_fn, "rl_value_update: optimizer belongs to another module");
     RL_REQUIRE(ctx, n_steps >= 0 && n_steps <= 100000, "rl_value_update: n_steps out of range");
-    if (!((int)traj->F == F && value_fn->in_dim == F && value_fn->out_dim == A && value_fn->hidden == 32 * UPL &&
-          value_fn->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_value_update: built for a %d->%d->1 ReLU critic (got %d->%d->%d)", F,
-                       32 * UPL, value_fn->in_dim, value_fn->hidden, value_fn->out_dim);
+    RL_REQUIRE(ctx, value_fn->out_dim == 1, "rl_value_update: a state-value module has one output");
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, value_fn, (int)traj->F, "rl_value_update", &pn));
     const int P = (int)value_fn->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
@@ -1335,7 +1702,7 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
     AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
     for (int s = 0; s < n_steps; ++s) {
         // n_backward_steps: loss -> zero_grad -> backward -> step (torch/agents/mod.rs:50-55, coptimizer.rs:13-27)
-        RL_TRY((pass_and_adam<F, A, UPL, PASS_VALUE>(ctx, plan, pa, value_fn, adam, ac, losses + s)));
+        RL_TRY(pass_and_adam_rt(ctx, plan, pa, PASS_VALUE, pn, value_fn, adam, ac, losses + s));
     }
     if (stats) {
         RL_CUDA(ctx, cudaEventRecord(ev1, ctx->stream));
@@ -1359,10 +1726,9 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
                          float *grad_host) {
     if (!traj || !targets_dev || !value_fn) return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_value_probe: NULL argument");
     rl_ctx *ctx = traj->ctx;
-    constexpr int F = 5, A = 1, UPL = 4;
-    if (!((int)traj->F == F && value_fn->in_dim == F && value_fn->out_dim == A && value_fn->hidden == 32 * UPL &&
-          value_fn->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_value_probe: built for a %d->%d->1 ReLU critic", F, 32 * UPL);
+    RL_REQUIRE(ctx, value_fn->out_dim == 1, "rl_value_probe: a state-value module has one output");
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, value_fn, (int)traj->F, "rl_value_probe", &pn));
     RL_REQUIRE(ctx, kernel == RL_PASS_KERNEL_FFMA || kernel == RL_PASS_KERNEL_TCGEN05, "rl_value_probe: unknown kernel");
     const int P = (int)value_fn->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
@@ -1373,7 +1739,7 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
     pa.theta = value_fn->params; pa.target = targets_dev;
     const int selected = pass_kernel();
     g_pass_kernel = kernel;
-    const rl_status launched = launch_pass<F, A, UPL, PASS_VALUE>(ctx, plan, pa);
+    const rl_status launched = launch_pass_rt(ctx, plan, pa, PASS_VALUE, pn);
     g_pass_kernel = selected;
     RL_TRY(launched);
     std::vector<double> host((size_t)plan.W);
@@ -1404,19 +1770,16 @@ static rl_status policy_adam_update(rl_traj *traj, const float *adv_dev, rl_mlp 
     if (!traj || !adv_dev || !policy || !adam)
         return rl_fail(traj ? traj->ctx : nullptr, RL_ERR_INVALID_ARG, "%s: NULL argument", what);
     rl_ctx *ctx = traj->ctx;
-    constexpr int F = 5, A = 2, UPL = 4;
     RL_REQUIRE(ctx, adam->mlp == policy, "policy update: optimizer belongs to another module");
     RL_REQUIRE(ctx, n_steps >= 0 && n_steps <= 100000, "policy update: opt_steps_per_update out of range");
-    if (!((int)traj->F == F && policy->in_dim == F && policy->out_dim == A && policy->hidden == 32 * UPL &&
-          policy->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "%s: built for a %d->%d->%d ReLU policy (got %d->%d->%d)", what, F, 32 * UPL, A,
-                       policy->in_dim, policy->hidden, policy->out_dim);
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, policy, (int)traj->F, what, &pn));
     const int P = (int)policy->n_params;
     const uint64_t T = traj->used_T ? traj->used_T : traj->T, TE = T * traj->E;
     PassPlan plan;
     const size_t loss_bytes = ((size_t)(n_steps + 2) * sizeof(double) + 255) / 256 * 256;
     char *ex;
-    RL_TRY(make_plan(ctx, P, TE, &plan, loss_bytes + TE * 2 * sizeof(float), (void **)&ex));
+    RL_TRY(make_plan(ctx, P, TE, &plan, loss_bytes + TE * (size_t)pn.sh.A * sizeof(float), (void **)&ex));
     double *losses = (double *)ex;
     float *logp0 = (float *)(ex + loss_bytes);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1433,13 +1796,13 @@ static rl_status policy_adam_update(rl_traj *traj, const float *adv_dev, rl_mlp 
     double *entropy_sum = losses + n_steps;  // [sum of entropies, N]
     if (ppo) {
         // initial log-probs and entropy under no_grad (ppo.rs:108-119)
-        RL_TRY((launch_pass<F, A, UPL, PASS_STATS>(ctx, plan, pa)));
+        RL_TRY(launch_pass_rt(ctx, plan, pa, PASS_STATS, pn));
         RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum, plan.sums + P + SC_ENTROPY, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum + 1, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-        for (int s = 0; s < n_steps; ++s) RL_TRY((pass_and_adam<F, A, UPL, PASS_PPO>(ctx, plan, pa, policy, adam, ac, losses + s)));
+        for (int s = 0; s < n_steps; ++s) RL_TRY(pass_and_adam_rt(ctx, plan, pa, PASS_PPO, pn, policy, adam, ac, losses + s));
     } else {
         for (int s = 0; s < n_steps; ++s) {
-            RL_TRY((pass_and_adam<F, A, UPL, PASS_REINFORCE>(ctx, plan, pa, policy, adam, ac, losses + s)));
+            RL_TRY(pass_and_adam_rt(ctx, plan, pa, PASS_REINFORCE, pn, policy, adam, ac, losses + s));
             if (s == 0) {  // entropies.get_or_insert_with: the distribution of the first loss evaluation (reinforce.rs:76)
                 RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum, plan.sums + P + SC_ENTROPY, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
                 RL_CUDA(ctx, cudaMemcpyAsync(entropy_sum + 1, plan.sums + P + SC_COUNT, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1628,15 +1991,13 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
     if (!rb || !q || !adam || !cfg)
         return rl_fail(q ? q->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_dqn_update: NULL argument");
     rl_ctx *ctx = rl_replay_ctx(rb);
-    constexpr int F = 5, A = 2, UPL = 4;
     RL_REQUIRE(ctx, q->ctx == ctx, "rl_dqn_update: network belongs to another context");
     RL_REQUIRE(ctx, adam->mlp == q, "rl_dqn_update: optimizer belongs to another module");
     RL_REQUIRE(ctx, cfg->opt_steps_per_update >= 0 && cfg->opt_steps_per_update <= 100000,
                "rl_dqn_update: opt_steps_per_update out of range");
-    if (!(rl_replay_num_features(rb) == F && q->in_dim == F && q->out_dim == A && q->hidden == 32 * UPL &&
-          q->act == RL_ACT_RELU))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_dqn_update: built for a %d->%d->%d ReLU action-value network (got %d->%d->%d)",
-                       F, 32 * UPL, A, q->in_dim, q->hidden, q->out_dim);
+    PassNet pn;
+    RL_TRY(pass_net_for(ctx, q, rl_replay_num_features(rb), "rl_dqn_update", &pn));
+    const size_t F = (size_t)pn.sh.F;
     const int P = (int)q->n_params;
     const int n_steps = cfg->opt_steps_per_update;
     // the minibatch planes hold at most minibatch_steps + one ring of columns; the plan is sized once
@@ -1669,7 +2030,7 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
         pa.T = 1; pa.E = mb.capacity;
         pa.theta = q->params; pa.target = mb.target + set * mb.capacity;
         // loss_fn + backward_step (dqn.rs:316-336, coptimizer.rs:13-27)
-        RL_TRY((pass_and_adam<F, A, UPL, PASS_QLOSS>(ctx, plan, pa, q, adam, ac, losses + s)));
+        RL_TRY(pass_and_adam_rt(ctx, plan, pa, PASS_QLOSS, pn, q, adam, ac, losses + s));
     }
     uint64_t m_last = 0;
     if (n_steps > 0) RL_TRY(rl_replay_sample_finish(rb, &m_last, nullptr));

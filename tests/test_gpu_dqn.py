@@ -249,6 +249,36 @@ def test_dqn_update_matches_oracle(ctx, filled, pass_kernel, td):
 _DRAWS = {}
 
 
+@pytest.mark.parametrize("td", [False, True])
+def test_dqn_update_other_network_shape(ctx, td):
+    """DqnAgent::batch_update with a module the default kernels do not serve (MemoryGame: 7 features, 4 actions; 64 tanh
+    units -> mlp_pass_any_kernel's Q-loss pass): same sampled episodes, same bound as the default-network test."""
+    cfg = R.MemoryGame(4, 3)
+    E, hidden, act = 24, 64, "tanh"
+    env, rb, models = _fill(ctx, cfg, 0, E, 80, R.HistoryDataBound(24, 4), periods=3, seed=44)
+    lanes = [rb.read_lane(e) for e in range(E)]
+    F, A = env.num_features, env.num_actions
+    params = R.init_params(np.random.default_rng(9), F, hidden, A)
+    steps, minibatch, seed = 5, 300, 77
+    agent = R.DqnConfig(action_value_fn_config=R.MlpConfig(hidden_sizes=[hidden], activation=act), minibatch_steps=minibatch,
+                        opt_steps_per_update=steps, target_one_step_td=td, sample_seed=seed, buffer_capacity=80).build_agent(env)
+    agent.action_value_fn.set_weights(params)
+    stats = agent.batch_update(rb, {})
+    new = agent.action_value_fn.get_weights()
+    mbs = [_oracle_minibatch(lanes, seed, s, minibatch) for s in range(steps)]
+    g = float(agent.discount_factor)
+    with TO.mlp_activation(act):
+        new64, losses64 = TO.dqn_update(params, F, hidden, A, mbs, g, one_step_td=td, dtype=torch.float64)
+        new32, _ = TO.dqn_update(params, F, hidden, A, mbs, g, one_step_td=td, dtype=torch.float32)
+    d, d64, d32 = new - params, new64 - params.astype(np.float64), new32 - params
+    rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / np.linalg.norm(b))
+    print(f"dqn {F}->{hidden}->{A} {act} td={td}: delta rel err vs f64 kernel {rel(d, d64):.2e}, torch-f32 {rel(d32, d64):.2e}")
+    assert stats.opt_steps == steps and stats.num_steps == sum(len(e["action"]) for e in mbs[-1])
+    np.testing.assert_allclose(stats.loss_first, losses64[0], rtol=1e-5)
+    np.testing.assert_allclose(stats.loss_last, losses64[-1], rtol=1e-4)
+    assert rel(d, d64) <= max(2e-4, 4 * rel(d32, d64) + 1e-5)
+
+
 def test_dqn_learns_cartpole(ctx):
     """Behavioural check in the spirit of agents/testing.rs / dqn.rs:391-414: a few DQN periods with the
     default Monte-Carlo targets raise the greedy policy's mean episode length."""
