@@ -334,7 +334,9 @@ typedef struct rl_trpo_stats {
     uint64_t num_steps;          /* global N */
     float policy_update_ms;
 } rl_trpo_stats;
-/* Returns RL_OK or one of RL_STEP_* (then the policy parameters are unchanged). */
+/* Returns RL_OK or one of RL_STEP_* (then the policy parameters are unchanged).  `policy` may be any one-hidden-layer
+ * module (<= 64 features, <= 1024 units, <= 16 actions; ReLU / tanh / sigmoid / identity); the reference's default
+ * 5 -> 128 -> 2 ReLU policy runs on tensor cores.  The same holds for the other rl_*_update entry points below. */
 rl_status rl_trpo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, const rl_trpo_cfg *cfg,
                          rl_trpo_stats *stats);
 
