@@ -1360,12 +1360,12 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             break;
         }
         if (lanes == 0) {
-            // auto, from the B200 sweep in profiles/r1_rollout_sweep.md: with few envs the step chain of a
-            // single warp is the bound, so the hidden layer is split over 8 threads (weights in registers);
-            // as envs grow the redundant per-warp physics costs more than the latency it hides.
-            // Above ~6 K envs the tensor-core kernel wins at every size measured (8 K: 0.33 ms per 256-step period vs
-            // 0.40 for LANES = 2; 1 M envs: 24 G env-steps/s vs 15.5 G for LANES = 1).
-            lanes = env->E <= 6144 ? 8 : RL_LANES_TENSOR_CORE;
+            // auto, from the B200 sweeps in profiles/r1_summary.md (sections 0 and 10): with few envs the step chain of a
+            // single warp is the bound, so the hidden layer is split over 8 threads (weights in registers) -- as long as
+            // those warps are resident at once (224 registers: 8 warps of 4 envs per SM, E <= 32 envs per SM = 4736).
+            // Beyond one wave the tensor-core kernel wins at every size measured (6 K envs: 0.31 ms per 256-step period
+            // vs 0.39 for LANES = 4; 1 M envs: 24 G env-steps/s vs 15.5 G for LANES = 1).
+            lanes = env->E <= (uint64_t)ctx->sm_count * 32 ? 8 : RL_LANES_TENSOR_CORE;
         }
         switch (lanes) {
         case 1: RL_TRY((launch_group<1>(ctx, env->cartpole, a, replay, &nblocks))); break;
