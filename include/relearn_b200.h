@@ -123,7 +123,8 @@ typedef enum {
     RL_ENV_CARTPOLE = 0,    /* CartPole (+ Visible / LatentStepLimit)  src/envs/cartpole.rs, wrappers/step_limit.rs */
     RL_ENV_CHAIN = 1,       /* Chain                          src/envs/chain.rs */
     RL_ENV_MEMORY_GAME = 2, /* MemoryGame                     src/envs/memory.rs */
-    RL_ENV_BANDIT_META = 3  /* MetaEnv<UniformBernoulliBandits> + TrialEpisodeLimit  src/envs/meta.rs, bandits.rs */
+    RL_ENV_BANDIT_META = 3, /* MetaEnv<UniformBernoulliBandits> + TrialEpisodeLimit  src/envs/meta.rs, bandits.rs */
+    RL_ENV_PARTITION_GAME = 4 /* PartitionGame (no configuration: cfg may be NULL)  src/envs/partition.rs */
 } rl_env_kind;
 
 /* CartPoleConfig {PhysicalConstants, EnvironmentParams} (cartpole.rs:157-216) wrapped by

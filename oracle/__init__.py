@@ -21,7 +21,7 @@ _SO = os.path.join(_HERE, "librelearn_oracle.so")
 
 CONTINUE, TERMINATE, INTERRUPT = 0, 1, 2
 STREAM_ENV_STEP, STREAM_ENV_RESET, STREAM_ACTOR = 0, 1, 2
-ENV_CARTPOLE, ENV_CHAIN, ENV_MEMORY, ENV_BANDIT_META = 0, 1, 2, 3
+ENV_CARTPOLE, ENV_CHAIN, ENV_MEMORY, ENV_BANDIT_META, ENV_PARTITION = 0, 1, 2, 3, 4
 BANDIT_UNIFORM_BERNOULLI, BANDIT_ROUND_ROBIN_DETERMINISTIC, BANDIT_ONE_HOT = 0, 1, 2
 ACTOR_REPLAY, ACTOR_RANDOM, ACTOR_POLICY, ACTOR_EPS_GREEDY_Q, ACTOR_TABULAR = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
@@ -226,6 +226,7 @@ def lib() -> C.CDLL:
         "ro_cfg_chain_default": (None, [P(EnvCfg)]),
         "ro_cfg_memory": (None, [P(EnvCfg), C.c_uint64, C.c_uint64]),
         "ro_cfg_bandit_meta": (None, [P(EnvCfg), C.c_uint64, C.c_uint64, C.c_int]),
+        "ro_cfg_partition": (None, [P(EnvCfg)]),
         "ro_env_init": (None, [P(Env), P(EnvCfg)]),
         "ro_env_num_features": (C.c_int, [P(Env)]),
         "ro_env_num_actions": (C.c_int, [P(Env)]),
@@ -326,6 +327,12 @@ def memory_cfg(num_actions: int = 2, history_len: int = 1) -> EnvCfg:
 def bandit_meta_cfg(num_arms: int = 2, episodes_per_trial: int = 10, dist: int = BANDIT_UNIFORM_BERNOULLI) -> EnvCfg:
     c = EnvCfg()
     lib().ro_cfg_bandit_meta(C.byref(c), num_arms, episodes_per_trial, dist)
+    return c
+
+
+def partition_cfg() -> EnvCfg:
+    c = EnvCfg()
+    lib().ro_cfg_partition(C.byref(c))
     return c
 
 

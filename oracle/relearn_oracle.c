@@ -196,6 +196,12 @@ void ro_cfg_bandit_meta(ro_env_cfg *c, uint64_t num_arms, uint64_t episodes_per_
     c->discount_factor = 1.0;   /* bandits.rs:53-55 */
 }
 
+void ro_cfg_partition(ro_env_cfg *c) {
+    memset(c, 0, sizeof(*c));
+    c->kind = RO_ENV_PARTITION;
+    c->discount_factor = 0.999; /* partition.rs: EnvStructure::discount_factor */
+}
+
 void ro_env_init(ro_env *env, const ro_env_cfg *cfg) {
     memset(env, 0, sizeof(*env));
     env->cfg = *cfg;
@@ -222,6 +228,8 @@ int ro_env_num_features(const ro_env *env) {
     case RO_ENV_CHAIN: f = (int)c->chain_size; break;         /* index.rs:97-115 one-hot */
     case RO_ENV_MEMORY: f = (int)(c->num_actions + c->history_len); break;
     case RO_ENV_BANDIT_META: return (int)c->num_arms + 4;     /* meta.rs:357-363 */
+    /* TupleSpace2<PowerSpace<Boolean, 10>, OptionSpace<TupleSpace2<PowerSpace<Boolean, 10>, IndexedTypeSpace<Classification>>>> */
+    case RO_ENV_PARTITION: return 2 * RO_PARTITION_FEATURES + 3;
     }
     if (has_step_limit(env) && c->step_limit_visible) f += 1; /* step_limit.rs:133-138 */
     return f;
@@ -233,6 +241,7 @@ int ro_env_num_actions(const ro_env *env) {
     case RO_ENV_CHAIN: return 2;
     case RO_ENV_MEMORY: return (int)env->cfg.num_actions;
     case RO_ENV_BANDIT_META: return (int)env->cfg.num_arms;
+    case RO_ENV_PARTITION: return 2;                          /* Action::{ClassifyLeft, ClassifyRight} */
     }
     return 0;
 }
@@ -252,6 +261,7 @@ void ro_env_reward_range(const ro_env *env, double *lo, double *hi) {
     case RO_ENV_CARTPOLE: *lo = 0.0; *hi = 1.0; break;        /* cartpole.rs:88-90 */
     case RO_ENV_CHAIN: *lo = 0.0; *hi = 10.0; break;          /* chain.rs:60-62 */
     case RO_ENV_MEMORY: *lo = -1.0; *hi = 1.0; break;         /* memory.rs:69-71 */
+    case RO_ENV_PARTITION: *lo = -1.0; *hi = 1.0; break;      /* partition.rs feedback_space */
     default: *lo = 0.0; *hi = 1.0; break;                     /* bandits.rs:160-162 */
     }
 }
@@ -299,6 +309,14 @@ void ro_cartpole_next_state(const ro_env *e, const ro_state *in, double force, r
     out->x = x; out->xd = xd; out->th = th; out->thd = thd; out->flag = positive;
 }
 
+/* rng.gen::<[bool; 10]>(): elements in index order, each `(next_u32() as i32) < 0` (rand 0.8.5 Standard for bool) */
+static uint64_t partition_element(ro_rng *rng, int stream) {
+    uint64_t bits = 0;
+    for (int i = 0; i < RO_PARTITION_FEATURES; ++i)
+        if (ro_next_u32(rng, stream) >> 31) bits |= 1ull << i;
+    return bits;
+}
+
 void ro_env_initial_state(ro_env *env, ro_state *s, ro_rng *rng) {
     const ro_env_cfg *c = &env->cfg;
     memset(s, 0, sizeof(*s));
@@ -332,6 +350,11 @@ void ro_env_initial_state(ro_env *env, ro_state *s, ro_rng *rng) {
         s->inner_done = 0;
         s->has_prev = 0;
         s->remaining_episodes = c->episodes_per_trial;
+        break;
+    case RO_ENV_PARTITION:                     /* partition.rs initial_state: supervisor axis, first element, no feedback */
+        s->s_init = ro_gen_range(rng, RO_STREAM_ENV_RESET, RO_PARTITION_FEATURES);
+        s->s = partition_element(rng, RO_STREAM_ENV_RESET);
+        s->has_prev = 0;
         break;
     }
     s->steps_remaining = c->max_steps_per_episode; /* step_limit.rs:187-192 */
@@ -368,6 +391,17 @@ void ro_env_observe(const ro_env *env, const ro_state *s, float *out) {
             out[2 + k] = (float)s->prev_reward;/* Interval<Reward> */
         }
         out[3 + k] = s->inner_done ? 1.0f : 0.0f; /* boolean.rs:125-139 */
+        return;
+    }
+    case RO_ENV_PARTITION: {                   /* (element, feedback): power.rs:106-115, option.rs:88-116, one-hot label */
+        const int n = RO_PARTITION_FEATURES;
+        for (int i = 0; i < n; ++i) out[i] = (s->s >> i) & 1 ? 1.0f : 0.0f;
+        if (!s->has_prev) {
+            out[n] = 1.0f;
+        } else {
+            for (int i = 0; i < n; ++i) out[n + 1 + i] = (s->prev_action >> i) & 1 ? 1.0f : 0.0f;
+            out[2 * n + 1 + (s->inner_done ? 1 : 0)] = 1.0f;   /* Classification::{Left, Right} */
+        }
         return;
     }
     }
@@ -407,6 +441,15 @@ int ro_env_step(ro_env *env, ro_state *s, uint64_t action, ro_rng *rng, double *
         }
         s->s = s->s < c->num_actions ? c->num_actions : s->s + 1;
         *reward = 0.0;
+        break;
+    }
+    case RO_ENV_PARTITION: {                   /* partition.rs step: never ends */
+        const int label = (int)((s->s >> s->s_init) & 1);      /* Supervisor::AxisAligned(axis).classify */
+        *reward = (uint64_t)label == action ? 1.0 : -1.0;
+        s->prev_action = s->s;
+        s->inner_done = label;
+        s->has_prev = 1;
+        s->s = partition_element(rng, RO_STREAM_ENV_STEP);
         break;
     }
     case RO_ENV_BANDIT_META: {                 /* meta.rs:165-202 + TrialEpisodeLimit meta.rs:594-616 */

@@ -87,7 +87,8 @@ double ro_u64_to_f64(uint64_t w);
 /* ------------------------------------------------------------------ */
 /* Environments                                                        */
 /* ------------------------------------------------------------------ */
-enum { RO_ENV_CARTPOLE = 0, RO_ENV_CHAIN = 1, RO_ENV_MEMORY = 2, RO_ENV_BANDIT_META = 3 };
+enum { RO_ENV_CARTPOLE = 0, RO_ENV_CHAIN = 1, RO_ENV_MEMORY = 2, RO_ENV_BANDIT_META = 3, RO_ENV_PARTITION = 4 };
+#define RO_PARTITION_FEATURES 10 /* partition.rs: NUM_FEATURES */
 enum { RO_BANDIT_UNIFORM_BERNOULLI = 0, RO_BANDIT_ROUND_ROBIN_DETERMINISTIC = 1, RO_BANDIT_ONE_HOT = 2 };
 #define RO_MAX_ARMS 32
 #define RO_MAX_FEATURES 64
@@ -113,13 +114,15 @@ void ro_cfg_cartpole_default(ro_env_cfg *c, uint64_t step_limit);
 void ro_cfg_chain_default(ro_env_cfg *c);
 void ro_cfg_memory(ro_env_cfg *c, uint64_t num_actions, uint64_t history_len);
 void ro_cfg_bandit_meta(ro_env_cfg *c, uint64_t num_arms, uint64_t episodes_per_trial, int dist);
+void ro_cfg_partition(ro_env_cfg *c);
 
 typedef struct ro_state {
     /* cartpole */
     double x, xd, th, thd;
     int flag;
     uint64_t steps_remaining;
-    /* chain / memory */
+    /* chain / memory; PartitionGame: s = element bits, s_init = supervisor axis, has_prev / prev_action / inner_done =
+     * feedback present / its element bits / its label */
     uint64_t s, s_init;
     /* meta bandit */
     double means[RO_MAX_ARMS];

@@ -4,7 +4,7 @@ Host-side mirror of the reference's interfaces for that path over a C-ABI CUDA l
 (`include/relearn_b200.h`, built in-tree by `__graft_entry__.build()`).  No CPU fallback exists.
 """
 from . import _lib  # noqa: F401
-from .envs import (BatchedEnv, CartPole, CartPoleConfig, Chain, LatentStepLimit, MemoryGame, MetaEnv, OneHotBandits, Successor,  # noqa: F401
+from .envs import (BatchedEnv, CartPole, CartPoleConfig, Chain, LatentStepLimit, MemoryGame, MetaEnv, OneHotBandits, PartitionGame, Successor,  # noqa: F401
                    TrialEpisodeLimit, UniformBernoulliBandits, VisibleStepLimit, build_env)
 from .modules import (GruLinear, GruLinearConfig, Mlp, MlpConfig, init_gru_linear_params, init_params)  # noqa: F401
 from .runtime import Context, DeviceBuffer  # noqa: F401

@@ -229,6 +229,12 @@ rl_status rl_env_create(rl_ctx *ctx, rl_env_kind kind, const void *cfg, uint64_t
         mean_planes = c->num_arms;
         break;
     }
+    case RL_ENV_PARTITION_GAME: {
+        st.num_features = PartitionEnv::MAXF; st.num_actions = 2; st.num_observations = 0;
+        st.reward_lo = -1.0; st.reward_hi = 1.0;  // partition.rs feedback_space
+        st.discount_factor = 0.999;               // partition.rs discount_factor
+        break;
+    }
     default:
         delete env;
         return rl_fail(ctx, RL_ERR_INVALID_ARG, "rl_env_create: unknown env kind %d", (int)kind);
@@ -309,6 +315,7 @@ rl_status rl_env_reset_all(rl_env *env) {
     case RL_ENV_CHAIN: return launch_reset<ChainEnv>(env, env->chain);
     case RL_ENV_MEMORY_GAME: return launch_reset<MemoryEnv>(env, env->memory);
     case RL_ENV_BANDIT_META: return launch_reset<BanditMetaEnv>(env, env->bandit);
+    case RL_ENV_PARTITION_GAME: return launch_reset<PartitionEnv>(env, env->partition);
     }
     return rl_fail(env->ctx, RL_ERR_INVALID_ARG, "bad env kind");
 }
@@ -321,6 +328,7 @@ rl_status rl_env_step(rl_env *env, const uint8_t *actions_dev, rl_step_out *out)
     case RL_ENV_CHAIN: s = launch_step<ChainEnv>(env, env->chain, actions_dev); break;
     case RL_ENV_MEMORY_GAME: s = launch_step<MemoryEnv>(env, env->memory, actions_dev); break;
     case RL_ENV_BANDIT_META: s = launch_step<BanditMetaEnv>(env, env->bandit, actions_dev); break;
+    case RL_ENV_PARTITION_GAME: s = launch_step<PartitionEnv>(env, env->partition, actions_dev); break;
     }
     if (s != RL_OK) return s;
     env->noise.step_counter += 1;

@@ -12,6 +12,7 @@ struct rl_env {
     ChainEnv::Params chain{};
     MemoryEnv::Params memory{};
     BanditMetaEnv::Params bandit{};
+    PartitionEnv::Params partition{};
     rl_env_structure structure{};
     EnvStatePtrs state{};
     NoiseSource noise{};

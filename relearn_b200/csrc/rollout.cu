@@ -1383,6 +1383,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     case RL_ENV_CHAIN: RL_TRY((launch_rollout<ChainEnv>(ctx, env->chain, a, net, replay, &nblocks))); break;
     case RL_ENV_MEMORY_GAME: RL_TRY((launch_rollout<MemoryEnv>(ctx, env->memory, a, net, replay, &nblocks))); break;
     case RL_ENV_BANDIT_META: RL_TRY((launch_rollout<BanditMetaEnv>(ctx, env->bandit, a, net, replay, &nblocks))); break;
+    case RL_ENV_PARTITION_GAME: RL_TRY((launch_rollout<PartitionEnv>(ctx, env->partition, a, net, replay, &nblocks))); break;
     }
     totals = a.partials - ST_COUNT;
     RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32 * ST_COUNT, 0, a.partials, nblocks, totals, traj->counts_dev);

@@ -100,6 +100,16 @@ class MemoryGame:
 
 
 @dataclass
+class PartitionGame:
+    """src/envs/partition.rs: classify 10-bit elements the way a hidden axis-aligned supervisor does (no parameters)."""
+
+    kind = L.RL_ENV_PARTITION_GAME
+
+    def c_cfg(self):
+        return C.c_uint64(0)  # rl_env_create ignores cfg for this kind
+
+
+@dataclass
 class UniformBernoulliBandits:
     """src/envs/bandits.rs:128-181"""
 

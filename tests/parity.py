@@ -26,6 +26,8 @@ def oracle_cfg_for(config) -> O.EnvCfg:
     if isinstance(config, R.MetaEnv):
         dist = O.BANDIT_ONE_HOT if isinstance(config.env_distribution, R.OneHotBandits) else O.BANDIT_UNIFORM_BERNOULLI
         return O.bandit_meta_cfg(config.env_distribution.num_arms, config.episodes_per_trial, dist)
+    if isinstance(config, R.PartitionGame):
+        return O.partition_cfg()
     raise TypeError(config)
 
 

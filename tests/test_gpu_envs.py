@@ -19,6 +19,7 @@ INT_ENVS = [
     pytest.param(R.MetaEnv(R.UniformBernoulliBandits(10), 7), id="bandit-10x7"),
     pytest.param(R.MetaEnv(R.OneHotBandits(3), 4), id="onehot-3x4"),
     pytest.param(R.MetaEnv(R.OneHotBandits(2), 10), id="onehot-2x10"),
+    pytest.param(R.PartitionGame(), id="partition"),
 ]
 
 
@@ -392,3 +393,27 @@ def test_tc_rollout_eps_greedy_cartpole(ctx):
     assert differing <= 2
     ref = P.oracle_rollout(SHORT, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=b["action"].copy(), env_words=ewords)
     P.compare_traj(b, ref, obs_rtol=1e-6, obs_atol=1e-7, what="K2t eps-greedy")
+
+
+@pytest.mark.parametrize("cfg", [pytest.param(R.PartitionGame(), id="partition-23f"), pytest.param(R.MemoryGame(4, 3), id="memory-7f")])
+def test_fused_rollout_policy_other_envs_consistent(ctx, cfg):
+    """The generic fused kernel (K2a) with a categorical MLP policy on envs with wider observations / more actions:
+    every action is the inverse-CDF choice of the oracle's softmax for the recorded observation, and replaying the
+    actions through the oracle reproduces the trajectory bit for bit."""
+    rng = np.random.default_rng(95)
+    E, T = 90, 30
+    env = R.build_env(ctx, cfg, E, seed=3)
+    F, A = env.num_features, env.num_actions
+    W = 24 * T + 64  # PartitionGame draws ten words per step
+    ewords, awords = P.random_words(rng, E, W), P.random_words(rng, E, W)
+    env.set_noise_replay(ewords, awords)
+    params = R.init_params(rng, F, 64, A) * 3.0
+    net = R.Mlp(ctx, F, [64], A)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net), R.HistoryDataBound(T, 0), traj)
+    host = traj.to_host()
+    checked, near = P.check_policy_consistency(host, params, 64, A, awords)
+    assert checked > E * (T - 2) and near <= 3
+    ref = P.oracle_rollout(cfg, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), env_words=ewords)
+    P.compare_traj(host, ref, what=f"policy on {cfg}")

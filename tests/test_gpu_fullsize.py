@@ -188,3 +188,56 @@ def test_replay_and_sampler_invariants_at_dqn_size(ctx):
     assert np.isin(mb["target"], gk[1:]).all()
     stats = agent.batch_update(rb, {})
     assert stats.opt_steps == 50 and np.isfinite(stats.loss_last) and stats.loss_last < stats.loss_first
+
+
+def test_tensor_core_rollout_at_65536_envs(ctx):
+    """configs[2] / configs[4] size: 65 536 envs on the tensor-core rollout kernel (K2t, what `lanes_per_env = 0` picks
+    there).  (i) the episode protocol invariants; (ii) K1 (one launch per step) replaying K2t's actions on the same
+    Philox noise reproduces all 4.2 M observations and successor codes exactly -- K2t only differs from the FP32-pipe
+    kernels in how the logits are rounded, never in the dynamics; (iii) two half-size shards with lane offsets equal
+    the full run bit for bit (tile position does not enter the arithmetic)."""
+    E, T = 65536, 64
+    params = R.init_params(np.random.default_rng(1), 5, 128, 2)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+
+    def run(n, off, lanes):
+        env = R.build_env(ctx, CARTPOLE, n, seed=78, lane_offset=off)
+        tr = R.Trajectory(env, T)
+        summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes),
+                         R.HistoryDataBound(T, 0), tr)
+        host = tr.to_host()
+        tr.close()
+        env.close()
+        return host, summ
+
+    host, summ = run(E, 0, 0)
+    explicit, _ = run(E, 0, L.RL_LANES_TENSOR_CORE)
+    for k in ("obs", "action", "succ", "lane_len"):
+        np.testing.assert_array_equal(host[k], explicit[k], err_msg=f"auto selection is not K2t at E = {E}: {k}")
+    succ, lane_len = host["succ"], host["lane_len"].astype(np.int64)
+    valid = succ != PAD
+    assert ((lane_len == T) | (lane_len == T - 1)).all()
+    assert valid.sum() == lane_len.sum() == summ.num_stored_steps
+    assert (valid == (np.arange(T)[:, None] < lane_len[None, :])).all()
+    assert (host["reward"][valid] == 1.0).all() and np.isin(host["action"][valid], [0, 1]).all()
+    assert summ.num_stored_episodes == (valid & (succ != CONT)).sum()
+    assert summ.step_reward.count == E * T
+    # both actions occur with a random-init policy, and episodes end
+    assert 0.3 < host["action"][valid].mean() < 0.7 and (succ == TERM).sum() > E
+    # (ii)
+    env2 = R.build_env(ctx, CARTPOLE, E, seed=78)
+    obs = env2.reset_all()
+    for t in range(T):
+        stored = host["lane_len"] > t
+        np.testing.assert_array_equal(obs[stored], host["obs"][t][stored], err_msg=f"step {t}")
+        out = env2.step(host["action"][t])
+        keep = host["lane_len"] > t + 1
+        np.testing.assert_array_equal(out["succ"][keep], host["succ"][t][keep])
+        obs = out["obs"]
+    env2.close()
+    # (iii)
+    a, _ = run(E // 2, 0, 0)
+    b, _ = run(E // 2, E // 2, 0)
+    for k in ("obs", "action", "succ"):
+        np.testing.assert_array_equal(np.concatenate([a[k], b[k]], axis=1), host[k])

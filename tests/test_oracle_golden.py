@@ -185,6 +185,49 @@ def test_one_hot_bandits_meta_env():
                 assert L.ro_env_step(C.byref(env), C.byref(st), 0, rng.ref, C.byref(r)) == CONT and r.value == 0.0
 
 
+def test_partition_game_oracle():
+    # partition.rs: supervisor axis = gen_range(0..10); element = gen::<[bool; 10]>() (MSB of ten u32 words, index
+    # order); reward +1 iff the action equals element[axis]; observation = (element, Some((previous element, label)))
+    # as [10 bools; is_none; 10 bools; one-hot(Left, Right)] (power.rs:106-115, option.rs:88-116); never ends.
+    cfg = O.partition_cfg()
+    env = O.make_env(cfg)
+    L = O.lib()
+    assert L.ro_env_num_features(C.byref(env)) == 23 and L.ro_env_num_actions(C.byref(env)) == 2
+    gen = np.random.default_rng(3)
+    words = gen.integers(0, 2**32, size=400, dtype=np.uint64).astype(np.uint32)
+    rng = O.ScriptRng(words)
+    st = O.State()
+    r = C.c_double()
+    L.ro_env_initial_state(C.byref(env), C.byref(st), rng.ref)
+    axis = int(st.s_init)
+    assert 0 <= axis < 10
+    # gen_range(0..10) consumed one u64 (two words) unless rejected; find where the element words start
+    for start in (2, 4, 6):
+        bits = [int(w >> 31) for w in words[start:start + 10]]
+        if sum(b << i for i, b in enumerate(bits)) == int(st.s):
+            break
+    else:
+        raise AssertionError("first element does not match the MSBs of ten consecutive words")
+    obs = _meta_obs(env, st)
+    np.testing.assert_array_equal(obs[:10], bits)
+    assert obs[10] == 1.0 and not obs[11:].any()
+    cursor = start + 10
+    for t in range(12):
+        element = [int((st.s >> i) & 1) for i in range(10)]
+        action = t % 2
+        code = L.ro_env_step(C.byref(env), C.byref(st), action, rng.ref, C.byref(r))
+        assert code == CONT
+        assert r.value == (1.0 if action == element[axis] else -1.0)
+        nxt = [int(w >> 31) for w in words[cursor:cursor + 10]]
+        cursor += 10
+        obs = _meta_obs(env, st)
+        np.testing.assert_array_equal(obs[:10], nxt)
+        assert obs[10] == 0.0
+        np.testing.assert_array_equal(obs[11:21], element)
+        np.testing.assert_array_equal(obs[21:], [1.0, 0.0] if element[axis] == 0 else [0.0, 1.0])
+        assert int(st.s_init) == axis
+
+
 def test_meta_trial_length_is_2n_minus_1():
     # a trial of n inner episodes is 2n-1 meta-steps
     for n in (1, 2, 10):
