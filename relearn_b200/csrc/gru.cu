@@ -19,9 +19,12 @@
 // trajectory write stream and the env arithmetic, like K2a.  The rl2-sized module (hidden 128, 1.1e5 FLOP per
 // env-step) is a dense [E, F+H] x [F+H, 3H] GEMM per step and belongs on tcgen05 tensor cores; that variant is
 // not built yet -- this FP32 kernel is the correct-but-slow path for it.
+#include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "handles.cuh"
+#include "tcgen05.cuh"
 
 struct rl_grunet {
     rl_ctx *ctx = nullptr;
@@ -29,6 +32,7 @@ struct rl_grunet {
     rl_activation act = RL_ACT_RELU;
     uint64_t n_params = 0;
     float *params = nullptr;  // w_ih[3H,in], w_hh[3H,H], b_ih[3H], b_hh[3H], kernel[out,H], bias[out]
+    float *wt = nullptr;      // K8h: k-major copy of w_ih / w_hh, [in + H][3H] (rebuilt before every tiled rollout)
 };
 
 namespace {
@@ -124,6 +128,7 @@ struct SeqArgs {
     int weights_in_smem;
     int F, A;
     double *partials;  // f64 [gridDim.x][SQ_COUNT]
+    const float *wt;   // K8h only: Wt[F + H][3H]
 };
 
 // XF / XA > 0: features / actions (and hidden = HMAX) fixed at compile time, see grunet_step<EXACT>.
@@ -273,6 +278,8 @@ __global__ void __launch_bounds__(32 * SQ_COUNT) seq_finalize_kernel(const doubl
     }
 }
 
+#include "gru_tile.cuh"
+
 // SeqPacked::seq_packed (gru.rs:72-102 -> chain.rs:157-168) over a stored trajectory: thread per lane, hidden
 // state zeroed at the first step of every episode.  out f32 [T][A][E]; PAD slots get zeros.
 template <int HMAX, int XF = 0, int XA = 0>
@@ -368,6 +375,7 @@ rl_status launch_seq(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bo
         if (H == 4 && a.F == 6 && a.A == 2 && p.num_arms == 2) return launch_seq_bandit_6_4_2(ctx, p, a, replay, smem, grid);
     }
     if (H <= 8) return launch_seq_h<EnvT, 8>(ctx, p, a, replay, smem, grid);
+    if (a.wt) return launch_seq_tile<EnvT>(ctx, p, a, replay);  // K8h: hidden 128
     return launch_seq_h<EnvT, 128>(ctx, p, a, replay, smem, grid);
 }
 
@@ -390,7 +398,19 @@ rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *t
     const size_t wbytes = net->n_params * sizeof(float);
     a.weights_in_smem = wbytes <= SEQ_SMEM_LIMIT;
     const size_t smem = a.weights_in_smem ? wbytes : 16;
-    const unsigned grid = rl_grid_for(a.E, 128);
+    // K8h (gru_tile.cuh) for the rl2-sized module; RL_GRU_KERNEL=thread keeps the thread-per-env kernel (diagnostics)
+    const char *pick = getenv("RL_GRU_KERNEL");
+    const bool tiled = net->hidden == GT_H && net->in_dim <= GT_MAXF && !(pick && strcmp(pick, "thread") == 0);
+    const unsigned grid = tiled ? (unsigned)((a.E + GT_ENVS - 1) / GT_ENVS) : rl_grid_for(a.E, 128);
+    if (tiled) {
+        const size_t wt_floats = (size_t)(net->in_dim + net->hidden) * 3 * net->hidden;
+        if (!net->wt) {
+            cudaError_t err = cudaMalloc((void **)&net->wt, wt_floats * sizeof(float));
+            if (err != cudaSuccess) return rl_fail(ctx, RL_ERR_OOM, "rl_rollout: %s", cudaGetErrorString(err));
+        }
+        RL_LAUNCH(ctx, gru_wt_kernel, 148, 256, 0, a.net, net->wt);
+        a.wt = net->wt;
+    }
     double *partials;
     RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * SQ_COUNT * sizeof(double), (void **)&partials));
     a.partials = partials + SQ_COUNT;
@@ -471,6 +491,7 @@ rl_status rl_grunet_destroy(rl_grunet *g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(g->params);
+    if (g->wt) cudaFree(g->wt);
     delete g;
     return RL_OK;
 }

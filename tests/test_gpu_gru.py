@@ -108,3 +108,68 @@ def test_gru_policy_rollout_cartpole_philox(ctx):
         np.testing.assert_array_equal(full[k][:, :32], a[k])
         np.testing.assert_array_equal(full[k][:, 32:], b[k])
     assert summ.step_reward.count == 64 * 120 and summ.episode_length.count > 64
+
+
+def test_gru128_tiled_rollout_matches_thread_per_env_kernel(ctx, monkeypatch):
+    """K8h (gru_tile.cuh: the hidden-128 cell as a register-tiled GEMM over 64-env CTAs) against K8a (one thread per
+    env) on the same replayed noise: several CTAs with a ragged last tile, slack, trial ends (hidden-state reset) and
+    dangling steps.  The two kernels sum the gate pre-activations in different orders, so a lane may part ways at a
+    near-tie of the sampled action; every other lane must agree in every stored byte, and the summaries with them."""
+    rng = np.random.default_rng(77)
+    arms, episodes, hidden = 10, 3, 128
+    cfg = R.MetaEnv(R.UniformBernoulliBandits(arms), episodes)
+    E, T, slack = 200, 3 * (2 * episodes - 1) + 2, 3
+    nwords = 8 * (T + slack) + 64 * arms
+    ewords, awords = P.random_words(rng, E, nwords), P.random_words(rng, E, nwords)
+    F, A = arms + 4, arms
+    params = R.init_gru_linear_params(rng, F, hidden, A)
+    params[3 * hidden * F + 3 * hidden * hidden:3 * hidden * F + 3 * hidden * hidden + 6 * hidden] = rng.normal(size=6 * hidden) * 0.3
+    params[-A * hidden - A:] *= 4.0  # sharper policy: fewer near-ties, more varied episodes
+
+    def run(kernel):
+        monkeypatch.setenv("RL_GRU_KERNEL", kernel)
+        env = R.build_env(ctx, cfg, E, seed=3)
+        env.set_noise_replay(ewords, awords)
+        net = R.GruLinear(ctx, F, hidden, A)
+        net.set_weights(params)
+        traj = R.Trajectory(env, T + slack)
+        summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(T, slack), traj)
+        return traj.to_host(), summ
+
+    tile, st = run("tile")
+    thread, sh = run("thread")
+    same = (tile["action"] == thread["action"]).all(axis=0) & (tile["lane_len"] == thread["lane_len"])
+    assert same.mean() >= 0.97, same.mean()
+    for k in ("obs", "next_obs", "reward", "succ"):
+        np.testing.assert_array_equal(tile[k][:, same], thread[k][:, same], err_msg=k)
+    if same.all():
+        assert st.num_stored_steps == sh.num_stored_steps and st.num_stored_episodes == sh.num_stored_episodes
+        assert st.step_reward.mean == sh.step_reward.mean and st.episode_length.count == sh.episode_length.count
+    # the tiled kernel's own trajectory is a valid one: the oracle reproduces it from its actions
+    ref = P.oracle_rollout(cfg, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=tile["action"].copy(), env_words=ewords)
+    P.compare_traj(tile, ref, what="K8h")
+    assert tile["num_steps"] == st.num_stored_steps == int(tile["lane_len"].sum())
+
+
+def test_gru128_tiled_rollout_philox_sharding(ctx):
+    """K8h under production noise on CartPole (5 features, 2 actions): tile position does not enter the arithmetic, so
+    two shards with lane offsets reproduce the single run bit for bit."""
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(40))
+    params = R.init_gru_linear_params(np.random.default_rng(2), 5, 128, 2)
+
+    def run(n, off):
+        env = R.build_env(ctx, cfg, n, seed=9, lane_offset=off)
+        net = R.GruLinear(ctx, 5, 128, 2)
+        net.set_weights(params)
+        traj = R.Trajectory(env, 90)
+        summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(90, 0), traj)
+        return traj.to_host(), summ
+
+    full, summ = run(160, 0)
+    a, _ = run(96, 0)
+    b, _ = run(64, 96)
+    for k in ("obs", "action", "reward", "succ"):
+        np.testing.assert_array_equal(full[k][:, :96], a[k])
+        np.testing.assert_array_equal(full[k][:, 96:], b[k])
+    assert summ.step_reward.count == 160 * 90 and summ.episode_length.count > 160
+    assert 0.2 < full["action"][full["succ"] != L.RL_PAD].mean() < 0.8
