@@ -559,6 +559,27 @@ def other_configs(ctx, R, L, hbm_peak):
                 "batch_steps": E4 * 19, "adv_est_ms": float(np.mean([u[0] for u in upd])),
                 "trpo_policy_ms": float(np.mean([u[1] for u in upd])), "critic_80_adam_ms": float(np.mean([u[2] for u in upd]))})
     traj5.close(); env4.close()
+    # ---- config 4, rl2-sized: k = 10 arms, n = 100 episodes per trial, GRU(14 -> 128) -> Linear(128 -> 10) (K8h) ----
+    E6, T6 = 148 * 64 * 2, 199
+    env6 = R.build_env(ctx, R.MetaEnv(R.UniformBernoulliBandits(10), 100), E6, seed=7)
+    net6 = R.GruLinear(ctx, env6.num_features, 128, env6.num_actions)
+    net6.set_weights(R.init_gru_linear_params(rng, env6.num_features, 128, env6.num_actions))
+    traj6 = R.Trajectory(env6, T6)
+    spec6 = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net6)
+    R.rollout(env6, spec6, R.HistoryDataBound(T6, 0), traj6, want_summary=False)
+    e0 = ctx.event().record()
+    for _ in range(3):
+        R.rollout(env6, spec6, R.HistoryDataBound(T6, 0), traj6, want_summary=False)
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / 3
+    flop = 2 * 3 * 128 * (env6.num_features + 128) + 2 * 128 * env6.num_actions
+    fp32_peak = ctx.fp32_peak_tflops()
+    out.append({"kernel": "config 4 rl2-sized: bandit meta-env (10 arms x 100 episodes) + GRU(14->128)->Linear(128->10), fused rollout "
+                          "K8h (64-env tiles, FP32 FFMA2 GEMM per step, weights streamed by cp.async.bulk)",
+                "envs": E6, "horizon": T6, "ms": ms, "env_steps_per_s": E6 * T6 / (ms * 1e-3), "flop_per_env_step": flop,
+                "fp32_tflops": flop * E6 * T6 / (ms * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
+                "frac_of_fp32_peak": flop * E6 * T6 / (ms * 1e-3) / 1e12 / fp32_peak})
+    traj6.close(); env6.close()
     return out
 
 

@@ -15,10 +15,13 @@
 //                                       broadcasts from shared memory when they fit, else through L1.
 //  K8b grunet_seq_kernel<HMAX>          SeqPacked::seq_packed over a stored trajectory (one thread per lane).
 //
+//  K8h rollout_seq_tile_kernel         gru_tile.cuh: hidden 128 (the rl2-sized module) as a register-tiled FP32 GEMM
+//                                       per step over 64-env CTAs, weights streamed through shared memory.
+//
 // For the benches/rnn.rs-sized module (hidden 4) the per-step cost is ~150 FMAs and the kernel is bound by the
 // trajectory write stream and the env arithmetic, like K2a.  The rl2-sized module (hidden 128, 1.1e5 FLOP per
-// env-step) is a dense [E, F+H] x [F+H, 3H] GEMM per step and belongs on tcgen05 tensor cores; that variant is
-// not built yet -- this FP32 kernel is the correct-but-slow path for it.
+// env-step) is a dense [E, F+H] x [F+H, 3H] GEMM per step: K8h runs it at 56 % of the FP32 FMA roof (27x K8a);
+// K8a stays as the cross-check (RL_GRU_KERNEL=thread) and for hidden sizes between 9 and 127.
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -129,6 +132,7 @@ struct SeqArgs {
     int F, A;
     double *partials;  // f64 [gridDim.x][SQ_COUNT]
     const float *wt;   // K8h only: Wt[F + H][3H]
+    int tile_envs;     // K8h only: envs per CTA (32 or 64)
 };
 
 // XF / XA > 0: features / actions (and hidden = HMAX) fixed at compile time, see grunet_step<EXACT>.
@@ -375,7 +379,9 @@ rl_status launch_seq(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bo
         if (H == 4 && a.F == 6 && a.A == 2 && p.num_arms == 2) return launch_seq_bandit_6_4_2(ctx, p, a, replay, smem, grid);
     }
     if (H <= 8) return launch_seq_h<EnvT, 8>(ctx, p, a, replay, smem, grid);
-    if (a.wt) return launch_seq_tile<EnvT>(ctx, p, a, replay);  // K8h: hidden 128
+    if constexpr (EnvT::MAXA <= GT_LW) {
+        if (a.wt) return launch_seq_tile<EnvT>(ctx, p, a, replay, a.tile_envs);  // K8h: hidden 128
+    }
     return launch_seq_h<EnvT, 128>(ctx, p, a, replay, smem, grid);
 }
 
@@ -400,8 +406,10 @@ rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *t
     const size_t smem = a.weights_in_smem ? wbytes : 16;
     // K8h (gru_tile.cuh) for the rl2-sized module; RL_GRU_KERNEL=thread keeps the thread-per-env kernel (diagnostics)
     const char *pick = getenv("RL_GRU_KERNEL");
-    const bool tiled = net->hidden == GT_H && net->in_dim <= GT_MAXF && !(pick && strcmp(pick, "thread") == 0);
-    const unsigned grid = tiled ? (unsigned)((a.E + GT_ENVS - 1) / GT_ENVS) : rl_grid_for(a.E, 128);
+    const bool tiled = net->hidden == GT_H && net->in_dim <= GT_MAXF && net->out_dim <= GT_LW &&
+                       env->kind != RL_ENV_MEMORY_GAME && !(pick && strcmp(pick, "thread") == 0);
+    a.tile_envs = (pick && strcmp(pick, "tile32") == 0) ? 32 : 64;
+    const unsigned grid = tiled ? (unsigned)((a.E + a.tile_envs - 1) / a.tile_envs) : rl_grid_for(a.E, 128);
     if (tiled) {
         const size_t wt_floats = (size_t)(net->in_dim + net->hidden) * 3 * net->hidden;
         if (!net->wt) {

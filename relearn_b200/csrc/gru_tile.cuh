@@ -15,17 +15,29 @@
 //     costs 3 LDS.128 of weights + 2 LDS.128 of state for 48 FFMA2; a warp covers 16 units x all 64 envs so that a
 //     quarter-warp touches 64 B of weights and 64 B of state per load (broadcast, conflict-free);
 //   * epilogue in registers: r, z = sigmoid, n = tanh(in + r * hn), h' = (h - n) z + n, written to the other state
-//     buffer; then four threads per env fold relu(h') into the A logits (two shuffles), and the env's owner thread
-//     samples the action, steps the env, stores the step record and writes the next observation into xs.
+//     buffer (gates on the SFU: MUFU.EX2 + MUFU.RCP); then four threads per env fold relu(h') into the A logits
+//     (FFMA2 over action pairs, two shuffles), and the env's owner thread samples the action, steps the env, stores
+//     the step record and writes the next observation into xs.
 // The owner's scalar state (env state, noise cursors, summary sums) lives in shared memory between steps so that the
 // GEMM phase has the register file to itself.
+// Measured (B200, 10 arms x 100 episodes, E = 18 944, T = 199): 337 M env-steps/s = 37.6 TFLOP/s = 56 % of the measured
+// FMA peak; K8a: 12.4 M.  ncu: the GEMM loop is 70 % of the time at ~71 % of the FMA roof, co-limited by operand
+// delivery (every LDS.128 moves 512 B into registers whatever the broadcast pattern: 160 shared-memory-pipe cycles per
+// 192 FMA-pipe cycles per k).
 #pragma once
 
 constexpr int GT_H = 128, GT_N3 = 3 * GT_H;
-constexpr int GT_ENVS = 64, GT_THREADS = 256;
-constexpr int GT_ROWS = 16, GT_NBUF = 3;
-constexpr int GT_HLD = GT_ENVS + 4;  // row stride of hs (floats): 16-byte aligned rows, shifted banks
 constexpr int GT_MAXF = 32;
+// Tile shapes: ENVS envs per CTA (4 threads per env), weight chunks of ROWS rows in a ring of NBUF buffers.
+//   <64, 16, 3>: 256 threads, 185 KB of shared memory, one CTA per SM
+//   <32, 8, 4>:  128 threads, 110 KB, two CTAs per SM -- one CTA's gate / sampling / env phase (few active lanes,
+//                latency bound) overlaps the other's GEMM (FMA-pipe bound)
+template <int ENVS, int ROWS, int NBUF>
+struct GtShape {
+    static constexpr int envs = ENVS, rows = ROWS, nbuf = NBUF, threads = 4 * ENVS;
+    static constexpr int hld = ENVS + 4;       // row stride of hs (floats): 16-byte aligned rows, shifted banks
+    static constexpr int ugw = 32 / (ENVS / 8);  // unit groups (of 4 units) per warp; a warp spans all ENVS envs
+};
 
 __device__ __forceinline__ void gt_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -35,6 +47,11 @@ __device__ __forceinline__ void gt_bulk_g2s(uint32_t dst, const void *src, uint3
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+
+// Gate nonlinearities on the SFU: exp2 (MUFU.EX2) and the approximate reciprocal (MUFU.RCP), ~2 ulp each; tanh as
+// 2 sigmoid(2 x) - 1 (absolute error ~2e-7, no cancellation that matters: n enters h' additively).
+__device__ __forceinline__ float gt_sigmoid(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float gt_tanh(float v) { return fmaf(2.0f, __fdividef(1.0f, 1.0f + __expf(-2.0f * v)), -1.0f); }
 
 // Wt[k][g * H + j] = k < F ? w_ih[g * H + j][k] : w_hh[g * H + j][k - F]
 __global__ void gru_wt_kernel(GruView m, float *__restrict__ wt) {
@@ -57,22 +74,26 @@ struct GtOwner {
     int succ_last, succ_prev;
 };
 
-template <class EnvT, bool REPLAY>
+constexpr int GT_LW = 16;  // row stride of the transposed Linear weights lin_w[unit][action]
+
+template <class EnvT, bool REPLAY, class S>
 constexpr size_t gt_smem_bytes() {
-    return (size_t)GT_NBUF * GT_ROWS * GT_N3 * 4 + (size_t)2 * GT_H * GT_HLD * 4 + (size_t)GT_MAXF * GT_ENVS * 4 +
-           (size_t)EnvT::MAXA * GT_H * 4 + 4 * GT_H * 4 + 64 + GT_ENVS * sizeof(GtOwner<EnvT, REPLAY>) + 64;
+    return (size_t)S::nbuf * S::rows * GT_N3 * 4 + (size_t)2 * GT_H * S::hld * 4 + (size_t)GT_MAXF * S::envs * 4 +
+           (size_t)GT_LW * GT_H * 4 + 4 * GT_H * 4 + 64 + S::envs * sizeof(GtOwner<EnvT, REPLAY>) + 64;
 }
 
-template <class EnvT, bool REPLAY>
-__global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typename EnvT::Params p, SeqArgs a) {
+template <class EnvT, bool REPLAY, class S>
+__global__ void __launch_bounds__(S::threads, 256 / S::threads) rollout_seq_tile_kernel(typename EnvT::Params p, SeqArgs a) {
+    constexpr int GT_ENVS = S::envs, GT_THREADS = S::threads, GT_ROWS = S::rows, GT_NBUF = S::nbuf, GT_HLD = S::hld;
     constexpr int MF = EnvT::MAXF, MA = EnvT::MAXA;
+    static_assert(MA <= GT_LW && MA % 2 == 0, "actions are folded as FFMA2 pairs");
     using Owner = GtOwner<EnvT, REPLAY>;
     extern __shared__ __align__(128) unsigned char gt_smem[];
     float *ring = reinterpret_cast<float *>(gt_smem);                // [NBUF][ROWS][384]
     float *hs = ring + GT_NBUF * GT_ROWS * GT_N3;                    // [2][128][HLD]
     float *xs = hs + 2 * GT_H * GT_HLD;                              // [MAXF][64]
-    float *lin_w = xs + GT_MAXF * GT_ENVS;                           // [A][128]
-    float *bias = lin_w + MA * GT_H;                                 // b_r, b_z, b_in, b_hn [128] each
+    float *lin_w = xs + GT_MAXF * GT_ENVS;                           // [128][GT_LW] (unit-major, zero padded)
+    float *bias = lin_w + GT_LW * GT_H;                              // b_r, b_z, b_in, b_hn [128] each
     float *lin_b = bias + 4 * GT_H;                                  // [16]
     Owner *owners = reinterpret_cast<Owner *>(lin_b + 16);           // [64]
     uint64_t *bars = reinterpret_cast<uint64_t *>(owners + GT_ENVS);  // [NBUF]
@@ -92,7 +113,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typenam
             bias[2 * GT_H + j] = b_ih[2 * GT_H + j];
             bias[3 * GT_H + j] = b_hh[2 * GT_H + j];
         }
-        for (int j = tid; j < A * GT_H; j += GT_THREADS) lin_w[j] = lw[j];
+        for (int j = tid; j < GT_LW * GT_H; j += GT_THREADS) {
+            const int unit = j / GT_LW, k = j - unit * GT_LW;
+            lin_w[j] = k < A ? lw[(size_t)k * GT_H + unit] : 0.0f;
+        }
         if (tid < 16) lin_b[tid] = tid < A ? lb[tid] : 0.0f;
         for (int j = tid; j < 2 * GT_H * GT_HLD; j += GT_THREADS) hs[j] = 0.0f;  // SeqIterative::initial_state (gru.rs:23-28)
         for (int j = tid; j < GT_MAXF * GT_ENVS; j += GT_THREADS) xs[j] = 0.0f;
@@ -152,7 +176,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typenam
 
     // GEMM tile of this thread: units u0 .. u0 + 3, envs e0 .. e0 + 7
     const int warp = tid >> 5, lane = tid & 31;
-    const int u0 = 16 * warp + 4 * (lane & 3), e0 = 8 * (lane >> 2);
+    const int u0 = 4 * S::ugw * warp + 4 * (lane % S::ugw), e0 = 8 * (lane / S::ugw);
     int cur = 0;
     while (any) {
         const float *hc = hs + (size_t)cur * GT_H * GT_HLD;
@@ -196,7 +220,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typenam
                 }
             } else {
                 const float *src = hc + (size_t)(c - nxc) * GT_ROWS * GT_HLD + e0;
-#pragma unroll 4
+#pragma unroll
                 for (int r = 0; r < GT_ROWS; ++r) {
                     const float4 wr = *reinterpret_cast<const float4 *>(wb + r * GT_N3);
                     const float4 wz = *reinterpret_cast<const float4 *>(wb + r * GT_N3 + GT_H);
@@ -222,35 +246,46 @@ __global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typenam
                 ++issued;
             }
         }
-        // gates and the new hidden state (gru.cu header: libtorch gru_cell)
+        // gates and the new hidden state (gru.cu header: libtorch gru_cell); unit-major so that the state moves as float4
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float rr[4] = {accR[q][0].x, accR[q][0].y, accR[q][1].x, accR[q][1].y};
-            const float zz[4] = {accZ[q][0].x, accZ[q][0].y, accZ[q][1].x, accZ[q][1].y};
-            const float ii[4] = {accI[q][0].x, accI[q][0].y, accI[q][1].x, accI[q][1].y};
-            const float hh[4] = {accH[q][0].x, accH[q][0].y, accH[q][1].x, accH[q][1].y};
+        for (int u = 0; u < 4; ++u) {
+            const float *hrow = hc + (size_t)(u0 + u) * GT_HLD + e0;
+            const float4 ha = *reinterpret_cast<const float4 *>(hrow), hb = *reinterpret_cast<const float4 *>(hrow + 4);
+            const float hold[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+            float hnew[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float r = sigmoidf_ref(rr[u]);
-                const float z = sigmoidf_ref(zz[u]);
-                const float n = tanhf(__fadd_rn(ii[u], __fmul_rn(hh[u], r)));
-                const float hold = hc[(size_t)(u0 + u) * GT_HLD + e0 + q];
-                hn[(size_t)(u0 + u) * GT_HLD + e0 + q] = __fadd_rn(__fmul_rn(__fsub_rn(hold, n), z), n);
+            for (int q = 0; q < 8; ++q) {
+                const float2 cr = accR[q][u >> 1], cz = accZ[q][u >> 1], ci = accI[q][u >> 1], ch = accH[q][u >> 1];
+                const float r = gt_sigmoid(u & 1 ? cr.y : cr.x);
+                const float z = gt_sigmoid(u & 1 ? cz.y : cz.x);
+                const float n = gt_tanh(__fadd_rn(u & 1 ? ci.y : ci.x, __fmul_rn(u & 1 ? ch.y : ch.x, r)));
+                hnew[q] = __fadd_rn(__fmul_rn(__fsub_rn(hold[q], n), z), n);
             }
+            float *nrow = hn + (size_t)(u0 + u) * GT_HLD + e0;
+            *reinterpret_cast<float4 *>(nrow) = make_float4(hnew[0], hnew[1], hnew[2], hnew[3]);
+            *reinterpret_cast<float4 *>(nrow + 4) = make_float4(hnew[4], hnew[5], hnew[6], hnew[7]);
         }
         __syncthreads();
         // Linear over activation(h'): thread (env oe, part) folds units part, part + 4, ...
-        float zl[MA];
+        float2 zp[MA / 2];
 #pragma unroll
-        for (int k = 0; k < MA; ++k) zl[k] = 0.0f;
+        for (int k = 0; k < MA / 2; ++k) zp[k] = make_float2(0.0f, 0.0f);
+#pragma unroll 4
         for (int j = part; j < GT_H; j += 4) {
             const float av = rl_activate(a.net.act, hn[(size_t)j * GT_HLD + oe]);
+            const float2 av2 = make_float2(av, av);
+            const float4 *wrow = reinterpret_cast<const float4 *>(lin_w + j * GT_LW);
 #pragma unroll
-            for (int k = 0; k < MA; ++k)
-                if (k < A) zl[k] = fmaf(lin_w[k * GT_H + j], av, zl[k]);
+            for (int k4 = 0; k4 < (MA + 3) / 4; ++k4) {
+                const float4 w4 = wrow[k4];
+                zp[2 * k4] = __ffma2_rn(make_float2(w4.x, w4.y), av2, zp[2 * k4]);
+                if (2 * k4 + 1 < MA / 2) zp[2 * k4 + 1] = __ffma2_rn(make_float2(w4.z, w4.w), av2, zp[2 * k4 + 1]);
+            }
         }
+        float zl[MA];
 #pragma unroll
         for (int k = 0; k < MA; ++k) {
+            zl[k] = k & 1 ? zp[k >> 1].y : zp[k >> 1].x;
             zl[k] += __shfl_xor_sync(0xffffffffu, zl[k], 1);
             zl[k] += __shfl_xor_sync(0xffffffffu, zl[k], 2);
             zl[k] += lin_b[k];
@@ -358,17 +393,27 @@ __global__ void __launch_bounds__(GT_THREADS, 1) rollout_seq_tile_kernel(typenam
     }
 }
 
-template <class EnvT>
-rl_status launch_seq_tile(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bool replay) {
-    const unsigned grid = (unsigned)((a.E + GT_ENVS - 1) / GT_ENVS);
+template <class EnvT, class S>
+rl_status launch_seq_tile_shape(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bool replay) {
+    const unsigned grid = (unsigned)((a.E + S::envs - 1) / S::envs);
     if (replay) {
-        constexpr size_t smem = gt_smem_bytes<EnvT, true>();
-        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_tile_kernel<EnvT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, (rollout_seq_tile_kernel<EnvT, true>), grid, GT_THREADS, smem, p, a);
+        constexpr size_t smem = gt_smem_bytes<EnvT, true, S>();
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_tile_kernel<EnvT, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_seq_tile_kernel<EnvT, true, S>), grid, S::threads, smem, p, a);
     } else {
-        constexpr size_t smem = gt_smem_bytes<EnvT, false>();
-        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_tile_kernel<EnvT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        RL_LAUNCH(ctx, (rollout_seq_tile_kernel<EnvT, false>), grid, GT_THREADS, smem, p, a);
+        constexpr size_t smem = gt_smem_bytes<EnvT, false, S>();
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_seq_tile_kernel<EnvT, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL_LAUNCH(ctx, (rollout_seq_tile_kernel<EnvT, false, S>), grid, S::threads, smem, p, a);
     }
     return RL_OK;
+}
+
+using GtWide = GtShape<64, 16, 3>;
+using GtPair = GtShape<32, 8, 4>;
+
+// tile_envs: 64 (the default) or 32 (two CTAs per SM; measured slower -- the two CTAs run in lockstep -- kept for tests)
+template <class EnvT>
+rl_status launch_seq_tile(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bool replay, int tile_envs) {
+    if (tile_envs == 64) return launch_seq_tile_shape<EnvT, GtWide>(ctx, p, a, replay);
+    return launch_seq_tile_shape<EnvT, GtPair>(ctx, p, a, replay);
 }

@@ -138,6 +138,9 @@ def test_gru128_tiled_rollout_matches_thread_per_env_kernel(ctx, monkeypatch):
 
     tile, st = run("tile")
     thread, sh = run("thread")
+    wide, _ = run("tile32")  # 32-env CTAs: same arithmetic per env as the 64-env tiles
+    for k in ("obs", "next_obs", "action", "reward", "succ", "lane_len"):
+        np.testing.assert_array_equal(tile[k], wide[k], err_msg=f"tile shapes differ: {k}")
     same = (tile["action"] == thread["action"]).all(axis=0) & (tile["lane_len"] == thread["lane_len"])
     assert same.mean() >= 0.97, same.mean()
     for k in ("obs", "next_obs", "reward", "succ"):
