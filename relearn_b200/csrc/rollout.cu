@@ -461,9 +461,17 @@ __global__ void __launch_bounds__(128) rollout_cartpole_coop_kernel(CartPoleEnv:
 // LANES consecutive 16-byte words (conflict-free) and the 32 / LANES groups read the same words
 // (broadcast): 4 LDS.128 + 7 FFMA2 + 2 FMNMX per pair.
 //   plane 0: w1[q][0] w1[q+64][0] w1[q][1] w1[q+64][1]     plane 2: w1[.][4] pair, b1 pair
-//   plane 1: w1[.][2] pair, w1[.][3] pair                  plane 3: w2[0][.] pair, w2[1][.] pair
+//   plane 1: w1[.][2] pair, w1[.][3] pair                  plane 3: (w2[1][.] - w2[0][.]) pair, unused
 // ------------------------------------------------------------------------------------------------
 constexpr int GK_H = 128, GK_PAIRS = 64;
+
+// Two-action categorical sampling as ONE comparison on the step chain.  Categorical::new + sample (categorical.rs:29-33,
+// 52-54) takes action 0 iff u < exp(log_softmax(z))[0] = 1 / (1 + exp(z1 - z0)), i.e. iff z1 - z0 < log((1 - u) / u).
+// The threshold depends only on the uniform, which is known before the policy is evaluated, so it is computed off the
+// dependent chain (an IEEE divide and a logf instead of an exp and a reciprocal ON it).  Identical in exact arithmetic;
+// decisions can differ only for u within ~1e-7 of the boundary, the near-tie class the logit summation order already allows.
+// u = 0 gives +inf (action 0 for every finite logit difference, like u < p0); a NaN difference compares false (action 1).
+__device__ __forceinline__ float rl_logit_threshold(float u) { return logf(__fdiv_rn(1.0f - u, u)); }
 
 __device__ __forceinline__ void stage_pair_weights(const MlpView &m, float4 *sw4, float *tail, const CartPoleEnv::Params &p,
                                                    int rem_entries) {
@@ -476,10 +484,12 @@ __device__ __forceinline__ void stage_pair_weights(const MlpView &m, float4 *sw4
         if (c == 0) v = make_float4(W1(j0, 0), W1(j1, 0), W1(j0, 1), W1(j1, 1));
         else if (c == 1) v = make_float4(W1(j0, 2), W1(j1, 2), W1(j0, 3), W1(j1, 3));
         else if (c == 2) v = make_float4(W1(j0, 4), W1(j1, 4), b1[j0], b1[j1]);
-        else v = make_float4(w2[j0], w2[j1], w2[GK_H + j0], w2[GK_H + j1]);
+        else v = make_float4(__fsub_rn(w2[GK_H + j0], w2[j0]), __fsub_rn(w2[GK_H + j1], w2[j1]), 0.0f, 0.0f);
         sw4[i] = v;
     }
-    if (threadIdx.x < 2) tail[threadIdx.x] = m.b2()[threadIdx.x];
+    // a two-action actor only needs z_1 - z_0 = sum_j (w2_1j - w2_0j) relu(pre_j) + (b2_1 - b2_0)
+    if (threadIdx.x == 0) tail[0] = __fsub_rn(m.b2()[1], m.b2()[0]);
+    if (threadIdx.x == 1) tail[1] = 0.0f;
     // StepLimitObs::remaining = steps_remaining as f64 / max_steps as f64, then `as f32` (step_limit.rs:194-200,
     // interval.rs:114): exact table instead of an f64 division per step
     for (int i = threadIdx.x; i < rem_entries; i += blockDim.x)
@@ -498,7 +508,7 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
     const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
     stage_pair_weights(a.net, sw4, tail, p, rem_table ? (int)p.max_steps + 1 : 0);
     __syncthreads();
-    const float b2a = tail[0], b2b = tail[1];
+    const float b2d = tail[0];
     const float *rem = tail + 2;
 
     const uint64_t gtid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,12 +518,14 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
     const int F = a.F;
     const bool needs_logits = AK == RL_ACTOR_CATEGORICAL_POLICY || a.eps < 1.0;
     constexpr bool REGW = PPL <= 8;  // LANES >= 8: at most 128 weight registers per thread
-    float4 wA[REGW ? PPL : 1], wB[REGW ? PPL : 1], wC[REGW ? PPL : 1], wD[REGW ? PPL : 1];
+    float4 wA[REGW ? PPL : 1], wB[REGW ? PPL : 1], wC[REGW ? PPL : 1];
+    float2 wD[REGW ? PPL : 1];
     if constexpr (REGW) {
 #pragma unroll
         for (int u = 0; u < PPL; ++u) {
             const int q = sub + LANES * u;
-            wA[u] = sw4[q]; wB[u] = sw4[GK_PAIRS + q]; wC[u] = sw4[2 * GK_PAIRS + q]; wD[u] = sw4[3 * GK_PAIRS + q];
+            wA[u] = sw4[q]; wB[u] = sw4[GK_PAIRS + q]; wC[u] = sw4[2 * GK_PAIRS + q];
+            wD[u] = make_float2(sw4[3 * GK_PAIRS + q].x, sw4[3 * GK_PAIRS + q].y);
         }
     }
 
@@ -575,68 +587,9 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
         EnvT::State cand = s;
         int cand_sc = RL_CONTINUE;
         if constexpr (SPEC) cand_sc = EnvT::step_fast(p, cand, sub >= LANES / 2 ? 1u : 0u);
-        float z0 = 0.0f, z1 = 0.0f;
-        if (needs_logits) {
-            const float2 o0 = make_float2(obs[0], obs[0]), o1 = make_float2(obs[1], obs[1]), o2 = make_float2(obs[2], obs[2]);
-            const float2 o3 = make_float2(obs[3], obs[3]), o4 = make_float2(obs[4], obs[4]);
-            float2 za = make_float2(0.0f, 0.0f), zb = make_float2(0.0f, 0.0f);
-            if constexpr (REGW) {
-                // this thread's pairs live in registers for the whole rollout: no shared-memory latency on the chain
-                float2 pre[PPL];
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].x, wA[u].y), o0, make_float2(wC[u].z, wC[u].w));
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].z, wA[u].w), o1, pre[u]);
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].x, wB[u].y), o2, pre[u]);
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].z, wB[u].w), o3, pre[u]);
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wC[u].x, wC[u].y), o4, pre[u]);
-                float2 zc = make_float2(0.0f, 0.0f), zd = make_float2(0.0f, 0.0f);  // second accumulator pair: shorter chains
-#pragma unroll
-                for (int u = 0; u < PPL; ++u) {
-                    const float2 h = make_float2(fmaxf(pre[u].x, 0.0f), fmaxf(pre[u].y, 0.0f));
-                    if (u & 1) {
-                        zc = __ffma2_rn(make_float2(wD[u].x, wD[u].y), h, zc);
-                        zd = __ffma2_rn(make_float2(wD[u].z, wD[u].w), h, zd);
-                    } else {
-                        za = __ffma2_rn(make_float2(wD[u].x, wD[u].y), h, za);
-                        zb = __ffma2_rn(make_float2(wD[u].z, wD[u].w), h, zb);
-                    }
-                }
-                za = __fadd2_rn(za, zc);
-                zb = __fadd2_rn(zb, zd);
-            } else {
-#pragma unroll(PPL < 8 ? PPL : 8)
-                for (int u = 0; u < PPL; ++u) {
-                    const int q = sub + LANES * u;
-                    const float4 A = sw4[q], B = sw4[GK_PAIRS + q], Cw = sw4[2 * GK_PAIRS + q], D = sw4[3 * GK_PAIRS + q];
-                    float2 pre = make_float2(Cw.z, Cw.w);
-                    pre = __ffma2_rn(make_float2(A.x, A.y), o0, pre);
-                    pre = __ffma2_rn(make_float2(A.z, A.w), o1, pre);
-                    pre = __ffma2_rn(make_float2(B.x, B.y), o2, pre);
-                    pre = __ffma2_rn(make_float2(B.z, B.w), o3, pre);
-                    pre = __ffma2_rn(make_float2(Cw.x, Cw.y), o4, pre);
-                    const float2 h = make_float2(fmaxf(pre.x, 0.0f), fmaxf(pre.y, 0.0f));
-                    za = __ffma2_rn(make_float2(D.x, D.y), h, za);
-                    zb = __ffma2_rn(make_float2(D.z, D.w), h, zb);
-                }
-            }
-            z0 = za.x + za.y;
-            z1 = zb.x + zb.y;
-#pragma unroll
-            for (int o = LANES / 2; o > 0; o >>= 1) {
-                z0 += __shfl_xor_sync(0xffffffffu, z0, o);
-                z1 += __shfl_xor_sync(0xffffffffu, z1, o);
-            }
-            z0 += b2a;
-            z1 += b2b;
-        }
-        uint32_t action = 0;
+        // the actor's uniform and its logit-space threshold: independent of the policy, issued ahead of it
+        float theta = 0.0f;
         if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
-            // policies/actor.rs:42-55; Categorical::new + sample (categorical.rs:29-33,52-54) as inverse CDF over
-            // exp(log_softmax(z)): action 0 iff u < p0 (the last category takes the rest)
             uint32_t w = 0;
             if constexpr (REPLAY) {
                 if (active) w = nz.template next_u32<RL_STREAM_ACTOR>();
@@ -652,17 +605,61 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
                     shared_word = (uint32_t)rl_philox_slot_impl(nz.seed, nz.lane, t0 + i - phase + sub, RL_STREAM_ACTOR, 0);
                 w = __shfl_sync(0xffffffffu, shared_word, (threadIdx.x & 31 & ~(LANES - 1)) + phase);
             }
-            const float u = rl_u32_to_f32(w);
-            // exp(log_softmax(z))[0] for two logits is the logistic of z0 - z1; evaluated as such (one exp and one
-            // reciprocal instead of three exps and a log on the step chain).  Identical in exact arithmetic and within
-            // rounding of the log_softmax route; decisions can differ only for u within ~1e-7 of the boundary, the
-            // same near-tie class the logit summation order already allows.
-            const float d = z1 - z0, ex = expf(-fabsf(d)), inv = __frcp_rn(1.0f + ex);
-            const float p0 = d <= 0.0f ? inv : ex * inv;
-            action = u < p0 ? 0u : 1u;
+            theta = rl_logit_threshold(rl_u32_to_f32(w));
+        }
+        float d = 0.0f;  // z_1 - z_0
+        if (needs_logits) {
+            const float2 o0 = make_float2(obs[0], obs[0]), o1 = make_float2(obs[1], obs[1]), o2 = make_float2(obs[2], obs[2]);
+            const float2 o3 = make_float2(obs[3], obs[3]), o4 = make_float2(obs[4], obs[4]);
+            float2 za = make_float2(0.0f, 0.0f);
+            if constexpr (REGW) {
+                // this thread's pairs live in registers for the whole rollout: no shared-memory latency on the chain
+                float2 pre[PPL];
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].x, wA[u].y), o0, make_float2(wC[u].z, wC[u].w));
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].z, wA[u].w), o1, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].x, wB[u].y), o2, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].z, wB[u].w), o3, pre[u]);
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wC[u].x, wC[u].y), o4, pre[u]);
+                float2 zc = make_float2(0.0f, 0.0f);  // second accumulator: shorter chains
+#pragma unroll
+                for (int u = 0; u < PPL; ++u) {
+                    const float2 h = make_float2(fmaxf(pre[u].x, 0.0f), fmaxf(pre[u].y, 0.0f));
+                    if (u & 1) zc = __ffma2_rn(wD[u], h, zc);
+                    else za = __ffma2_rn(wD[u], h, za);
+                }
+                za = __fadd2_rn(za, zc);
+            } else {
+#pragma unroll(PPL < 8 ? PPL : 8)
+                for (int u = 0; u < PPL; ++u) {
+                    const int q = sub + LANES * u;
+                    const float4 A = sw4[q], B = sw4[GK_PAIRS + q], Cw = sw4[2 * GK_PAIRS + q];
+                    const float2 D = *reinterpret_cast<const float2 *>(&sw4[3 * GK_PAIRS + q]);
+                    float2 pre = make_float2(Cw.z, Cw.w);
+                    pre = __ffma2_rn(make_float2(A.x, A.y), o0, pre);
+                    pre = __ffma2_rn(make_float2(A.z, A.w), o1, pre);
+                    pre = __ffma2_rn(make_float2(B.x, B.y), o2, pre);
+                    pre = __ffma2_rn(make_float2(B.z, B.w), o3, pre);
+                    pre = __ffma2_rn(make_float2(Cw.x, Cw.y), o4, pre);
+                    const float2 h = make_float2(fmaxf(pre.x, 0.0f), fmaxf(pre.y, 0.0f));
+                    za = __ffma2_rn(D, h, za);
+                }
+            }
+            d = za.x + za.y;
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+            d += b2d;
+        }
+        uint32_t action = 0;
+        if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
+            action = d < theta ? 0u : 1u;  // policies/actor.rs:42-55 (see rl_logit_threshold)
         } else if (active) {  // dqn.rs:360-379
             if (rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps)) action = rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, 2u);
-            else action = z1 > z0 ? 1u : 0u;
+            else action = d > 0.0f ? 1u : 0u;
         }
         if (active) {
             if (owns[0]) a.obs[io] = obs[0];
@@ -908,8 +905,10 @@ __global__ void __launch_bounds__(128, SPEC ? 2 : TK_CTAS_PER_SM) rollout_cartpo
         uint32_t w = 0;
         bool explore = false;
         uint32_t explore_action = 0;
+        float theta = 0.0f;  // logit-space threshold of this step's uniform (rl_logit_threshold), computed under the MMA
         if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
             if (!REPLAY || active) w = nz.template next_u32<RL_STREAM_ACTOR>();
+            theta = rl_logit_threshold(rl_u32_to_f32(w));
         } else if (active) {  // dqn.rs:360-379
             explore = rl_gen_bool<REPLAY, RL_STREAM_ACTOR>(nz, a.eps);
             if (explore) explore_action = rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, 2u);
@@ -972,10 +971,7 @@ __global__ void __launch_bounds__(128, SPEC ? 2 : TK_CTAS_PER_SM) rollout_cartpo
         uint32_t action;
         if (AK == RL_ACTOR_CATEGORICAL_POLICY) {
             // policies/actor.rs:42-55; exp(log_softmax(z))[0] for two logits is the logistic of z_0 - z_1 (see K2c)
-            const float u = rl_u32_to_f32(w);
-            const float ex = expf(-fabsf(d)), inv = __frcp_rn(1.0f + ex);
-            const float p0 = d <= 0.0f ? inv : ex * inv;
-            action = u < p0 ? 0u : 1u;
+            action = d < theta ? 0u : 1u;
         } else {
             action = explore ? explore_action : (d > 0.0f ? 1u : 0u);
         }
