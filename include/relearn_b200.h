@@ -258,6 +258,9 @@ typedef enum {
 
 /* rl_actor_cfg.lanes_per_env value selecting the tensor-core rollout kernel (CartPole + 5/4-128-2 ReLU network) */
 #define RL_LANES_TENSOR_CORE 128
+/* rl_actor_cfg.lanes_per_env value selecting the warp-specialised rollout kernel (K2w: policy and dynamics of an env on
+ * different warps; CartPole + 5/4-128-2 ReLU network, categorical actor, Philox noise) */
+#define RL_LANES_WARP_SPECIALIZED 160
 typedef struct rl_actor_cfg {
     int32_t kind;                 /* rl_actor_kind */
     rl_mlp *net;                  /* CATEGORICAL_POLICY / EPS_GREEDY_Q */

@@ -754,6 +754,279 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2w: K2c with the two halves of the step chain on different warps (few envs: E <= ~8 K).
+//
+// In K2c a warp carries 4 envs x 8 threads and issues BOTH the policy (obs -> hidden layer -> logit difference ->
+// compare) and the f64 dynamics of its envs, the latter redundantly in all 8 threads of an env; with two such warps
+// per scheduler the period is set by their combined instruction stream (~1940 clk per step at E = 4096).  Here a CTA
+// owns 16 envs: four POLICY warps (4 envs x 8 threads each, exactly K2c's register-resident hidden layer) and one
+// DYNAMICS warp whose lane (env, a) steps env `env` with action `a` speculatively -- both actions of 16 envs fill the
+// warp, so nothing is computed redundantly -- plus half of the would-be reset state (the action-0 lane draws x, x',
+// the action-1 lane theta, theta': one Philox block each, exchanged by shuffle).  The halves meet through two named
+// barriers and a 16-row mailbox in shared memory:
+//     dynamics: select cand[action], reset if the episode ended, write obs_{t+1} -> bar.arrive 1 ... bar.sync 2
+//     policy:   bar.sync 1, read obs_t, hidden layer, d < theta ?, write action  -> bar.arrive 2
+// so a step costs max(dynamics, policy) + two hand-offs instead of their sum, and every warp issues only its own half.
+// Same operations on the same operands as K2c<8> (summation order of the logits included): bit-identical trajectories
+// and summaries (tests/test_gpu_envs.py).  Philox noise and the categorical actor only; K2c serves the rest.
+// ------------------------------------------------------------------------------------------------
+constexpr int WK_ENVS = 16, WK_THREADS = 160, WK_ROW = 8;
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+constexpr size_t WK_SMEM = 4 * GK_PAIRS * sizeof(float4) + (4 + GK_REM_TABLE_MAX) * sizeof(float) +
+                           WK_ENVS * WK_ROW * sizeof(float) + WK_ENVS * sizeof(uint32_t) + 16;
+
+__global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPoleEnv::Params p, RolloutArgs a) {
+    using EnvT = CartPoleEnv;
+    constexpr int LANES = 8, PPL = GK_PAIRS / LANES;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char gk_smem[];
+    float4 *sw4 = reinterpret_cast<float4 *>(gk_smem);
+    float *tail = reinterpret_cast<float *>(sw4 + 4 * GK_PAIRS);
+    float *obs_s = tail + 4 + GK_REM_TABLE_MAX;                                      // [16][8]: obs 0..4, active flag (16-byte aligned rows)
+    uint32_t *act_s = reinterpret_cast<uint32_t *>(obs_s + WK_ENVS * WK_ROW);        // [16]
+    uint32_t *ctl_s = act_s + WK_ENVS;                                               // [0]: some env of the CTA is active
+    const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
+    stage_pair_weights(a.net, sw4, tail, p, rem_table ? (int)p.max_steps + 1 : 0);
+    __syncthreads();
+    const float *rem = tail + 2;
+    auto remaining_feature = [&](uint32_t r) {
+        return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
+    };
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t e_base = (uint64_t)blockIdx.x * WK_ENVS;
+    const uint32_t t0 = a.noise.step_counter;
+    const uint64_t seed = a.noise.seed;
+    const int F = a.F;
+    const uint64_t FE = (uint64_t)F * a.E;
+    LaneStats st;
+    st.init();
+    bool contributes = false;
+
+    if (warp == WK_ENVS / 4) {
+        // ------------------------------ dynamics warp: lane = (env el, action act) ------------------------------
+        const int el = lane & 15, act = lane >> 4;
+        const uint64_t e = e_base + el;
+        const bool valid = e < a.E;
+        const uint64_t e_safe = valid ? e : 0, lane_global = a.lane_offset + e_safe;
+        const float rem_full = remaining_feature(p.max_steps);
+        // CartPole::initial_state (cartpole.rs:103-115) at noise step `step`: four uniform draws in field order = Philox
+        // blocks 0 (x, x') and 1 (theta, theta') of the reset stream; this lane computes block `act`.
+        auto fresh_state = [&](uint32_t step, EnvT::State &f) {
+            uint32_t o[4];
+            rl_philox4x32_10((uint32_t)lane_global, (uint32_t)(lane_global >> 32), step, (uint32_t)RL_STREAM_ENV_RESET * 64u + (uint32_t)act,
+                             (uint32_t)seed, (uint32_t)(seed >> 32), o);
+            const double v0 = rl_u64_to_uniform((uint64_t)o[0] | ((uint64_t)o[1] << 32), p.reset_low, p.reset_scale);
+            const double v1 = rl_u64_to_uniform((uint64_t)o[2] | ((uint64_t)o[3] << 32), p.reset_low, p.reset_scale);
+            const double w0 = __shfl_xor_sync(FULL, v0, 16), w1 = __shfl_xor_sync(FULL, v1, 16);
+            f.x = act ? w0 : v0; f.xd = act ? w1 : v1; f.th = act ? v0 : w0; f.thd = act ? v1 : w1;
+            f.meta = 0x80000000u | p.max_steps;
+        };
+        EnvT::State s;
+        s.x = s.xd = s.th = s.thd = 0.0;
+        s.meta = 0x80000000u | p.max_steps;
+        uint32_t n = (valid && a.min_steps) ? a.min_steps + a.slack : 0;
+        uint32_t i = 0, cur_len = 0;
+        int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+        double n_eps = 0.0, sum_el = 0.0, sum_el2 = 0.0;
+        float cur_obs[5] = {0, 0, 0, 0, 0}, last_obs[5] = {0, 0, 0, 0, 0};
+        {
+            EnvT::State f;
+            fresh_state(t0, f);
+            if (n > 0) {
+                s = f;
+                cur_obs[0] = (float)s.x; cur_obs[1] = (float)s.xd; cur_obs[2] = (float)s.th; cur_obs[3] = (float)s.thd;
+                cur_obs[4] = rem_full;
+            }
+        }
+        bool any = __any_sync(FULL, n > 0);
+        if (act == 0) {
+            obs_s[el * WK_ROW + 0] = cur_obs[0]; obs_s[el * WK_ROW + 1] = cur_obs[1]; obs_s[el * WK_ROW + 2] = cur_obs[2];
+        } else {
+            obs_s[el * WK_ROW + 3] = cur_obs[3]; obs_s[el * WK_ROW + 4] = cur_obs[4];
+            reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = n > 0 ? 1u : 0u;
+        }
+        if (lane == 0) ctl_s[0] = any ? 1u : 0u;
+        __syncwarp();
+        named_bar_arrive(1, WK_THREADS);
+        while (any) {
+            const bool active = n > 0;
+            // before the action is known: this lane's candidate step, its half of the would-be reset state, and the
+            // `remaining` feature of the next observation
+            EnvT::State cand = s;
+            const int cand_sc = EnvT::step_fast(p, cand, (uint32_t)act);
+            EnvT::State fresh;
+            fresh_state(t0 + i + 1, fresh);
+            const uint32_t r_now = s.meta & 0x7FFFFFFFu;
+            const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
+            named_bar_sync(2, WK_THREADS);
+            const uint32_t action = act_s[el];
+            const int src = el + 16 * (int)action;
+            EnvT::State post;
+            post.x = __shfl_sync(FULL, cand.x, src);
+            post.xd = __shfl_sync(FULL, cand.xd, src);
+            post.th = __shfl_sync(FULL, cand.th, src);
+            post.thd = __shfl_sync(FULL, cand.thd, src);
+            post.meta = __shfl_sync(FULL, cand.meta, src);
+            const int sc = __shfl_sync(FULL, cand_sc, src);
+            const bool ended = sc != RL_CONTINUE;  // steps.rs:116-124: the next call starts a new episode
+            s.x = ended ? fresh.x : post.x; s.xd = ended ? fresh.xd : post.xd;
+            s.th = ended ? fresh.th : post.th; s.thd = ended ? fresh.thd : post.thd;
+            s.meta = ended ? fresh.meta : post.meta;
+            uint32_t n_next = n;
+            if (active) {
+                n_next = n - 1;
+                if (ended && n_next <= a.slack) n_next = 0;  // take_steps.rs:83-88
+            }
+            float nobs[5];
+            nobs[0] = (float)s.x; nobs[1] = (float)s.xd; nobs[2] = (float)s.th; nobs[3] = (float)s.thd;
+            nobs[4] = ended ? rem_full : rem_cont;
+            if (act == 0) {
+                obs_s[el * WK_ROW + 0] = nobs[0]; obs_s[el * WK_ROW + 1] = nobs[1]; obs_s[el * WK_ROW + 2] = nobs[2];
+            } else {
+                obs_s[el * WK_ROW + 3] = nobs[3]; obs_s[el * WK_ROW + 4] = nobs[4];
+                reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = n_next > 0 ? 1u : 0u;
+            }
+            const bool any_next = __any_sync(FULL, n_next > 0);
+            if (lane == 0) ctl_s[0] = any_next ? 1u : 0u;
+            __syncwarp();
+            named_bar_arrive(1, WK_THREADS);
+            // ---- off the chain: the rest of the step record and the statistics ----
+            if (active) {
+                const uint64_t is = (uint64_t)i * a.E + e_safe;
+                if (act == 1) a.reward[is] = 1.0f;  // cartpole.rs:140
+                if (act == 0) a.succ[is] = (uint8_t)sc;
+                if (sc == RL_INTERRUPT && act == 0) {  // rare: once per max_steps; the post-step observation (remaining == 0)
+                    const float io4 = remaining_feature(post.meta & 0x7FFFFFFFu);
+                    const uint64_t io = (uint64_t)i * FE + e_safe;
+                    a.next_obs[io] = (float)post.x;
+                    a.next_obs[io + a.E] = (float)post.xd;
+                    a.next_obs[io + 2 * a.E] = (float)post.th;
+                    a.next_obs[io + 3 * a.E] = (float)post.thd;
+                    if (F > 4) a.next_obs[io + 4 * a.E] = io4;
+                }
+                cur_len += 1;
+                if (ended) {
+                    const double ld = (double)cur_len;
+                    n_eps += 1.0;
+                    sum_el += ld;
+                    sum_el2 = fma(ld, ld, sum_el2);
+                    cur_len = 0;
+                }
+#pragma unroll
+                for (int f = 0; f < 5; ++f) last_obs[f] = cur_obs[f];
+                succ_prev = succ_last;
+                succ_last = sc;
+                i += 1;
+            }
+#pragma unroll
+            for (int f = 0; f < 5; ++f) cur_obs[f] = nobs[f];
+            n = n_next;
+            any = any_next;
+        }
+        st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
+        st.v[ST_EPS] = n_eps; st.v[ST_ER] = st.v[ST_EL] = sum_el; st.v[ST_ER2] = st.v[ST_EL2] = sum_el2;
+        if (valid && act == 0) {
+            // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261); same thread as the in-loop
+            // stores of succ, so program order applies
+            uint32_t len = i, flags = 0;
+            double eps = n_eps;
+            if (i > 0 && succ_last == RL_CONTINUE) {
+                len = i - 1;
+                flags = 1;
+                a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+                if (len > 0 && succ_prev == RL_CONTINUE) {
+                    flags = 3;
+                    a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+#pragma unroll
+                    for (int f = 0; f < 5; ++f)
+                        if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
+                    eps += 1.0;
+                }
+            }
+            a.lane_len[e] = len;
+            a.lane_flags[e] = (uint8_t)flags;
+            st.v[ST_STORED_STEPS] = (double)len;
+            st.v[ST_STORED_EPS] = eps;
+            contributes = true;
+        }
+    } else {
+        // ------------------------------ policy warps: 4 envs x 8 threads (K2c<8>) ------------------------------
+        const int grp = lane >> 3, sub = lane & 7, el = 4 * warp + grp;
+        const uint64_t e = e_base + el;
+        const bool valid = e < a.E;
+        const uint64_t e_safe = valid ? e : 0, lane_global = a.lane_offset + e_safe;
+        const float b2d = tail[0];
+        float4 wA[PPL], wB[PPL], wC[PPL];
+        float2 wD[PPL];
+#pragma unroll
+        for (int u = 0; u < PPL; ++u) {
+            const int q = sub + LANES * u;
+            wA[u] = sw4[q]; wB[u] = sw4[GK_PAIRS + q]; wC[u] = sw4[2 * GK_PAIRS + q];
+            wD[u] = make_float2(sw4[3 * GK_PAIRS + q].x, sw4[3 * GK_PAIRS + q].y);
+        }
+        bool owns[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) owns[k] = valid && sub == k && (k >= 5 || k < F);
+        uint32_t shared_word = 0;
+        for (uint32_t i = 0;; ++i) {
+            // the uniform of step i and its logit-space threshold, ahead of the observation (see K2c)
+            const uint32_t phase = i & (LANES - 1);
+            if (phase == 0) shared_word = (uint32_t)rl_philox_slot_impl(seed, lane_global, t0 + i + sub, RL_STREAM_ACTOR, 0);
+            const uint32_t w = __shfl_sync(FULL, shared_word, (lane & ~(LANES - 1)) + phase);
+            const float theta = rl_logit_threshold(rl_u32_to_f32(w));
+            named_bar_sync(1, WK_THREADS);
+            if (ctl_s[0] == 0u) break;
+            const float4 ov = *reinterpret_cast<const float4 *>(obs_s + el * WK_ROW);
+            const float ob4 = obs_s[el * WK_ROW + 4];
+            const bool active = reinterpret_cast<const uint32_t *>(obs_s)[el * WK_ROW + 5] != 0u;
+            const float2 o0 = make_float2(ov.x, ov.x), o1 = make_float2(ov.y, ov.y), o2 = make_float2(ov.z, ov.z);
+            const float2 o3 = make_float2(ov.w, ov.w), o4 = make_float2(ob4, ob4);
+            float2 pre[PPL];
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].x, wA[u].y), o0, make_float2(wC[u].z, wC[u].w));
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wA[u].z, wA[u].w), o1, pre[u]);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].x, wB[u].y), o2, pre[u]);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wB[u].z, wB[u].w), o3, pre[u]);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) pre[u] = __ffma2_rn(make_float2(wC[u].x, wC[u].y), o4, pre[u]);
+            float2 za = make_float2(0.0f, 0.0f), zc = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < PPL; ++u) {
+                const float2 h = make_float2(fmaxf(pre[u].x, 0.0f), fmaxf(pre[u].y, 0.0f));
+                if (u & 1) zc = __ffma2_rn(wD[u], h, zc);
+                else za = __ffma2_rn(wD[u], h, za);
+            }
+            za = __fadd2_rn(za, zc);
+            float d = za.x + za.y;
+#pragma unroll
+            for (int o = LANES / 2; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+            d += b2d;
+            const uint32_t action = d < theta ? 0u : 1u;  // policies/actor.rs:42-55 (rl_logit_threshold)
+            if (sub == 0) act_s[el] = action;
+            __syncwarp();
+            named_bar_arrive(2, WK_THREADS);
+            // ---- off the chain: the observation and the action of the step record ----
+            if (active) {
+                const uint64_t io = (uint64_t)i * FE + e_safe, is = (uint64_t)i * a.E + e_safe;
+                if (owns[0]) a.obs[io] = ov.x;
+                if (owns[1]) a.obs[io + a.E] = ov.y;
+                if (owns[2]) a.obs[io + 2 * a.E] = ov.z;
+                if (owns[3]) a.obs[io + 3 * a.E] = ov.w;
+                if (owns[4]) a.obs[io + 4 * a.E] = ob4;
+                if (owns[5]) a.action[is] = (uint8_t)action;
+            }
+        }
+    }
+    block_reduce_stats(st, contributes, a.partials);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2t: CartPole + 5->128->2 ReLU network with the hidden layer on the tensor cores (tcgen05 + TMEM), for env counts
 // at which the actor GEMM is dense: a CTA owns 128 envs, one env per thread and per TMEM lane, and every step of the
 // rollout is one  pre[128 envs x 128 units] = X[128 x 48] . W1e[48 x 128]  (3 x tcgen05.mma, K = 16) whose operands
@@ -1168,6 +1441,16 @@ rl_status launch_tc(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, b
     return launch_tc_ak<RL_ACTOR_EPS_GREEDY_Q>(ctx, p, a, replay, nblocks_out);
 }
 
+rl_status launch_ws(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    const unsigned grid = (unsigned)((a.E + WK_ENVS - 1) / WK_ENVS);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    RL_LAUNCH(ctx, rollout_cartpole_ws_kernel, grid, WK_THREADS, WK_SMEM, p, a);
+    return RL_OK;
+}
+
 template <int LANES>
 rl_status launch_group(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
     if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
@@ -1371,8 +1654,14 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
         case 16: RL_TRY((launch_group<16>(ctx, env->cartpole, a, replay, &nblocks))); break;
         case 32: RL_TRY((launch_group<32>(ctx, env->cartpole, a, replay, &nblocks))); break;
         case RL_LANES_TENSOR_CORE: RL_TRY(launch_tc(ctx, env->cartpole, a, replay, &nblocks)); break;
+        case RL_LANES_WARP_SPECIALIZED:
+            if (replay || a.actor_kind != RL_ACTOR_CATEGORICAL_POLICY)
+                return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
+            RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
+            break;
         default:
-            return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env must be 0, 1, 2, 4, 8, 16, 32 or RL_LANES_TENSOR_CORE");
+            return rl_fail(ctx, RL_ERR_UNSUPPORTED,
+                           "rl_rollout: lanes_per_env must be 0, 1, 2, 4, 8, 16, 32, RL_LANES_TENSOR_CORE or RL_LANES_WARP_SPECIALIZED");
         }
         break;
     }

@@ -417,3 +417,54 @@ def test_fused_rollout_policy_other_envs_consistent(ctx, cfg):
     assert checked > E * (T - 2) and near <= 3
     ref = P.oracle_rollout(cfg, E, T, 0, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), env_words=ewords)
     P.compare_traj(host, ref, what=f"policy on {cfg}")
+
+
+@pytest.mark.parametrize("E,T,slack,limit,visible", [(4096, 64, 0, 500, True), (1000, 70, 9, 20, True), (37, 45, 3, 15, False),
+                                                     (16, 33, 0, 500, True)])
+def test_warp_specialized_rollout_is_bit_identical_to_k2c(ctx, E, T, slack, limit, visible):
+    """K2w (policy and dynamics of an env on different warps, hand-off through named barriers) performs the same
+    operations on the same operands as K2c with 8 threads per env: under Philox noise every stored byte, the lane
+    lengths and the summary must be identical -- ragged last CTA, slack, step-limit Interrupts, latent limit (F = 4),
+    resets, dangling steps."""
+    wrap = R.VisibleStepLimit(limit) if visible else R.LatentStepLimit(limit)
+    cfg = R.CartPoleConfig().wrap(wrap)
+    F = 5 if visible else 4
+    params = R.init_params(np.random.default_rng(E), F, 128, 2) * 2.0
+    net = R.Mlp(ctx, F, [128], 2)
+    net.set_weights(params)
+
+    def run(lanes, periods=2):
+        env = R.build_env(ctx, cfg, E, seed=21, lane_offset=5)
+        traj = R.Trajectory(env, T + slack)
+        out = []
+        for _ in range(periods):  # the second period starts from the advanced Philox step counter
+            summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=lanes),
+                             R.HistoryDataBound(T, slack), traj)
+            out.append((traj.to_host(), summ))
+        return out
+
+    for (ws, sw), (gk, sg) in zip(run(L.RL_LANES_WARP_SPECIALIZED), run(8)):
+        for k in ("lane_len", "succ"):
+            np.testing.assert_array_equal(ws[k], gk[k], err_msg=k)
+        valid = gk["succ"] != L.RL_PAD  # slots past a lane's last step are never written by either kernel
+        for k in ("action", "reward", "obs"):
+            np.testing.assert_array_equal(ws[k][valid], gk[k][valid], err_msg=k)
+        intr = gk["succ"] == L.RL_INTERRUPT
+        assert intr.any() or limit >= T
+        np.testing.assert_array_equal(ws["next_obs"][intr], gk["next_obs"][intr])
+        assert ws["num_steps"] == gk["num_steps"]
+        for name in ("step_reward", "episode_reward", "episode_length"):
+            a, b = getattr(sw, name), getattr(sg, name)
+            assert (a.mean, a.squared_residual_sum, a.count) == (b.mean, b.squared_residual_sum, b.count), name
+        assert (sw.num_stored_steps, sw.num_stored_episodes) == (sg.num_stored_steps, sg.num_stored_episodes)
+
+
+def test_warp_specialized_rollout_rejects_replayed_noise(ctx):
+    env = R.build_env(ctx, CARTPOLE, 32, seed=1)
+    env.set_noise_replay(P.random_words(np.random.default_rng(0), 32, 256), P.random_words(np.random.default_rng(1), 32, 256))
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(R.init_params(np.random.default_rng(2), 5, 128, 2))
+    traj = R.Trajectory(env, 8)
+    with pytest.raises(Exception):
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=L.RL_LANES_WARP_SPECIALIZED),
+                  R.HistoryDataBound(8, 0), traj)
