@@ -785,9 +785,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     extern __shared__ __align__(16) unsigned char gk_smem[];
     float4 *sw4 = reinterpret_cast<float4 *>(gk_smem);
     float *tail = reinterpret_cast<float *>(sw4 + 4 * GK_PAIRS);
-    float *obs_s = tail + 4 + GK_REM_TABLE_MAX;                                      // [16][8]: obs 0..4, active flag (16-byte aligned rows)
+    // mailbox rows [16][8], 16-byte aligned: obs 0..4, flags (bit 0: this env takes the step, bit 1: some env of the CTA does)
+    float *obs_s = tail + 4 + GK_REM_TABLE_MAX;
     uint32_t *act_s = reinterpret_cast<uint32_t *>(obs_s + WK_ENVS * WK_ROW);        // [16]
-    uint32_t *ctl_s = act_s + WK_ENVS;                                               // [0]: some env of the CTA is active
     const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
     stage_pair_weights(a.net, sw4, tail, p, rem_table ? (int)p.max_steps + 1 : 0);
     __syncthreads();
@@ -846,9 +846,8 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             obs_s[el * WK_ROW + 0] = cur_obs[0]; obs_s[el * WK_ROW + 1] = cur_obs[1]; obs_s[el * WK_ROW + 2] = cur_obs[2];
         } else {
             obs_s[el * WK_ROW + 3] = cur_obs[3]; obs_s[el * WK_ROW + 4] = cur_obs[4];
-            reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = n > 0 ? 1u : 0u;
+            reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = (n > 0 ? 1u : 0u) | (any ? 2u : 0u);
         }
-        if (lane == 0) ctl_s[0] = any ? 1u : 0u;
         __syncwarp();
         named_bar_arrive(1, WK_THREADS);
         while (any) {
@@ -887,10 +886,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
                 obs_s[el * WK_ROW + 0] = nobs[0]; obs_s[el * WK_ROW + 1] = nobs[1]; obs_s[el * WK_ROW + 2] = nobs[2];
             } else {
                 obs_s[el * WK_ROW + 3] = nobs[3]; obs_s[el * WK_ROW + 4] = nobs[4];
-                reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = n_next > 0 ? 1u : 0u;
             }
             const bool any_next = __any_sync(FULL, n_next > 0);
-            if (lane == 0) ctl_s[0] = any_next ? 1u : 0u;
+            if (act == 1) reinterpret_cast<uint32_t *>(obs_s)[el * WK_ROW + 5] = (n_next > 0 ? 1u : 0u) | (any_next ? 2u : 0u);
             __syncwarp();
             named_bar_arrive(1, WK_THREADS);
             // ---- off the chain: the rest of the step record and the statistics ----
@@ -967,21 +965,26 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             wA[u] = sw4[q]; wB[u] = sw4[GK_PAIRS + q]; wC[u] = sw4[2 * GK_PAIRS + q];
             wD[u] = make_float2(sw4[3 * GK_PAIRS + q].x, sw4[3 * GK_PAIRS + q].y);
         }
-        bool owns[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) owns[k] = valid && sub == k && (k >= 5 || k < F);
-        uint32_t shared_word = 0;
+        // Thread `sub` stores column `sub` of the step record: observation feature sub (< F) or, sub == 5, the action.
+        const bool stores_obs = valid && sub < 5 && sub < F, stores_action = valid && sub == 5;
+        float *obs_ptr = a.obs + (uint64_t)(sub < 5 ? sub : 0) * a.E + e_safe;
+        uint8_t *act_ptr = a.action + e_safe;
+        float shared_theta = 0.0f;
         for (uint32_t i = 0;; ++i) {
-            // the uniform of step i and its logit-space threshold, ahead of the observation (see K2c)
+            // The uniform of step i and its logit-space threshold (rl_logit_threshold), ahead of the observation.  As in
+            // K2c thread `sub` draws the Philox word of step (i rounded down to 8) + sub once every 8 steps; here it also
+            // turns it into the threshold, so a step costs one shuffle instead of a divide and a logarithm per thread.
             const uint32_t phase = i & (LANES - 1);
-            if (phase == 0) shared_word = (uint32_t)rl_philox_slot_impl(seed, lane_global, t0 + i + sub, RL_STREAM_ACTOR, 0);
-            const uint32_t w = __shfl_sync(FULL, shared_word, (lane & ~(LANES - 1)) + phase);
-            const float theta = rl_logit_threshold(rl_u32_to_f32(w));
+            if (phase == 0)
+                shared_theta = rl_logit_threshold(rl_u32_to_f32((uint32_t)rl_philox_slot_impl(seed, lane_global, t0 + i + sub, RL_STREAM_ACTOR, 0)));
+            const float theta = __shfl_sync(FULL, shared_theta, (lane & ~(LANES - 1)) + phase);
             named_bar_sync(1, WK_THREADS);
-            if (ctl_s[0] == 0u) break;
             const float4 ov = *reinterpret_cast<const float4 *>(obs_s + el * WK_ROW);
-            const float ob4 = obs_s[el * WK_ROW + 4];
-            const bool active = reinterpret_cast<const uint32_t *>(obs_s)[el * WK_ROW + 5] != 0u;
+            const float2 tailv = *reinterpret_cast<const float2 *>(obs_s + el * WK_ROW + 4);
+            const float ob4 = tailv.x;
+            const uint32_t flags = __float_as_uint(tailv.y);
+            if ((flags & 2u) == 0u) break;
+            const bool active = (flags & 1u) != 0u;
             const float2 o0 = make_float2(ov.x, ov.x), o1 = make_float2(ov.y, ov.y), o2 = make_float2(ov.z, ov.z);
             const float2 o3 = make_float2(ov.w, ov.w), o4 = make_float2(ob4, ob4);
             float2 pre[PPL];
@@ -1012,15 +1015,11 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             __syncwarp();
             named_bar_arrive(2, WK_THREADS);
             // ---- off the chain: the observation and the action of the step record ----
-            if (active) {
-                const uint64_t io = (uint64_t)i * FE + e_safe, is = (uint64_t)i * a.E + e_safe;
-                if (owns[0]) a.obs[io] = ov.x;
-                if (owns[1]) a.obs[io + a.E] = ov.y;
-                if (owns[2]) a.obs[io + 2 * a.E] = ov.z;
-                if (owns[3]) a.obs[io + 3 * a.E] = ov.w;
-                if (owns[4]) a.obs[io + 4 * a.E] = ob4;
-                if (owns[5]) a.action[is] = (uint8_t)action;
-            }
+            const float mine = sub == 0 ? ov.x : sub == 1 ? ov.y : sub == 2 ? ov.z : sub == 3 ? ov.w : ob4;
+            if (active && stores_obs) *obs_ptr = mine;
+            if (active && stores_action) *act_ptr = (uint8_t)action;
+            obs_ptr += FE;
+            act_ptr += a.E;
         }
     }
     block_reduce_stats(st, contributes, a.partials);
