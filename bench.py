@@ -41,11 +41,11 @@ FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
 # MMA1 128x128x48, MMA3 128x32x128, MMA2 128x32x128  =>  2 * (786432 + 524288 + 524288) / 128 = 28672 FLOP per sample.
 FLOP_PER_SAMPLE_CRITIC = 4608
 FLOP_ISSUED_PER_SAMPLE_CRITIC_TC = 28672
-# dram__bytes_read.sum + dram__bytes_write.sum of one K2c launch at E = 4096, T = 256 from the round-1
-# `ncu --set full` capture (profiles/r1_summary.md section 2): 36.1 KB + 2.6 KB.  The 27 MB trajectory of a
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2w launch (the kernel `lanes_per_env = 0` picks) at E = 4096,
+# T = 256 from the round-1 `ncu --set full` capture (profiles/r1_summary.md section 13): 49.4 KB + 2.8 KB.  The 27 MB trajectory of a
 # period stays in the 126 MB L2 while the kernel runs and drains afterwards, so the in-kernel DRAM traffic
 # is far BELOW the algorithmic 26 B/env-step, not above it.
-K2C_NCU_DRAM_BYTES_PER_LAUNCH = 38656
+K2C_NCU_DRAM_BYTES_PER_LAUNCH = 52224
 
 
 def measured_peaks():
@@ -312,8 +312,8 @@ def run_ours(args):
     achieved = B_PER_STEP_ROLLOUT * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": K2C_NCU_DRAM_BYTES_PER_LAUNCH if (E == 4096 and T == 256) else None,
-                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s2); trajectory is L2-resident during the kernel",
-                "peak_source": peak_src, "kernel": "rollout_cartpole (fused step+policy+sample)",
+                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s13); trajectory is L2-resident during the kernel",
+                "peak_source": peak_src, "kernel": "rollout_cartpole_ws_kernel K2w (fused step+policy+sample; policy and dynamics on different warps)",
                 "note": "K2 is FP32-FMA/latency bound by design (26 B of trajectory writes per env-step); see fp32 and kernels[]"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -983,6 +983,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             const float2 tailv = *reinterpret_cast<const float2 *>(obs_s + el * WK_ROW + 4);
             const float ob4 = tailv.x;
             const uint32_t flags = __float_as_uint(tailv.y);
+            const float mine = obs_s[el * WK_ROW + (sub < 5 ? sub : 0)];  // the column this thread stores (branch-free)
             if ((flags & 2u) == 0u) break;
             const bool active = (flags & 1u) != 0u;
             const float2 o0 = make_float2(ov.x, ov.x), o1 = make_float2(ov.y, ov.y), o2 = make_float2(ov.z, ov.z);
@@ -1015,7 +1016,6 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             __syncwarp();
             named_bar_arrive(2, WK_THREADS);
             // ---- off the chain: the observation and the action of the step record ----
-            const float mine = sub == 0 ? ov.x : sub == 1 ? ov.y : sub == 2 ? ov.z : sub == 3 ? ov.w : ob4;
             if (active && stores_obs) *obs_ptr = mine;
             if (active && stores_action) *act_ptr = (uint8_t)action;
             obs_ptr += FE;
@@ -1644,6 +1644,12 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             // Beyond one wave the tensor-core kernel wins at every size measured (6 K envs: 0.31 ms per 256-step period
             // vs 0.39 for LANES = 4; 1 M envs: 24 G env-steps/s vs 15.5 G for LANES = 1).
             lanes = env->E <= (uint64_t)ctx->sm_count * 32 ? 8 : RL_LANES_TENSOR_CORE;
+            // ... and within that one wave the warp-specialised kernel (K2w: bit-identical to K2c<8>, policy and dynamics
+            // on different warps) is 30 % faster (E = 4096: 0.178 vs 0.254 ms per 256-step period); it serves the
+            // categorical actor on Philox noise.  RL_ROLLOUT_WS=0 keeps K2c (measurements).
+            static const char *ws_env = getenv("RL_ROLLOUT_WS");
+            if (lanes == 8 && !replay && a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY && !(ws_env && ws_env[0] == '0'))
+                lanes = RL_LANES_WARP_SPECIALIZED;
         }
         switch (lanes) {
         case 1: RL_TRY((launch_group<1>(ctx, env->cartpole, a, replay, &nblocks))); break;
