@@ -297,7 +297,7 @@ def run_ours(args):
         flush.zero()
         ctx.synchronize()
         t0 = time.perf_counter()
-        agent.policy.policy_fn.set_weights(w_pinned)
+        agent.policy.policy_fn.set_weights_async(w_pinned)
         summ = R.rollout(env, actor, bound, traj, want_summary=True)
         dt = time.perf_counter() - t0
         if k >= max(3, min(args.warmup, 5)):
@@ -324,7 +324,7 @@ def run_ours(args):
                    "lanes_per_env": args.lanes, "l2": "flushed between timed iterations (256 MiB memset)",
                    "noise": "philox4x32-10", "parallelism": f"dp{world} (lanes sharded, no collective)"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "rl_mlp_set_weights(pinned host) + rl_rollout + StepsSummary read-back per period"},
+                "what": "rl_mlp_set_weights_async(pinned host) + rl_rollout + StepsSummary read-back per period"},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline,
         "wall_s_timed_region": wall, "sm_count": info["sm_count"],
     }

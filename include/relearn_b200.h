@@ -220,6 +220,11 @@ rl_status rl_mlp_create(rl_ctx *ctx, int32_t in_dim, const int32_t *hidden_sizes
 rl_status rl_mlp_destroy(rl_mlp *mlp);
 rl_status rl_mlp_num_params(rl_mlp *mlp, uint64_t *n);
 rl_status rl_mlp_set_weights(rl_mlp *mlp, const float *host, uint64_t n);
+/* The same copy enqueued on the context stream without waiting for it (the per-period weight refresh of an actor,
+ * train.rs:124-158: no host round trip between the update and the next rollout).  `pinned_host` must be page-locked
+ * (rl_malloc_host; RL_ERR_INVALID_ARG otherwise) and must not change until the next call that synchronises the context
+ * (rl_ctx_synchronize, rl_rollout with a summary, any read-back). */
+rl_status rl_mlp_set_weights_async(rl_mlp *mlp, const float *pinned_host, uint64_t n);
 rl_status rl_mlp_get_weights(rl_mlp *mlp, float *host, uint64_t n);
 /* Forward on feature planes: x f32 [F][n] -> out f32 [out_dim][n] (Mlp::forward mlp.rs:139-151). */
 rl_status rl_mlp_forward(rl_mlp *mlp, const float *x_dev, uint64_t n, float *out_dev);

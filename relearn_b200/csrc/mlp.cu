@@ -92,6 +92,19 @@ rl_status rl_mlp_set_weights(rl_mlp *m, const float *host, uint64_t n) {
     return RL_OK;
 }
 
+rl_status rl_mlp_set_weights_async(rl_mlp *m, const float *pinned_host, uint64_t n) {
+    if (!m || !pinned_host) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_set_weights_async: NULL argument");
+    RL_REQUIRE(m->ctx, n == m->n_params, "rl_mlp_set_weights_async: wrong parameter count");
+    cudaPointerAttributes attr{};
+    const cudaError_t e = cudaPointerGetAttributes(&attr, pinned_host);
+    if (e != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+        cudaGetLastError();
+        return rl_fail(m->ctx, RL_ERR_INVALID_ARG, "rl_mlp_set_weights_async: the source must be page-locked host memory (rl_malloc_host)");
+    }
+    RL_CUDA(m->ctx, cudaMemcpyAsync(m->params, pinned_host, n * sizeof(float), cudaMemcpyHostToDevice, m->ctx->stream));
+    return RL_OK;
+}
+
 rl_status rl_mlp_get_weights(rl_mlp *m, float *host, uint64_t n) {
     if (!m || !host) return rl_fail(m ? m->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_mlp_get_weights: NULL argument");
     RL_REQUIRE(m->ctx, n == m->n_params, "rl_mlp_get_weights: wrong parameter count");

@@ -1338,7 +1338,8 @@ __global__ void __launch_bounds__(128, SPEC ? 2 : TK_CTAS_PER_SM) rollout_cartpo
 // lane l adds rows l, l + 32, ... (independent coalesced-by-row loads), then a shuffle tree combines the lanes.
 __global__ void __launch_bounds__(32 * ST_COUNT) rollout_finalize_kernel(const double *__restrict__ partials, int nblocks,
                                                                         double *__restrict__ out,
-                                                                        double *__restrict__ traj_counts) {
+                                                                        double *__restrict__ traj_counts,
+                                                                        double *__restrict__ host_out = nullptr) {
     const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (i >= ST_COUNT) return;
     double s = 0.0;
@@ -1347,6 +1348,8 @@ __global__ void __launch_bounds__(32 * ST_COUNT) rollout_finalize_kernel(const d
     s = warp_sum(s);
     if (lane == 0) {
         out[i] = s;
+        // the caller's summary: written straight into page-locked host memory (no separate device-to-host copy)
+        if (host_out) host_out[i] = s;
         if (i == ST_STORED_STEPS) traj_counts[0] = s;
         if (i == ST_STORED_EPS) traj_counts[1] = s;
     }
@@ -1611,7 +1614,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     RL_CUDA(ctx, cudaMemsetAsync(traj->succ, RL_PAD, (size_t)traj->T * traj->E, ctx->stream));
     const bool replay = env->noise.mode == RL_NOISE_REPLAY;
     int nblocks = 0;
-    double *totals = nullptr;
+    double *totals = nullptr, *summary_host = nullptr;
     if (seq_policy) {
         RL_TRY(rl_rollout_seq(env, actor->seq_net, bound, traj, &totals));
     } else {
@@ -1676,14 +1679,17 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     case RL_ENV_PARTITION_GAME: RL_TRY((launch_rollout<PartitionEnv>(ctx, env->partition, a, net, replay, &nblocks))); break;
     }
     totals = a.partials - ST_COUNT;
-    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32 * ST_COUNT, 0, a.partials, nblocks, totals, traj->counts_dev);
+    if (summary) RL_TRY(rl_ctx_pinned(ctx, ST_COUNT * sizeof(double), (void **)&summary_host));
+    RL_LAUNCH(ctx, rollout_finalize_kernel, 1, 32 * ST_COUNT, 0, a.partials, nblocks, totals, traj->counts_dev, summary_host);
     }
     env->noise.step_counter += (uint32_t)cap + 1;  // fresh noise for the next period
     traj->used_T = cap;
     if (summary) {
-        double *host;
-        RL_TRY(rl_ctx_pinned(ctx, ST_COUNT * sizeof(double), (void **)&host));
-        RL_CUDA(ctx, cudaMemcpyAsync(host, totals, ST_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        double *host = summary_host;
+        if (!host) {  // sequence policies: their finalize kernel leaves the totals on the device
+            RL_TRY(rl_ctx_pinned(ctx, ST_COUNT * sizeof(double), (void **)&host));
+            RL_CUDA(ctx, cudaMemcpyAsync(host, totals, ST_COUNT * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
         RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         auto mv = [&](int n_i, int s_i, int s2_i) {
             rl_mean_var m{};

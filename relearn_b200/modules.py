@@ -68,6 +68,12 @@ class Mlp:
         a = np.ascontiguousarray(flat, dtype=np.float32)
         L.check(self._lib.rl_mlp_set_weights(self.handle, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)
 
+    def set_weights_async(self, pinned: np.ndarray):
+        """The same copy enqueued without a host round trip; `pinned` must be a page-locked f32 array
+        (`Context.pinned_array`) that stays unchanged until the next synchronising call."""
+        assert pinned.dtype == np.float32 and pinned.flags["C_CONTIGUOUS"]
+        L.check(self._lib.rl_mlp_set_weights_async(self.handle, pinned.ctypes.data, pinned.size), self.ctx.handle)
+
     def get_weights(self) -> np.ndarray:
         a = np.empty(self.num_params, np.float32)
         L.check(self._lib.rl_mlp_get_weights(self.handle, a.ctypes.data_as(C.c_void_p), a.size), self.ctx.handle)

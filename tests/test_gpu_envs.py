@@ -468,3 +468,26 @@ def test_warp_specialized_rollout_rejects_replayed_noise(ctx):
     with pytest.raises(Exception):
         R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=L.RL_LANES_WARP_SPECIALIZED),
                   R.HistoryDataBound(8, 0), traj)
+
+
+def test_set_weights_async_from_pinned_memory(ctx):
+    """rl_mlp_set_weights_async: the stream-ordered weight refresh (no host round trip) gives the rollout the same
+    weights as the synchronous copy, and refuses pageable memory."""
+    rng = np.random.default_rng(5)
+    params = R.init_params(rng, 5, 128, 2)
+    net_a, net_b = R.Mlp(ctx, 5, [128], 2), R.Mlp(ctx, 5, [128], 2)
+    net_a.set_weights(params)
+    pinned = ctx.pinned_array((params.size,), np.float32)
+    pinned[:] = params
+    net_b.set_weights_async(pinned)
+    outs = []
+    for net in (net_a, net_b):
+        env = R.build_env(ctx, CARTPOLE, 300, seed=4)
+        traj = R.Trajectory(env, 40)
+        R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net), R.HistoryDataBound(40, 0), traj)
+        outs.append(traj.to_host())
+    for k in ("obs", "action", "succ", "lane_len"):
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+    np.testing.assert_array_equal(net_b.get_weights(), params)
+    with pytest.raises(L.RelearnB200Error):
+        net_b.set_weights_async(np.ascontiguousarray(params))  # pageable
