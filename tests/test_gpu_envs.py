@@ -491,3 +491,30 @@ def test_set_weights_async_from_pinned_memory(ctx):
     np.testing.assert_array_equal(net_b.get_weights(), params)
     with pytest.raises(L.RelearnB200Error):
         net_b.set_weights_async(np.ascontiguousarray(params))  # pageable
+
+
+def test_warp_specialized_rollout_against_the_oracle(ctx):
+    """K2w directly against the CPU oracle under production noise: (i) replaying its actions through the oracle, which
+    regenerates the Philox reset draws itself, reproduces the trajectory (Terminate / Interrupt codes, lane lengths and
+    summary exactly, CartPole observations to 1e-6: sin/cos differ from glibc by <= 1 ulp); (ii) every action is the
+    inverse-CDF choice of the oracle's softmax for the recorded observation and the step's Philox uniform."""
+    E, T, slack, seed, off, t0 = 200, 60, 4, 0xBEEF, 77, 9
+    params = R.init_params(np.random.default_rng(8), 5, 128, 2) * 2.0
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    env = R.build_env(ctx, CARTPOLE, E, seed=seed, lane_offset=off)
+    env.set_noise_philox(seed, t0)
+    traj = R.Trajectory(env, T + slack)
+    summ = R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=L.RL_LANES_WARP_SPECIALIZED),
+                     R.HistoryDataBound(T, slack), traj)
+    host = traj.to_host()
+    ref = P.oracle_rollout(CARTPOLE, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=host["action"].copy(), philox_seed=seed,
+                           lane_offset=off, t0=t0)
+    P.compare_traj(host, ref, obs_rtol=1e-6, obs_atol=1e-7, what="K2w vs oracle")
+    P.compare_summary(summ, ref["summary"])
+    lib = L.lib()
+    awords = np.array([[lib.rl_philox_slot(seed, off + e, t0 + i, 2, 0) & 0xFFFFFFFF for i in range(T + slack)] for e in range(E)],
+                      dtype=np.uint64).astype(np.uint32)
+    checked, near = P.check_policy_consistency(host, params, 128, 2, awords)
+    assert checked == int(host["lane_len"].sum()) and near <= 3
+    assert (host["succ"] == L.RL_INTERRUPT).any() and (host["succ"] == L.RL_TERMINATE).any()
