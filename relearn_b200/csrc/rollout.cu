@@ -775,8 +775,9 @@ constexpr int WK_ENVS = 16, WK_THREADS = 160, WK_ROW = 8;
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
+constexpr int WK_RING = 8;  // steps of would-be reset states kept ahead of the dynamics warp
 constexpr size_t WK_SMEM = 4 * GK_PAIRS * sizeof(float4) + (4 + GK_REM_TABLE_MAX) * sizeof(float) +
-                           WK_ENVS * WK_ROW * sizeof(float) + WK_ENVS * sizeof(uint32_t) + 16;
+                           WK_ENVS * WK_ROW * sizeof(float) + WK_ENVS * sizeof(uint32_t) + WK_RING * WK_ENVS * 4 * sizeof(double) + 16;
 
 __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPoleEnv::Params p, RolloutArgs a) {
     using EnvT = CartPoleEnv;
@@ -788,6 +789,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     // mailbox rows [16][8], 16-byte aligned: obs 0..4, flags (bit 0: this env takes the step, bit 1: some env of the CTA does)
     float *obs_s = tail + 4 + GK_REM_TABLE_MAX;
     uint32_t *act_s = reinterpret_cast<uint32_t *>(obs_s + WK_ENVS * WK_ROW);        // [16]
+    // reset_s[slot][env] = (x, x', theta, theta') CartPole::initial_state would draw at noise step t0 + slot-step: filled by
+    // the policy warps four steps at a time (they have idle issue slots; the dynamics warp does not), eight steps deep
+    double *reset_s = reinterpret_cast<double *>(act_s + WK_ENVS);                   // [8][16][4], 16-byte aligned
     const bool rem_table = p.max_steps != 0 && p.max_steps < GK_REM_TABLE_MAX;
     stage_pair_weights(a.net, sw4, tail, p, rem_table ? (int)p.max_steps + 1 : 0);
     __syncthreads();
@@ -805,6 +809,26 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     st.init();
     bool contributes = false;
 
+    // Would-be reset states (cartpole.rs:103-115: four uniform draws in field order = Philox blocks 0 (x, x') and 1 (theta,
+    // theta') of the reset stream at noise step t0 + k).  A policy warp fills the slots of steps k0 .. k0 + 3 for its four
+    // envs in one go: lane = (env of the warp, step offset, block).
+    auto fill_resets = [&](uint32_t k0) {
+        const int genv = lane >> 3, off = (lane >> 1) & 3, blk = lane & 1, el_w = 4 * warp + genv;
+        const uint64_t eg = e_base + el_w, lg = a.lane_offset + (eg < a.E ? eg : 0);
+        const uint32_t k = k0 + (uint32_t)off;
+        uint32_t o[4];
+        rl_philox4x32_10((uint32_t)lg, (uint32_t)(lg >> 32), t0 + k, (uint32_t)RL_STREAM_ENV_RESET * 64u + (uint32_t)blk, (uint32_t)seed,
+                         (uint32_t)(seed >> 32), o);
+        const double v0 = rl_u64_to_uniform((uint64_t)o[0] | ((uint64_t)o[1] << 32), p.reset_low, p.reset_scale);
+        const double v1 = rl_u64_to_uniform((uint64_t)o[2] | ((uint64_t)o[3] << 32), p.reset_low, p.reset_scale);
+        *reinterpret_cast<double2 *>(reset_s + (((size_t)(k & (WK_RING - 1)) * WK_ENVS + el_w) * 4 + 2 * blk)) = make_double2(v0, v1);
+    };
+    if (warp < WK_ENVS / 4) {
+        fill_resets(0);  // steps 0 .. 3 (step 0 is the initial state) and 4 .. 7
+        fill_resets(4);
+    }
+    __syncthreads();
+
     if (warp == WK_ENVS / 4) {
         // ------------------------------ dynamics warp: lane = (env el, action act) ------------------------------
         const int el = lane & 15, act = lane >> 4;
@@ -812,16 +836,11 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
         const bool valid = e < a.E;
         const uint64_t e_safe = valid ? e : 0, lane_global = a.lane_offset + e_safe;
         const float rem_full = remaining_feature(p.max_steps);
-        // CartPole::initial_state (cartpole.rs:103-115) at noise step `step`: four uniform draws in field order = Philox
-        // blocks 0 (x, x') and 1 (theta, theta') of the reset stream; this lane computes block `act`.
-        auto fresh_state = [&](uint32_t step, EnvT::State &f) {
-            uint32_t o[4];
-            rl_philox4x32_10((uint32_t)lane_global, (uint32_t)(lane_global >> 32), step, (uint32_t)RL_STREAM_ENV_RESET * 64u + (uint32_t)act,
-                             (uint32_t)seed, (uint32_t)(seed >> 32), o);
-            const double v0 = rl_u64_to_uniform((uint64_t)o[0] | ((uint64_t)o[1] << 32), p.reset_low, p.reset_scale);
-            const double v1 = rl_u64_to_uniform((uint64_t)o[2] | ((uint64_t)o[3] << 32), p.reset_low, p.reset_scale);
-            const double w0 = __shfl_xor_sync(FULL, v0, 16), w1 = __shfl_xor_sync(FULL, v1, 16);
-            f.x = act ? w0 : v0; f.xd = act ? w1 : v1; f.th = act ? v0 : w0; f.thd = act ? v1 : w1;
+        // the reset state of noise step t0 + k, from the ring the policy warps keep eight steps ahead
+        auto fresh_state = [&](uint32_t k, EnvT::State &f) {
+            const double2 *slot = reinterpret_cast<const double2 *>(reset_s + ((size_t)(k & (WK_RING - 1)) * WK_ENVS + el) * 4);
+            const double2 lo = slot[0], hi = slot[1];
+            f.x = lo.x; f.xd = lo.y; f.th = hi.x; f.thd = hi.y;
             f.meta = 0x80000000u | p.max_steps;
         };
         EnvT::State s;
@@ -834,7 +853,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
         float cur_obs[5] = {0, 0, 0, 0, 0}, last_obs[5] = {0, 0, 0, 0, 0};
         {
             EnvT::State f;
-            fresh_state(t0, f);
+            fresh_state(0, f);
             if (n > 0) {
                 s = f;
                 cur_obs[0] = (float)s.x; cur_obs[1] = (float)s.xd; cur_obs[2] = (float)s.th; cur_obs[3] = (float)s.thd;
@@ -850,6 +869,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
         }
         __syncwarp();
         named_bar_arrive(1, WK_THREADS);
+        uint32_t it = 0;  // loop counter (= step index of the envs still active)
         while (any) {
             const bool active = n > 0;
             // before the action is known: this lane's candidate step, its half of the would-be reset state, and the
@@ -857,7 +877,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             EnvT::State cand = s;
             const int cand_sc = EnvT::step_fast(p, cand, (uint32_t)act);
             EnvT::State fresh;
-            fresh_state(t0 + i + 1, fresh);
+            fresh_state(it + 1, fresh);
             const uint32_t r_now = s.meta & 0x7FFFFFFFu;
             const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
             named_bar_sync(2, WK_THREADS);
@@ -923,6 +943,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             for (int f = 0; f < 5; ++f) cur_obs[f] = nobs[f];
             n = n_next;
             any = any_next;
+            it += 1;
         }
         st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
         st.v[ST_EPS] = n_eps; st.v[ST_ER] = st.v[ST_EL] = sum_el; st.v[ST_ER2] = st.v[ST_EL2] = sum_el2;
@@ -978,6 +999,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
             if (phase == 0)
                 shared_theta = rl_logit_threshold(rl_u32_to_f32((uint32_t)rl_philox_slot_impl(seed, lane_global, t0 + i + sub, RL_STREAM_ACTOR, 0)));
             const float theta = __shfl_sync(FULL, shared_theta, (lane & ~(LANES - 1)) + phase);
+            // Reset states: the dynamics warp is at iteration i - 1 or i and reads slots up to step i + 1; steps i + 4 .. i + 7
+            // reuse the slots of steps i - 4 .. i - 1, whose readers (iterations <= i - 2) are done.
+            if ((i & 3u) == 0u && i > 0) fill_resets(i + 4);
             named_bar_sync(1, WK_THREADS);
             const float4 ov = *reinterpret_cast<const float4 *>(obs_s + el * WK_ROW);
             const float2 tailv = *reinterpret_cast<const float2 *>(obs_s + el * WK_ROW + 4);
