@@ -38,6 +38,7 @@ struct RolloutArgs {
     const double *qtable;
     int S, A, F;
     double *partials;  // f64 [gridDim.x][ST_COUNT]
+    int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
 };
 
 struct LaneStats {
@@ -799,7 +800,13 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     auto remaining_feature = [&](uint32_t r) {
         return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
     };
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Warp roles.  Warps map to the four sub-partitions by index, so warps 0 and 4 share one; the dynamics warp is the
+    // critical one, and the second CTA of an SM (block index >= SM count when the grid is at most two waves) puts it
+    // on a different sub-partition than the first.
+    const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int dyn_warp = (int)blockIdx.x >= a.sm_count ? 2 : 4;
+    const bool is_dyn = hw_warp == dyn_warp;
+    const int warp = hw_warp < dyn_warp ? hw_warp : hw_warp - 1;  // policy warp index 0..3 (unused by the dynamics warp)
     const uint64_t e_base = (uint64_t)blockIdx.x * WK_ENVS;
     const uint32_t t0 = a.noise.step_counter;
     const uint64_t seed = a.noise.seed;
@@ -823,13 +830,13 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
         const double v1 = rl_u64_to_uniform((uint64_t)o[2] | ((uint64_t)o[3] << 32), p.reset_low, p.reset_scale);
         *reinterpret_cast<double2 *>(reset_s + (((size_t)(k & (WK_RING - 1)) * WK_ENVS + el_w) * 4 + 2 * blk)) = make_double2(v0, v1);
     };
-    if (warp < WK_ENVS / 4) {
+    if (!is_dyn) {
         fill_resets(0);  // steps 0 .. 3 (step 0 is the initial state) and 4 .. 7
         fill_resets(4);
     }
     __syncthreads();
 
-    if (warp == WK_ENVS / 4) {
+    if (is_dyn) {
         // ------------------------------ dynamics warp: lane = (env el, action act) ------------------------------
         const int el = lane & 15, act = lane >> 4;
         const uint64_t e = e_base + el;
@@ -1473,6 +1480,7 @@ rl_status launch_ws(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, i
     RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
     a.partials = partials + ST_COUNT;
     *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
     RL_LAUNCH(ctx, rollout_cartpole_ws_kernel, grid, WK_THREADS, WK_SMEM, p, a);
     return RL_OK;
 }
