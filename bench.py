@@ -189,10 +189,11 @@ def cpu_rollout_rate(params: np.ndarray, lanes: int, horizon: int, threads: int,
     import oracle as O
 
     cfg = O.cartpole_cfg(500)
-    mlp = O.mlp_struct(params, 5, 128, 2)
+    mlp = O.mlp_struct(params, 5, 128, 2) if params is not None else None  # None: RandomAgent (env only)
     summ = O.Summary()
     t = time.perf_counter()
-    O.lib().ro_rollout_lanes_philox(C.byref(cfg), C.byref(mlp), lanes, 0, horizon, 0, seed, t0, threads, C.byref(summ))
+    O.lib().ro_rollout_lanes_philox(C.byref(cfg), C.byref(mlp) if mlp is not None else None, lanes, 0, horizon, 0, seed, t0,
+                                    threads, C.byref(summ))
     dt = time.perf_counter() - t
     return lanes * horizon / dt, dt, summ
 
@@ -385,6 +386,14 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": periods * E * T / cpu_s, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{periods} periods of {E} lanes x {T} steps ({cpu_s:.1f} s wall) of the same "
                                           f"workload, C oracle port of Steps::step + PolicyActor::act, {cores} threads"}
+        # env-only (RandomAgent: no policy network), SURVEY 8d's second CPU number: ~3 s of the same lanes on all cores
+        env_s, env_periods = 0.0, 0
+        while env_s < 3.0:
+            _, dt, _ = cpu_rollout_rate(None, E, T, cores, t0=env_periods * (T + 1))
+            env_s += dt
+            env_periods += 1
+        line["cpu_baseline"]["env_only"] = {"value": env_periods * E * T / env_s, "unit": UNIT,
+                                            "sample": f"{env_periods} periods of {E} lanes x {T} steps, RandomAgent, {cores} threads"}
         if not args.no_update:
             try:
                 line["update"]["cpu_baseline"] = cpu_update_baseline(1 << 16)

@@ -420,14 +420,14 @@ def test_fused_rollout_policy_other_envs_consistent(ctx, cfg):
 
 
 @pytest.mark.parametrize("E,T,slack,limit,visible", [(4096, 64, 0, 500, True), (1000, 70, 9, 20, True), (37, 45, 3, 15, False),
-                                                     (16, 33, 0, 500, True)])
+                                                     (16, 33, 0, 500, True), (300, 50, 2, 0, False)])
 def test_warp_specialized_rollout_is_bit_identical_to_k2c(ctx, E, T, slack, limit, visible):
     """K2w (policy and dynamics of an env on different warps, hand-off through named barriers) performs the same
     operations on the same operands as K2c with 8 threads per env: under Philox noise every stored byte, the lane
     lengths and the summary must be identical -- ragged last CTA, slack, step-limit Interrupts, latent limit (F = 4),
     resets, dangling steps."""
     wrap = R.VisibleStepLimit(limit) if visible else R.LatentStepLimit(limit)
-    cfg = R.CartPoleConfig().wrap(wrap)
+    cfg = R.CartPoleConfig().wrap(wrap) if limit else R.CartPoleConfig()  # limit 0: the bare env, episodes end by Terminate only
     F = 5 if visible else 4
     params = R.init_params(np.random.default_rng(E), F, 128, 2) * 2.0
     net = R.Mlp(ctx, F, [128], 2)
@@ -450,7 +450,7 @@ def test_warp_specialized_rollout_is_bit_identical_to_k2c(ctx, E, T, slack, limi
         for k in ("action", "reward", "obs"):
             np.testing.assert_array_equal(ws[k][valid], gk[k][valid], err_msg=k)
         intr = gk["succ"] == L.RL_INTERRUPT
-        assert intr.any() or limit >= T
+        assert intr.any() or limit >= T or limit == 0
         np.testing.assert_array_equal(ws["next_obs"][intr], gk["next_obs"][intr])
         assert ws["num_steps"] == gk["num_steps"]
         for name in ("step_reward", "episode_reward", "episode_length"):
