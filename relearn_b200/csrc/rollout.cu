@@ -755,21 +755,26 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2w: K2c with the two halves of the step chain on different warps (few envs: E <= ~8 K).
+// K2w: K2c with the two halves of the step chain on different warps (few envs: E <= 32 per SM).
 //
 // In K2c a warp carries 4 envs x 8 threads and issues BOTH the policy (obs -> hidden layer -> logit difference ->
 // compare) and the f64 dynamics of its envs, the latter redundantly in all 8 threads of an env; with two such warps
 // per scheduler the period is set by their combined instruction stream (~1940 clk per step at E = 4096).  Here a CTA
 // owns 16 envs: four POLICY warps (4 envs x 8 threads each, exactly K2c's register-resident hidden layer) and one
 // DYNAMICS warp whose lane (env, a) steps env `env` with action `a` speculatively -- both actions of 16 envs fill the
-// warp, so nothing is computed redundantly -- plus half of the would-be reset state (the action-0 lane draws x, x',
-// the action-1 lane theta, theta': one Philox block each, exchanged by shuffle).  The halves meet through two named
-// barriers and a 16-row mailbox in shared memory:
+// warp, so nothing is computed redundantly.  The halves meet through two named barriers and a 16-row mailbox in
+// shared memory:
 //     dynamics: select cand[action], reset if the episode ended, write obs_{t+1} -> bar.arrive 1 ... bar.sync 2
 //     policy:   bar.sync 1, read obs_t, hidden layer, d < theta ?, write action  -> bar.arrive 2
 // so a step costs max(dynamics, policy) + two hand-offs instead of their sum, and every warp issues only its own half.
+// The dynamics warp is the bound (its dependent f64 chain), so everything that can leave it has: the would-be reset
+// states (Philox) are produced by the policy warps four steps at a time into a shared-memory ring, the policy warps
+// store the observation / action columns, and the second CTA of an SM runs its dynamics on warp 2 instead of warp 4
+// so that the two critical warps of the SM sit on different sub-partitions.
 // Same operations on the same operands as K2c<8> (summation order of the logits included): bit-identical trajectories
 // and summaries (tests/test_gpu_envs.py).  Philox noise and the categorical actor only; K2c serves the rest.
+// 168 registers on purpose: 16 K registers per sub-partition / 32 lanes / 3 warps = 170 -- one more register class and
+// only one CTA fits an SM.
 // ------------------------------------------------------------------------------------------------
 constexpr int WK_ENVS = 16, WK_THREADS = 160, WK_ROW = 8;
 
