@@ -39,6 +39,7 @@ struct RolloutArgs {
     int S, A, F;
     double *partials;  // f64 [gridDim.x][ST_COUNT]
     int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
+    int dyn_first, dyn_second;  // K2w: warp index of the dynamics warp in the first / later CTAs of an SM
 };
 
 struct LaneStats {
@@ -769,8 +770,8 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
 // so a step costs max(dynamics, policy) + two hand-offs instead of their sum, and every warp issues only its own half.
 // The dynamics warp is the bound (its dependent f64 chain), so everything that can leave it has: the would-be reset
 // states (Philox) are produced by the policy warps four steps at a time into a shared-memory ring, the policy warps
-// store the observation / action columns, and the second CTA of an SM runs its dynamics on warp 2 instead of warp 4
-// so that the two critical warps of the SM sit on different sub-partitions.
+// store the observation / action columns, and the dynamics run on warp 2 rather than warp 4, which shares its
+// sub-partition with warp 0 (measured placements in launch_ws).
 // Same operations on the same operands as K2c<8> (summation order of the logits included): bit-identical trajectories
 // and summaries (tests/test_gpu_envs.py).  Philox noise and the categorical actor only; K2c serves the rest.
 // 168 registers on purpose: 16 K registers per sub-partition / 32 lanes / 3 warps = 170 -- one more register class and
@@ -806,10 +807,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
         return p.max_steps == 0 ? 0.0f : rem_table ? rem[r] : (float)__ddiv_rn((double)r, (double)p.max_steps);
     };
     // Warp roles.  Warps map to the four sub-partitions by index, so warps 0 and 4 share one; the dynamics warp is the
-    // critical one, and the second CTA of an SM (block index >= SM count when the grid is at most two waves) puts it
-    // on a different sub-partition than the first.
+    // critical one and sits on warp 2 (launch_ws: measured placements; the first and the later CTAs of an SM can differ).
     const int hw_warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int dyn_warp = (int)blockIdx.x >= a.sm_count ? 2 : 4;
+    const int dyn_warp = (int)blockIdx.x >= a.sm_count ? a.dyn_second : a.dyn_first;
     const bool is_dyn = hw_warp == dyn_warp;
     const int warp = hw_warp < dyn_warp ? hw_warp : hw_warp - 1;  // policy warp index 0..3 (unused by the dynamics warp)
     const uint64_t e_base = (uint64_t)blockIdx.x * WK_ENVS;
@@ -1486,6 +1486,16 @@ rl_status launch_ws(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, i
     a.partials = partials + ST_COUNT;
     *nblocks_out = (int)grid;
     a.sm_count = ctx->sm_count;
+    // The dynamics warp is warp 2 of its CTA: warps 0 and 4 of a 5-warp CTA share a sub-partition, and of the 25
+    // (first CTA, second CTA of an SM) placements measured at E = 4096 (profiles/r1_summary.md section 13) the ones with the
+    // second CTA's dynamics on warp 1 or 2 are fastest (0.156 ms; 0.162 with warp 4, 0.167 with warp 3).
+    // RL_WS_DYN="a,b" overrides (measurements).
+    a.dyn_first = 2;
+    a.dyn_second = 2;
+    if (const char *ov = getenv("RL_WS_DYN")) {
+        int x = 0, y = 0;
+        if (sscanf(ov, "%d,%d", &x, &y) == 2 && x >= 0 && x <= 4 && y >= 0 && y <= 4) { a.dyn_first = x; a.dyn_second = y; }
+    }
     RL_LAUNCH(ctx, rollout_cartpole_ws_kernel, grid, WK_THREADS, WK_SMEM, p, a);
     return RL_OK;
 }
