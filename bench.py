@@ -42,10 +42,11 @@ FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
 FLOP_PER_SAMPLE_CRITIC = 4608
 FLOP_ISSUED_PER_SAMPLE_CRITIC_TC = 28672
 # dram__bytes_read.sum + dram__bytes_write.sum of one K2w launch (the kernel `lanes_per_env = 0` picks) at E = 4096,
-# T = 256 from the round-1 `ncu --set full` capture (profiles/r1_summary.md section 13): 49.4 KB + 2.8 KB.  The 27 MB trajectory of a
+# T = 256 from the round-1 `ncu --set full` capture of the final kernel (profiles/r1i_k2w_e4096.md): 50.7 KB + 17.4 KB
+# (the write figure is whatever part of the trajectory L2 happened to write back during the launch: 2.8 .. 22 KB over captures).  The 27 MB trajectory of a
 # period stays in the 126 MB L2 while the kernel runs and drains afterwards, so the in-kernel DRAM traffic
 # is far BELOW the algorithmic 26 B/env-step, not above it.
-K2C_NCU_DRAM_BYTES_PER_LAUNCH = 52224
+K2C_NCU_DRAM_BYTES_PER_LAUNCH = 68096
 
 
 def measured_peaks():
