@@ -316,7 +316,7 @@ def run_ours(args):
                 "traffic": K2C_NCU_DRAM_BYTES_PER_LAUNCH if (E == 4096 and T == 256) else None,
                 "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s13); trajectory is L2-resident during the kernel",
                 "peak_source": peak_src, "kernel": "rollout_cartpole_ws_kernel K2w (fused step+policy+sample; policy and dynamics on different warps)",
-                "note": "K2 is FP32-FMA/latency bound by design (26 B of trajectory writes per env-step); see fp32 and kernels[]"}
+                "note": "K2w moves 26 B of trajectory per env-step, so HBM is not its bound: at 4096 envs the period is 256 x the latency of the dynamics warp's dependent f64 step (~1200 clk, DESIGN section 4); the HBM-bound kernels of the path are in kernels[] (77-81 % of peak)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
