@@ -1697,8 +1697,11 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             // ... and within that one wave the warp-specialised kernel (K2w: bit-identical to K2c<8>, policy and dynamics
             // on different warps) is 30 % faster (E = 4096: 0.178 vs 0.254 ms per 256-step period); it serves the
             // categorical actor on Philox noise.  RL_ROLLOUT_WS=0 keeps K2c (measurements).
+            // It also stays ahead of K2t through a second wave of CTAs (E <= 64 per SM = 9472: 0.27 .. 0.30 ms against K2t's
+            // 0.32); from the third wave on K2t wins.
             static const char *ws_env = getenv("RL_ROLLOUT_WS");
-            if (lanes == 8 && !replay && a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY && !(ws_env && ws_env[0] == '0'))
+            if (env->E <= (uint64_t)ctx->sm_count * 64 && !replay && a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY &&
+                !(ws_env && ws_env[0] == '0'))
                 lanes = RL_LANES_WARP_SPECIALIZED;
         }
         switch (lanes) {
