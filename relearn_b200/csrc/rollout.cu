@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(128) rollout_cartpole_group_kernel(CartPoleEnv
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2w: K2c with the two halves of the step chain on different warps (few envs: E <= 32 per SM).
+// K2w: K2c with the two halves of the step chain on different warps (few envs: E <= 64 per SM, two waves of CTAs).
 //
 // In K2c a warp carries 4 envs x 8 threads and issues BOTH the policy (obs -> hidden layer -> logit difference ->
 // compare) and the f64 dynamics of its envs, the latter redundantly in all 8 threads of an env; with two such warps
