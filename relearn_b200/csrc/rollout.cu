@@ -40,6 +40,8 @@ struct RolloutArgs {
     double *partials;  // f64 [gridDim.x][ST_COUNT]
     int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
     int dyn_first, dyn_second;  // K2w: warp index of the dynamics warp in the first / later CTAs of an SM
+    int aux_first, aux_second;  // K2x / K2y: warp index of the aux (noise) warp
+    int head_first, head_second;  // K2y: warp index of the head warp
 };
 
 struct LaneStats {
@@ -1061,6 +1063,9 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     block_reduce_stats(st, contributes, a.partials);
 }
 
+#include "rollout_ws2.cuh"
+#include "rollout_ws3.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // K2t: CartPole + 5->128->2 ReLU network with the hidden layer on the tensor cores (tcgen05 + TMEM), for env counts
 // at which the actor GEMM is dense: a CTA owns 128 envs, one env per thread and per TMEM lane, and every step of the
@@ -1500,6 +1505,60 @@ rl_status launch_ws(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, i
     return RL_OK;
 }
 
+rl_status launch_ws2(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    const unsigned grid = (unsigned)((a.E + XK_ENVS - 1) / XK_ENVS);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
+    // Warps map to the four sub-partitions by index: the dynamics warp sits alone on one (warp 2), the aux warp shares
+    // warp 1's.  RL_WS2_ROLES="d1,a1,d2,a2" overrides the (first CTA, later CTAs of an SM) placements (measurements).
+    a.dyn_first = 2; a.aux_first = 5; a.dyn_second = 2; a.aux_second = 5;
+    if (const char *ov = getenv("RL_WS2_ROLES")) {
+        int d1, a1, d2, a2;
+        if (sscanf(ov, "%d,%d,%d,%d", &d1, &a1, &d2, &a2) == 4 && d1 >= 0 && d1 <= 5 && a1 >= 0 && a1 <= 5 && d1 != a1 &&
+            d2 >= 0 && d2 <= 5 && a2 >= 0 && a2 <= 5 && d2 != a2) {
+            a.dyn_first = d1; a.aux_first = a1; a.dyn_second = d2; a.aux_second = a2;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XkShared)));
+        attr_set = true;
+    }
+    RL_LAUNCH(ctx, rollout_cartpole_ws2_kernel, grid, XK_THREADS, sizeof(XkShared), p, a);
+    return RL_OK;
+}
+
+rl_status launch_ws3(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    const unsigned grid = (unsigned)((a.E + YK_ENVS - 1) / YK_ENVS);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
+    // Warps 4..7 sit on sub-partitions 0..3 next to policy warps 0..3.  RL_WS3_ROLES="d1,h1,a1,d2,h2,a2" overrides the
+    // (first CTA, later CTAs of an SM) placements of the dynamics / head / aux warps (measurements).
+    a.dyn_first = 4; a.head_first = 5; a.aux_first = 6; a.dyn_second = 6; a.head_second = 7; a.aux_second = 4;
+    if (const char *ov = getenv("RL_WS3_ROLES")) {
+        int v[6];
+        if (sscanf(ov, "%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) == 6) {
+            bool ok = true;
+            for (int k = 0; k < 6; ++k) ok = ok && v[k] >= 4 && v[k] <= 7;
+            ok = ok && v[0] != v[1] && v[0] != v[2] && v[1] != v[2] && v[3] != v[4] && v[3] != v[5] && v[4] != v[5];
+            if (ok) { a.dyn_first = v[0]; a.head_first = v[1]; a.aux_first = v[2]; a.dyn_second = v[3]; a.head_second = v[4]; a.aux_second = v[5]; }
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YkShared)));
+        attr_set = true;
+    }
+    RL_LAUNCH(ctx, rollout_cartpole_ws3_kernel, grid, YK_THREADS, sizeof(YkShared), p, a);
+    return RL_OK;
+}
+
 template <int LANES>
 rl_status launch_group(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
     if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
@@ -1715,7 +1774,12 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
         case RL_LANES_WARP_SPECIALIZED:
             if (replay || a.actor_kind != RL_ACTOR_CATEGORICAL_POLICY)
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
-            RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
+            {
+                static const char *ws_variant = getenv("RL_WS_VARIANT");  // 1 = K2w, 2 = K2x, 3 = K2y
+                if (ws_variant && ws_variant[0] == '2') RL_TRY(launch_ws2(ctx, env->cartpole, a, &nblocks));
+                else if (ws_variant && ws_variant[0] == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
+                else RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
+            }
             break;
         default:
             return rl_fail(ctx, RL_ERR_UNSUPPORTED,

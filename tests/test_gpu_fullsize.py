@@ -241,3 +241,112 @@ def test_tensor_core_rollout_at_65536_envs(ctx):
     b, _ = run(E // 2, E // 2, 0)
     for k in ("obs", "action", "succ"):
         np.testing.assert_array_equal(np.concatenate([a[k], b[k]], axis=1), host[k])
+
+
+# ------------------------------------------------------------------------------------------------
+# Full-size runs against the ORACLE itself (not a sibling kernel): the oracle regenerates the Philox noise per lane,
+# so a sample of lanes of the BASELINE-size runs is replayed through it in milliseconds.
+# ------------------------------------------------------------------------------------------------
+def _check_lanes_against_oracle(host, lanes, T, seed, params, what):
+    import oracle as O
+    from tests import parity as P
+
+    lib = L.lib()
+    for lane in lanes:
+        sub = {k: np.ascontiguousarray(host[k][:, lane:lane + 1]) for k in ("obs", "next_obs", "action", "reward", "succ")}
+        sub["lane_len"] = host["lane_len"][lane:lane + 1].copy()
+        ref = P.oracle_rollout(CARTPOLE, 1, T, 0, actor_kind=O.ACTOR_REPLAY, actions=sub["action"].copy(), philox_seed=seed,
+                               lane_offset=int(lane), t0=0)
+        # CartPole observations to 1e-6: the device polynomial sin/cos differs from glibc's by <= 1 ulp of f64
+        P.compare_traj(sub, ref, obs_rtol=1e-6, obs_atol=1e-7, what=f"{what} lane {lane}")
+        awords = np.array([[lib.rl_philox_slot(seed, int(lane), i, 2, 0) & 0xFFFFFFFF for i in range(T)]], dtype=np.uint64).astype(np.uint32)
+        checked, near = P.check_policy_consistency(sub, params, 128, 2, awords)
+        assert checked == int(sub["lane_len"][0]) and near <= 1, (what, lane, near)
+
+
+def test_bench_size_rollout_lanes_against_the_oracle(ctx, trpo_batch):
+    """configs[1] at its full size (E = 4096, T = 256, the kernel `lanes_per_env = 0` picks = K2w): 64 evenly spaced lanes
+    replayed through the CPU oracle -- successor codes, lane lengths, rewards exactly, observations to 1e-6, and every
+    action the inverse-CDF choice of the oracle's softmax under the step's Philox uniform."""
+    env, agent, traj, summ, host, params = trpo_batch
+    _check_lanes_against_oracle(host, np.linspace(0, 4095, 64).astype(int), 256, 77, params, "K2w E=4096")
+
+
+def test_tensor_core_rollout_lanes_against_the_oracle(ctx):
+    """configs[2] size (E = 65 536 on K2t): 64 evenly spaced lanes replayed through the CPU oracle."""
+    E, T, seed = 65536, 64, 79
+    params = R.init_params(np.random.default_rng(3), 5, 128, 2)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    env = R.build_env(ctx, CARTPOLE, E, seed=seed)
+    env.set_noise_philox(seed, 0)
+    tr = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=L.RL_LANES_TENSOR_CORE),
+              R.HistoryDataBound(T, 0), tr)
+    host = tr.to_host()
+    tr.close()
+    env.close()
+    _check_lanes_against_oracle(host, np.linspace(0, E - 1, 64).astype(int), T, seed, params, "K2t E=65536")
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_trpo_and_critic_update_at_1m_steps_against_the_f64_oracle(ctx, trpo_batch):
+    """One TRPO step (trpo.rs:97-164: CG, step size, line search) and one 80-step Adam critic update (opt.rs:100-127) on
+    the whole 1 048 576-step batch, against oracle/tensor_oracle.py run in f64 on the same batch (CPU, tens of seconds).
+    hpv_reg_coeff = 0.1 keeps ten f32 CG iterations well conditioned (tests/test_gpu_update.py explains why the
+    reference's own 1e-5 is not): the parameter delta must agree with f64 to 1e-4 relative (north_star's 1e-5 class; the
+    small-batch tests show torch's own f32 run at 0.6e-5 .. 3e-5), decisions and log values to 1e-5."""
+    torch = pytest.importorskip("torch")
+    import oracle as O
+    from oracle import tensor_oracle as TO
+
+    env, agent, traj, summ, host, params = trpo_batch
+    E, T = 4096, 256
+    valid = host["succ"] != PAD
+    rng = np.random.default_rng(21)
+    vparams = R.init_params(rng, 5, 128, 1)
+    critic = R.ValuesOpt(ctx, R.ValuesOptConfig(), 5, 0.99)  # fresh Adam state
+    critic.state_value_fn.set_weights(vparams)
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(params)
+    adv_d = critic.advantages(traj)
+    adv = adv_d.download((T, E), np.float32)
+    reg = 0.1
+    policy = R.Trpo(net, R.TrpoConfig(optimizer_config=R.ConjugateGradientOptimizerConfig(hpv_reg_coeff=reg)))
+    log = {}
+    status = policy.update(traj, adv_d, log)
+    new = net.get_weights()
+    obs, act, a = host["obs"][valid], host["action"][valid], adv[valid]
+    new64, log64 = TO.trpo_update(params, 5, 128, 2, obs, act, a, cfg=TO.CgConfig(hpv_reg_coeff=reg), dtype=torch.float64)
+    d, d64 = new - params, new64 - params.astype(np.float64)
+    print(f"N={int(valid.sum())} TRPO: status {status}, backtracks {log['num_backtracks']}/{log64['num_backtracks']}, "
+          f"step_size {log['step_size']:.6e}/{log64['step_size']:.6e}, delta rel err vs f64 {_rel(d, d64):.2e}")
+    assert status == L.RL_OK and log64["error"] is None and log["num_steps"] == int(valid.sum())
+    # (f32 CG can cross the residual tolerance one iteration apart from f64: conjugate_gradient.rs:125-179 stops on r.r < tol)
+    assert log["num_backtracks"] == log64["num_backtracks"] and abs(log["cg_iterations"] - log64["cg_iterations"]) <= 1
+    np.testing.assert_allclose(log["entropy"], log64["entropy"], rtol=1e-5)
+    np.testing.assert_allclose(log["step_size"], log64["step_size"], rtol=1e-4)
+    np.testing.assert_allclose(log["loss_initial"], log64["loss_initial"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(log["loss_final"], log64["loss_final"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(log["constraint_val_final"], log64["constraint_val_final"], rtol=1e-4, atol=1e-8)
+    assert _rel(d, d64) <= 1e-4
+    # critic: 80 Adam steps on mse(V(obs), reward-to-go)
+    steps = 80
+    stats = critic.update(traj)
+    vnew = critic.state_value_fn.get_weights()
+    rtg = np.zeros((T, E), np.float32)
+    for e in range(E):
+        n = int(host["lane_len"][e])
+        rtg[:n, e] = O.discounted_cumsum_lane(host["reward"][:n, e], host["succ"][:n, e], np.float32(0.99))
+    vnew64, losses64, _ = TO.value_update(vparams, 5, 128, obs, rtg[valid], n_steps=steps, dtype=torch.float64)
+    dv, dv64 = vnew - vparams, vnew64 - vparams.astype(np.float64)
+    print(f"critic: loss first/last {stats.loss_first:.6f}/{stats.loss_last:.6f} vs f64 {losses64[0]:.6f}/{losses64[-1]:.6f}, "
+          f"delta rel err vs f64 {_rel(dv, dv64):.2e}")
+    assert stats.num_steps == int(valid.sum()) and stats.opt_steps == steps
+    np.testing.assert_allclose(stats.loss_first, losses64[0], rtol=1e-5)
+    np.testing.assert_allclose(stats.loss_last, losses64[-1], rtol=1e-4)
+    assert _rel(dv, dv64) <= 2e-4
