@@ -1065,6 +1065,7 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
 
 #include "rollout_ws2.cuh"
 #include "rollout_ws3.cuh"
+#include "rollout_ws4.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K2t: CartPole + 5->128->2 ReLU network with the hidden layer on the tensor cores (tcgen05 + TMEM), for env counts
@@ -1559,6 +1560,32 @@ rl_status launch_ws3(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, 
     return RL_OK;
 }
 
+rl_status launch_ws4(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    const unsigned grid = (unsigned)((a.E + VK_ENVS - 1) / VK_ENVS);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
+    // Warps map to the four sub-partitions by index (warps 0 / 4 and 1 / 5 share one).  RL_WS4_ROLES="d1,a1,d2,a2" overrides
+    // the (first CTA, later CTAs of an SM) placements of the dynamics / aux warps (measurements).
+    a.dyn_first = 2; a.aux_first = 5; a.dyn_second = 2; a.aux_second = 5;
+    if (const char *ov = getenv("RL_WS4_ROLES")) {
+        int d1, a1, d2, a2;
+        if (sscanf(ov, "%d,%d,%d,%d", &d1, &a1, &d2, &a2) == 4 && d1 >= 0 && d1 <= 5 && a1 >= 0 && a1 <= 5 && d1 != a1 &&
+            d2 >= 0 && d2 <= 5 && a2 >= 0 && a2 <= 5 && d2 != a2) {
+            a.dyn_first = d1; a.aux_first = a1; a.dyn_second = d2; a.aux_second = a2;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VkShared)));
+        attr_set = true;
+    }
+    RL_LAUNCH(ctx, rollout_cartpole_ws4_kernel, grid, VK_THREADS, sizeof(VkShared), p, a);
+    return RL_OK;
+}
+
 template <int LANES>
 rl_status launch_group(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
     if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
@@ -1778,6 +1805,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
                 static const char *ws_variant = getenv("RL_WS_VARIANT");  // 1 = K2w, 2 = K2x, 3 = K2y
                 if (ws_variant && ws_variant[0] == '2') RL_TRY(launch_ws2(ctx, env->cartpole, a, &nblocks));
                 else if (ws_variant && ws_variant[0] == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
+                else if (ws_variant && ws_variant[0] == '4') RL_TRY(launch_ws4(ctx, env->cartpole, a, &nblocks));
                 else RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
             }
             break;
