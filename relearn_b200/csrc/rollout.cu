@@ -40,7 +40,7 @@ struct RolloutArgs {
     double *partials;  // f64 [gridDim.x][ST_COUNT]
     int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
     int dyn_first, dyn_second;  // K2w: warp index of the dynamics warp in the first / later CTAs of an SM
-    int aux_first, aux_second;  // K2x / K2y: warp index of the aux (noise) warp
+    int aux_first, aux_second;  // K2v / K2y: warp index of the aux (noise) warp
     int head_first, head_second;  // K2y: warp index of the head warp
 };
 
@@ -1063,7 +1063,6 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
     block_reduce_stats(st, contributes, a.partials);
 }
 
-#include "rollout_ws2.cuh"
 #include "rollout_ws3.cuh"
 #include "rollout_ws4.cuh"
 
@@ -1506,32 +1505,6 @@ rl_status launch_ws(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, i
     return RL_OK;
 }
 
-rl_status launch_ws2(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
-    const unsigned grid = (unsigned)((a.E + XK_ENVS - 1) / XK_ENVS);
-    double *partials;
-    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
-    a.partials = partials + ST_COUNT;
-    *nblocks_out = (int)grid;
-    a.sm_count = ctx->sm_count;
-    // Warps map to the four sub-partitions by index: the dynamics warp sits alone on one (warp 2), the aux warp shares
-    // warp 1's.  RL_WS2_ROLES="d1,a1,d2,a2" overrides the (first CTA, later CTAs of an SM) placements (measurements).
-    a.dyn_first = 2; a.aux_first = 5; a.dyn_second = 2; a.aux_second = 5;
-    if (const char *ov = getenv("RL_WS2_ROLES")) {
-        int d1, a1, d2, a2;
-        if (sscanf(ov, "%d,%d,%d,%d", &d1, &a1, &d2, &a2) == 4 && d1 >= 0 && d1 <= 5 && a1 >= 0 && a1 <= 5 && d1 != a1 &&
-            d2 >= 0 && d2 <= 5 && a2 >= 0 && a2 <= 5 && d2 != a2) {
-            a.dyn_first = d1; a.aux_first = a1; a.dyn_second = d2; a.aux_second = a2;
-        }
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(XkShared)));
-        attr_set = true;
-    }
-    RL_LAUNCH(ctx, rollout_cartpole_ws2_kernel, grid, XK_THREADS, sizeof(XkShared), p, a);
-    return RL_OK;
-}
-
 rl_status launch_ws3(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
     const unsigned grid = (unsigned)((a.E + YK_ENVS - 1) / YK_ENVS);
     double *partials;
@@ -1802,10 +1775,13 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             if (replay || a.actor_kind != RL_ACTOR_CATEGORICAL_POLICY)
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
             {
-                static const char *ws_variant = getenv("RL_WS_VARIANT");  // 1 = K2w, 2 = K2x, 3 = K2y
-                if (ws_variant && ws_variant[0] == '2') RL_TRY(launch_ws2(ctx, env->cartpole, a, &nblocks));
-                else if (ws_variant && ws_variant[0] == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
-                else if (ws_variant && ws_variant[0] == '4') RL_TRY(launch_ws4(ctx, env->cartpole, a, &nblocks));
+                // K2v while the 16-env CTAs fit one per SM (E = 1024: 0.124 ms per period against K2w's 0.131), K2w beyond
+                // (two CTAs per SM: the same 0.155 ms at E = 4096).  RL_WS_VARIANT = 1 | 3 | 4 forces K2w / K2y / K2v
+                // (measurements: profiles/r2_summary.md).
+                static const char *ws_variant = getenv("RL_WS_VARIANT");
+                const char v = ws_variant ? ws_variant[0] : (a.E <= (uint64_t)WK_ENVS * ctx->sm_count ? '4' : '1');
+                if (v == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
+                else if (v == '4') RL_TRY(launch_ws4(ctx, env->cartpole, a, &nblocks));
                 else RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
             }
             break;

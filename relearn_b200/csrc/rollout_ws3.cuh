@@ -1,7 +1,9 @@
 // rollout_ws3.cuh -- K2y: the warp-specialised CartPole rollout with a six-role CTA.  Included by rollout.cu inside its
-// anonymous namespace (after rollout_ws2.cuh, whose XkSlot / barrier helpers it shares).
+// anonymous namespace.  A MEASURED EXPERIMENT (profiles/r2_summary.md): bit-identical to K2w, 6 % slower at the bench
+// size; selected by RL_WS_VARIANT=3 only.  Kept for its parts: the software-pipelined f64 step (CartPoleEnv::Head), the
+// setmaxnreg register split by role and the explicit shared-memory addressing K2v (rollout_ws4.cuh) uses.
 //
-// K2x (rollout_ws2.cuh) took the action-independent work off the per-step chain but left all of it on ONE dynamics
+// K2x (round 2's first attempt, in the history) took the action-independent work off the per-step chain but left all of it on ONE dynamics
 // warp: ~430 SASS instructions per step (124 of them f64, 64 moves of polynomial constants), which that warp issues in
 // ~1050 clk -- its own instruction stream, not the chain, set the period (profiles/r2_summary.md, capture r2b).  K2y
 // keeps K2x's protocol (both candidate rows published before the action is known, the policy warps pick theirs) and
@@ -19,6 +21,15 @@
 //
 // Same operations on the same operands as K2c<8> / K2w: bit-identical trajectories (tests/test_gpu_envs.py).
 #pragma once
+
+struct XkSlot {      // would-be reset state of one env at one noise step
+    double x, xd, th, thd;
+    double sn, cs, yp, ym;  // CartPoleEnv::Head of th
+};
+// Named barriers, alternating by step parity so that a warp running ahead can never arrive twice in one phase:
+// rows of step t are handed over on barrier 1 + 2 (t & 1), the action of step t on barrier 2 + 2 (t & 1).
+__device__ __forceinline__ int xk_bar_rows(uint32_t t) { return 1 + 2 * (int)(t & 1u); }
+__device__ __forceinline__ int xk_bar_act(uint32_t t) { return 2 + 2 * (int)(t & 1u); }
 
 constexpr int YK_ENVS = 16, YK_THREADS = 256, YK_RING = 16, YK_CHUNK = 4, YK_AHEAD = 11;
 constexpr int YK_SYNC = 192;  // policy x 4 + dynamics + head
