@@ -48,6 +48,8 @@ struct rl_ctx {
     // pinned host scratch for scalar read-backs
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    // timing events of the update entry points (created once, destroyed with the context: no leak on an early return)
+    cudaEvent_t upd_ev[2] = {nullptr, nullptr};
 };
 
 std::string &rl_tls_error();

@@ -75,18 +75,31 @@ void x_setup(rl_ctx *ctx) {
     const size_t bytes = x_data_bytes(world) + x_flag_bytes(world) + 256;
     struct Msg { cudaIpcMemHandle_t h; int ok; int pad[3]; };
     Msg mine{};
+    // The gather and vote buffers come first: a rank that cannot even allocate them must not leave its peers waiting in
+    // the collectives below, so it uses the context's scratch (rl_ctx_scratch) and, failing that too, aborts the group
+    // set-up on every rank through the communicator's own error (ncclCommAbort is not bound; the allgather then fails
+    // on all ranks alike).
     char *gather = nullptr;
-    bool ok = cudaMalloc(&ctx->x_local, bytes) == cudaSuccess && cudaMemset(ctx->x_local, 0, bytes) == cudaSuccess &&
+    double *vote = nullptr;
+    bool own_bufs = cudaMalloc(&gather, (size_t)(world + 1) * sizeof(Msg)) == cudaSuccess && cudaMalloc(&vote, sizeof(double)) == cudaSuccess;
+    if (!own_bufs) {
+        cudaGetLastError();
+        if (gather) cudaFree(gather);
+        gather = nullptr;
+        void *sc = nullptr;
+        if (rl_ctx_scratch(ctx, (size_t)(world + 1) * sizeof(Msg) + 64, &sc) != RL_OK) return;
+        gather = static_cast<char *>(sc);
+        vote = reinterpret_cast<double *>(gather + (((size_t)(world + 1) * sizeof(Msg) + 15) & ~(size_t)15));
+    }
+    bool ok = own_bufs && cudaMalloc(&ctx->x_local, bytes) == cudaSuccess && cudaMemset(ctx->x_local, 0, bytes) == cudaSuccess &&
               cudaIpcGetMemHandle(&mine.h, ctx->x_local) == cudaSuccess;
     mine.ok = ok ? 1 : 0;
     // every rank takes part in the gather whatever happened locally, so that nobody waits for a missing peer
     std::string all((size_t)world * sizeof(Msg), '\0');
-    if (cudaMalloc(&gather, (size_t)(world + 1) * sizeof(Msg)) != cudaSuccess) { cudaGetLastError(); return; }
     cudaMemcpyAsync(gather + (size_t)world * sizeof(Msg), &mine, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream);
     int r = api().allgather(gather + (size_t)world * sizeof(Msg), gather, sizeof(Msg), NCCL_INT8, ctx->nccl_comm, ctx->stream);
     cudaMemcpyAsync(&all[0], gather, (size_t)world * sizeof(Msg), cudaMemcpyDeviceToHost, ctx->stream);
     ok = ok && r == 0 && cudaStreamSynchronize(ctx->stream) == cudaSuccess;
-    cudaFree(gather);
     const Msg *msgs = reinterpret_cast<const Msg *>(all.data());
     for (int p = 0; ok && p < world; ++p) ok = msgs[p].ok == 1;
     for (int p = 0; ok && p < world; ++p) {
@@ -103,13 +116,12 @@ void x_setup(rl_ctx *ctx) {
     cudaGetLastError();
     // consensus: the mailboxes are used only if every rank mapped every peer
     {
-        double *vote = nullptr, host = ok ? 1.0 : 0.0;
-        if (cudaMalloc(&vote, sizeof(double)) != cudaSuccess) { cudaGetLastError(); return; }
+        double host = ok ? 1.0 : 0.0;
         cudaMemcpyAsync(vote, &host, sizeof host, cudaMemcpyHostToDevice, ctx->stream);
         const int rr = api().allreduce(vote, vote, 1, NCCL_FLOAT64, NCCL_SUM, ctx->nccl_comm, ctx->stream);
         cudaMemcpyAsync(&host, vote, sizeof host, cudaMemcpyDeviceToHost, ctx->stream);
         const bool synced = cudaStreamSynchronize(ctx->stream) == cudaSuccess;
-        cudaFree(vote);
+        if (own_bufs) { cudaFree(vote); cudaFree(gather); }
         ok = ok && rr == 0 && synced && host == (double)world;
     }
     if (!ok) return;

@@ -1685,6 +1685,11 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     RL_REQUIRE(ctx, traj->env == env, "rl_rollout: trajectory belongs to another env");
     const uint64_t cap = bound.min_steps ? bound.min_steps + bound.slack_steps : 0;
     RL_REQUIRE(ctx, cap <= traj->T, "rl_rollout: min_steps + slack_steps exceeds the trajectory capacity");
+    // The Philox step index is 32 bits wide: past 2^32 steps per lane the (seed, lane, step) counters would recur and
+    // every reset state and action uniform would be replayed.  Fail instead of wrapping; rl_env_set_noise_philox
+    // with a fresh seed starts a new stream.
+    RL_REQUIRE(ctx, (uint64_t)env->noise.step_counter + cap + 1 <= 0xFFFFFFFFull,
+               "rl_rollout: the 32-bit Philox step counter of this env would wrap; reseed with rl_env_set_noise_philox");
     const rl_env_structure &es = env->structure;
     rl_mlp *net = actor->net;
     const bool seq_policy = actor->kind == RL_ACTOR_CATEGORICAL_POLICY && actor->seq_net != nullptr;

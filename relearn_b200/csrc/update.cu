@@ -1088,7 +1088,8 @@ __global__ void __launch_bounds__(256)
     __shared__ double cnt_part[8], loss_part[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int col = blockIdx.x * 32 + lane;
-    const bool skip = skip_flag && *skip_flag;
+    // (a timeout in an earlier reduction is sticky: nothing is written from then on, x_error_check reports it)
+    const bool skip = (skip_flag && *skip_flag) || *reinterpret_cast<const volatile int *>(x.error) != 0;
     double s = 0.0;
     if (col < W && !skip) {
 #pragma unroll 8
@@ -1135,17 +1136,20 @@ __global__ void __launch_bounds__(256)
         *f = seq;
     }
     // ---- wait for every source rank's message in the own mailbox ----
+    bool timed_out = false;
     if (lane < x.world) {
         const volatile unsigned long long *f = x.flag[x.rank] + (par * x.world + lane) * RL_X_BLOCKS + blockIdx.x;
         const long long t0 = clock64();
         while (*f != seq) {
             if (clock64() - t0 > 20000000000ll) {  // ~10 s: a peer never arrived
                 atomicExch(x.error, 1);
+                timed_out = true;
                 break;
             }
         }
     }
-    __syncwarp();
+    // a mailbox that never filled holds stale data: write neither the sums nor the Adam step
+    if (__any_sync(0xffffffffu, timed_out)) return;
     __threadfence_system();
     double tot = 0.0, Ntot = 0.0, ltot = 0.0;
     for (int src = 0; src < x.world; ++src) {
@@ -1192,6 +1196,29 @@ size_t pass_smem_bytes() {
     constexpr int H = 32 * UPL, P = H * F + H + A * H + A;
     const int nwarps = PASS_THREADS / 32;
     return (size_t)nwarps * P * sizeof(double) + (size_t)nwarps * 32 * 12 * sizeof(float);
+}
+
+// The two timing events of an update entry point: per context, created on first use (rl_ctx_destroy frees them).
+rl_status update_events(rl_ctx *ctx, cudaEvent_t *ev0, cudaEvent_t *ev1) {
+    for (int k = 0; k < 2; ++k)
+        if (!ctx->upd_ev[k]) RL_CUDA(ctx, cudaEventCreate(&ctx->upd_ev[k]));
+    *ev0 = ctx->upd_ev[0];
+    *ev1 = ctx->upd_ev[1];
+    return RL_OK;
+}
+
+// Data-parallel group: did a peer-mailbox wait time out (reduce_rows_x_kernel)?  From the failing reduction on every
+// launch of that kernel leaves sums and parameters untouched; the update entry points end with this check and report it.
+rl_status x_error_check(rl_ctx *ctx, const char *what) {
+    if (ctx->world <= 1 || !ctx->x_ok) return RL_OK;
+    int *host;
+    RL_TRY(rl_ctx_pinned(ctx, 64, (void **)&host));
+    RL_CUDA(ctx, cudaMemcpyAsync(host, ctx->x.error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*host)
+        return rl_fail(ctx, RL_ERR_NCCL, "%s: a rank of the data-parallel group never arrived at a reduction (peer mailbox wait timed out); "
+                       "sums and parameters were left untouched from that reduction on", what);
+    return RL_OK;
 }
 
 // rows of plan.partials -> plan.sums, summed over the data-parallel group: one fused kernel over the peer
@@ -1473,8 +1500,7 @@ rl_status trpo_update_generic(rl_ctx *ctx, int P, float *theta, const PassPlan &
     float *descent = (float *)(ex + 256 + 5 * vec_bytes);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_TRY(update_events(ctx, &ev0, &ev1));
         RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
     const float reg = (float)cfg->hpv_reg_coeff;
@@ -1512,10 +1538,10 @@ rl_status trpo_update_generic(rl_ctx *ctx, int P, float *theta, const PassPlan &
         stats->step_scale = host->step_scale; stats->num_backtracks = host->num_backtracks;
         stats->cg_iterations = host->cg_iters; stats->num_steps = (uint64_t)host->N;
         cudaEventElapsedTime(&stats->policy_update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
-    return (rl_status)host->status;
+    const rl_status trpo_status = (rl_status)host->status;  // (x_error_check reuses the pinned scratch)
+    RL_TRY(x_error_check(ctx, "TRPO update"));
+    return trpo_status;
 }
 
 // Recurrent module: plan with one block of RL_SEQ_BLOCK lanes per partial row, scratch for hbuf / dzbuf / logp0.
@@ -1692,8 +1718,7 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
     RL_TRY(make_plan(ctx, P, TE, &plan, (size_t)(n_steps + 1) * sizeof(double), (void **)&losses));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_TRY(update_events(ctx, &ev0, &ev1));
         RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
     PassArgs pa{};
@@ -1716,10 +1741,8 @@ rl_status rl_value_update(rl_traj *traj, const float *targets_dev, rl_mlp *value
         stats->num_steps = n_steps > 0 ? (uint64_t)host[n_steps] : 0;
         stats->opt_steps = (uint64_t)n_steps;
         cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
-    return RL_OK;
+    return x_error_check(ctx, "rl_value_update");
 }
 
 rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_fn, int32_t kernel, double *loss,
@@ -1784,8 +1807,7 @@ static rl_status policy_adam_update(rl_traj *traj, const float *adv_dev, rl_mlp 
     float *logp0 = (float *)(ex + loss_bytes);
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_TRY(update_events(ctx, &ev0, &ev1));
         RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
     PassArgs pa{};
@@ -1822,10 +1844,8 @@ static rl_status policy_adam_update(rl_traj *traj, const float *adv_dev, rl_mlp 
         stats->entropy = have && host[n_steps + 1] > 0 ? host[n_steps] / host[n_steps + 1] : 0.0;
         stats->opt_steps = (uint64_t)n_steps;
         cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
-    return RL_OK;
+    return x_error_check(ctx, "policy Adam update");
 }
 
 rl_status rl_ppo_update(rl_traj *traj, const float *adv_dev, rl_mlp *policy, rl_adam *adam, const rl_ppo_cfg *cfg,
@@ -1958,8 +1978,7 @@ rl_status rl_value_update_seq(rl_traj *traj, const float *targets_dev, rl_grunet
     a.target = targets_dev;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_TRY(update_events(ctx, &ev0, &ev1));
         RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
     AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
@@ -1981,10 +2000,8 @@ rl_status rl_value_update_seq(rl_traj *traj, const float *targets_dev, rl_grunet
         stats->num_steps = n_steps > 0 ? (uint64_t)host[n_steps] : 0;
         stats->opt_steps = (uint64_t)n_steps;
         cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
-    return RL_OK;
+    return x_error_check(ctx, "rl_value_update_seq");
 }
 
 rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cfg *cfg, rl_opt_stats *stats) {
@@ -2004,8 +2021,7 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
     rl_minibatch_dev mb{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (stats) {
-        RL_CUDA(ctx, cudaEventCreate(&ev0));
-        RL_CUDA(ctx, cudaEventCreate(&ev1));
+        RL_TRY(update_events(ctx, &ev0, &ev1));
         RL_CUDA(ctx, cudaEventRecord(ev0, ctx->stream));
     }
     AdamArgs ac{adam->cfg.learning_rate, adam->cfg.beta1, adam->cfg.beta2, adam->cfg.weight_decay, adam->cfg.eps};
@@ -2045,10 +2061,8 @@ rl_status rl_dqn_update(rl_replay *rb, rl_mlp *q, rl_adam *adam, const rl_dqn_cf
         stats->num_steps = m_last;
         stats->opt_steps = (uint64_t)n_steps;
         cudaEventElapsedTime(&stats->update_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
-    return RL_OK;
+    return x_error_check(ctx, "rl_dqn_update");
 }
 
 }  // extern "C"
