@@ -49,6 +49,18 @@ FLOP_ISSUED_PER_SAMPLE_CRITIC_TC = 28672
 K2C_NCU_DRAM_BYTES_PER_LAUNCH = 68096
 
 
+WORKLOAD = "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy: env step + policy act + sample + trajectory write)"
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` of the JSON line: the same keys and values in both arms (the reference arm runs a bounded sample of
+    this workload per step; cpu_baseline.sample says how much)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": args.envs, "horizon": args.horizon,
+            "env_steps_per_step": world * args.envs * args.horizon, "lanes_per_env": args.lanes,
+            "l2": "GPU arm: flushed between timed iterations (256 MiB memset)", "noise": "philox4x32-10",
+            "parallelism": f"dp{world} (lanes sharded, no collective)"}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -77,6 +89,7 @@ def cpu_update_baseline(n_steps: int, seed: int = 0):
     from oracle import tensor_oracle as TO
     from relearn_b200.modules import init_params
 
+    torch.set_num_threads(os.cpu_count() or 1)  # intra-op threads = all cores for updates
     rng = np.random.default_rng(seed)
     obs = rng.uniform(-1, 1, size=(n_steps, 5)).astype(np.float32)
     act = rng.integers(0, 2, n_steps)
@@ -110,7 +123,7 @@ class ClockSampler:
             os.close(fd)
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -184,19 +197,42 @@ def barrier(dist, ctx):
 # ------------------------------------------------------------------------------------------------
 # CPU arm (the reference's own CPU path, as the C oracle port)
 # ------------------------------------------------------------------------------------------------
-def cpu_rollout_rate(params: np.ndarray, lanes: int, horizon: int, threads: int, seed: int = 1, t0: int = 0):
+def cpu_rollout_rate(params: np.ndarray, lanes: int, horizon: int, threads: int, seed: int = 1, t0: int = 0, aten: bool = False):
+    """One period of `lanes` lanes x `horizon` steps on `threads` host threads.  aten = False: the C oracle port (scalar C
+    MLP); aten = True: the same env loop with PolicyActor::act as batch-1 ATen calls against libtorch_cpu.so
+    (oracle/aten_actor.cpp), the calls `tch` forwards the reference's actor to."""
     import ctypes as C
 
     import oracle as O
 
     cfg = O.cartpole_cfg(500)
-    mlp = O.mlp_struct(params, 5, 128, 2) if params is not None else None  # None: RandomAgent (env only)
     summ = O.Summary()
+    if aten:
+        p32 = np.ascontiguousarray(params, np.float32)
+        fn = O.aten_lib().ro_rollout_lanes_aten
+        t = time.perf_counter()
+        fn(C.byref(cfg), p32.ctypes.data_as(C.POINTER(C.c_float)), 5, 128, 2, lanes, 0, horizon, 0, seed, t0, threads, C.byref(summ))
+        dt = time.perf_counter() - t
+        return lanes * horizon / dt, dt, summ
+    mlp = O.mlp_struct(params, 5, 128, 2) if params is not None else None  # None: RandomAgent (env only)
     t = time.perf_counter()
     O.lib().ro_rollout_lanes_philox(C.byref(cfg), C.byref(mlp) if mlp is not None else None, lanes, 0, horizon, 0, seed, t0,
                                     threads, C.byref(summ))
     dt = time.perf_counter() - t
     return lanes * horizon / dt, dt, summ
+
+
+def cpu_aten_sample(params: np.ndarray, horizon: int, cores: int, budget_s: float):
+    """~budget_s seconds of the ATen-actor CPU rollout on all cores (a bounded sample: it runs ~20x slower than the port)."""
+    try:
+        rate, _, _ = cpu_rollout_rate(params, max(cores, 8), horizon, cores, aten=True)
+        lanes = int(max(cores, rate * budget_s / horizon))
+        v, dt, _ = cpu_rollout_rate(params, lanes, horizon, cores, t0=horizon + 1, aten=True)
+        return {"value": v, "unit": UNIT, "cores": cores, "kind": "port-aten",
+                "sample": f"{lanes} lanes x {horizon} steps ({dt:.1f} s wall), oracle env loop + batch-1 ATen linear/relu/linear/"
+                          f"log_softmax/exp/multinomial per env-step (libtorch_cpu.so), {cores} threads"}
+    except Exception as exc:  # no torch / no g++ on the box
+        return {"unavailable": repr(exc)[:200]}
 
 
 def run_reference(args):
@@ -220,13 +256,17 @@ def run_reference(args):
     dt = time.perf_counter() - t
     value = lanes * horizon * args.steps / dt
     sample = f"{lanes} lanes x {horizon} steps per step on {cores} threads (C oracle port of Steps::step + PolicyActor::act)"
+    # Two restatements of the reference's CPU path are timed: the scalar C port (above) and the batch-1 ATen actor the
+    # reference really calls through tch.  The line's value is the FASTER of the two, so the speed-up the driver computes
+    # from it is the conservative one.
+    kind = "port"
+    extra = {"aten": cpu_aten_sample(params, horizon, cores, 5.0)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 dynamics / f32 policy", "data": "synthetic",
-        "config": {"workload": "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy)",
-                   "envs_per_step": lanes, "horizon": horizon, "host": "cpu"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -271,11 +311,13 @@ def run_ours(args):
         if timed_events is not None:
             timed_events[1].record()
 
+    # clocks / throttle reasons are sampled every 20 ms from the warm-up to the end of the e2e loop (the device-timed
+    # region alone lasts ~16 ms at the default 100 steps)
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(max(args.warmup, 3)):
         one_period()
     barrier(dist, ctx)
-    clocks = ClockSampler(local)
-    clocks.start()
     evs = [(ctx.event(), ctx.event()) for _ in range(args.steps)]
     launches0 = ctx.launch_count
     barrier(dist, ctx)
@@ -287,7 +329,6 @@ def run_ours(args):
     launches = ctx.launch_count - launches0
     kernel_ms = sum(a.elapsed_ms(b) for a, b in evs)
     total_ms = max_over_ranks(dist, local, kernel_ms)
-    clock_info = clocks.stop()
     steps_per_period = E * T
     value = world * steps_per_period * args.steps / (total_ms * 1e-3)
 
@@ -305,36 +346,45 @@ def run_ours(args):
         if k >= max(3, min(args.warmup, 5)):
             e2e_s += dt
     e2e_s = max_over_ranks(dist, local, e2e_s)
+    clock_info = clocks.stop()
     e2e_value = world * steps_per_period * args.steps / e2e_s
     h2d = int(params.nbytes)
     d2h = 10 * 8
 
-    # ---- roofline of the dominant kernel (fused rollout: trajectory write stream) ----
+    # ---- roofline of the dominant kernel.  SURVEY 8(d) row K2: the fused rollout is bound by the FP32 FMA pipe / the
+    #      latency of its dependent step chain, NOT by HBM (26 B of trajectory per env-step); the roof it is reported
+    #      against is the measured FP32 FMA peak, and the HBM figure is given for the write stream only. ----
     hbm_peak, peak_src = measured_peaks()
-    achieved = B_PER_STEP_ROLLOUT * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+    write_gbs = B_PER_STEP_ROLLOUT * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e9
+    fp32_peak = ctx.fp32_peak_tflops() if rank == 0 else None
+    policy_tflops = FLOP_PER_STEP_POLICY * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e12
+    roofline = {"bound": "fp32-fma / step-chain latency (SURVEY 8d row K2; not hbm)", "achieved": policy_tflops,
+                "peak": fp32_peak, "unit": "TFLOP/s", "frac": (policy_tflops / fp32_peak) if fp32_peak else None,
+                "peak_source": "FFMA probe kernel timed in this run (rl_ctx_fp32_peak)",
+                "flop_per_env_step": FLOP_PER_STEP_POLICY,
                 "traffic": K2C_NCU_DRAM_BYTES_PER_LAUNCH if (E == 4096 and T == 256) else None,
-                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s13); trajectory is L2-resident during the kernel",
-                "peak_source": peak_src, "kernel": "rollout_cartpole_ws_kernel K2w (fused step+policy+sample; policy and dynamics on different warps)",
-                "note": "K2w moves 26 B of trajectory per env-step, so HBM is not its bound: at 4096 envs the period is 256 x the latency of the dynamics warp's dependent f64 step (~1200 clk, DESIGN section 4); the HBM-bound kernels of the path are in kernels[] (77-81 % of peak)"}
+                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s13).  The 27 MB trajectory of a period stays in "
+                                "the 126 MB L2 while the kernel runs; its write-back to HBM happens in the untimed L2 flush "
+                                "between iterations, i.e. OUTSIDE the timed region",
+                "hbm_write_stream": {"achieved": write_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": write_gbs / hbm_peak,
+                                     "bytes_per_env_step": B_PER_STEP_ROLLOUT, "peak_source": peak_src},
+                "kernel": "rollout_cartpole_ws_kernel K2w (fused step+policy+sample; policy and dynamics on different warps)",
+                "note": "at 4096 envs (28 per SM) the period is 256 x the latency of one step chain (~1200 clk: policy warps' hidden "
+                        "layer + the dynamics warp's dependent f64 step, profiles/r2_summary.md); no pipe is busy (ncu: FMA 23 %, "
+                        "FP64 9 %, issue 40 %).  The HBM-bound kernels of the path are in kernels[] (77-81 % of the HBM peak)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 dynamics / f32 policy", "data": "synthetic",
-        "config": {"workload": "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy, fused)",
-                   "envs_per_gpu": E, "horizon": T, "env_steps_per_step": world * steps_per_period,
-                   "lanes_per_env": args.lanes, "l2": "flushed between timed iterations (256 MiB memset)",
-                   "noise": "philox4x32-10", "parallelism": f"dp{world} (lanes sharded, no collective)"},
+        "config": workload_config(args, world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "what": "rl_mlp_set_weights_async(pinned host) + rl_rollout + StepsSummary read-back per period"},
         "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline,
         "wall_s_timed_region": wall, "sm_count": info["sm_count"],
     }
 
-    if rank == 0 and not args.quick:
-        fp32_peak = ctx.fp32_peak_tflops()
-        line["fp32"] = {"policy_tflops": FLOP_PER_STEP_POLICY * steps_per_period * args.steps / (kernel_ms * 1e-3) / 1e12,
-                        "measured_fma_peak_tflops": fp32_peak}
+    if rank == 0:
+        line["fp32"] = {"policy_tflops": policy_tflops, "measured_fma_peak_tflops": fp32_peak}
     # ---- the update that consumes the rollout: GAE + TRPO + critic (ms per iteration) ----
     if not args.no_update:
         upd = {"adv_est_ms": [], "policy_ms": [], "critic_ms": [], "status": []}
@@ -368,11 +418,19 @@ def run_ours(args):
                            if ctx.comm_peer_info()["peer_mailboxes"] else "reduce + ncclAllReduce (f64 sums)"),
             # the critic's 80 passes + Adam steps as one region: the network's own FLOPs per second (compare with the
             # FP32 FMA peak, which bounds any non-tensor implementation) and the bf16 FLOPs the MMAs issue
-            "critic_roofline": {"bound": "tensor", "achieved": issued, "peak": tpeak, "unit": "TFLOP/s", "frac": issued / tpeak,
-                                "peak_source": tpeak_src, "algorithmic_tflops": alg, "fp32_fma_peak_tflops": fp32_peak,
-                                "note": "achieved = bf16 FLOPs issued by the three MMAs per tile (pieces + padding, 28 672 per "
-                                        "sample); algorithmic_tflops = 4608 FLOP per sample per iteration of the f32 network"},
+            "critic_roofline": {"bound": "tensor", "achieved": alg, "peak": tpeak, "unit": "TFLOP/s", "frac": alg / tpeak,
+                                "peak_source": tpeak_src, "issued_bf16_tflops": issued, "fp32_fma_peak_tflops": fp32_peak,
+                                "note": "achieved = ALGORITHMIC FLOPs (4608 per sample per Adam iteration of the f32 network, SURVEY 8d "
+                                        "row K6) / time; issued_bf16_tflops = what the three MMAs issue per tile (bf16 pieces + "
+                                        "padding, 28 672 per sample)"},
         }
+    # ---- driver-visible correctness of the data-parallel update, and BASELINE configs 3 / 4 at this world size ----
+    if not args.no_update and not args.quick:
+        if world > 1:
+            par = update_parity(ctx, R, L, args, rank, world, dist, local, params, vparams)
+            line["update"]["parity_vs_single"] = par
+            assert par["params_identical_across_ranks"], "ranks hold different parameters after a data-parallel update"
+        line["configs"] = scaled_configs(ctx, R, L, hbm_peak, rank, world, dist, local)
     # ---- per-kernel rooflines for the HBM-bound kernels (rank 0, 1 GPU only) ----
     if rank == 0 and world == 1 and not args.quick:
         line["kernels"] = kernel_rooflines(ctx, R, L, hbm_peak)
@@ -393,11 +451,12 @@ def run_ours(args):
             _, dt, _ = cpu_rollout_rate(None, E, T, cores, t0=env_periods * (T + 1))
             env_s += dt
             env_periods += 1
+        line["cpu_baseline"]["aten"] = cpu_aten_sample(params, T, cores, 5.0)
         line["cpu_baseline"]["env_only"] = {"value": env_periods * E * T / env_s, "unit": UNIT,
                                             "sample": f"{env_periods} periods of {E} lanes x {T} steps, RandomAgent, {cores} threads"}
         if not args.no_update:
             try:
-                line["update"]["cpu_baseline"] = cpu_update_baseline(1 << 16)
+                line["update"]["cpu_baseline"] = cpu_update_baseline(steps_per_period if args.cpu_update_full else 1 << 16)
             except Exception as exc:  # torch missing on the box: report, do not fail the bench
                 line["update"]["cpu_baseline"] = {"unavailable": repr(exc)[:200]}
     if rank == 0:
@@ -486,25 +545,31 @@ def kernel_rooflines(ctx, R, L, hbm_peak):
             # bf16 FLOPs the MMAs issue: [128 x 48] . [48 x 128] per 128 env-steps
             rec["mma_bf16_tflops"] = 2 * 48 * 128 * E3 * T3 / (ms * 1e-3) / 1e12
         out.append(rec)
-    out += other_configs(ctx, R, L, hbm_peak)
+    out += rl2_sized_rollout(ctx, R, L)
     return out
 
 
-def other_configs(ctx, R, L, hbm_peak):
-    """BASELINE configs 3 and 4 at their per-GPU sizes (timed alone, CUDA events): DQN collection + replay append +
-    update at 65 536 envs, and the bandit meta-env with the rnn.rs-sized GRU policy at 131 072 envs."""
+def scaled_configs(ctx, R, L, hbm_peak, rank, world, dist, local):
+    """BASELINE configs 3 and 4, run by EVERY rank (any world size; timed alone with CUDA events, max over ranks):
+    config 3 cartpole-dqn: 65 536 envs in total, sharded over the ranks, each rank with the replay rings of its own lanes
+    (one ReplayBuffer per worker, dqn.rs:228-230), minibatch_steps / world sampled locally and the Q-loss gradient
+    reduced over the group in every Adam step; config 4: the bandit meta-env with the rnn.rs-sized GRU policy at
+    131 072 envs per GPU (1 048 576 on 8) and the GAE + TRPO + critic update through the GRU with reduced sums."""
     out = []
     rng = np.random.default_rng(3)
-    # ---- config 3: cartpole-dqn, 65 536 envs ----
-    E, cfg = 65536, R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
-    env = R.build_env(ctx, cfg, E, seed=5)
-    agent = R.DqnConfig(buffer_capacity=762).build_agent(env)  # 50 M steps of replay per GPU (examples/cartpole-dqn.rs:34-42)
+    mx = lambda v: max_over_ranks(dist, local, float(v))
+    # ---- config 3: cartpole-dqn, 65 536 envs over the group ----
+    E_total = 65536
+    E, cfg = E_total // world, R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    env = R.build_env(ctx, cfg, E, seed=5, lane_offset=rank * E)
+    agent = R.DqnConfig(buffer_capacity=762).build_agent(env)  # 50 M steps of replay over the group (examples/cartpole-dqn.rs:34-42)
     agent.action_value_fn.set_weights(R.init_params(rng, 5, 128, 2))
     rb = agent.buffer()
     bound = R.HistoryDataBound(16, 5)  # first update: 1 M steps over 65 536 lanes
     traj = R.Trajectory(env, bound.min_steps + bound.slack_steps)
     times = {"rollout_ms": [], "append_ms": [], "update_ms": []}
     for it in range(4):
+        barrier(dist, ctx)
         e0 = ctx.event().record()
         R.rollout(env, agent.actor(), bound, traj, want_summary=False)
         e1 = ctx.event().record()
@@ -517,17 +582,19 @@ def other_configs(ctx, R, L, hbm_peak):
             times["update_ms"].append(stats.update_ms)
     st = rb.stats()
     steps = traj.view().num_steps
-    app_ms = float(np.mean(times["append_ms"]))
-    out.append({"kernel": "config 3 cartpole-dqn: eps-greedy rollout + replay append + 50 x (sample 100k, Q loss, Adam)",
-                "envs": E, "steps_per_period": int(steps), "rollout_ms": float(np.mean(times["rollout_ms"])),
-                "append_ms": app_ms, "append_gbs": 2 * 26 * steps / (app_ms * 1e-3) / 1e9,
-                "dqn_update_50_steps_ms": float(np.mean(times["update_ms"])), "replay_steps": int(st.num_steps),
-                "replay_episodes": int(st.num_episodes)})
+    app_ms = mx(np.mean(times["append_ms"]))
+    qhash = params_identical(dist, agent.action_value_fn.get_weights())
+    out.append({"config": "3 cartpole-dqn: eps-greedy rollout + replay append + 50 x (sample 100k over the group, Q loss, Adam)",
+                "envs_total": E_total, "envs_per_gpu": E, "steps_per_period_per_gpu": int(steps),
+                "rollout_ms": mx(np.mean(times["rollout_ms"])), "append_ms": app_ms,
+                "append_gbs_per_gpu": 2 * 26 * steps / (app_ms * 1e-3) / 1e9,
+                "dqn_update_50_steps_ms": mx(np.mean(times["update_ms"])), "replay_steps_per_gpu": int(st.num_steps),
+                "replay_episodes_per_gpu": int(st.num_episodes), "q_params_identical_across_ranks": qhash})
     traj.close(); rb.close(); env.close()
     # ---- config 4: bandit meta-env (k = 2 arms, n = 10 episodes per trial) + GRU(6 -> 4) -> Linear(4 -> 2) ----
     E4, trials = 131072, 10
     mcfg = R.MetaEnv(R.UniformBernoulliBandits(2), 10)
-    env4 = R.build_env(ctx, mcfg, E4, seed=6)
+    env4 = R.build_env(ctx, mcfg, E4, seed=6, lane_offset=rank * E4)
     net = R.GruLinear(ctx, env4.num_features, 4, env4.num_actions)
     net.set_weights(R.init_gru_linear_params(rng, env4.num_features, 4, env4.num_actions))
     T4 = trials * 19
@@ -536,15 +603,16 @@ def other_configs(ctx, R, L, hbm_peak):
     for _ in range(2):
         R.rollout(env4, spec, R.HistoryDataBound(T4, 0), traj4, want_summary=False)
     reps = 5
+    barrier(dist, ctx)
     e0 = ctx.event().record()
     for _ in range(reps):
         R.rollout(env4, spec, R.HistoryDataBound(T4, 0), traj4, want_summary=False)
     e1 = ctx.event().record()
-    ms = e0.elapsed_ms(e1) / reps
+    ms = mx(e0.elapsed_ms(e1) / reps)
     bytes_per_step = 4 * env4.num_features + 6  # obs planes + action + reward + succ
-    out.append({"kernel": "config 4 bandit meta-env + GRU(6->4)->Linear policy, fused rollout (thread per env)", "envs": E4,
-                "horizon": T4, "ms": ms, "env_steps_per_s": E4 * T4 / (ms * 1e-3), "bytes_per_step": bytes_per_step,
-                "trajectory_write_gbs": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9,
+    out.append({"config": "4 bandit meta-env + GRU(6->4)->Linear policy, fused rollout (thread per env)", "envs_total": E4 * world,
+                "envs_per_gpu": E4, "horizon": T4, "ms": ms, "env_steps_per_s": world * E4 * T4 / (ms * 1e-3),
+                "bytes_per_step": bytes_per_step, "trajectory_write_gbs_per_gpu": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak": bytes_per_step * E4 * T4 / (ms * 1e-3) / 1e9 / hbm_peak})
     traj4.close()
     # the update that consumes it: GAE + TRPO + 80-step critic through Chain<Gru, Linear> on one trial per lane (T = 19)
@@ -557,6 +625,7 @@ def other_configs(ctx, R, L, hbm_peak):
     upd = []
     for it in range(3):
         R.rollout(env4, agent4.actor(), R.HistoryDataBound(19, 0), traj5, want_summary=False)
+        barrier(dist, ctx)
         e0 = ctx.event().record()
         adv = agent4.critic.advantages(traj5)
         e1 = ctx.event().record()
@@ -565,11 +634,72 @@ def other_configs(ctx, R, L, hbm_peak):
         cs = agent4.critic.update(traj5, log)
         if it > 0:
             upd.append((e0.elapsed_ms(e1), log["policy/update_time"] * 1e3, cs.update_ms))
-    out.append({"kernel": "config 4 update: GAE + TRPO + 80-step critic through GRU(6->4)->Linear (BPTT pass kernel)", "envs": E4,
-                "batch_steps": E4 * 19, "adv_est_ms": float(np.mean([u[0] for u in upd])),
-                "trpo_policy_ms": float(np.mean([u[1] for u in upd])), "critic_80_adam_ms": float(np.mean([u[2] for u in upd]))})
+    ghash = params_identical(dist, np.concatenate([agent4.policy.policy_fn.get_weights(), agent4.critic.state_value_fn.get_weights()]))
+    out.append({"config": "4 update: GAE + TRPO + 80-step critic through GRU(6->4)->Linear (BPTT pass kernel), sums reduced over the group",
+                "envs_per_gpu": E4, "batch_steps_per_gpu": E4 * 19, "adv_est_ms": mx(np.mean([u[0] for u in upd])),
+                "trpo_policy_ms": mx(np.mean([u[1] for u in upd])), "critic_80_adam_ms": mx(np.mean([u[2] for u in upd])),
+                "params_identical_across_ranks": ghash})
     traj5.close(); env4.close()
-    # ---- config 4, rl2-sized: k = 10 arms, n = 100 episodes per trial, GRU(14 -> 128) -> Linear(128 -> 10) (K8h) ----
+    return out
+
+
+def params_identical(dist, params: np.ndarray):
+    """Every rank must hold bit-identical parameters after a data-parallel update (the reduced sums are identical on
+    every rank by construction; no broadcast happens).  True / False from an all-gather of a digest; None on one GPU."""
+    if dist is None:
+        return None
+    import hashlib
+
+    digest = hashlib.sha1(np.ascontiguousarray(params).tobytes()).hexdigest()
+    digests = [None] * dist.get_world_size()
+    dist.all_gather_object(digests, digest)
+    return all(d == digests[0] for d in digests)
+
+
+def update_parity(ctx, R, L, args, rank, world, dist, local, params, vparams):
+    """Driver-visible correctness of the data-parallel update (world > 1): one GAE + TRPO + critic update on this bench's
+    own per-GPU batch (E x T env-steps per rank, lanes rank*E ..) with the sums reduced over the group, against rank 0
+    re-running the same update on the CONCATENATED batch (world x E lanes, no communicator) on its own GPU.  The
+    rollouts agree bit for bit (Philox is keyed by the global lane; both sides run the warp-specialised kernel)."""
+    E, T, seed = args.envs, args.horizon, 4321
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+
+    def run(context, n_lanes, offset):
+        env = R.build_env(context, cfg, n_lanes, seed=seed, lane_offset=offset)
+        # hpv_reg_coeff 0.1: ten f32 CG iterations stay well conditioned, so the comparison measures the reduction and not
+        # the amplification of rounding by the reference's own 1e-5 (tests/test_gpu_update.py quantifies that)
+        pcfg = R.TrpoConfig(optimizer_config=R.ConjugateGradientOptimizerConfig(hpv_reg_coeff=0.1))
+        agent = R.ActorCriticConfig(policy_config=pcfg).build_agent(env)
+        agent.policy.policy_fn.set_weights(params)
+        agent.critic.state_value_fn.set_weights(vparams)
+        traj = R.Trajectory(env, T)
+        R.rollout(env, agent.actor(L.RL_LANES_WARP_SPECIALIZED), R.HistoryDataBound(T, 0), traj, want_summary=False)
+        log = {}
+        status = agent.batch_update(traj, log)
+        p, v = agent.policy.policy_fn.get_weights(), agent.critic.state_value_fn.get_weights()
+        traj.close(); env.close()
+        return p, v, int(status), log
+
+    p_s, v_s, st_s, log_s = run(ctx, E, rank * E)
+    same = params_identical(dist, np.concatenate([p_s, v_s]))
+    res = {"params_identical_across_ranks": same, "num_steps_group": int(log_s["num_steps"])}
+    if rank == 0:
+        solo = R.Context(local)  # no communicator: the whole batch on one GPU
+        p_f, v_f, st_f, log_f = run(solo, E * world, 0)
+        rel = lambda a, b, base: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b.astype(np.float64) - base), 1e-30))
+        res.update({"max_rel": max(rel(p_s, p_f, params), rel(v_s, v_f, vparams)), "policy_delta_rel": rel(p_s, p_f, params),
+                    "critic_delta_rel": rel(v_s, v_f, vparams), "num_steps_single": int(log_f["num_steps"]),
+                    "status": [st_s, st_f], "num_backtracks": [int(log_s["num_backtracks"]), int(log_f["num_backtracks"])],
+                    "hpv_reg_coeff": 0.1,
+                    "what": f"one GAE+TRPO+critic update on {world} x {E * T} env-steps with reduced sums vs the same update on the "
+                            f"concatenated {world * E * T}-step batch on one GPU; rel = |delta_group - delta_single| / |delta_single|"})
+        solo.close() if hasattr(solo, "close") else None
+    return res
+
+
+def rl2_sized_rollout(ctx, R, L):
+    """config 4, rl2-sized: k = 10 arms, n = 100 episodes per trial, GRU(14 -> 128) -> Linear(128 -> 10) (K8h); one GPU."""
+    rng = np.random.default_rng(4)
     E6, T6 = 148 * 64 * 2, 199
     env6 = R.build_env(ctx, R.MetaEnv(R.UniformBernoulliBandits(10), 100), E6, seed=7)
     net6 = R.GruLinear(ctx, env6.num_features, 128, env6.num_actions)
@@ -584,13 +714,69 @@ def other_configs(ctx, R, L, hbm_peak):
     ms = e0.elapsed_ms(e1) / 3
     flop = 2 * 3 * 128 * (env6.num_features + 128) + 2 * 128 * env6.num_actions
     fp32_peak = ctx.fp32_peak_tflops()
-    out.append({"kernel": "config 4 rl2-sized: bandit meta-env (10 arms x 100 episodes) + GRU(14->128)->Linear(128->10), fused rollout "
-                          "K8h (64-env tiles, FP32 FFMA2 GEMM per step, weights streamed by cp.async.bulk)",
-                "envs": E6, "horizon": T6, "ms": ms, "env_steps_per_s": E6 * T6 / (ms * 1e-3), "flop_per_env_step": flop,
-                "fp32_tflops": flop * E6 * T6 / (ms * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
-                "frac_of_fp32_peak": flop * E6 * T6 / (ms * 1e-3) / 1e12 / fp32_peak})
+    rec = {"kernel": "config 4 rl2-sized: bandit meta-env (10 arms x 100 episodes) + GRU(14->128)->Linear(128->10), fused rollout "
+                     "K8h (64-env tiles, FP32 FFMA2 GEMM per step, weights streamed by cp.async.bulk)",
+           "envs": E6, "horizon": T6, "ms": ms, "env_steps_per_s": E6 * T6 / (ms * 1e-3), "flop_per_env_step": flop,
+           "fp32_tflops": flop * E6 * T6 / (ms * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
+           "frac_of_fp32_peak": flop * E6 * T6 / (ms * 1e-3) / 1e12 / fp32_peak}
     traj6.close(); env6.close()
-    return out
+    return [rec]
+
+
+def run_sweep(args):
+    """BASELINE config 5: rollout throughput of the config-2 env + policy over E_total = 2^10 .. 2^24 envs sharded over the
+    ranks, T = 512 steps per lane where the trajectory fits (else the largest power of two whose trajectory stays under
+    ~60 GB per GPU; the line says which), fused kernel picked by lanes_per_env = 0, plus the unfused step kernel (K1).
+    One JSON line per E on stdout (rank 0)."""
+    import relearn_b200 as R
+    from relearn_b200 import _lib as L
+
+    rank, world, local, dist = dist_setup()
+    ctx = R.Context(local)
+    cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
+    net = R.Mlp(ctx, 5, [128], 2)
+    net.set_weights(R.init_params(np.random.default_rng(0), 5, 128, 2))
+    for lg in range(10, 25, 2):
+        E_total = 1 << lg
+        if E_total < world:
+            continue
+        E = E_total // world
+        T = 512
+        while E * T * 52 > 60e9 and T > 8:  # obs + next_obs planes, action, reward, succ
+            T //= 2
+        env = R.build_env(ctx, cfg, E, seed=1, lane_offset=rank * E)
+        traj = R.Trajectory(env, T)
+        spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net, lanes_per_env=0)
+        bound = R.HistoryDataBound(T, 0)
+        for _ in range(2):
+            R.rollout(env, spec, bound, traj, want_summary=False)
+        reps = 5 if E * T <= (1 << 28) else 2
+        barrier(dist, ctx)
+        e0 = ctx.event().record()
+        for _ in range(reps):
+            R.rollout(env, spec, bound, traj, want_summary=False)
+        e1 = ctx.event().record()
+        ms = max_over_ranks(dist, local, e0.elapsed_ms(e1) / reps)
+        # unfused step kernel (K1) on the same lanes: one launch per step, actions resident
+        env.reset_all()
+        actions = ctx.to_device(np.random.default_rng(0).integers(0, 2, E).astype(np.uint8))
+        for _ in range(3):
+            env.step_device(actions)
+        ksteps = 20
+        barrier(dist, ctx)
+        e0 = ctx.event().record()
+        for _ in range(ksteps):
+            env.step_device(actions)
+        e1 = ctx.event().record()
+        ms1 = max_over_ranks(dist, local, e0.elapsed_ms(e1) / ksteps)
+        if rank == 0:
+            emit({"sweep": "config 5", "n_gpus": world, "envs_total": E_total, "envs_per_gpu": E, "horizon": T,
+                  "fused_ms_per_period": ms, "fused_env_steps_per_s": E_total * T / (ms * 1e-3),
+                  "unfused_ms_per_step": ms1, "unfused_env_steps_per_s": E_total / (ms1 * 1e-3),
+                  "unfused_gbs_per_gpu": B_PER_STEP_UNFUSED * E / (ms1 * 1e-3) / 1e9})
+        traj.close(); env.close()
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 _REAL_STDOUT = None
@@ -624,8 +810,13 @@ def main():
     ap.add_argument("--update-iters", type=int, default=3)
     ap.add_argument("--no-update", action="store_true")
     ap.add_argument("--quick", action="store_true", help="skip the per-kernel rooflines and the CPU baseline")
+    ap.add_argument("--cpu-update-sample", dest="cpu_update_full", action="store_false",
+                    help="time the CPU update baseline on a 65 536-step sample instead of the full batch")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: rollout throughput over E = 2^10 .. 2^24 (see run_sweep)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

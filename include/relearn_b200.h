@@ -422,11 +422,14 @@ rl_status rl_reinforce_update(rl_traj *traj, const float *adv_dev, rl_mlp *polic
 /* ------------------------------------------------------------------------------------------ */
 /* Tabular Q (BaseTabularQLearningAgent src/agents/tabular.rs:84-232)                           */
 /* One table per replica; a replica folds its own lane's steps in order (bit-exact f64/u64).     */
+/* num_replicas = 1 with E > 1 lanes = the reference under train_parallel: every lane acts from  */
+/* the one table and rl_tabq_update folds lane 0, lane 1, ... into it in order (train.rs:98-186).*/
 /* ------------------------------------------------------------------------------------------ */
 rl_status rl_tabq_create(rl_ctx *ctx, uint64_t num_replicas, int32_t num_observations, int32_t num_actions,
                          double discount_factor, rl_tabq **out);
 rl_status rl_tabq_destroy(rl_tabq *t);
-/* BatchUpdate::batch_update: replica r folds lane r of the trajectory (tabular.rs:197-207). */
+/* BatchUpdate::batch_update: replica r folds lane r of the trajectory; a single shared table folds every lane in
+ * lane order (tabular.rs:197-207). */
 rl_status rl_tabq_update(rl_tabq *t, rl_traj *traj);
 /* q: f64 [R][S][A], counts: u64 [R][S][A] (host) */
 rl_status rl_tabq_get_table(rl_tabq *t, double *q_host, uint64_t *counts_host);

@@ -139,6 +139,8 @@ class Actor(C.Structure):
         ("q_table", C.POINTER(C.c_double)),
         ("n_obs", C.c_int),
         ("n_act", C.c_int),
+        ("act_fn", C.c_void_p),
+        ("act_ud", C.c_void_p),
     ]
 
 
@@ -195,6 +197,37 @@ class TabQ(C.Structure):
 
 
 _lib = None
+_aten = None
+_SO_ATEN = os.path.join(_HERE, "librelearn_oracle_aten.so")
+
+
+def build_aten(force: bool = False) -> str:
+    """Compile the ATen-actor variant of the CPU rollout baseline (``make -C oracle aten``): the oracle's env loop
+    with ``PolicyActor::act`` as batch-1 ATen calls against the torch wheel's libtorch_cpu.so (BASELINE.md section 2)."""
+    build(force)
+    src = os.path.join(_HERE, "aten_actor.cpp")
+    stale = force or not os.path.exists(_SO_ATEN) or os.path.getmtime(_SO_ATEN) < max(os.path.getmtime(src), os.path.getmtime(_SO))
+    if stale:
+        r = subprocess.run(["make", "-C", _HERE, "aten"], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building oracle/aten_actor.cpp failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    return _SO_ATEN
+
+
+def aten_lib() -> C.CDLL:
+    """ctypes handle of librelearn_oracle_aten.so (ro_rollout_lanes_aten); imports torch first so that the wheel's
+    shared libraries are the ones already loaded."""
+    global _aten
+    if _aten is None:
+        import torch  # noqa: F401
+
+        lib()
+        A = C.CDLL(build_aten())
+        A.ro_rollout_lanes_aten.restype = C.c_uint64
+        A.ro_rollout_lanes_aten.argtypes = [C.POINTER(EnvCfg), C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                            C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(Summary)]
+        _aten = A
+    return _aten
 
 
 def lib() -> C.CDLL:

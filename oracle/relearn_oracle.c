@@ -573,6 +573,8 @@ static uint64_t actor_act(ro_actor *a, const ro_env *env, const ro_state *st, co
         if (a->training && ro_gen_f64(rng, RO_STREAM_ACTOR) < a->exploration_rate)
             return ro_gen_range(rng, RO_STREAM_ACTOR, (uint64_t)a->n_act);
         return (uint64_t)ro_argmax_f64(a->q_table + ro_env_observe_index(env, st) * a->n_act, a->n_act);
+    case RO_ACTOR_CALLBACK:
+        return a->act_fn(a->act_ud, obs, ro_env_num_features(env));
     }
     return 0;
 }

@@ -179,7 +179,8 @@ enum {
     RO_ACTOR_RANDOM = 1,         /* action_space.sample(rng) = gen_range(0..A) (index.rs:66) */
     RO_ACTOR_POLICY = 2,         /* PolicyActor::act (policies/actor.rs:42-55) */
     RO_ACTOR_EPS_GREEDY_Q = 3,   /* DqnActor::act (dqn.rs:360-379) */
-    RO_ACTOR_TABULAR = 4         /* tabular.rs:222-232 */
+    RO_ACTOR_TABULAR = 4,        /* tabular.rs:222-232 */
+    RO_ACTOR_CALLBACK = 5        /* act_fn(act_ud, obs, F): an externally evaluated policy (oracle/aten_actor.cpp) */
 };
 typedef struct ro_actor {
     int kind;
@@ -188,6 +189,7 @@ typedef struct ro_actor {
     double exploration_rate;                                 /* EPS_GREEDY_Q / TABULAR */
     int training;                                            /* TABULAR: ActorMode::Training */
     const double *q_table; int n_obs, n_act;                 /* TABULAR (row-major [S,A]) */
+    uint64_t (*act_fn)(void *ud, const float *obs, int n_features); void *act_ud; /* CALLBACK */
 } ro_actor;
 
 /* ------------------------------------------------------------------ */

@@ -8,7 +8,9 @@ from .envs import (BatchedEnv, CartPole, CartPoleConfig, Chain, LatentStepLimit,
                    TrialEpisodeLimit, UniformBernoulliBandits, VisibleStepLimit, build_env)
 from .modules import (GruLinear, GruLinearConfig, Mlp, MlpConfig, init_gru_linear_params, init_params)  # noqa: F401
 from .runtime import Context, DeviceBuffer  # noqa: F401
-from .simulation import ActorSpec, HistoryDataBound, Trajectory, rollout  # noqa: F401
+from .simulation import (ActorSpec, HistoryDataBound, TrainParallelConfig, Trajectory, rollout, train_device,  # noqa: F401
+                         train_serial)
+from .logging import DisplayLogger, HistoryLogger, NullLogger, StatsLogger  # noqa: F401
 
 __version__ = "0.1.0"
 from .agents import TabularQ  # noqa: F401,E402

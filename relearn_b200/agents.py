@@ -12,7 +12,13 @@ from .simulation import ActorSpec, Trajectory
 
 
 class TabularQ:
-    """BaseTabularQLearningAgent (src/agents/tabular.rs:84-232), one table per replica (= lane)."""
+    """BaseTabularQLearningAgent (src/agents/tabular.rs:84-232).
+
+    `num_replicas = 1` over an env with E > 1 lanes is the reference under `train_parallel`: every lane (worker) acts
+    from the one shared table, frozen while a period runs, and `batch_update` folds the lanes' buffers into it one after
+    the other in lane order (tabular.rs:197-207) -- bit-identical to the reference's sequential fold.
+    `num_replicas = E` trains E INDEPENDENT agents, one table per lane, each seeing only its own lane's data: replicas
+    for sweeps, not a faster way to train one agent (sample efficiency per table is that of a single worker)."""
 
     def __init__(self, ctx: Context, num_replicas: int, num_observations: int, num_actions: int,
                  discount_factor: float, exploration_rate: float = 0.2):
@@ -40,11 +46,17 @@ class TabularQ:
         return ActorSpec(kind=L.RL_ACTOR_TABULAR_EPS_GREEDY, table=self, exploration_rate=self.exploration_rate,
                          training=training)
 
-    def update(self, traj: Trajectory):
+    def update(self, traj: Trajectory, logger=None):
         """BatchUpdate::batch_update (tabular.rs:197-207)."""
         L.check(self._lib.rl_tabq_update(self.handle, traj.handle), self.ctx.handle)
 
     batch_update = update
+
+    def min_update_size(self):
+        """tabular.rs:190-195: one step (the training loop's min_worker_steps sets the period)."""
+        from .simulation import HistoryDataBound
+
+        return HistoryDataBound(1, 0)
 
     def get_table(self):
         q = np.empty(self.shape, np.float64)

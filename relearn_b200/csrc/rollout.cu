@@ -36,6 +36,7 @@ struct RolloutArgs {
     double eps;
     int training;
     const double *qtable;
+    uint64_t qtable_lane_stride;  // S * A with one table per lane, 0 with one table shared by every lane (tabular.rs:148-156)
     int S, A, F;
     double *partials;  // f64 [gridDim.x][ST_COUNT]
     int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
@@ -212,7 +213,7 @@ __device__ __forceinline__ uint32_t actor_act(const RolloutArgs &a, const typena
     case RL_ACTOR_TABULAR_EPS_GREEDY: {  // tabular.rs:222-232
         if (a.training && rl_u64_to_f64(nz.template next_u64<RL_STREAM_ACTOR>()) < a.eps)
             return rl_gen_range<REPLAY, RL_STREAM_ACTOR>(nz, (uint32_t)a.A);
-        const double *row = a.qtable + ((uint64_t)e * a.S + EnvT::observe_index(p, s)) * a.A;
+        const double *row = a.qtable + (uint64_t)e * a.qtable_lane_stride + (uint64_t)EnvT::observe_index(p, s) * a.A;
         uint32_t best = 0;
         double bv = row[0];
         for (int k = 1; k < a.A; ++k)
@@ -1704,8 +1705,9 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     if (actor->kind == RL_ACTOR_REPLAY_ACTIONS) RL_REQUIRE(ctx, actor->actions_dev, "rl_rollout: actions_dev is NULL");
     if (actor->kind == RL_ACTOR_TABULAR_EPS_GREEDY) {
         RL_REQUIRE(ctx, actor->table, "rl_rollout: table is NULL");
-        RL_REQUIRE(ctx, actor->table->R == env->E && actor->table->S == es.num_observations && actor->table->A == es.num_actions,
-                   "rl_rollout: table shape does not match the environment (one replica per lane)");
+        RL_REQUIRE(ctx, (actor->table->R == env->E || actor->table->R == 1) && actor->table->S == es.num_observations &&
+                            actor->table->A == es.num_actions,
+                   "rl_rollout: table shape does not match the environment (one replica per lane, or one shared table)");
     }
     RolloutArgs a{};
     a.E = env->E; a.lane_offset = env->lane_offset; a.Tcap = traj->T;
@@ -1720,6 +1722,7 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     a.eps = actor->exploration_rate;
     a.training = actor->training;
     a.qtable = actor->table ? actor->table->q : nullptr;
+    a.qtable_lane_stride = (actor->table && actor->table->R == env->E) ? (uint64_t)actor->table->S * actor->table->A : 0;
     a.S = es.num_observations; a.A = es.num_actions; a.F = es.num_features;
 
     RL_CUDA(ctx, cudaMemsetAsync(traj->succ, RL_PAD, (size_t)traj->T * traj->E, ctx->stream));

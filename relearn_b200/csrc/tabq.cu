@@ -14,10 +14,13 @@ __global__ void __launch_bounds__(128)
                        double discount, const float *__restrict__ obs, const float *__restrict__ next_obs,
                        const uint8_t *__restrict__ action, const float *__restrict__ reward,
                        const uint8_t *__restrict__ succ, uint64_t T, uint64_t E, int F) {
-    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    double *tq = q + r * (uint64_t)S * A;
-    unsigned long long *tc = counts + r * (uint64_t)S * A;
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= R) return;
+    double *tq = q + tid * (uint64_t)S * A;
+    unsigned long long *tc = counts + tid * (uint64_t)S * A;
+    // one table per lane: replica tid folds lane tid; one shared table (R == 1): thread 0 folds every lane in order
+    const uint64_t lane_begin = R == E ? tid : 0, lane_end = R == E ? tid + 1 : E;
+    for (uint64_t r = lane_begin; r < lane_end; ++r) {
     // finite observation spaces are stored one-hot (index.rs:97-115); recover the index
     auto obs_index = [&](const float *planes, uint64_t t) {
         int idx = 0;
@@ -57,6 +60,7 @@ __global__ void __launch_bounds__(128)
         tq[idx] = qv;
         if (sc == RL_CONTINUE) cur = nxt;
         else if (t + 1 < T && succ[(t + 1) * E + r] != RL_PAD) cur = obs_index(obs, t + 1);
+    }
     }
 }
 
@@ -98,7 +102,7 @@ rl_status rl_tabq_destroy(rl_tabq *t) {
 rl_status rl_tabq_update(rl_tabq *t, rl_traj *traj) {
     if (!t || !traj) return rl_fail(t ? t->ctx : nullptr, RL_ERR_INVALID_ARG, "rl_tabq_update: NULL argument");
     rl_ctx *ctx = t->ctx;
-    RL_REQUIRE(ctx, traj->E == t->R, "rl_tabq_update: one replica per lane required");
+    RL_REQUIRE(ctx, traj->E == t->R || t->R == 1, "rl_tabq_update: one replica per lane, or one shared table (num_replicas = 1)");
     RL_REQUIRE(ctx, (int)traj->F == t->S, "rl_tabq_update: observation space size mismatch");
     const uint64_t T = traj->used_T ? traj->used_T : traj->T;
     const unsigned block = 128, grid = rl_grid_for(t->R, block);

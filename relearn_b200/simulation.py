@@ -1,11 +1,15 @@
-"""Rollouts: Steps + TakeAlignedSteps + write_experience + StepsSummary (src/simulation).
+"""Rollouts and the training loop: Steps + TakeAlignedSteps + write_experience + StepsSummary + train_parallel
+(src/simulation).
 
-`rollout()` is one collection period of `train_parallel` (src/simulation/train.rs:108-158) with one
-GPU lane per reference worker thread.
+`rollout()` is one collection period of `train_parallel` (src/simulation/train.rs:108-158) with one GPU lane per
+reference worker thread; `train_device()` is the loop around it (train.rs:68-186): collect -> log the merged
+StepsSummary -> `batch_update`, with the reference's log ids.
 """
 from __future__ import annotations
 
 import ctypes as C
+import math
+import time
 from dataclasses import dataclass
 
 import numpy as np
@@ -130,3 +134,136 @@ def rollout(env: BatchedEnv, actor: ActorSpec, bound: HistoryDataBound, traj: Tr
         env.ctx.synchronize()
         keep.free()
     return summ
+
+
+# ------------------------------------------------------------------------------------------------
+# train_parallel / train_serial over device lanes (src/simulation/train.rs:15-186)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class TrainParallelConfig:
+    """train.rs:51-60.  `num_threads` is the number of reference worker threads = device lanes (it must equal the
+    env's lane count: a lane IS a worker, with its own buffer and its own noise streams)."""
+
+    num_periods: int = 1
+    num_threads: int = 1
+    min_worker_steps: int = 0
+
+
+def _log_summary(summary, logger, collect_s: float) -> None:
+    """The `sim/*` block of train_parallel (train.rs:160-178)."""
+    sim = logger.with_scope("sim")
+    ep = sim.with_scope("ep")
+    num_episodes = int(summary.episode_length.count)
+    if num_episodes > 0:
+        fbk = ep.with_scope("fbk").with_scope("reward")  # RewardSummary::log -> OnlineMeanVariance::log (stats.rs:48-69)
+        fbk.log_scalar("mean", summary.episode_reward.mean)
+        fbk.log_scalar("stddev", math.sqrt(summary.episode_reward.variance()))
+        ep.log_scalar("length_mean", summary.episode_length.mean)
+        ep.log_scalar("length_stddev", math.sqrt(summary.episode_length.variance()))
+    ep.log_counter_increment("count", num_episodes)
+    step = sim.with_scope("step")
+    if summary.step_reward.count > 0:
+        fbk = step.with_scope("fbk").with_scope("reward")
+        fbk.log_scalar("mean", summary.step_reward.mean)
+        fbk.log_scalar("stddev", math.sqrt(summary.step_reward.variance()))
+    step.log_counter_increment("count", int(summary.step_reward.count))
+    sim.log_duration("time", collect_s)
+
+
+def train_device(agent, env: BatchedEnv, config: TrainParallelConfig, logger=None, on_period=None) -> None:
+    """`train_parallel` (train.rs:68-186) with the worker threads as device lanes.
+
+    Per period: `worker_update_size = agent.min_update_size().divide(num_threads).max(min_worker_steps)` (train.rs:111-118),
+    one fused rollout collects that much experience on every lane with `agent.actor(Training)` -- created once per period,
+    so the policy / table / exploration rate is frozen while the period runs, as in the reference --, the lanes'
+    StepsSummaries arrive merged (Chan et al., train.rs:153-156) and are logged under `sim/...`, then
+    `agent.batch_update(buffers)` runs and `agent_update/{time,count}` are logged.
+
+    `agent` is any of the package's batch-update agents: `ActorCriticAgent` (trajectory buffer), `DqnAgent` (replay
+    rings, one per lane, appended every period), `TabularQ` (one shared table with `num_replicas = 1`, or one per lane).
+    `on_period(period_index, summary)` is an optional hook (e.g. checkpointing, early stopping when it returns True)."""
+    from .logging import NullLogger
+
+    if config.num_threads != env.num_envs:
+        raise ValueError(f"num_threads ({config.num_threads}) must equal the env's lane count ({env.num_envs}): one lane per worker")
+    logger = logger if logger is not None else NullLogger()
+    replay = None
+    traj, traj_cap = None, -1
+    try:
+        for period in range(config.num_periods):
+            collect_start = time.perf_counter()
+            bound = agent.min_update_size().divide(config.num_threads).max(HistoryDataBound(config.min_worker_steps, 0))
+            cap = bound.min_steps + bound.slack_steps
+            if traj is None or cap > traj_cap:
+                if traj is not None:
+                    traj.close()
+                traj, traj_cap = Trajectory(env, cap), cap
+            summary = rollout(env, agent.actor(), bound, traj, want_summary=True)
+            update_start = time.perf_counter()
+            _log_summary(summary, logger, update_start - collect_start)
+            if hasattr(agent, "buffer") and getattr(agent, "uses_replay", False):
+                if replay is None:
+                    replay = agent.buffer()
+                replay.write_experience(traj)
+                agent.batch_update(replay, _ScopeDict(logger))
+            else:
+                agent.batch_update(traj, _ScopeDict(logger))
+            env.ctx.synchronize()
+            upd = logger.with_scope("agent_update")
+            upd.log_duration("time", time.perf_counter() - update_start)
+            upd.log_counter_increment("count", 1)
+            if on_period is not None and on_period(period, summary):
+                break
+    finally:
+        if traj is not None:
+            traj.close()
+        if replay is not None:
+            replay.close()
+    logger.flush()
+
+
+def train_serial(agent, env: BatchedEnv, num_periods: int, logger=None) -> None:
+    """`train_serial` (train.rs:15-49): the same loop with the full `min_update_size` on every lane (one lane = the
+    reference's single thread)."""
+    from .logging import NullLogger
+
+    logger = logger if logger is not None else NullLogger()
+    traj = None
+    try:
+        for _ in range(num_periods):
+            bound = agent.min_update_size()
+            cap = bound.min_steps + bound.slack_steps
+            if traj is None or traj.step_capacity < cap:
+                if traj is not None:
+                    traj.close()
+                traj = Trajectory(env, cap)
+            rollout(env, agent.actor(), bound, traj, want_summary=False)
+            agent.batch_update(traj, _ScopeDict(logger))
+    finally:
+        if traj is not None:
+            traj.close()
+    logger.flush()
+
+
+class _ScopeDict(dict):
+    """The agents' update methods log into a dict (`logger[name] = value`); this forwards every item to a StatsLogger
+    as a scalar (durations for `*time`), keeping the dict interface the tests use."""
+
+    def __init__(self, logger):
+        super().__init__()
+        self._logger = logger
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        try:
+            v = float(value)
+        except (TypeError, ValueError):
+            return
+        if key.endswith("time"):
+            self._logger.log_duration(key, v)
+        else:
+            self._logger.log_scalar(key, v)
+
+    def update(self, other=(), **kw):
+        for k, v in dict(other, **kw).items():
+            self[k] = v

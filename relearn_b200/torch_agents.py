@@ -417,6 +417,8 @@ class DqnAgent:
     """Agent + BatchUpdate (dqn.rs:186-337) over a batched env on one GPU; every lane is one worker with
     its own ReplayBuffer."""
 
+    uses_replay = True  # train_device appends every period's trajectory to the replay rings before batch_update
+
     def __init__(self, env: BatchedEnv, cfg: DqnConfig):
         self.env, self.cfg, self.ctx, self._lib = env, cfg, env.ctx, env.ctx._lib
         self.action_value_fn = cfg.action_value_fn_config.build_module(env.ctx, env.num_features, env.num_actions)
