@@ -50,9 +50,6 @@ struct rl_ctx {
     size_t pinned_bytes = 0;
     // timing events of the update entry points (created once, destroyed with the context: no leak on an early return)
     cudaEvent_t upd_ev[2] = {nullptr, nullptr};
-    // the fused tail of the tensor-core passes (pass_tail.cuh): self-resetting tickets, and whether the last launch fused
-    unsigned int *tail_tickets = nullptr;
-    bool tail_done = false;
 };
 
 std::string &rl_tls_error();

@@ -78,7 +78,6 @@ rl_status rl_ctx_destroy(rl_ctx *ctx) {
     rl_nccl_teardown(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    if (ctx->tail_tickets) cudaFree(ctx->tail_tickets);
     for (cudaEvent_t ev : ctx->upd_ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);

@@ -79,8 +79,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, TcPass<A, MODE>::CTAS_PER_SM) 
     constexpr bool FVP = K::FVP, BACKWARD = K::BACKWARD, IS_POLICY = K::IS_POLICY;
     constexpr int N3 = K::N3, YB = K::YBLOCKS, N2 = K::N2;
     constexpr int RED = tc_red(K::BLOCKS, YB);
-    const bool skipped = a.skip_flag && *a.skip_flag;
-    if (skipped && (a.tail.mode == PT_NONE || !a.tail.use_x)) return;  // (with peers the tail's exchange still runs: parities stay aligned)
+    if (a.skip_flag && *a.skip_flag) return;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *sA1 = smem + TC_A1, *sB1 = smem + TC_B1, *sA2 = smem + TC_A2, *sB2 = smem + TC_B2, *sB3 = smem + tc_b3(YB);
     double *red = reinterpret_cast<double *>(smem + RED);
@@ -177,7 +176,7 @@ __global__ void __launch_bounds__(tc::TC_THREADS, TcPass<A, MODE>::CTAS_PER_SM) 
     constexpr uint32_t IDESC3 = make_idesc(128, N3, false, true);    // Mask (K-major) . C (MN-major)
     const uint32_t aA1 = smem_u32(sA1), aB1 = smem_u32(sB1), aA2 = smem_u32(sA2), aB2 = smem_u32(sB2), aB3 = smem_u32(sB3);
 
-    const uint64_t TE = skipped ? 0 : a.T * a.E, ntiles = (TE + 127) / 128;  // (a skipped pass only takes part in the tail)
+    const uint64_t TE = a.T * a.E, ntiles = (TE + 127) / 128;
     double G[BACKWARD ? YB * NY : 1], sc[NSCALAR], gb2_acc[YB];
 #pragma unroll
     for (int n = 0; n < (BACKWARD ? YB * NY : 1); ++n) G[n] = 0.0;
@@ -480,6 +479,4 @@ __global__ void __launch_bounds__(tc::TC_THREADS, TcPass<A, MODE>::CTAS_PER_SM) 
         tmem_dealloc(tmem_d1, 128);
         if (BACKWARD) tmem_dealloc(tmem_d2, K::D2_COLS);
     }
-    // ---- the last CTAs to finish reduce the rows (and exchange them with the peers, and step Adam): pass_tail.cuh ----
-    pass_tail_run<TC_THREADS>(a.tail, a.partials, W, P, reinterpret_cast<int *>(smem + RED + 512 + 48), red, skipped);
 }

@@ -40,12 +40,6 @@ constexpr float F32_LOWEST = -3.402823466e+38f;
 constexpr int PASS_THREADS = 256;
 constexpr int FLUSH_TILES = 4;
 
-struct AdamArgs {
-    double lr, beta1, beta2, weight_decay, eps;
-};
-
-#include "pass_tail.cuh"
-
 struct PassArgs {
     const float *obs;
     const uint8_t *action, *succ;
@@ -57,7 +51,6 @@ struct PassArgs {
     double *partials;     // f64 [gridDim.x][P + NSCALAR]
     const int *skip_flag;
     float clip_lo, clip_hi;  // PASS_PPO: 1 -+ clip_distance as f32 (ppo.rs:131-132)
-    PassTail tail;           // mlp_pass_tc_kernel only: reduction (+ peer exchange, + Adam) by the last CTAs to finish
 };
 
 template <int A>
@@ -985,6 +978,9 @@ __global__ void trpo_ls_finish_kernel(TrpoState *st, float *theta, const float *
 }
 
 // libtorch Adam::step (non-amsgrad) on the mean gradient; records the loss of this step
+struct AdamArgs {
+    double lr, beta1, beta2, weight_decay, eps;
+};
 __global__ void __launch_bounds__(VEC_THREADS)
     adam_step_kernel(const double *sums, int P, float *theta, float *m, float *v, AdamArgs c, uint64_t step,
                      double *loss_out) {
@@ -1193,7 +1189,6 @@ struct PassPlan {
     int grid_tc;  // CTAs of the tcgen05 passes (mlp_pass_tc_kernel); the partial rows hold max(grid, grid_tc)
     size_t smem;
     double *partials, *sums;
-    double *group_rows = nullptr;  // [PT_MAX_GROUPS][W]: level 1 of the fused tail (pass_tail.cuh)
 };
 
 template <int F, int A, int UPL>
@@ -1292,16 +1287,6 @@ int pass_rows(const rl_ctx *ctx, const PassPlan &plan) {
     return plan.grid;
 }
 
-// RL_PASS_TAIL=0: the reductions stay in their own launches (measurements)
-bool tail_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("RL_PASS_TAIL");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
-
 template <int A, int MODE>
 rl_status launch_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool reduce) {
     constexpr int smem = TcPass<A, MODE>::SMEM;
@@ -1312,34 +1297,6 @@ rl_status launch_pass_tc(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool 
     }
     args.partials = plan.partials;
     const int grid = tc_grid<A, MODE>(ctx, plan);
-    // The reduction of the partial rows (requested by `reduce`, or together with Adam by pass_and_adam through
-    // args.tail.mode == PT_ADAM) runs in the tail of the pass kernel itself when the group's sum can too: one GPU, or the
-    // peer mailboxes.  (NCCL all-reduce fallback: separate launches as before.)
-    const PassTail req = args.tail;
-    args.tail = PassTail{};
-    ctx->tail_done = false;
-    const bool group_ok = ctx->world == 1 || (ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS);
-    if ((reduce || req.mode == PT_ADAM) && tail_enabled() && plan.group_rows && plan.W <= tc::TC_THREADS * 16 &&
-        grid <= PT_GROUP * PT_MAX_GROUPS && group_ok) {
-        if (!ctx->tail_tickets) {
-            RL_CUDA(ctx, cudaMalloc((void **)&ctx->tail_tickets, (1 + PT_MAX_GROUPS) * sizeof(unsigned int)));
-            RL_CUDA(ctx, cudaMemsetAsync(ctx->tail_tickets, 0, (1 + PT_MAX_GROUPS) * sizeof(unsigned int), ctx->stream));
-        }
-        args.tail = req;
-        args.tail.mode = req.mode == PT_ADAM ? PT_ADAM : PT_REDUCE;
-        args.tail.tickets = ctx->tail_tickets;
-        args.tail.group_rows = plan.group_rows;
-        args.tail.sums = plan.sums;
-        args.tail.use_x = ctx->world > 1 ? 1 : 0;
-        if (ctx->world > 1) {
-            args.tail.x = ctx->x;
-            ctx->x_seq += 1;
-            args.tail.seq = ctx->x_seq;
-        }
-        RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), grid, tc::TC_THREADS, smem, args);
-        ctx->tail_done = true;
-        return RL_OK;
-    }
     RL_LAUNCH(ctx, (mlp_pass_tc_kernel<A, MODE>), grid, tc::TC_THREADS, smem, args);
     if (!reduce) return RL_OK;
     return reduce_over_group(ctx, plan, grid, args.skip_flag);
@@ -1376,45 +1333,27 @@ rl_status launch_pass(rl_ctx *ctx, const PassPlan &plan, PassArgs args, bool red
 
 // One optimizer step on the sums of the pass just launched: pass -> [reduce -> all-reduce] -> Adam
 // (n_backward_steps: zero_grad, backward, step; torch/agents/mod.rs:50-55, coptimizer.rs:13-27).
-// Adam request for the fused tail of a tensor-core pass (pass_tail.cuh); kernels without a tail ignore it
-PassArgs with_adam_tail(const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac, double *loss_out) {
-    PassArgs out = pa;
-    out.tail = PassTail{};
-    out.tail.mode = PT_ADAM;
-    out.tail.theta = net->params; out.tail.m = adam->m; out.tail.v = adam->v;
-    out.tail.c = ac; out.tail.step = adam->step; out.tail.loss_out = loss_out;
-    return out;
-}
-
-// What follows a pass that did NOT fuse its tail: [reduce -> all-reduce] -> Adam in one or two more launches
-rl_status reduce_and_adam(rl_ctx *ctx, const PassPlan &plan, int rows, rl_mlp *net, rl_adam *adam, const AdamArgs &ac, double *loss_out) {
-    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
-        // ONE kernel: row reduction + peer exchange + Adam
-        ctx->x_seq += 1;
-        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
-                  ctx->x, ctx->x_seq, (const int *)nullptr, (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
-    } else if (ctx->world > 1) {
-        RL_TRY(reduce_over_group(ctx, plan, rows, nullptr));
-        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
-                  loss_out);
-    } else {
-        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
-                  net->params, adam->m, adam->v, ac, adam->step, loss_out);
-    }
-    return RL_OK;
-}
-
-// One optimizer step on the sums of the pass just launched: pass -> [reduce -> all-reduce] -> Adam
-// (n_backward_steps: zero_grad, backward, step; torch/agents/mod.rs:50-55, coptimizer.rs:13-27).  The tensor-core pass
-// does all of it in its own tail (ctx->tail_done).
 template <int F, int A, int UPL, int MODE>
 rl_status pass_and_adam(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa, rl_mlp *net, rl_adam *adam, const AdamArgs &ac,
                         double *loss_out) {
     adam->step += 1;
-    ctx->tail_done = false;
-    RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, with_adam_tail(pa, net, adam, ac, loss_out), false)));
-    if (ctx->tail_done) return RL_OK;
-    return reduce_and_adam(ctx, plan, (pass_rows<F, A, UPL, MODE>(ctx, plan)), net, adam, ac, loss_out);
+    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
+        // pass -> ONE kernel: row reduction + peer exchange + Adam
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
+        ctx->x_seq += 1;
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(ctx, plan)),
+                  plan.W, plan.P, plan.sums, ctx->x, ctx->x_seq, (const int *)nullptr,
+                  (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
+    } else if (ctx->world > 1) {
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa)));
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
+                  loss_out);
+    } else {
+        RL_TRY((launch_pass<F, A, UPL, MODE>(ctx, plan, pa, false)));
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, (pass_rows<F, A, UPL, MODE>(ctx, plan)),
+                  plan.W, plan.P, plan.sums, net->params, adam->m, adam->v, ac, adam->step, loss_out);
+    }
+    return RL_OK;
 }
 
 rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extra_bytes, void **extra) {
@@ -1428,11 +1367,8 @@ rl_status make_plan(rl_ctx *ctx, int P, uint64_t TE, PassPlan *plan, size_t extr
     plan->grid_tc = (int)(tiles_tc < cap_tc ? (tiles_tc ? tiles_tc : 1) : cap_tc);
     const size_t rows = (size_t)(plan->grid > plan->grid_tc ? plan->grid : plan->grid_tc) * plan->W * sizeof(double),
                  sums = (size_t)plan->W * sizeof(double);
-    const size_t groups = ((size_t)PT_MAX_GROUPS * plan->W * sizeof(double) + 255) / 256 * 256;
     char *buf;
-    RL_TRY(rl_ctx_scratch(ctx, groups + rows + sums + extra_bytes + 256, (void **)&buf));
-    plan->group_rows = (double *)buf;
-    buf += groups;
+    RL_TRY(rl_ctx_scratch(ctx, rows + sums + extra_bytes + 256, (void **)&buf));
     plan->partials = (double *)buf;
     plan->sums = (double *)(buf + rows);
     if (extra) *extra = buf + rows + ((sums + 255) / 256) * 256;
@@ -1525,11 +1461,24 @@ rl_status pass_and_adam_rt(rl_ctx *ctx, const PassPlan &plan, const PassArgs &pa
                            rl_adam *adam, const AdamArgs &ac, double *loss_out) {
     adam->step += 1;
     int rows = plan.grid;
-    ctx->tail_done = false;
-    RL_TRY(launch_pass_rt(ctx, plan, with_adam_tail(pa, net, adam, ac, loss_out), mode, pn, false, &rows));
-    if (ctx->tail_done) return RL_OK;
-    return reduce_and_adam(ctx, plan, rows, net, adam, ac, loss_out);
+    if (ctx->world > 1 && ctx->x_ok && rl_div_up(plan.W, 32) <= RL_X_BLOCKS) {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn, false, &rows));
+        ctx->x_seq += 1;
+        RL_LAUNCH(ctx, reduce_rows_x_kernel<true>, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
+                  ctx->x, ctx->x_seq, (const int *)nullptr, (XAdam{net->params, adam->m, adam->v, ac, adam->step, loss_out, plan.P}));
+    } else if (ctx->world > 1) {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn));
+        RL_LAUNCH(ctx, adam_step_kernel, 1, VEC_THREADS, 0, plan.sums, plan.P, net->params, adam->m, adam->v, ac, adam->step,
+                  loss_out);
+    } else {
+        RL_TRY(launch_pass_rt(ctx, plan, pa, mode, pn, false, &rows));
+        RL_LAUNCH(ctx, reduce_rows_adam_kernel, rl_div_up(plan.W, 32), 256, 0, plan.partials, rows, plan.W, plan.P, plan.sums,
+                  net->params, adam->m, adam->v, ac, adam->step, loss_out);
+    }
+    return RL_OK;
 }
+
+
 
 // ------------------------------------------------------------------------------------------------
 // Trust-region step, network-agnostic: `pass(mode, vec, skip_flag)` runs one full-batch pass of the policy
