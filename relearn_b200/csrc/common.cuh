@@ -45,6 +45,9 @@ struct rl_ctx {
     // scratch for small reductions (lazily grown)
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    // second scratch (the planes of the GEMM-form recurrent passes, gru_big.cu: live at the same time as the first)
+    void *scratch2 = nullptr;
+    size_t scratch2_bytes = 0;
     // pinned host scratch for scalar read-backs
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -98,6 +101,7 @@ inline rl_status rl_fail(rl_ctx *ctx, rl_status st, const char *fmt, ...) {
 void rl_nccl_teardown(rl_ctx *ctx);
 rl_status rl_allreduce_f64_inplace(rl_ctx *ctx, double *buf_dev, size_t n);
 rl_status rl_ctx_scratch(rl_ctx *ctx, size_t bytes, void **out);
+rl_status rl_ctx_scratch2(rl_ctx *ctx, size_t bytes, void **out);
 rl_status rl_ctx_pinned(rl_ctx *ctx, size_t bytes, void **out);
 
 inline unsigned rl_div_up(uint64_t a, uint64_t b) { return (unsigned)((a + b - 1) / b); }

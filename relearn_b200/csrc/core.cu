@@ -77,6 +77,7 @@ rl_status rl_ctx_destroy(rl_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     rl_nccl_teardown(ctx);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (cudaEvent_t ev : ctx->upd_ev)
         if (ev) cudaEventDestroy(ev);
@@ -170,6 +171,22 @@ rl_status rl_ctx_scratch(rl_ctx *ctx, size_t bytes, void **out) {
         ctx->scratch_bytes = want;
     }
     *out = ctx->scratch;
+    return RL_OK;
+}
+
+rl_status rl_ctx_scratch2(rl_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch2_bytes) {
+        if (ctx->scratch2) {
+            RL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            RL_CUDA(ctx, cudaFree(ctx->scratch2));
+            ctx->scratch2 = nullptr;
+            ctx->scratch2_bytes = 0;
+        }
+        cudaError_t e = cudaMalloc(&ctx->scratch2, bytes);
+        if (e != cudaSuccess) return rl_fail(ctx, RL_ERR_OOM, "scratch of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        ctx->scratch2_bytes = bytes;
+    }
+    *out = ctx->scratch2;
     return RL_OK;
 }
 

@@ -1572,7 +1572,23 @@ rl_status make_seq_plan(rl_ctx *ctx, const rl_grunet_view &net, uint64_t T, uint
     return RL_OK;
 }
 
+// RL_SEQ_FORCE_BIG=1 sends every size through the GEMM formulation (tests: K10 against K9 on the same small module)
+bool seq_force_big() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RL_SEQ_FORCE_BIG");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 rl_status seq_pass(rl_ctx *ctx, const PassPlan &plan, int mode, const rl_seq_pass_args &a) {
+    if (!rl_seq_pass_supports(a.F, a.H, a.A) || seq_force_big()) {
+        // K10 (gru_big.cu): tiled GEMMs over the lanes of a step; one partial row
+        RL_TRY(rl_seq_big_pass_launch(ctx, mode, a));
+        RL_TRY(reduce_over_group(ctx, plan, 1, a.skip_flag));
+        return RL_OK;
+    }
     RL_TRY(rl_seq_pass_launch(ctx, mode, a, plan.grid));
     RL_TRY(reduce_over_group(ctx, plan, plan.grid, a.skip_flag));
     return RL_OK;
@@ -1581,8 +1597,8 @@ rl_status seq_pass(rl_ctx *ctx, const PassPlan &plan, int mode, const rl_seq_pas
 rl_status seq_check(rl_ctx *ctx, rl_traj *traj, const rl_grunet_view &net, int out_dim_expected, const char *what) {
     RL_REQUIRE(ctx, net.ctx == ctx, "recurrent update: module belongs to another context");
     if ((int)traj->F != net.in_dim || (out_dim_expected > 0 && net.out_dim != out_dim_expected) ||
-        !rl_seq_pass_supports(net.in_dim, net.hidden, net.out_dim))
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "%s: recurrent passes are built for hidden <= 8, features <= 20, outputs <= 16 "
+        !(rl_seq_pass_supports(net.in_dim, net.hidden, net.out_dim) || rl_seq_big_supports(net.in_dim, net.hidden, net.out_dim)))
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "%s: recurrent passes are built for hidden <= 128, features <= 64, outputs <= 32 "
                        "(got %d -> %d -> %d on %d features)", what, net.in_dim, net.hidden, net.out_dim, (int)traj->F);
     return RL_OK;
 }

@@ -52,9 +52,12 @@ def _per_episode(x, spans):
     return [x[a:b, e] for e, a, b in spans]
 
 
-@pytest.mark.parametrize("hidden,arms,episodes,activation", [(4, 2, 10, "relu"), (8, 5, 4, "tanh"), (3, 3, 6, "relu")])
+# hidden > 8 runs K10 (gru_big.cu: tiled GEMMs over the lanes of a step); (128, 10, .) is the rl2-sized module
+# (rl2-bandits.rs:379-393: GRU(14 -> 128) -> ReLU -> Linear(128 -> 10))
+@pytest.mark.parametrize("hidden,arms,episodes,activation", [(4, 2, 10, "relu"), (8, 5, 4, "tanh"), (3, 3, 6, "relu"),
+                                                             (24, 3, 4, "tanh"), (128, 10, 4, "relu")])
 def test_seq_trpo_probe_loss_grad_fvp(ctx, hidden, arms, episodes, activation):
-    E, T = 80, 2 * (2 * episodes - 1) + 5
+    E, T = (80 if hidden <= 24 else 45), 2 * (2 * episodes - 1) + 5
     env, traj, net, params, host, spans = _collect(ctx, hidden, arms, episodes, E, T, seed=hidden + arms, scale=1.5,
                                                    activation=activation)
     F, A = env.num_features, env.num_actions
@@ -77,9 +80,9 @@ def test_seq_trpo_probe_loss_grad_fvp(ctx, hidden, arms, episodes, activation):
     assert _rel(got["fvp"], hv64) <= 1e-5
 
 
-@pytest.mark.parametrize("hidden,arms,episodes,reg", [(4, 2, 10, 0.1), (8, 4, 5, 0.1)])
+@pytest.mark.parametrize("hidden,arms,episodes,reg", [(4, 2, 10, 0.1), (8, 4, 5, 0.1), (128, 10, 3, 0.1)])
 def test_seq_trpo_update_matches_f64(ctx, hidden, arms, episodes, reg):
-    E, T = 96, 2 * (2 * episodes - 1) + 3
+    E, T = (96 if hidden <= 8 else 40), 2 * (2 * episodes - 1) + 3
     env, traj, net, params, host, spans = _collect(ctx, hidden, arms, episodes, E, T, seed=7 + hidden, scale=1.5)
     F, A = env.num_features, env.num_actions
     rng = np.random.default_rng(11)
@@ -112,10 +115,10 @@ def _value_params(rng, F, hidden):
     return p.astype(np.float32)
 
 
-def test_seq_gae_and_value_update(ctx):
+@pytest.mark.parametrize("hidden,arms,episodes,E,steps", [(4, 2, 6, 72, 20), (128, 10, 4, 40, 6)])
+def test_seq_gae_and_value_update(ctx, hidden, arms, episodes, E, steps):
     """ValuesOpt<Chain<Gru, Linear>>: GAE over SeqPacked values (interrupted trials bootstrap from one more step of
-    the same sequence, critics/mod.rs:116-131) and 20 Adam steps on the reward-to-go targets."""
-    hidden, arms, episodes, E, steps = 4, 2, 6, 72, 20
+    the same sequence, critics/mod.rs:116-131) and Adam steps on the reward-to-go targets."""
     T = 2 * (2 * episodes - 1) + 4
     env, traj, net, params, host, spans = _collect(ctx, hidden, arms, episodes, E, T, seed=21)
     F = env.num_features
@@ -163,21 +166,30 @@ def test_seq_gae_and_value_update(ctx):
     assert _rel(d, d64) <= max(2e-4, 4 * _rel(d32, d64) + 1e-5)
 
 
-def test_seq_updates_reject_unsupported_sizes(ctx):
-    env = R.build_env(ctx, R.MetaEnv(R.UniformBernoulliBandits(2), 3), 8, seed=1)
-    net = R.GruLinear(ctx, env.num_features, 24, env.num_actions)
-    net.set_weights(R.init_gru_linear_params(np.random.default_rng(0), env.num_features, 24, env.num_actions))
-    traj = R.Trajectory(env, 8)
-    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(8, 0), traj)
-    with pytest.raises(L.RelearnB200Error) as ei:
-        R.Trpo(net, R.TrpoConfig()).update(traj, ctx.to_device(np.zeros((8, 8), np.float32)), {})
-    assert "hidden <= 8" in str(ei.value)
+def test_gemm_formulation_serves_the_small_modules_too():
+    """K10 against the oracle on the modules K9 (one thread per lane) normally serves: the same tests in a child process
+    with RL_SEQ_FORCE_BIG=1 (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("RL_SEQ_FORCE_BIG") == "1":
+        pytest.skip("already the forced run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RL_SEQ_FORCE_BIG="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_gru_update.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "(probe or update_matches or gae_and_value) and not 128 and not 24"], capture_output=True, text=True,
+                       env=env, cwd=root, timeout=1200)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0
 
 
-def test_rl2_actor_critic_learns_bandits(ctx):
+@pytest.mark.parametrize("hidden", [8, 128])
+def test_rl2_actor_critic_learns_bandits(ctx, hidden):
     """Behavioural check in the spirit of rl2-bandits.rs / agents/testing.rs: TRPO with a GRU policy and a GRU critic
-    on 2-armed Bernoulli bandit trials raises the mean per-step reward of the meta-episodes."""
-    hidden, arms, episodes, E = 8, 2, 10, 2048
+    on 2-armed Bernoulli bandit trials raises the mean per-step reward of the meta-episodes (hidden 128 = the module size
+    of rl2-bandits.rs:379-393, served by K10)."""
+    arms, episodes, E = 2, 10, 2048
     T = 2 * episodes - 1
     env = R.build_env(ctx, R.MetaEnv(R.UniformBernoulliBandits(arms), episodes), E, seed=4)
     gcfg = R.GruLinearConfig(hidden_dim=hidden)
