@@ -719,8 +719,32 @@ def rl2_sized_rollout(ctx, R, L):
            "envs": E6, "horizon": T6, "ms": ms, "env_steps_per_s": E6 * T6 / (ms * 1e-3), "flop_per_env_step": flop,
            "fp32_tflops": flop * E6 * T6 / (ms * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
            "frac_of_fp32_peak": flop * E6 * T6 / (ms * 1e-3) / 1e12 / fp32_peak}
+    out = [rec]
+    # the update that consumes it (K10, gru_big.cu: tiled FP32 GEMMs over the lanes of a step): one gradient pass and one
+    # Fisher-vector product through GRU(14->128)->Linear(128->10) on a quarter of those lanes (942 464 steps)
+    E7 = E6 // 4
+    env7 = R.build_env(ctx, R.MetaEnv(R.UniformBernoulliBandits(10), 100), E7, seed=8)
+    traj7 = R.Trajectory(env7, T6)
+    R.rollout(env7, spec6, R.HistoryDataBound(T6, 0), traj7, want_summary=False)
+    pol = R.Trpo(net6, R.TrpoConfig())
+    adv = ctx.to_device(np.random.default_rng(5).normal(size=(T6, E7)).astype(np.float32))
+    vec = np.random.default_rng(6).normal(size=net6.num_params).astype(np.float32)
+    pol.probe(traj7, adv, vec)
+    e0 = ctx.event().record()
+    pol.probe(traj7, adv, vec)  # stats + loss/KL + gradient + one Fisher-vector product
+    e1 = ctx.event().record()
+    ms7 = e0.elapsed_ms(e1)
+    Fh, Hh, Ah = env7.num_features, 128, env7.num_actions
+    cell = 2 * 3 * Hh * (Fh + Hh)                       # gru_cell forward FLOP per step
+    # stats fwd + eval fwd + grad (fwd + dh GEMM + weight grads) + FVP (fwd + tangent 2 GEMMs + dh + weight grads)
+    flop7 = (2 * cell + (cell + 2 * Hh * 3 * Hh + cell) + (cell + cell + 2 * 3 * Hh * Hh + 2 * Hh * 3 * Hh + cell)) * E7 * T6
+    out.append({"kernel": "config 4 rl2-sized update K10: stats + loss/KL + gradient + Fisher-vector product through GRU(14->128)->Linear "
+                          "(tiled FP32 GEMMs per step, split-K weight gradients)", "envs": E7, "horizon": T6, "batch_steps": E7 * T6,
+                "probe_ms": ms7, "algorithmic_tflops": flop7 / (ms7 * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
+                "frac_of_fp32_peak": flop7 / (ms7 * 1e-3) / 1e12 / fp32_peak})
+    traj7.close(); env7.close()
     traj6.close(); env6.close()
-    return [rec]
+    return out
 
 
 def run_sweep(args):

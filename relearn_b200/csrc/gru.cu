@@ -460,6 +460,10 @@ rl_status rl_grunet_seq_enqueue(rl_grunet *g, rl_traj *traj, float *out_dev, flo
         RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RL_LAUNCH(ctx, grunet_seq_kernel<8>, grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,
                   out_next_dev);
+    } else if (rl_seq_big_supports(g->in_dim, g->hidden, g->out_dim) && !(getenv("RL_GRU_KERNEL") && !strcmp(getenv("RL_GRU_KERNEL"), "thread"))) {
+        // hidden 9 .. 128: the GEMM form (gru_big.cu); the thread-per-lane kernel below stays as the cross-check
+        return rl_seq_big_forward(ctx, g->params, g->in_dim, g->hidden, g->out_dim, (int)g->act, traj->obs, traj->next_obs, traj->succ, T, E,
+                                  out_dev, out_next_dev);
     } else {
         RL_CUDA(ctx, cudaFuncSetAttribute(grunet_seq_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         RL_LAUNCH(ctx, grunet_seq_kernel<128>, grid, 128, smem, v, in_smem, traj->obs, traj->next_obs, traj->succ, T, E, out_dev,

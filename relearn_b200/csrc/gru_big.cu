@@ -20,8 +20,8 @@
 //
 // The Hessian of mean KL(p0 || p_theta) at theta0 is J^T (diag p - p p^T) J for any network, so forward tangent +
 // backward is the reference's double-backward Hessian-vector product (gru_update.cu header).
-// GEMMs: hand-written FP32 register-tiled kernels (64 x 128 x 16 tiles, 4 x 8 per thread; the split-K one contracts over
-// lanes with f64 flushes).  FP32, not tensor cores: the parity bar is 1e-5-class against f64 autograd, which bf16/tf32
+// GEMMs: hand-written FP32 register-tiled kernels (128 x 128 x 8 tiles, 8 x 8 per thread, register-prefetched; the split-K
+// one contracts over lanes with f64 flushes).  FP32, not tensor cores: the parity bar is 1e-5-class against f64 autograd, which bf16/tf32
 // inputs miss; the bf16-piece tcgen05 form used by pass_tc.cuh is the next step.
 #include "handles.cuh"
 
@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int BM = 64, BN = 128, BK = 16, GEMM_THREADS = 256;
+constexpr int BN = 128, GEMM_THREADS = 256;
 constexpr float F32_LOWEST_B = -3.402823466e+38f;
 
 __device__ __forceinline__ float sigm_b(float v) { return __fdividef(1.0f, 1.0f + expf(-v)); }
@@ -45,60 +45,84 @@ __device__ __forceinline__ float act_grad_b(int act, float pre, float out) {
 // ---------------------------------------------------------------------------------------------------------------------
 // C [M x N] (+)= A [M x K] . B [K x N] (+ bias[m]);  A row-major (lda), B rows 0 .. K0-1 from B0 and K0 .. K-1 from B1 (both
 // with row stride ldb = N's plane stride), C row-major (ldc).  N = lanes: every load along n is coalesced.
+// (16 TM) x 128 tiles, K in chunks of 8, TM x 8 accumulators per thread (TM = 8: 64 FMAs per four LDS.128); the next chunk's
+// global loads are in flight while the current one is multiplied.
 // ---------------------------------------------------------------------------------------------------------------------
+template <int TM>
 __global__ void __launch_bounds__(GEMM_THREADS)
     gemm_nn_kernel(const float *__restrict__ A, int lda, const float *__restrict__ B0, const float *__restrict__ B1, int K0,
                    uint64_t ldb, float *__restrict__ C, uint64_t ldc, const float *__restrict__ bias, int accumulate, int M,
                    uint64_t N, int K, const int *skip_flag) {
+    constexpr int TBM = 16 * TM, TBK = 8, AL = TBM * TBK / GEMM_THREADS;  // A values per thread and chunk: 4 (TM 8) or 2 (TM 4)
     if (skip_flag && *skip_flag) return;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty * 4 .. + 3, cols tx * 8 .. + 7
-    const int m0 = blockIdx.y * BM;
+    __shared__ __align__(16) float As[TBK][TBM + 4];
+    __shared__ __align__(16) float Bs[TBK][BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // thread tile: rows ty * TM .. , cols tx * 4 .. + 3 and 64 + tx * 4 .. + 3
+    const int m0 = blockIdx.y * TBM;
     const uint64_t n0 = (uint64_t)blockIdx.x * BN;
-    float acc[4][8];
+    float acc[TM][8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-    for (int k0 = 0; k0 < K; k0 += BK) {
-        // A tile: 64 x 16 = 1024 values, 4 per thread (k fastest: consecutive threads read consecutive k of a row)
+    float ra[AL], rb[4];
+    const int bk = tid >> 5, bn = (tid & 31) * 4;  // B chunk: 8 rows x 128 lanes, one float4 per thread
+    const bool vec_ok = (ldb & 3) == 0 && ((n0 + bn + 3) < N) && ((reinterpret_cast<uintptr_t>(B0) | reinterpret_cast<uintptr_t>(B1)) & 15) == 0;
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * GEMM_THREADS, m = idx >> 4, k = idx & 15;
-            As[k][m] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.0f;
+        for (int i = 0; i < AL; ++i) {
+            const int idx = tid + i * GEMM_THREADS, m = idx >> 3, k = idx & 7;
+            ra[i] = (m0 + m < M && k0 + k < K) ? A[(size_t)(m0 + m) * lda + k0 + k] : 0.0f;
         }
-        // B tile: 16 x 128 = 2048 values, 8 per thread (n fastest)
+        const int kk = k0 + bk;
+        if (kk < K) {
+            const float *src = kk < K0 ? B0 + (uint64_t)kk * ldb : B1 + (uint64_t)(kk - K0) * ldb;
+            if (vec_ok) {
+                const float4 v = *reinterpret_cast<const float4 *>(src + n0 + bn);
+                rb[0] = v.x; rb[1] = v.y; rb[2] = v.z; rb[3] = v.w;
+            } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int idx = tid + i * GEMM_THREADS, k = idx >> 7, n = idx & 127;
-            const int kk = k0 + k;
-            float v = 0.0f;
-            if (kk < K && n0 + n < N) v = kk < K0 ? B0[(uint64_t)kk * ldb + n0 + n] : B1[(uint64_t)(kk - K0) * ldb + n0 + n];
-            Bs[k][n] = v;
+                for (int j = 0; j < 4; ++j) rb[j] = (n0 + bn + j < N) ? src[n0 + bn + j] : 0.0f;
+            }
+        } else {
+            rb[0] = rb[1] = rb[2] = rb[3] = 0.0f;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += TBK) {
+#pragma unroll
+        for (int i = 0; i < AL; ++i) {
+            const int idx = tid + i * GEMM_THREADS;
+            As[idx & 7][idx >> 3] = ra[i];
+        }
+        *reinterpret_cast<float4 *>(&Bs[bk][bn]) = make_float4(rb[0], rb[1], rb[2], rb[3]);
         __syncthreads();
+        if (k0 + TBK < K) fetch(k0 + TBK);
 #pragma unroll
-        for (int k = 0; k < BK; ++k) {
-            const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
-            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8]), b1 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 8 + 4]);
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        for (int k = 0; k < TBK; ++k) {
+            float av[TM], bv[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < TM; i += 4) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&As[k][ty * TM + i]);
+                av[i] = a4.x; av[i + 1] = a4.y; av[i + 2] = a4.z; av[i + 3] = a4.w;
+            }
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]), b1 = *reinterpret_cast<const float4 *>(&Bs[k][64 + tx * 4]);
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
         if (m >= M) continue;
         const float b = bias ? bias[m] : 0.0f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint64_t n = n0 + tx * 8 + j;
+            const uint64_t n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
             if (n >= N) continue;
             float *c = C + (uint64_t)m * ldc + n;
             *c = accumulate ? *c + (acc[i][j] + b) : acc[i][j] + b;
@@ -108,70 +132,91 @@ __global__ void __launch_bounds__(GEMM_THREADS)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Split-K "A . B^T" over all (t, e):  part[s][m][n] = sum over the split's (t, e) of D[t][m][e] * In[t][n][e], where In's rows
-// come from src0 (rows0 rows), src1 (rows1 rows) and a row of ones (n == rows0 + rows1).  64 x 64 output tiles, 32 lanes per
-// step, 4 x 4 per thread; f32 accumulators are flushed into f64 every 64 steps.
+// come from src0 (rows0 rows), src1 (rows1 rows) and a row of ones (n == rows0 + rows1).  128 x 64 output tiles, 16 lanes per
+// unit, 8 x 4 per thread from lane-major shared tiles (three LDS.128 per 32 FMAs); f32 accumulators are flushed into f64
+// every 128 units.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int NT_BM = 64, NT_BN = 64, NT_BK = 32, NT_THREADS = 256;
+constexpr int NT_BM = 128, NT_BN = 64, NT_BK = 16, NT_THREADS = 256;
 __global__ void __launch_bounds__(NT_THREADS)
     gemm_nt_splitk_kernel(const float *__restrict__ D, int M, const float *__restrict__ src0, int rows0, const float *__restrict__ src1,
                           int rows1, uint64_t T, uint64_t E, double *__restrict__ part, int NB, int splits, const int *skip_flag) {
     if (skip_flag && *skip_flag) return;
-    __shared__ float Ds[NT_BM][NT_BK + 1];
-    __shared__ float Is[NT_BN][NT_BK + 1];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ __align__(16) float Ds[NT_BK][NT_BM + 4];
+    __shared__ __align__(16) float Is[NT_BK][NT_BN + 4];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // rows ty * 8 .. + 7, cols tx * 4 .. + 3
     const int m0 = blockIdx.y * NT_BM, n0 = blockIdx.x * NT_BN, s = blockIdx.z;
-    const uint64_t upt = (E + NT_BK - 1) / NT_BK, units = T * upt;  // unit = 32 lanes of one step
+    const uint64_t upt = (E + NT_BK - 1) / NT_BK, units = T * upt;  // unit = 16 lanes of one step
     const uint64_t u_begin = units * (uint64_t)s / (uint64_t)splits, u_end = units * (uint64_t)(s + 1) / (uint64_t)splits;
-    float acc[4][4];
-    double tot[4][4];
+    float acc[8][4];
+    double tot[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j] = 0.0f; tot[i][j] = 0.0; }
     const int NIN = rows0 + rows1;  // index of the ones row
     uint32_t since_flush = 0;
-    for (uint64_t u = u_begin; u < u_end; ++u) {
+    float rd[8], ri[4];
+    auto fetch = [&](uint64_t u) {
         const uint64_t t = u / upt, e0 = (u - t * upt) * NT_BK;
-        // D tile [64 m][32 e], In tile [64 n][32 e]: 2048 values each, 8 per thread, e fastest
+        // D tile [128 m][16 e]: 8 values per thread; In tile [64 n][16 e]: 4 per thread; e fastest
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int idx = tid + i * NT_THREADS, r = idx >> 5, k = idx & 31;
+            const int idx = tid + i * NT_THREADS, r = idx >> 4, k = idx & 15;
             const uint64_t e = e0 + k;
-            const int m = m0 + r, n = n0 + r;
-            Ds[r][k] = (m < M && e < E) ? D[(t * M + m) * E + e] : 0.0f;
+            const int m = m0 + r;
+            rd[i] = (m < M && e < E) ? D[(t * M + m) * E + e] : 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * NT_THREADS, r = idx >> 4, k = idx & 15;
+            const uint64_t e = e0 + k;
+            const int n = n0 + r;
             float v = 0.0f;
             if (e < E) {
                 if (n < rows0) v = src0[(t * rows0 + n) * E + e];
                 else if (n < NIN) v = src1[(t * rows1 + (n - rows0)) * E + e];
                 else if (n == NIN) v = 1.0f;
             }
-            Is[r][k] = v;
+            ri[i] = v;
+        }
+    };
+    if (u_begin < u_end) fetch(u_begin);
+    for (uint64_t u = u_begin; u < u_end; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * NT_THREADS;
+            Ds[idx & 15][idx >> 4] = rd[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * NT_THREADS;
+            Is[idx & 15][idx >> 4] = ri[i];
         }
         __syncthreads();
+        if (u + 1 < u_end) fetch(u + 1);
 #pragma unroll
         for (int k = 0; k < NT_BK; ++k) {
-            float dv[4], iv[4];
+            const float4 d0 = *reinterpret_cast<const float4 *>(&Ds[k][ty * 8]), d1 = *reinterpret_cast<const float4 *>(&Ds[k][ty * 8 + 4]);
+            const float4 i4 = *reinterpret_cast<const float4 *>(&Is[k][tx * 4]);
+            const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            const float iv[4] = {i4.x, i4.y, i4.z, i4.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dv[i] = Ds[ty * 4 + i][k];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) iv[j] = Is[tx * 4 + j][k];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], iv[j], acc[i][j]);
         }
         __syncthreads();
-        if (++since_flush == 64) {
+        if (++since_flush == 128) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { tot[i][j] += (double)acc[i][j]; acc[i][j] = 0.0f; }
             since_flush = 0;
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + ty * 8 + i;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
@@ -488,6 +533,33 @@ __global__ void big_assemble_kernel(const double *__restrict__ dWc, const double
     }
 }
 
+// outputs of the Linear head for one step: out[k][e] = lb[k] + sum_j lw[k][j] act(hnew[j][e]); zero where `only` is given and
+// the step's successor code differs from it (out_next: only interrupted steps), and on padding
+__global__ void __launch_bounds__(128) big_head_out_kernel(const float *__restrict__ theta, int o_lw, int act, const float *__restrict__ HNEW,
+                                                          const uint8_t *__restrict__ succ_t, int only, float *__restrict__ out_t, int H,
+                                                          int A, uint64_t E) {
+    extern __shared__ float hsm2[];  // lw [A][H], lb [A]
+    for (int i = threadIdx.x; i < A * H + A; i += blockDim.x) hsm2[i] = theta[o_lw + i];
+    __syncthreads();
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint8_t sc = succ_t[e];
+    const bool live = sc != RL_PAD && (only < 0 || sc == only);
+    float z[HEAD_MAXA];
+#pragma unroll
+    for (int k = 0; k < HEAD_MAXA; ++k) z[k] = k < A ? hsm2[A * H + k] : 0.0f;
+    if (live)
+        for (int j = 0; j < H; ++j) {
+            const float av = rl_activate(act, HNEW[(uint64_t)j * E + e]);
+#pragma unroll
+            for (int k = 0; k < HEAD_MAXA; ++k)
+                if (k < A) z[k] = fmaf(hsm2[k * H + j], av, z[k]);
+        }
+#pragma unroll
+    for (int k = 0; k < HEAD_MAXA; ++k)
+        if (k < A) out_t[(uint64_t)k * E + e] = live ? z[k] : 0.0f;
+}
+
 template <int MODE>
 rl_status launch_head(rl_ctx *ctx, const rl_seq_pass_args &a, const BigPlanes &pl, double *scal_part, int blocks) {
     const size_t smem = (size_t)2 * (a.A * a.H + a.A) * sizeof(float);
@@ -497,8 +569,15 @@ rl_status launch_head(rl_ctx *ctx, const rl_seq_pass_args &a, const BigPlanes &p
 
 rl_status gemm_nn(rl_ctx *ctx, const float *A, int lda, const float *B0, const float *B1, int K0, uint64_t ldb, float *C, uint64_t ldc,
                   const float *bias, int accumulate, int M, uint64_t N, int K, const int *skip_flag) {
-    dim3 grid((unsigned)rl_div_up(N, BN), (unsigned)rl_div_up(M, BM));
-    RL_LAUNCH(ctx, gemm_nn_kernel, grid, GEMM_THREADS, 0, A, lda, B0, B1, K0, ldb, C, ldc, bias, accumulate, M, N, K, skip_flag);
+    // 128-row tiles while they give at least two CTAs per SM, else 64-row tiles (the H-row carry GEMM of the backward sweep)
+    const uint64_t ctas128 = rl_div_up(N, BN) * rl_div_up(M, 128);
+    if (M >= 128 && ctas128 >= (uint64_t)2 * ctx->sm_count) {
+        dim3 grid((unsigned)rl_div_up(N, BN), (unsigned)rl_div_up(M, 128));
+        RL_LAUNCH(ctx, gemm_nn_kernel<8>, grid, GEMM_THREADS, 0, A, lda, B0, B1, K0, ldb, C, ldc, bias, accumulate, M, N, K, skip_flag);
+    } else {
+        dim3 grid((unsigned)rl_div_up(N, BN), (unsigned)rl_div_up(M, 64));
+        RL_LAUNCH(ctx, gemm_nn_kernel<4>, grid, GEMM_THREADS, 0, A, lda, B0, B1, K0, ldb, C, ldc, bias, accumulate, M, N, K, skip_flag);
+    }
     return RL_OK;
 }
 
@@ -589,5 +668,44 @@ rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &
         RL_LAUNCH(ctx, splitk_reduce_kernel, (unsigned)rl_div_up(A * NH, 256), 256, 0, partH, splits, A * NH, dHead, skip);
     }
     RL_LAUNCH(ctx, big_assemble_kernel, 32, 256, 0, dWc, dHead, scal_part, head_blocks, F, H, A, backward ? 1 : 0, a.partials, skip);
+    return RL_OK;
+}
+
+// SeqPacked::seq_packed over a stored trajectory (gru.rs:72-102 -> chain.rs:157-168) in the GEMM form: out f32 [T][A][E] (zeros
+// on padding) and, when out_next is given, the module's output on the successor observation of every interrupted step
+// (features.rs:139-185: one more step of the same sequence).  What rl_gae_seq needs from a hidden-128 critic.
+rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int A, int act, const float *obs, const float *next_obs,
+                             const uint8_t *succ, uint64_t T, uint64_t E, float *out, float *out_next) {
+    const int KP = F + H;
+    const uint64_t HE = (uint64_t)H * E;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += al(bytes); return o; };
+    const size_t o_Wc = take((size_t)4 * H * KP * 4), o_bc = take((size_t)4 * H * 4), o_G = take(4 * HE * 4);
+    const size_t o_tmp = take(4 * HE * 4), o_hn = take(HE * 4), o_h2 = take(HE * 4), o_ha = take(HE * 4), o_hb = take(HE * 4);
+    char *base;
+    RL_TRY(rl_ctx_scratch2(ctx, off + 256, (void **)&base));
+    float *Wc = (float *)(base + o_Wc), *bc = (float *)(base + o_bc), *G = (float *)(base + o_G), *tmp = (float *)(base + o_tmp);
+    float *hnew = (float *)(base + o_hn), *h2 = (float *)(base + o_h2), *hcur = (float *)(base + o_ha), *hnxt = (float *)(base + o_hb);
+    const unsigned pw_grid = (unsigned)rl_div_up(HE, 256), e_grid = (unsigned)rl_div_up(E, 128);
+    const int o_lw = 3 * H * F + 3 * H * H + 6 * H;
+    const size_t hsmem = (size_t)(A * H + A) * sizeof(float);
+    RL_LAUNCH(ctx, big_comb_kernel, 64, 256, 0, params, F, H, Wc, bc, (float *)nullptr);
+    RL_LAUNCH(ctx, big_zero_kernel, 256, 256, 0, hcur, HE, (const int *)nullptr);
+    for (uint64_t t = 0; t < T; ++t) {
+        const uint8_t *succ_t = succ + t * E;
+        RL_TRY(gemm_nn(ctx, Wc, KP, obs + t * (uint64_t)F * E, hcur, F, E, G, E, bc, 0, 4 * H, E, KP, nullptr));
+        RL_LAUNCH(ctx, big_gates_kernel, pw_grid, 256, 0, G, hcur, succ_t, tmp, tmp + HE, tmp + 2 * HE, tmp + 3 * HE, hnew, hnxt, H, E,
+                  (const int *)nullptr);
+        RL_LAUNCH(ctx, big_head_out_kernel, e_grid, 128, hsmem, params, o_lw, act, hnew, succ_t, -1, out + t * (uint64_t)A * E, H, A, E);
+        if (out_next) {
+            RL_TRY(gemm_nn(ctx, Wc, KP, next_obs + t * (uint64_t)F * E, hnew, F, E, G, E, bc, 0, 4 * H, E, KP, nullptr));
+            RL_LAUNCH(ctx, big_gates_kernel, pw_grid, 256, 0, G, hnew, succ_t, tmp, tmp + HE, tmp + 2 * HE, tmp + 3 * HE, h2, (float *)nullptr, H,
+                      E, (const int *)nullptr);
+            RL_LAUNCH(ctx, big_head_out_kernel, e_grid, 128, hsmem, params, o_lw, act, h2, succ_t, (int)RL_INTERRUPT,
+                      out_next + t * (uint64_t)A * E, H, A, E);
+        }
+        std::swap(hcur, hnxt);
+    }
     return RL_OK;
 }

@@ -98,6 +98,8 @@ bool rl_seq_pass_supports(int F, int H, int A);
 // gru_big.cu (K10): the same passes as tiled GEMMs over the lanes of a step, hidden <= 128; ONE partial row at a.partials
 bool rl_seq_big_supports(int F, int H, int A);
 rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a);
+rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int A, int act, const float *obs, const float *next_obs,
+                             const uint8_t *succ, uint64_t T, uint64_t E, float *out, float *out_next);
 struct rl_grunet_view { rl_ctx *ctx; int in_dim, hidden, out_dim, act; uint64_t n_params; float *params; };
 rl_grunet_view rl_grunet_view_of(rl_grunet *g);
 rl_status rl_grunet_seq_enqueue(rl_grunet *g, rl_traj *traj, float *out_dev, float *out_next_dev);
