@@ -110,7 +110,7 @@ class ClockSampler:
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,timestamp")
 
     def __init__(self, device_index: int):
         self.idx = device_index
@@ -127,8 +127,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        """Wall-clock start of the region whose samples count (the sampler itself starts earlier: with 8 GPUs nvidia-smi
+        needs more than a second before its first line)."""
+        self.t_begin = time.time()
+
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        t_end = time.time()
         if self.proc is None:
             return out
         time.sleep(0.15)
@@ -138,26 +144,29 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, smax, reasons = [], [], set()
+        import datetime
+
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
+                if len(p) < 10:
                     continue
                 try:
-                    sm.append(float(p[1]))
-                    smax.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[9], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[1]), float(p[2]), [n for n, v in zip(names, p[5:9]) if v.lower().startswith("active")]))
                 except ValueError:
                     continue
-                for n, v in zip(names, p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons), samples=len(sm))
+        t0 = getattr(self, "t_begin", 0.0)
+        inside = [r for r in rows if t0 - 0.05 <= r[0] <= t_end + 0.05]
+        use, where = (inside, "timed + e2e region") if inside else (rows[-5:], "last samples before the region ended (none fell inside)")
+        if use:
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       reasons=sorted({n for r in use for n in r[3]}), samples=len(use), window=where)
         return out
 
 
@@ -282,6 +291,10 @@ def run_ours(args):
 
     rank, world, local, dist = dist_setup()
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    # clocks / throttle reasons: nvidia-smi every 20 ms, started first (its start-up takes over a second on an 8-GPU box);
+    # only the samples stamped inside the timed + e2e region are used
+    clocks = ClockSampler(local)
+    clocks.start()
     ctx = R.Context(local)
     info = ctx.device_info()
     E, T = args.envs, args.horizon
@@ -311,13 +324,10 @@ def run_ours(args):
         if timed_events is not None:
             timed_events[1].record()
 
-    # clocks / throttle reasons are sampled every 20 ms from the warm-up to the end of the e2e loop (the device-timed
-    # region alone lasts ~16 ms at the default 100 steps)
-    clocks = ClockSampler(local)
-    clocks.start()
     for _ in range(max(args.warmup, 3)):
         one_period()
     barrier(dist, ctx)
+    clocks.mark_begin()
     evs = [(ctx.event(), ctx.event()) for _ in range(args.steps)]
     launches0 = ctx.launch_count
     barrier(dist, ctx)

@@ -36,13 +36,18 @@ def main():
 
     # 2. + 3. sharded vs full
     E, T, seed = 512, 96, 11
+    REG = float(os.environ.get("RL_CHECK_HPV_REG", "0.1"))
     cfg = R.CartPoleConfig().wrap(R.VisibleStepLimit(500))
     rng = np.random.default_rng(0)
     pparams, vparams = R.init_params(rng, 5, 128, 2), R.init_params(rng, 5, 128, 1)
 
     def run(context, n_lanes, offset):
         env = R.build_env(context, cfg, n_lanes, seed=seed, lane_offset=offset)
-        agent = R.ActorCriticConfig(critic_config=R.ValuesOptConfig(opt_steps_per_update=10)).build_agent(env)
+        # hpv_reg_coeff 0.1: ten f32 CG iterations stay well conditioned, so the comparison measures the reduction over the
+        # ranks and not the amplification of its rounding by the reference's own 1e-5 (tests/test_gpu_update.py; with 1e-5
+        # this 48 k-step batch gives 0 at 2 ranks and 3e-3 at 8)
+        agent = R.ActorCriticConfig(policy_config=R.TrpoConfig(optimizer_config=R.ConjugateGradientOptimizerConfig(hpv_reg_coeff=REG)),
+                                    critic_config=R.ValuesOptConfig(opt_steps_per_update=10)).build_agent(env)
         agent.policy.policy_fn.set_weights(pparams)
         agent.critic.state_value_fn.set_weights(vparams)
         traj = R.Trajectory(env, T)
@@ -62,7 +67,7 @@ def main():
             assert np.array_equal(host_f[k][:, :per], host_s[k]), f"shard 0 differs from the full env in {k}"
         rel = lambda a, b: float(np.linalg.norm(a.astype(np.float64) - b) / max(np.linalg.norm(b - (pparams if b.size == pparams.size else vparams)), 1e-30))
         dp, dv = rel(p_s, p_f), rel(v_s, v_f)
-        print(f"world={world}: N={log_s['num_steps']} (full {log_f['num_steps']}), status {st_s}/{st_f}, backtracks "
+        print(f"world={world} hpv_reg_coeff={REG}: N={log_s['num_steps']} (full {log_f['num_steps']}), status {st_s}/{st_f}, backtracks "
               f"{log_s['num_backtracks']}/{log_f['num_backtracks']}, policy delta rel diff {dp:.2e}, critic delta rel diff {dv:.2e}",
               flush=True)
         ok = (log_s["num_steps"] == log_f["num_steps"] and st_s == st_f and log_s["num_backtracks"] == log_f["num_backtracks"]
