@@ -311,8 +311,10 @@ __global__ void big_gates_tan_kernel(const float *__restrict__ tG, const float *
 }
 
 // Linear head + the per-step algebra of gru_pass_kernel over all (t, e); one partial of the four scalar sums per block
-constexpr int HEAD_THREADS = 128, HEAD_MAXA = 32;
-template <int MODE>
+constexpr int HEAD_THREADS = 128, HEAD_MAXA_ALL = 32;
+// HEAD_MAXA = the compile-time bound of the per-thread arrays over the outputs (logits, probabilities, cotangent): 16 keeps
+// them in registers for the module sizes of the experiments (2 .. 10 arms); 32 serves the rest through local memory
+template <int MODE, int HEAD_MAXA>
 __global__ void __launch_bounds__(HEAD_THREADS) big_head_kernel(rl_seq_pass_args a, const float *__restrict__ HNEW,
                                                                 const float *__restrict__ THNEW, double *__restrict__ scal_part) {
     constexpr bool BACKWARD = MODE == RL_PASS_GRAD || MODE == RL_PASS_FVP || MODE == RL_PASS_VALUE || MODE == RL_PASS_PPO ||
@@ -526,10 +528,19 @@ __global__ void big_assemble_kernel(const double *__restrict__ dWc, const double
         }
         row[i] = v;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 4) {
+    if (blockIdx.x == 0) {
+        // the four scalar sums over the head kernel's block partials: 64 strided chains per scalar, then a fixed-order tree
+        __shared__ double red[4][64];
+        const int sc = threadIdx.x >> 6, ln = threadIdx.x & 63;  // 256 threads = 4 scalars x 64 chains
         double s = 0.0;
-        for (int b = 0; b < nscal; ++b) s += scal_part[(size_t)b * 4 + threadIdx.x];
-        row[P + threadIdx.x] = s;
+        for (int b = ln; b < nscal; b += 64) s += scal_part[(size_t)b * 4 + sc];
+        red[sc][ln] = s;
+        __syncthreads();
+        for (int w = 32; w > 0; w >>= 1) {
+            if (ln < w) red[sc][ln] += red[sc][ln + w];
+            __syncthreads();
+        }
+        if (ln == 0) row[P + sc] = red[sc][0];
     }
 }
 
@@ -545,6 +556,7 @@ __global__ void __launch_bounds__(128) big_head_out_kernel(const float *__restri
     if (e >= E) return;
     const uint8_t sc = succ_t[e];
     const bool live = sc != RL_PAD && (only < 0 || sc == only);
+    constexpr int HEAD_MAXA = HEAD_MAXA_ALL;
     float z[HEAD_MAXA];
 #pragma unroll
     for (int k = 0; k < HEAD_MAXA; ++k) z[k] = k < A ? hsm2[A * H + k] : 0.0f;
@@ -560,10 +572,47 @@ __global__ void __launch_bounds__(128) big_head_out_kernel(const float *__restri
         if (k < A) out_t[(uint64_t)k * E + e] = live ? z[k] : 0.0f;
 }
 
+#include "gru_big_tc.cuh"
+
+// RL_SEQ_TC=0 keeps the per-step GEMMs on the FP32 pipe (cross-check / measurements)
+bool seq_tc_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("RL_SEQ_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <int N, int EPI>
+rl_status launch_tc(rl_ctx *ctx, const bt::BtArgs &a_in) {
+    bt::BtArgs a = a_in;
+    static long long *dbg = nullptr;
+    static int dbg_left = getenv("RL_SEQ_TC_DEBUG") ? 3 : 0;
+    if (dbg_left > 0) {
+        if (!dbg) cudaMallocManaged(&dbg, 64);
+        cudaDeviceSynchronize();
+        a.dbg = dbg;
+    }
+    static bool configured = false;
+    if (!configured) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(bt::big_gemm_tc_kernel<N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::bt_smem(N)));
+        configured = true;
+    }
+    RL_LAUNCH(ctx, (bt::big_gemm_tc_kernel<N, EPI>), (unsigned)rl_div_up(a.E, bt::BT_LANES), bt::BT_THREADS, bt::bt_smem(N), a);
+    if (dbg_left > 0) {
+        cudaDeviceSynchronize();
+        fprintf(stderr, "big_gemm_tc<%d,%d> nsteps %d: setup %lld clk, steps %lld clk, epilogue %lld clk\n", N, EPI, a.nsteps, dbg[0], dbg[1], dbg[2]);
+        --dbg_left;
+    }
+    return RL_OK;
+}
+
 template <int MODE>
 rl_status launch_head(rl_ctx *ctx, const rl_seq_pass_args &a, const BigPlanes &pl, double *scal_part, int blocks) {
     const size_t smem = (size_t)2 * (a.A * a.H + a.A) * sizeof(float);
-    RL_LAUNCH(ctx, big_head_kernel<MODE>, blocks, HEAD_THREADS, smem, a, pl.HNEW, pl.THNEW, scal_part);
+    if (a.A <= 16) RL_LAUNCH(ctx, (big_head_kernel<MODE, 16>), blocks, HEAD_THREADS, smem, a, pl.HNEW, pl.THNEW, scal_part);
+    else RL_LAUNCH(ctx, (big_head_kernel<MODE, HEAD_MAXA_ALL>), blocks, HEAD_THREADS, smem, a, pl.HNEW, pl.THNEW, scal_part);
     return RL_OK;
 }
 
@@ -583,7 +632,7 @@ rl_status gemm_nn(rl_ctx *ctx, const float *A, int lda, const float *B0, const f
 
 }  // namespace
 
-bool rl_seq_big_supports(int F, int H, int A) { return F >= 1 && F <= 64 && H >= 1 && H <= 128 && A >= 1 && A <= HEAD_MAXA; }
+bool rl_seq_big_supports(int F, int H, int A) { return F >= 1 && F <= 64 && H >= 1 && H <= 128 && A >= 1 && A <= HEAD_MAXA_ALL; }
 
 // One pass through the GEMM formulation; writes ONE partial row of P + 4 doubles at a.partials.
 rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a) {
@@ -607,8 +656,21 @@ rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &
     const size_t o_AV = take(backward ? plane : 0), o_TH = take(fvp ? plane : 0), o_D = take(backward ? 4 * plane : 0);
     const size_t o_partW = take(backward ? (size_t)splits * 4 * H * NB * 8 : 0), o_partH = take(backward ? (size_t)splits * A * NH * 8 : 0);
     const size_t o_dWc = take((size_t)4 * H * NB * 8), o_dHead = take((size_t)A * NH * 8), o_scal = take((size_t)head_blocks * 4 * 8);
+    // tensor-core form of the per-step GEMMs (gru_big_tc.cuh): weight pieces of the three matrices
+    const bool use_tc = H == 128 && seq_tc_enabled();
+    const int stW = (KP + 15) / 16, stT = (KP + H + 15) / 16, stB = (3 * H + 15) / 16;
+    const size_t o_wpW = take(use_tc ? (size_t)stW * bt::bt_b_stage(512) : 0), o_wpT = take(use_tc && fvp ? (size_t)stT * bt::bt_b_stage(512) : 0);
+    const size_t o_wpB = take(use_tc && backward ? (size_t)stB * bt::bt_b_stage(128) : 0);
+    // weight gradients on the tensor cores: one split per SM and M half, f32 slabs drained every NT_DRAIN steps
+    const bool nt_tc = use_tc && backward && KP + 1 <= bt::NT_ROWS_B;
+    const int nt_splits = ctx->sm_count / 2 > 0 ? ctx->sm_count / 2 : 1;
+    const uint64_t nt_units = T * ((E + 15) / 16);
+    const int nt_nd = (int)rl_div_up(rl_div_up(nt_units, (uint64_t)nt_splits) + 1, (uint64_t)bt::NT_DRAIN);
+    const size_t nt_part_bytes = (size_t)nt_splits * nt_nd * 2 * bt::NT_ROWS_A * bt::NT_ROWS_B * sizeof(float);
+    const size_t o_ntpart = take(nt_tc ? nt_part_bytes : 0);
     char *base;
     RL_TRY(rl_ctx_scratch2(ctx, off + 256, (void **)&base));
+    uint16_t *wpW = (uint16_t *)(base + o_wpW), *wpT = (uint16_t *)(base + o_wpT), *wpB = (uint16_t *)(base + o_wpB);
     float *Wc = (float *)(base + o_Wc), *bc = (float *)(base + o_bc), *WhT = (float *)(base + o_WhT);
     float *Vc = (float *)(base + o_Vc), *vbc = (float *)(base + o_vbc);
     BigPlanes pl{};
@@ -618,15 +680,44 @@ rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &
     double *partW = (double *)(base + o_partW), *partH = (double *)(base + o_partH), *dWc = (double *)(base + o_dWc),
            *dHead = (double *)(base + o_dHead), *scal_part = (double *)(base + o_scal);
     const unsigned pw_grid = (unsigned)rl_div_up(HE, 256);
+    if (use_tc) {
+        // The tensor-core GEMMs take 184 .. 196 KB of shared memory; the pointwise kernels launched between them take none.
+        // Asking for the same (maximum) carve-out everywhere keeps the SMs from re-partitioning L1 / shared memory at every
+        // launch boundary of the per-step sequences.
+        static bool carved = false;
+        if (!carved) {
+            cudaFuncSetAttribute(big_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(big_zero_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(big_head_out_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carved = true;
+        }
+    }
 
     // ---- forward (and the tangent along a.vec) ----
     RL_LAUNCH(ctx, big_comb_kernel, 64, 256, 0, a.theta, F, H, Wc, bc, WhT);
     if (fvp) RL_LAUNCH(ctx, big_comb_kernel, 64, 256, 0, a.vec, F, H, Vc, vbc, (float *)nullptr);
+    if (use_tc) {
+        RL_LAUNCH(ctx, bt::big_pieces_kernel, 128, 256, 0, Wc, KP, KP, (const float *)nullptr, 0, 0, 4 * H, stW, wpW);
+        if (fvp) RL_LAUNCH(ctx, bt::big_pieces_kernel, 128, 256, 0, Vc, KP, KP, Wc + F, KP, H, 4 * H, stT, wpT);
+        if (backward) RL_LAUNCH(ctx, bt::big_pieces_kernel, 128, 256, 0, WhT, 3 * H, 3 * H, (const float *)nullptr, 0, 0, H, stB, wpB);
+    }
     RL_LAUNCH(ctx, big_zero_kernel, 256, 256, 0, a.hbuf, HE, skip);  // SeqIterative::initial_state (gru.rs:23-28)
     if (fvp) RL_LAUNCH(ctx, big_zero_kernel, 256, 256, 0, pl.thp, HE, skip);
     for (uint64_t t = 0; t < T; ++t) {
         const float *x_t = a.obs + t * (uint64_t)F * E, *hp_t = a.hbuf + t * HE;
         const uint8_t *succ_t = a.succ + t * E;
+        if (use_tc) {
+            bt::BtArgs g{};
+            g.src0 = x_t; g.src1 = hp_t; g.src2 = hp_t; g.k0 = F; g.k1 = KP; g.K = KP; g.nsteps = stW; g.wp = wpW; g.E = E; g.bias = bc;
+            g.succ_t = succ_t; g.R = pl.R + t * HE; g.U = pl.U + t * HE; g.Nn = pl.N + t * HE; g.HN = pl.HN + t * HE; g.HNEW = pl.HNEW + t * HE;
+            g.hnext = t + 1 < T ? a.hbuf + (t + 1) * HE : nullptr; g.skip_flag = skip;
+            RL_TRY((launch_tc<512, bt::EPI_GATES>(ctx, g)));
+            if (fvp) {
+                g.src2 = pl.thp; g.K = KP + H; g.nsteps = stT; g.wp = wpT; g.bias = vbc; g.THNEW = pl.THNEW + t * HE; g.thp = pl.thp;
+                RL_TRY((launch_tc<512, bt::EPI_TAN>(ctx, g)));
+            }
+            continue;
+        }
         RL_TRY(gemm_nn(ctx, Wc, KP, x_t, hp_t, F, E, pl.G, E, bc, 0, 4 * H, E, KP, skip));
         RL_LAUNCH(ctx, big_gates_kernel, pw_grid, 256, 0, pl.G, hp_t, succ_t, pl.R + t * HE, pl.U + t * HE, pl.N + t * HE, pl.HN + t * HE,
                   pl.HNEW + t * HE, t + 1 < T ? a.hbuf + (t + 1) * HE : (float *)nullptr, H, E, skip);
@@ -657,12 +748,34 @@ rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &
                       pl.AV + t * HE, H, A, E, skip);
             if (t > 0) {
                 const float *D_t = pl.D + (uint64_t)t * 4 * HE;
-                RL_TRY(gemm_nn(ctx, WhT, 3 * H, D_t, D_t, 3 * H, E, pl.dh, E, nullptr, 1, H, E, 3 * H, skip));
+                if (use_tc) {
+                    bt::BtArgs g{};
+                    g.src0 = D_t; g.src1 = D_t; g.src2 = D_t; g.k0 = 3 * H; g.k1 = 3 * H; g.K = 3 * H; g.nsteps = stB; g.wp = wpB; g.E = E;
+                    g.out = pl.dh; g.skip_flag = skip;
+                    RL_TRY((launch_tc<128, bt::EPI_ACC>(ctx, g)));
+                } else {
+                    RL_TRY(gemm_nn(ctx, WhT, 3 * H, D_t, D_t, 3 * H, E, pl.dh, E, nullptr, 1, H, E, 3 * H, skip));
+                }
             }
         }
-        dim3 gW((unsigned)rl_div_up(NB, NT_BN), (unsigned)rl_div_up(4 * H, NT_BM), (unsigned)splits);
-        RL_LAUNCH(ctx, gemm_nt_splitk_kernel, gW, NT_THREADS, 0, pl.D, 4 * H, a.obs, F, a.hbuf, H, T, E, partW, NB, splits, skip);
-        RL_LAUNCH(ctx, splitk_reduce_kernel, (unsigned)rl_div_up(4 * H * NB, 256), 256, 0, partW, splits, 4 * H * NB, dWc, skip);
+        if (nt_tc) {
+            float *ntpart = (float *)(base + o_ntpart);
+            RL_CUDA(ctx, cudaMemsetAsync(ntpart, 0, nt_part_bytes, ctx->stream));
+            static bool nt_configured = false;
+            if (!nt_configured) {
+                RL_CUDA(ctx, cudaFuncSetAttribute(bt::big_nt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bt::nt_smem()));
+                nt_configured = true;
+            }
+            bt::NtArgs na{};
+            na.D = pl.D; na.src0 = a.obs; na.src1 = a.hbuf; na.rows0 = F; na.rows1 = H; na.T = T; na.E = E; na.part = ntpart;
+            na.splits = nt_splits; na.nd = nt_nd; na.skip_flag = skip;
+            RL_LAUNCH(ctx, bt::big_nt_tc_kernel, dim3((unsigned)nt_splits, 2), bt::BT_THREADS, bt::nt_smem(), na);
+            RL_LAUNCH(ctx, bt::splitk_reduce_f32_kernel, (unsigned)rl_div_up(512 * bt::NT_ROWS_B, 256), 256, 0, ntpart, nt_splits * nt_nd, NB, dWc, skip);
+        } else {
+            dim3 gW((unsigned)rl_div_up(NB, NT_BN), (unsigned)rl_div_up(4 * H, NT_BM), (unsigned)splits);
+            RL_LAUNCH(ctx, gemm_nt_splitk_kernel, gW, NT_THREADS, 0, pl.D, 4 * H, a.obs, F, a.hbuf, H, T, E, partW, NB, splits, skip);
+            RL_LAUNCH(ctx, splitk_reduce_kernel, (unsigned)rl_div_up(4 * H * NB, 256), 256, 0, partW, splits, 4 * H * NB, dWc, skip);
+        }
         dim3 gH((unsigned)rl_div_up(NH, NT_BN), (unsigned)rl_div_up(A, NT_BM), (unsigned)splits);
         RL_LAUNCH(ctx, gemm_nt_splitk_kernel, gH, NT_THREADS, 0, a.dzbuf, A, pl.AV, H, (const float *)nullptr, 0, T, E, partH, NH, splits, skip);
         RL_LAUNCH(ctx, splitk_reduce_kernel, (unsigned)rl_div_up(A * NH, 256), 256, 0, partH, splits, A * NH, dHead, skip);
@@ -683,8 +796,12 @@ rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int
     auto take = [&](size_t bytes) { const size_t o = off; off += al(bytes); return o; };
     const size_t o_Wc = take((size_t)4 * H * KP * 4), o_bc = take((size_t)4 * H * 4), o_G = take(4 * HE * 4);
     const size_t o_tmp = take(4 * HE * 4), o_hn = take(HE * 4), o_h2 = take(HE * 4), o_ha = take(HE * 4), o_hb = take(HE * 4);
+    const bool use_tc = H == 128 && seq_tc_enabled();
+    const int stW = (KP + 15) / 16;
+    const size_t o_wpW = take(use_tc ? (size_t)stW * bt::bt_b_stage(512) : 0);
     char *base;
     RL_TRY(rl_ctx_scratch2(ctx, off + 256, (void **)&base));
+    uint16_t *wpW = (uint16_t *)(base + o_wpW);
     float *Wc = (float *)(base + o_Wc), *bc = (float *)(base + o_bc), *G = (float *)(base + o_G), *tmp = (float *)(base + o_tmp);
     float *hnew = (float *)(base + o_hn), *h2 = (float *)(base + o_h2), *hcur = (float *)(base + o_ha), *hnxt = (float *)(base + o_hb);
     const unsigned pw_grid = (unsigned)rl_div_up(HE, 256), e_grid = (unsigned)rl_div_up(E, 128);
@@ -692,8 +809,26 @@ rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int
     const size_t hsmem = (size_t)(A * H + A) * sizeof(float);
     RL_LAUNCH(ctx, big_comb_kernel, 64, 256, 0, params, F, H, Wc, bc, (float *)nullptr);
     RL_LAUNCH(ctx, big_zero_kernel, 256, 256, 0, hcur, HE, (const int *)nullptr);
+    if (use_tc) RL_LAUNCH(ctx, bt::big_pieces_kernel, 128, 256, 0, Wc, KP, KP, (const float *)nullptr, 0, 0, 4 * H, stW, wpW);
+    auto cell_tc = [&](const float *x, const float *hp, const uint8_t *succ_t, float *hout, float *hnext) -> rl_status {
+        bt::BtArgs g{};
+        g.src0 = x; g.src1 = hp; g.src2 = hp; g.k0 = F; g.k1 = KP; g.K = KP; g.nsteps = stW; g.wp = wpW; g.E = E; g.bias = bc;
+        g.succ_t = succ_t; g.R = tmp; g.U = tmp + HE; g.Nn = tmp + 2 * HE; g.HN = tmp + 3 * HE; g.HNEW = hout; g.hnext = hnext;
+        return launch_tc<512, bt::EPI_GATES>(ctx, g);
+    };
     for (uint64_t t = 0; t < T; ++t) {
         const uint8_t *succ_t = succ + t * E;
+        if (use_tc) {
+            RL_TRY(cell_tc(obs + t * (uint64_t)F * E, hcur, succ_t, hnew, hnxt));
+            RL_LAUNCH(ctx, big_head_out_kernel, e_grid, 128, hsmem, params, o_lw, act, hnew, succ_t, -1, out + t * (uint64_t)A * E, H, A, E);
+            if (out_next) {
+                RL_TRY(cell_tc(next_obs + t * (uint64_t)F * E, hnew, succ_t, h2, nullptr));
+                RL_LAUNCH(ctx, big_head_out_kernel, e_grid, 128, hsmem, params, o_lw, act, h2, succ_t, (int)RL_INTERRUPT,
+                          out_next + t * (uint64_t)A * E, H, A, E);
+            }
+            std::swap(hcur, hnxt);
+            continue;
+        }
         RL_TRY(gemm_nn(ctx, Wc, KP, obs + t * (uint64_t)F * E, hcur, F, E, G, E, bc, 0, 4 * H, E, KP, nullptr));
         RL_LAUNCH(ctx, big_gates_kernel, pw_grid, 256, 0, G, hcur, succ_t, tmp, tmp + HE, tmp + 2 * HE, tmp + 3 * HE, hnew, hnxt, H, E,
                   (const int *)nullptr);
