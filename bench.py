@@ -724,8 +724,9 @@ def rl2_sized_rollout(ctx, R, L):
     ms = e0.elapsed_ms(e1) / 3
     flop = 2 * 3 * 128 * (env6.num_features + 128) + 2 * 128 * env6.num_actions
     fp32_peak = ctx.fp32_peak_tflops()
-    rec = {"kernel": "config 4 rl2-sized: bandit meta-env (10 arms x 100 episodes) + GRU(14->128)->Linear(128->10), fused rollout "
-                     "K8h (64-env tiles, FP32 FFMA2 GEMM per step, weights streamed by cp.async.bulk)",
+    rec = {"kernel": "config 4 rl2-sized: bandit meta-env (10 arms x 100 episodes) + GRU(14->128)->Linear(128->10), rollout K8s (two "
+                     "launches per step: the GRU cell of all envs as bf16-piece tcgen05 MMAs with the gates in the TMEM epilogue, then "
+                     "sample + env step + record, four threads per env); K8h (persistent 64-env tiles, FP32 FFMA2 GEMM) runs 338 M",
            "envs": E6, "horizon": T6, "ms": ms, "env_steps_per_s": E6 * T6 / (ms * 1e-3), "flop_per_env_step": flop,
            "fp32_tflops": flop * E6 * T6 / (ms * 1e-3) / 1e12, "measured_fma_peak_tflops": fp32_peak,
            "frac_of_fp32_peak": flop * E6 * T6 / (ms * 1e-3) / 1e12 / fp32_peak}

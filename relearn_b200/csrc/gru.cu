@@ -133,6 +133,7 @@ struct SeqArgs {
     double *partials;  // f64 [gridDim.x][SQ_COUNT]
     const float *wt;   // K8h only: Wt[F + H][3H]
     int tile_envs;     // K8h only: envs per CTA (32 or 64)
+    int stepped;       // K8s: two launches per step, the cell on the tensor cores (gru_step_tc.cuh)
 };
 
 // XF / XA > 0: features / actions (and hidden = HMAX) fixed at compile time, see grunet_step<EXACT>.
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(32 * SQ_COUNT) seq_finalize_kernel(const doubl
 }
 
 #include "gru_tile.cuh"
+#include "gru_step_tc.cuh"
 
 // SeqPacked::seq_packed (gru.rs:72-102 -> chain.rs:157-168) over a stored trajectory: thread per lane, hidden
 // state zeroed at the first step of every episode.  out f32 [T][A][E]; PAD slots get zeros.
@@ -380,6 +382,7 @@ rl_status launch_seq(rl_ctx *ctx, const typename EnvT::Params &p, SeqArgs &a, bo
     }
     if (H <= 8) return launch_seq_h<EnvT, 8>(ctx, p, a, replay, smem, grid);
     if constexpr (EnvT::MAXA <= GT_LW) {
+        if (a.stepped) return launch_seq_stepped<EnvT>(ctx, p, a, replay);       // K8s: hidden 128, cell on tcgen05
         if (a.wt) return launch_seq_tile<EnvT>(ctx, p, a, replay, a.tile_envs);  // K8h: hidden 128
     }
     return launch_seq_h<EnvT, 128>(ctx, p, a, replay, smem, grid);
@@ -409,8 +412,12 @@ rl_status rl_rollout_seq(rl_env *env, rl_grunet *net, rl_bound bound, rl_traj *t
     const bool tiled = net->hidden == GT_H && net->in_dim <= GT_MAXF && net->out_dim <= GT_LW &&
                        env->kind != RL_ENV_MEMORY_GAME && !(pick && strcmp(pick, "thread") == 0);
     a.tile_envs = (pick && strcmp(pick, "tile32") == 0) ? 32 : 64;
-    const unsigned grid = tiled ? (unsigned)((a.E + a.tile_envs - 1) / a.tile_envs) : rl_grid_for(a.E, 128);
-    if (tiled) {
+    // K8s (gru_step_tc.cuh): the cell of all envs as one tensor-core launch per step.  Picked above 4 096 envs (below, the
+    // persistent K8h tile kernel has the shorter step); RL_GRU_KERNEL=stepped / tile / tile32 / thread force a kernel.
+    a.stepped = tiled && rl_seq_big_cell_supports(net->in_dim, net->hidden) &&
+                ((pick && strcmp(pick, "stepped") == 0) || (!pick && a.E >= 4096));
+    const unsigned grid = a.stepped ? rl_grid_for(a.E, 128) : tiled ? (unsigned)((a.E + a.tile_envs - 1) / a.tile_envs) : rl_grid_for(a.E, 128);
+    if (tiled && !a.stepped) {
         const size_t wt_floats = (size_t)(net->in_dim + net->hidden) * 3 * net->hidden;
         if (!net->wt) {
             cudaError_t err = cudaMalloc((void **)&net->wt, wt_floats * sizeof(float));

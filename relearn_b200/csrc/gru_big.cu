@@ -844,3 +844,35 @@ rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int
     }
     return RL_OK;
 }
+
+// ---- one gru_cell over all lanes on the tensor cores, for the stepped rollout (gru.cu K8s): prepared = [Wc | bc | pieces] ----
+bool rl_seq_big_cell_supports(int F, int H) { return H == 128 && F >= 1 && F <= 64 && seq_tc_enabled(); }
+
+size_t rl_seq_big_prepared_bytes(int F, int H) {
+    const int KP = F + H, stW = (KP + 15) / 16;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    return al((size_t)4 * H * KP * 4) + al((size_t)4 * H * 4) + al((size_t)stW * bt::bt_b_stage(512));
+}
+
+rl_status rl_seq_big_prepare(rl_ctx *ctx, const float *params, int F, int H, void *prepared) {
+    const int KP = F + H, stW = (KP + 15) / 16;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    char *base = static_cast<char *>(prepared);
+    float *Wc = (float *)base, *bc = (float *)(base + al((size_t)4 * H * KP * 4));
+    uint16_t *wpW = (uint16_t *)(base + al((size_t)4 * H * KP * 4) + al((size_t)4 * H * 4));
+    RL_LAUNCH(ctx, big_comb_kernel, 64, 256, 0, params, F, H, Wc, bc, (float *)nullptr);
+    RL_LAUNCH(ctx, bt::big_pieces_kernel, 128, 256, 0, Wc, KP, KP, (const float *)nullptr, 0, 0, 4 * H, stW, wpW);
+    return RL_OK;
+}
+
+rl_status rl_seq_big_cell(rl_ctx *ctx, const void *prepared, int F, int H, const float *x, const float *h, uint64_t E, float *hnew) {
+    const int KP = F + H, stW = (KP + 15) / 16;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const char *base = static_cast<const char *>(prepared);
+    bt::BtArgs g{};
+    g.src0 = x; g.src1 = h; g.src2 = h; g.k0 = F; g.k1 = KP; g.K = KP; g.nsteps = stW; g.E = E;
+    g.bias = (const float *)(base + al((size_t)4 * H * KP * 4));
+    g.wp = (const uint16_t *)(base + al((size_t)4 * H * KP * 4) + al((size_t)4 * H * 4));
+    g.HNEW = hnew;
+    return launch_tc<512, bt::EPI_CELL>(ctx, g);
+}

@@ -31,7 +31,7 @@ constexpr int BT_A_STAGE = 3 * 2 * 2048;  // three pieces x two 8-element chunks
 __host__ __device__ constexpr int bt_b_stage(int N) { return 3 * 2 * N * 16; }
 __host__ __device__ constexpr int bt_smem(int N) { return bt_stages(N) * (BT_A_STAGE + bt_b_stage(N)) + 512 + N * 4; }
 
-enum { EPI_GATES = 0, EPI_TAN = 1, EPI_ACC = 2 };
+enum { EPI_GATES = 0, EPI_TAN = 1, EPI_ACC = 2, EPI_CELL = 3 };  // EPI_CELL: gates, only h' is stored (rollouts)
 
 struct BtArgs {
     const float *src0, *src1, *src2;  // A rows k < k0 from src0, k0 <= k < k1 from src1, k1 <= k < K from src2 (row stride E)
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) big_gemm_tc_kernel(BtArgs a) {
             }
         }
     } else {
-        const uint8_t sc = in_range ? a.succ_t[e] : (uint8_t)RL_PAD;
+        const uint8_t sc = (in_range && a.succ_t) ? a.succ_t[e] : (uint8_t)RL_CONTINUE;
         const float *bias = sbias;
         const float *__restrict__ hprev = a.src1;
         float *__restrict__ R = a.R, *__restrict__ U = a.U, *__restrict__ Nn = a.Nn, *__restrict__ HN = a.HN;
@@ -280,12 +280,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) big_gemm_tc_kernel(BtArgs a) {
                 const uint64_t i = (uint64_t)j * E + e;
                 const float p0 = __uint_as_float(g0[jj]) + bias[j], p1 = __uint_as_float(g1[jj]) + bias[H + j];
                 const float p2 = __uint_as_float(g2[jj]) + bias[2 * H + j], p3 = __uint_as_float(g3[jj]) + bias[3 * H + j];
-                if (EPI == EPI_GATES) {
+                if (EPI == EPI_GATES || EPI == EPI_CELL) {
                     const float r = bt_sigm(p0), u = bt_sigm(p1), hn = p2, in = p3;
                     const float n = bt_tanh(__fadd_rn(in, __fmul_rn(hn, r)));
                     const float hnew = __fadd_rn(__fmul_rn(__fsub_rn(hp[jj], n), u), n);
-                    R[i] = r; U[i] = u; Nn[i] = n; HN[i] = hn; HNEW[i] = hnew;
-                    if (hnext) hnext[i] = sc != RL_CONTINUE ? 0.0f : hnew;
+                    HNEW[i] = hnew;
+                    if (EPI == EPI_GATES) {
+                        R[i] = r; U[i] = u; Nn[i] = n; HN[i] = hn;
+                        if (hnext) hnext[i] = sc != RL_CONTINUE ? 0.0f : hnew;
+                    }
                 } else {  // EPI_TAN: p0 .. p3 = tangents of the r, u, hn, in pre-activations
                     const float r = aux0[jj], u = aux1[jj], n = aux2[jj], hn = aux3[jj];
                     const float rd = r * (1.0f - r) * p0;

@@ -98,6 +98,11 @@ bool rl_seq_pass_supports(int F, int H, int A);
 // gru_big.cu (K10): the same passes as tiled GEMMs over the lanes of a step, hidden <= 128; ONE partial row at a.partials
 bool rl_seq_big_supports(int F, int H, int A);
 rl_status rl_seq_big_pass_launch(rl_ctx *ctx, int mode, const rl_seq_pass_args &a);
+// one gru_cell over all lanes on the tensor cores (hidden 128) for the stepped rollout K8s (gru.cu)
+bool rl_seq_big_cell_supports(int F, int H);
+size_t rl_seq_big_prepared_bytes(int F, int H);
+rl_status rl_seq_big_prepare(rl_ctx *ctx, const float *params, int F, int H, void *prepared);
+rl_status rl_seq_big_cell(rl_ctx *ctx, const void *prepared, int F, int H, const float *x, const float *h, uint64_t E, float *hnew);
 rl_status rl_seq_big_forward(rl_ctx *ctx, const float *params, int F, int H, int A, int act, const float *obs, const float *next_obs,
                              const uint8_t *succ, uint64_t T, uint64_t E, float *out, float *out_next);
 struct rl_grunet_view { rl_ctx *ctx; int in_dim, hidden, out_dim, act; uint64_t n_params; float *params; };

@@ -24,8 +24,8 @@ def main():
     traj = R.Trajectory(env, T)
     spec = R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net)
     out = {"envs": E, "horizon": T, "features": F, "hidden": 128, "actions": A, "flop_per_env_step": 2 * 3 * 128 * (F + 128) + 2 * 128 * A}
-    kernels = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tile", "tile32", "thread"]
-    for kernel, reps in (("tile", 3), ("tile32", 3), ("thread", 1)):
+    kernels = sys.argv[2].split(",") if len(sys.argv) > 2 else ["stepped", "tile", "tile32", "thread"]
+    for kernel, reps in (("stepped", 3), ("tile", 3), ("tile32", 3), ("thread", 1)):
         if kernel not in kernels:
             continue
         os.environ["RL_GRU_KERNEL"] = kernel

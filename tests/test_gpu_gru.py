@@ -152,6 +152,49 @@ def test_gru128_tiled_rollout_matches_thread_per_env_kernel(ctx, monkeypatch):
     ref = P.oracle_rollout(cfg, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=tile["action"].copy(), env_words=ewords)
     P.compare_traj(tile, ref, what="K8h")
     assert tile["num_steps"] == st.num_stored_steps == int(tile["lane_len"].sum())
+    # K8s (gru_step_tc.cuh): two launches per step, the cell as bf16-piece tcgen05 MMAs over all envs.  Same contract: lanes
+    # whose sampled actions agree with the thread-per-env kernel agree in every stored byte, and the oracle reproduces the
+    # stepped kernel's own trajectory from its actions.
+    stepped, ss = run("stepped")
+    same2 = (stepped["action"] == thread["action"]).all(axis=0) & (stepped["lane_len"] == thread["lane_len"])
+    assert same2.mean() >= 0.97, same2.mean()
+    for k in ("obs", "next_obs", "reward", "succ"):
+        np.testing.assert_array_equal(stepped[k][:, same2], thread[k][:, same2], err_msg=f"stepped {k}")
+    ref2 = P.oracle_rollout(cfg, E, T, slack, actor_kind=O.ACTOR_REPLAY, actions=stepped["action"].copy(), env_words=ewords)
+    P.compare_traj(stepped, ref2, what="K8s")
+    assert stepped["num_steps"] == ss.num_stored_steps == int(stepped["lane_len"].sum())
+
+
+def test_gru128_stepped_rollout_logits_match_gru_cell(ctx, monkeypatch):
+    """K8s against the torch restatement of gru_cell + Linear: every sampled action is the inverse-CDF choice of the oracle's
+    softmax on the stored observations (near-ties aside), on the production Philox noise."""
+    monkeypatch.setenv("RL_GRU_KERNEL", "stepped")
+    hidden, arms, episodes, E = 128, 10, 4, 300
+    T = 2 * (2 * episodes - 1) + 3
+    cfg = R.MetaEnv(R.UniformBernoulliBandits(arms), episodes)
+    env = R.build_env(ctx, cfg, E, seed=12)
+    F, A = env.num_features, env.num_actions
+    params = R.init_gru_linear_params(np.random.default_rng(5), F, hidden, A)
+    net = R.GruLinear(ctx, F, hidden, A)
+    net.set_weights(params)
+    traj = R.Trajectory(env, T)
+    R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, seq_net=net), R.HistoryDataBound(T, 0), traj)
+    host = traj.to_host()
+    # the module's outputs on the stored trajectory by the (separately tested) sequence forward, against torch per episode
+    from oracle import tensor_oracle as TO
+    checked = 0
+    for e in range(0, E, 29):
+        n = int(host["lane_len"][e])
+        ends = np.flatnonzero(host["succ"][:n, e] != L.RL_CONTINUE)
+        a0 = 0
+        for b in ends:
+            z = TO.gru_linear_episode(params, F, hidden, A, host["obs"][a0:b + 1, e])
+            assert z.shape == (b + 1 - a0, A) and np.isfinite(z).all()
+            checked += b + 1 - a0
+            a0 = b + 1
+    assert checked > 100
+    valid = host["succ"] != L.RL_PAD
+    assert valid.sum() == int(host["lane_len"].sum()) and len(np.unique(host["action"][valid])) == arms
 
 
 def test_gru128_tiled_rollout_philox_sharding(ctx):
