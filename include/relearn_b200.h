@@ -385,7 +385,9 @@ rl_status rl_value_probe(rl_traj *traj, const float *targets_dev, rl_mlp *value_
 /* The same updates for a recurrent module (Chain<Gru, Linear>; rl2-bandits.rs:379-430): TRPO with   */
 /* back-propagation through time and a forward-tangent + BPTT Fisher-vector product in place of the  */
 /* reference's autograd double backward, ValuesOpt with a GRU critic, GAE over SeqPacked values.     */
-/* Built for hidden <= 8, features <= 20, actions <= 16; RL_ERR_UNSUPPORTED otherwise.               */
+/* hidden <= 8 (features <= 20, outputs <= 16): one thread per lane (K9).  Up to hidden 128, 64       */
+/* features, 32 outputs -- the rl2-sized GRU(14 -> 128) -> Linear(128 -> 10) -- as tiled GEMMs over  */
+/* the lanes of a step (K10; hidden 128 on tcgen05 tensor cores).  RL_ERR_UNSUPPORTED beyond.        */
 /* ------------------------------------------------------------------------------------------ */
 rl_status rl_trpo_update_seq(rl_traj *traj, const float *adv_dev, rl_grunet *policy, const rl_trpo_cfg *cfg,
                              rl_trpo_stats *stats);
