@@ -41,12 +41,12 @@ FLOP_PER_STEP_POLICY = 1792  # 2 * (5*128 + 128*2)
 # MMA1 128x128x48, MMA3 128x32x128, MMA2 128x32x128  =>  2 * (786432 + 524288 + 524288) / 128 = 28672 FLOP per sample.
 FLOP_PER_SAMPLE_CRITIC = 4608
 FLOP_ISSUED_PER_SAMPLE_CRITIC_TC = 28672
-# dram__bytes_read.sum + dram__bytes_write.sum of one K2w launch (the kernel `lanes_per_env = 0` picks) at E = 4096,
-# T = 256 from the round-1 `ncu --set full` capture of the final kernel (profiles/r1i_k2w_e4096.md): 50.7 KB + 17.4 KB
+# dram__bytes_read.sum + dram__bytes_write.sum of one K2q launch (the kernel `lanes_per_env = 0` picks) at E = 4096,
+# T = 256 from the round-2 `ncu --set full` capture of the final kernel (profiles/r2A_k2q_e4096.md): 58.6 KB + 3.6 KB
 # (the write figure is whatever part of the trajectory L2 happened to write back during the launch: 2.8 .. 22 KB over captures).  The 27 MB trajectory of a
 # period stays in the 126 MB L2 while the kernel runs and drains afterwards, so the in-kernel DRAM traffic
 # is far BELOW the algorithmic 26 B/env-step, not above it.
-K2C_NCU_DRAM_BYTES_PER_LAUNCH = 68096
+K2C_NCU_DRAM_BYTES_PER_LAUNCH = 62208
 
 
 WORKLOAD = "cartpole-trpo rollout (CartPole+VisibleStepLimit(500), MLP 5-128-2 policy: env step + policy act + sample + trajectory write)"
@@ -373,15 +373,17 @@ def run_ours(args):
                 "peak_source": "FFMA probe kernel timed in this run (rl_ctx_fp32_peak)",
                 "flop_per_env_step": FLOP_PER_STEP_POLICY,
                 "traffic": K2C_NCU_DRAM_BYTES_PER_LAUNCH if (E == 4096 and T == 256) else None,
-                "traffic_note": "ncu dram bytes of one launch (profiles/r1_summary.md s13).  The 27 MB trajectory of a period stays in "
+                "traffic_note": "ncu dram bytes of one launch (profiles/r2A_k2q_e4096.md).  The 27 MB trajectory of a period stays in "
                                 "the 126 MB L2 while the kernel runs; its write-back to HBM happens in the untimed L2 flush "
                                 "between iterations, i.e. OUTSIDE the timed region",
                 "hbm_write_stream": {"achieved": write_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": write_gbs / hbm_peak,
                                      "bytes_per_env_step": B_PER_STEP_ROLLOUT, "peak_source": peak_src},
-                "kernel": "rollout_cartpole_ws_kernel K2w (fused step+policy+sample; policy and dynamics on different warps)",
-                "note": "at 4096 envs (28 per SM) the period is 256 x the latency of one step chain (~1200 clk: policy warps' hidden "
-                        "layer + the dynamics warp's dependent f64 step, profiles/r2_summary.md); no pipe is busy (ncu: FMA 23 %, "
-                        "FP64 9 %, issue 40 %).  The HBM-bound kernels of the path are in kernels[] (77-81 % of the HBM peak)"}
+                "kernel": "rollout_cartpole_ws6_kernel K2q (fused step+policy+sample; one CTA per SM: one dynamics warp of 28 envs x both "
+                          "actions alone on its sub-partition, seven policy warps, an aux Philox warp)",
+                "note": "at 4096 envs (28 per SM) the period is 256 x the latency of one step (~980 clk; profiles/r2_summary.md section 5: "
+                        "dynamics warp 570 clk for both actions + select / publish, beside it three lock-step policy warps per "
+                        "sub-partition at ~750 clk row -> action); ncu: FMA 27 %, FP64 9 %, issue 39 %, barrier 2.9 of 7.5 stall cycles "
+                        "per instruction.  The HBM-bound kernels of the path are in kernels[] (77-81 % of the HBM peak)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -43,6 +43,8 @@ struct RolloutArgs {
     int dyn_first, dyn_second;  // K2w: warp index of the dynamics warp in the first / later CTAs of an SM
     int aux_first, aux_second;  // K2v / K2y: warp index of the aux (noise) warp
     int head_first, head_second;  // K2y: warp index of the head warp
+    uint64_t role_table;          // K2q: four bits per hardware warp (policy index 0..7, QK_ROLE_DYN / _AUX / _IDLE)
+    int policy_warps;             // K2q: policy warps per CTA (4 envs each)
 };
 
 struct LaneStats {
@@ -1066,6 +1068,8 @@ __global__ void __launch_bounds__(WK_THREADS) rollout_cartpole_ws_kernel(CartPol
 
 #include "rollout_ws3.cuh"
 #include "rollout_ws4.cuh"
+#include "rollout_ws5.cuh"
+#include "rollout_ws6.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // K2t: CartPole + 5->128->2 ReLU network with the hidden layer on the tensor cores (tcgen05 + TMEM), for env counts
@@ -1560,6 +1564,79 @@ rl_status launch_ws4(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, 
     return RL_OK;
 }
 
+rl_status launch_ws5(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    const unsigned grid = (unsigned)((a.E + VK_ENVS - 1) / VK_ENVS);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
+    // Warps map to the four sub-partitions by index (warps 0 / 4 and 1 / 5 share one).  RL_WS4_ROLES="d1,a1,d2,a2" overrides
+    // the (first CTA, later CTAs of an SM) placements of the dynamics / aux warps (measurements).
+    a.dyn_first = 2; a.aux_first = 5; a.dyn_second = 2; a.aux_second = 5;
+    if (const char *ov = getenv("RL_WS4_ROLES")) {
+        int d1, a1, d2, a2;
+        if (sscanf(ov, "%d,%d,%d,%d", &d1, &a1, &d2, &a2) == 4 && d1 >= 0 && d1 <= 5 && a1 >= 0 && a1 <= 5 && d1 != a1 &&
+            d2 >= 0 && d2 <= 5 && a2 >= 0 && a2 <= 5 && d2 != a2) {
+            a.dyn_first = d1; a.aux_first = a1; a.dyn_second = d2; a.aux_second = a2;
+        }
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ZkShared)));
+        attr_set = true;
+    }
+    RL_LAUNCH(ctx, rollout_cartpole_ws5_kernel, grid, VK_THREADS, sizeof(ZkShared), p, a);
+    return RL_OK;
+}
+
+rl_status launch_ws6(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, int *nblocks_out) {
+    // Twelve warps; warp w runs on sub-partition w % 4.  The dynamics warp (3) has its scheduler to itself (7 and 11 idle),
+    // the aux warp (10) shares one with two policy warps.  With seven policy warps (28 envs per CTA) warp 9 idles too.
+    // 28 envs per CTA when that still fits one CTA per SM (E = 4096: 147 CTAs instead of 128: less work per SM).
+    // RL_WS6_TABLE="r0,...,r11" (policy index 0..7, 8 = dynamics, 9 = aux, 15 = idle) overrides (measurements).
+    int table[QK_THREADS / 32] = {0, 1, 2, QK_ROLE_DYN, 3, 4, 5, QK_ROLE_IDLE, 6, 7, QK_ROLE_AUX, QK_ROLE_IDLE};
+    int npw = QK_POLICY_WARPS;
+    if ((a.E + 27) / 28 <= (uint64_t)ctx->sm_count && (a.E + 31) / 32 < (a.E + 27) / 28) {
+        npw = 7;
+        table[9] = QK_ROLE_IDLE;
+    }
+    if (const char *ov = getenv("RL_WS6_TABLE")) {
+        int v[12], seen = 0, count = 0, dyn = 0, aux = 0;
+        if (sscanf(ov, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7], &v[8], &v[9],
+                   &v[10], &v[11]) == 12) {
+            bool ok = true;
+            for (int i = 0; i < 12; ++i) {
+                if (v[i] >= 0 && v[i] < 8) { ok = ok && !((seen >> v[i]) & 1); seen |= 1 << v[i]; ++count; }
+                else if (v[i] == QK_ROLE_DYN) ++dyn;
+                else if (v[i] == QK_ROLE_AUX) ++aux;
+                else ok = ok && v[i] == QK_ROLE_IDLE;
+            }
+            ok = ok && dyn == 1 && aux == 1 && count >= 1 && seen == (1 << count) - 1;
+            if (ok) {
+                for (int i = 0; i < 12; ++i) table[i] = v[i];
+                npw = count;
+            }
+        }
+    }
+    a.policy_warps = npw;
+    a.role_table = 0;
+    for (int i = 0; i < QK_THREADS / 32; ++i) a.role_table |= (uint64_t)table[i] << (4 * i);
+    const unsigned envs = 4u * (unsigned)npw, grid = (unsigned)((a.E + envs - 1) / envs);
+    double *partials;
+    RL_TRY(rl_ctx_scratch(ctx, ((size_t)grid + 1) * ST_COUNT * sizeof(double), (void **)&partials));
+    a.partials = partials + ST_COUNT;
+    *nblocks_out = (int)grid;
+    a.sm_count = ctx->sm_count;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_cartpole_ws6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(QkShared)));
+        attr_set = true;
+    }
+    RL_LAUNCH(ctx, rollout_cartpole_ws6_kernel, grid, QK_THREADS, sizeof(QkShared), p, a);
+    return RL_OK;
+}
+
 template <int LANES>
 rl_status launch_group(rl_ctx *ctx, const CartPoleEnv::Params &p, RolloutArgs &a, bool replay, int *nblocks_out) {
     if (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY)
@@ -1783,12 +1860,16 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             if (replay || a.actor_kind != RL_ACTOR_CATEGORICAL_POLICY)
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
             {
-                // K2v while the 16-env CTAs fit one per SM (E = 1024: 0.124 ms per period against K2w's 0.131), K2w beyond
-                // (two CTAs per SM: the same 0.155 ms at E = 4096).  RL_WS_VARIANT = 1 | 3 | 4 forces K2w / K2y / K2v
-                // (measurements: profiles/r2_summary.md).
+                // K2v while its 16-env CTAs fit one per SM (E = 1024: 0.123 ms per period against K2w's 0.131), K2q while its
+                // 32-env CTAs do (E = 4096: 0.127 ms against K2w's 0.156), K2w beyond (two and more CTAs per SM).
+                // RL_WS_VARIANT = 1 | 3 | 4 | 5 | 6 forces K2w / K2y / K2v / K2z / K2q (measurements: profiles/r2_summary.md).
                 static const char *ws_variant = getenv("RL_WS_VARIANT");
-                const char v = ws_variant ? ws_variant[0] : (a.E <= (uint64_t)WK_ENVS * ctx->sm_count ? '4' : '1');
-                if (v == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
+                const char v = ws_variant ? ws_variant[0]
+                               : a.E <= (uint64_t)VK_ENVS * ctx->sm_count ? '4'
+                               : a.E <= (uint64_t)QK_ENVS * ctx->sm_count ? '6' : '1';
+                if (v == '6') RL_TRY(launch_ws6(ctx, env->cartpole, a, &nblocks));
+                else if (v == '5') RL_TRY(launch_ws5(ctx, env->cartpole, a, &nblocks));
+                else if (v == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));
                 else if (v == '4') RL_TRY(launch_ws4(ctx, env->cartpole, a, &nblocks));
                 else RL_TRY(launch_ws(ctx, env->cartpole, a, &nblocks));
             }

@@ -22,6 +22,17 @@ struct VkShared {
 };
 #define VK_OFF(member) ((uint32_t)offsetof(VkShared, member))
 
+#ifdef RL_WS_CLOCKS  // measurement build only (scripts/ws_clocks.sh): per-phase clocks of the dynamics / policy loops of two CTAs
+__device__ __forceinline__ long long vk_clk(double dep, uint32_t dep2) {
+    long long c;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(c) : "d"(dep), "r"(dep2) : "memory");
+    return c;
+}
+#define VK_CLK(var, dep, dep2) const long long var = vk_clk(dep, dep2)
+#else
+#define VK_CLK(var, dep, dep2)
+#endif
+
 __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(CartPoleEnv::Params p, RolloutArgs a) {
     using EnvT = CartPoleEnv;
     constexpr int LANES = 8, PPL = GK_PAIRS / LANES;
@@ -149,7 +160,11 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
         __syncwarp();
         named_bar_arrive(1, VK_SYNC);
         uint32_t it = 0;  // loop counter (= step index of the envs still active)
+#ifdef RL_WS_CLOCKS
+        long long ck[5] = {0, 0, 0, 0, 0};
+#endif
         while (any) {
+            VK_CLK(c0, s.x, it);
             const bool active = n > 0;
             if ((it & 3u) == 0u && lane == 0) yk_stu(sb + VK_OFF(cons), it);
             if ((it & 3u) == 3u) {  // the reset states of steps it + 1 .. it + 4
@@ -164,7 +179,9 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
             fresh_state(it + 1, fresh);
             const uint32_t r_now = s.meta & 0x7FFFFFFFu;
             const float rem_cont = remaining_feature(r_now > 0 ? r_now - 1 : 0);
+            VK_CLK(c1, cand.x + cand.thd + fresh.x, (uint32_t)cand_sc + __float_as_uint(rem_cont));
             named_bar_sync(2, VK_SYNC);
+            VK_CLK(c2, 0.0, 0u);
             const uint32_t action = yk_ldu(act_addr);
             const int src = el + 16 * (int)action;
             EnvT::State post;
@@ -195,6 +212,7 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
             if (act == 1) yk_stu(row + 20, (n_next > 0 ? 1u : 0u) | (any_next ? 2u : 0u));
             __syncwarp();
             named_bar_arrive(1, VK_SYNC);
+            VK_CLK(c3, 0.0, 0u);
             // ---- off the chain: the rest of the step record and the statistics ----
             if (active) {
                 const uint64_t is = (uint64_t)i * a.E + e_safe;
@@ -228,7 +246,17 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
             n = n_next;
             any = any_next;
             it += 1;
+#ifdef RL_WS_CLOCKS
+            const long long c4 = vk_clk(sum_el2 + cur_obs[0], i + cur_len);
+            ck[0] += c1 - c0; ck[1] += c2 - c1; ck[2] += c3 - c2; ck[3] += c4 - c3; ck[4] += 1;
+#endif
         }
+#ifdef RL_WS_CLOCKS
+        if (lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+            printf("K2v dyn cta %d: %lld iterations; clk per iteration: candidate step %.1f, wait for the action %.1f, select + publish %.1f, "
+                   "off-chain record %.1f\n", (int)blockIdx.x, ck[4], (double)ck[0] / ck[4], (double)ck[1] / ck[4], (double)ck[2] / ck[4],
+                   (double)ck[3] / ck[4]);
+#endif
         if (lane == 0) yk_stu(sb + VK_OFF(done), 1u);
         st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
         st.v[ST_EPS] = n_eps; st.v[ST_ER] = st.v[ST_EL] = sum_el; st.v[ST_ER2] = st.v[ST_EL2] = sum_el2;
@@ -277,7 +305,11 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
         uint8_t *act_ptr = a.action + e_safe;
         const uint32_t row = sb + VK_OFF(rows) + 32u * (uint32_t)el, mine_addr = row + 4u * (uint32_t)(sub < 5 ? sub : 0);
         const uint32_t thr_addr = sb + VK_OFF(thr) + 4u * (uint32_t)el, act_addr = sb + VK_OFF(act) + 4u * (uint32_t)el;
+#ifdef RL_WS_CLOCKS
+        long long pk[4] = {0, 0, 0, 0};
+#endif
         for (uint32_t i = 0;; ++i) {
+            VK_CLK(q0, 0.0, i);
             if ((i & 3u) == 0u) {  // thresholds of steps i .. i + 3
                 // (`done`: the dynamics warp has left its loop and the aux warp may have stopped; this iteration only breaks)
                 while (yk_ldu(sb + VK_OFF(prod)) < i + 4u && !yk_ldu(sb + VK_OFF(done))) { }
@@ -285,11 +317,19 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
             }
             const float theta = yk_ldf(thr_addr + 64u * (i & (VK_RING - 1)));
             named_bar_sync(1, VK_SYNC);
+            VK_CLK(q1, 0.0, 0u);
             const float4 ov = yk_ld4(row);
             const float4 tv = yk_ld4(row + 16);
             const float mine = yk_ldf(mine_addr);
             const float ob4 = tv.x;
             const uint32_t flags = __float_as_uint(tv.y);
+#ifdef RL_WS_CLOCKS
+            if ((flags & 2u) == 0u) {
+                if (warp == 0 && lane == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+                    printf("K2v policy cta %d: %lld iterations; clk per iteration: wait for the row %.1f, row -> action published %.1f, "
+                           "record stores %.1f\n", (int)blockIdx.x, pk[3], (double)pk[0] / pk[3], (double)pk[1] / pk[3], (double)pk[2] / pk[3]);
+            }
+#endif
             if ((flags & 2u) == 0u) break;
             const bool active = (flags & 1u) != 0u;
             const float2 o0 = make_float2(ov.x, ov.x), o1 = make_float2(ov.y, ov.y), o2 = make_float2(ov.z, ov.z);
@@ -321,11 +361,16 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws4_kernel(Car
             if (sub == 0) yk_stu(act_addr, action);
             __syncwarp();
             named_bar_arrive(2, VK_SYNC);
+            VK_CLK(q2, 0.0, action);
             // ---- off the chain: the observation and the action of the step record ----
             if (active && stores_obs) *obs_ptr = mine;
             if (active && stores_action) *act_ptr = (uint8_t)action;
             obs_ptr += FE;
             act_ptr += a.E;
+#ifdef RL_WS_CLOCKS
+            const long long q3 = vk_clk(0.0, (uint32_t)(uintptr_t)act_ptr);
+            pk[0] += q1 - q0; pk[1] += q2 - q1; pk[2] += q3 - q2; pk[3] += 1;
+#endif
         }
     }
     block_reduce_stats(st, contributes, a.partials);
