@@ -214,7 +214,9 @@ rl_status rl_encode_features(rl_ctx *ctx, rl_space_kind kind, uint64_t size, con
 typedef enum { RL_ACT_IDENTITY = 0, RL_ACT_RELU = 1, RL_ACT_SIGMOID = 2, RL_ACT_TANH = 3 } rl_activation;
 /* MlpConfig{hidden_sizes, activation, output_activation = Identity} (mlp.rs:25-34).  Parameters are
  * flat f32 in Module::variables() order: per Linear kernel[out,in] row-major then bias[out]
- * (linear.rs:108-110, mlp.rs:126-128). */
+ * (linear.rs:108-110, mlp.rs:126-128).  n_hidden = 1 (<= 1024 units; the default [128] takes the tensor-core /
+ * warp-specialised kernels), 2 or 3 (<= 256 units per layer, <= 48 K parameters: layer-generic kernels);
+ * anything else returns RL_ERR_UNSUPPORTED. */
 rl_status rl_mlp_create(rl_ctx *ctx, int32_t in_dim, const int32_t *hidden_sizes, int32_t n_hidden, int32_t out_dim,
                         rl_activation activation, rl_mlp **out);
 rl_status rl_mlp_destroy(rl_mlp *mlp);

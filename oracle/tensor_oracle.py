@@ -23,15 +23,22 @@ F32_MIN = float(torch.finfo(torch.float32).min)
 # ------------------------------------------------------------------------------------------------
 # modules (src/torch/modules/ff/mlp.rs:139-151, linear.rs:118-123)
 # ------------------------------------------------------------------------------------------------
-def unflatten_mlp(flat: torch.Tensor, n_in: int, hidden: int, n_out: int):
-    """Module::variables() order: W1[H,F], b1[H], W2[A,H], b2[A] (linear.rs:108-110, mlp.rs:126-128)."""
+def unflatten_mlp(flat: torch.Tensor, n_in: int, hidden, n_out: int):
+    """Module::variables() order: [W, b] per Linear, layers in order (linear.rs:108-110, mlp.rs:126-128); `hidden` is
+    MlpConfig::hidden_sizes (an int for the default single hidden layer)."""
+    sizes = [hidden] if isinstance(hidden, (int, np.integer)) else list(hidden)
     o = 0
-    shapes = [(hidden, n_in), (hidden,), (n_out, hidden), (n_out,)]
+    shapes = []
+    prev = n_in
+    for h in sizes + [n_out]:
+        shapes += [(h, prev), (h,)]
+        prev = h
     out = []
     for s in shapes:
         n = int(np.prod(s))
         out.append(flat[o:o + n].reshape(s))
         o += n
+    assert o == flat.numel(), (o, flat.numel())
     return out
 
 
@@ -58,9 +65,14 @@ class mlp_activation:
 
 
 def mlp_forward(params, x):
-    w1, b1, w2, b2 = params
-    h = _ACTIVATIONS[_MLP_ACTIVATION](torch.nn.functional.linear(x, w1, b1))
-    return torch.nn.functional.linear(h, w2, b2)
+    """Mlp::forward (mlp.rs:139-151): the activation between Linear layers, none on the output (output_activation Identity)."""
+    h = x
+    n_layers = len(params) // 2
+    for l in range(n_layers):
+        h = torch.nn.functional.linear(h, params[2 * l], params[2 * l + 1])
+        if l + 1 < n_layers:
+            h = _ACTIVATIONS[_MLP_ACTIVATION](h)
+    return h
 
 
 # ------------------------------------------------------------------------------------------------

@@ -21,14 +21,29 @@ struct rl_env {
     uint8_t *succ = nullptr;
 };
 
+// MlpConfig::hidden_sizes (mlp.rs:25-34): one hidden layer takes the specialised kernels; two or three take the
+// layer-generic paths (rl_mlp_eval_deep below, mlp_pass_any_kernel's DEEP form in update.cu).
+constexpr int RL_MLP_MAX_HIDDEN_LAYERS = 3, RL_DEEP_MAXH = 256;
+
 struct rl_mlp {
     rl_ctx *ctx = nullptr;
-    int in_dim = 0, hidden = 0, out_dim = 0;
+    int in_dim = 0, hidden = 0, out_dim = 0;  // hidden = hid[0]
+    int n_hidden = 1, hid[RL_MLP_MAX_HIDDEN_LAYERS] = {0, 0, 0};
     rl_activation act = RL_ACT_RELU;
     uint64_t n_params = 0;
     float *params = nullptr;  // device, flat in Module::variables() order
     __host__ __device__ static uint64_t count(int in, int hidden, int out) {
         return (uint64_t)hidden * in + hidden + (uint64_t)out * hidden + out;
+    }
+    // [W, b] per Linear, layers in order (mlp.rs:126-128)
+    __host__ __device__ static uint64_t count_layers(int in, const int *hid, int n_hidden, int out) {
+        uint64_t n = 0;
+        int prev = in;
+        for (int l = 0; l < n_hidden; ++l) {
+            n += (uint64_t)hid[l] * prev + hid[l];
+            prev = hid[l];
+        }
+        return n + (uint64_t)out * prev + out;
     }
 };
 
@@ -125,6 +140,8 @@ struct rl_tabq {
 struct MlpView {
     const float *params;
     int in_dim, hidden, out_dim, act;
+    int n_hidden, hid[RL_MLP_MAX_HIDDEN_LAYERS];
+    uint32_t n_params;
     __device__ const float *w1() const { return params; }
     __device__ const float *b1() const { return params + (size_t)hidden * in_dim; }
     __device__ const float *w2() const { return b1() + hidden; }
@@ -138,6 +155,9 @@ inline MlpView rl_mlp_view(const rl_mlp *m) {
     v.hidden = m ? m->hidden : 0;
     v.out_dim = m ? m->out_dim : 0;
     v.act = m ? (int)m->act : 0;
+    v.n_hidden = m ? m->n_hidden : 1;
+    for (int l = 0; l < RL_MLP_MAX_HIDDEN_LAYERS; ++l) v.hid[l] = m ? m->hid[l] : 0;
+    v.n_params = m ? (uint32_t)m->n_params : 0u;
     return v;
 }
 
@@ -147,5 +167,33 @@ __device__ __forceinline__ float rl_activate(int act, float v) {
     case RL_ACT_SIGMOID: return 1.0f / (1.0f + expf(-v));
     case RL_ACT_TANH: return tanhf(v);
     default: return v;
+    }
+}
+
+// Mlp::forward (mlp.rs:139-151) for one input on one thread, two or three hidden layers: x[in_dim] -> z[out_dim].
+// `w` is the flat parameter vector (shared or global memory).  Activations ping-pong through two local arrays; the
+// one-hidden-layer modules never come here (their kernels stream the hidden units without storing them).
+static __device__ __noinline__ void rl_mlp_eval_deep(const MlpView &m, const float *w, const float *x, float *z) {
+    float ha[RL_DEEP_MAXH], hb[RL_DEEP_MAXH];
+    const float *in = x;
+    int n_in = m.in_dim;
+    for (int l = 0; l < m.n_hidden; ++l) {
+        float *out = (l & 1) ? hb : ha;
+        const int H = m.hid[l];
+        const float *W = w, *b = w + (size_t)H * n_in;
+        for (int j = 0; j < H; ++j) {
+            float acc = b[j];
+            for (int f = 0; f < n_in; ++f) acc = fmaf(W[(size_t)j * n_in + f], in[f], acc);
+            out[j] = rl_activate(m.act, acc);
+        }
+        w = b + H;
+        in = out;
+        n_in = H;
+    }
+    const float *W = w, *b = w + (size_t)m.out_dim * n_in;
+    for (int k = 0; k < m.out_dim; ++k) {
+        float acc = b[k];
+        for (int f = 0; f < n_in; ++f) acc = fmaf(W[(size_t)k * n_in + f], in[f], acc);
+        z[k] = acc;
     }
 }

@@ -11,7 +11,7 @@ template <int FT, int OT>
 __global__ void __launch_bounds__(256) mlp_forward_kernel(MlpView m, const float *__restrict__ x, uint64_t n,
                                                          float *__restrict__ out) {
     extern __shared__ float sw[];
-    const uint64_t np = rl_mlp::count(m.in_dim, m.hidden, m.out_dim);
+    const uint64_t np = m.n_params;
     for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
     __syncthreads();
     const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -21,6 +21,11 @@ __global__ void __launch_bounds__(256) mlp_forward_kernel(MlpView m, const float
     float xi[FT], z[OT];
 #pragma unroll
     for (int f = 0; f < FT; ++f) xi[f] = f < F ? x[(uint64_t)f * n + s] : 0.0f;
+    if (m.n_hidden > 1) {
+        rl_mlp_eval_deep(m, sw, xi, z);
+        for (int k = 0; k < O; ++k) out[(uint64_t)k * n + s] = z[k];
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < OT; ++k) z[k] = k < O ? b2[k] : 0.0f;
     for (int j = 0; j < H; ++j) {
@@ -45,20 +50,28 @@ extern "C" {
 rl_status rl_mlp_create(rl_ctx *ctx, int32_t in_dim, const int32_t *hidden_sizes, int32_t n_hidden, int32_t out_dim,
                         rl_activation activation, rl_mlp **out) {
     RL_REQUIRE(ctx, ctx && out && hidden_sizes, "rl_mlp_create: NULL argument");
-    if (n_hidden != 1)
-        return rl_fail(ctx, RL_ERR_UNSUPPORTED,
-                       "rl_mlp_create: only one hidden layer is implemented (MlpConfig default hidden_sizes=[128])");
+    if (n_hidden < 1 || n_hidden > RL_MLP_MAX_HIDDEN_LAYERS)
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_mlp_create: one to %d hidden layers are implemented (MlpConfig::hidden_sizes, got %d)",
+                       RL_MLP_MAX_HIDDEN_LAYERS, n_hidden);
     RL_REQUIRE(ctx, in_dim >= 1 && in_dim <= 36 && out_dim >= 1 && out_dim <= 32, "rl_mlp_create: dims out of range");
-    RL_REQUIRE(ctx, hidden_sizes[0] >= 1 && hidden_sizes[0] <= 1024, "rl_mlp_create: hidden size out of range");
+    for (int l = 0; l < n_hidden; ++l)
+        RL_REQUIRE(ctx, hidden_sizes[l] >= 1 && hidden_sizes[l] <= (n_hidden == 1 ? 1024 : RL_DEEP_MAXH),
+                   "rl_mlp_create: hidden size out of range (<= 1024 with one hidden layer, <= 256 with two or three)");
     RL_CUDA(ctx, cudaSetDevice(ctx->device));
     rl_mlp *m = new (std::nothrow) rl_mlp();
     if (!m) return rl_fail(ctx, RL_ERR_OOM, "rl_mlp_create: host allocation failed");
     m->ctx = ctx;
     m->in_dim = in_dim;
     m->hidden = hidden_sizes[0];
+    m->n_hidden = n_hidden;
+    for (int l = 0; l < n_hidden; ++l) m->hid[l] = hidden_sizes[l];
     m->out_dim = out_dim;
     m->act = activation;
-    m->n_params = rl_mlp::count(in_dim, m->hidden, out_dim);
+    m->n_params = rl_mlp::count_layers(in_dim, m->hid, n_hidden, out_dim);
+    if (n_hidden > 1 && m->n_params > 48 * 1024) {  // the layer-generic kernels stage the parameters in shared memory
+        delete m;
+        return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_mlp_create: modules with two or three hidden layers are built for <= 48 K parameters");
+    }
     cudaError_t e = cudaMalloc((void **)&m->params, m->n_params * sizeof(float));
     if (e != cudaSuccess) {
         delete m;

@@ -362,7 +362,7 @@ template <int FT, int AT>
 __global__ void __launch_bounds__(256)
     q_values_kernel(MlpView m, MinibatchPtrs mb, const SampleMeta *__restrict__ meta) {
     extern __shared__ float sw[];
-    const uint64_t np = rl_mlp::count(m.in_dim, m.hidden, m.out_dim);
+    const uint64_t np = m.n_params;
     for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
     __syncthreads();
     const uint64_t col = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +378,12 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int k = 0; k < AT; ++k) z[k] = zn[k] = k < A ? b2[k] : 0.0f;
-    for (int j = 0; j < H; ++j) {
+    const bool deep = m.n_hidden > 1;  // MlpConfig::hidden_sizes with two or three entries
+    if (deep) {
+        rl_mlp_eval_deep(m, sw, x, z);
+        if (intr) rl_mlp_eval_deep(m, sw, xn, zn);
+    }
+    for (int j = 0; j < (deep ? 0 : H); ++j) {
         float acc = b1[j], accn = b1[j];
 #pragma unroll
         for (int f = 0; f < FT; ++f)

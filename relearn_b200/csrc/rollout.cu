@@ -136,7 +136,7 @@ template <bool PACK8>
 __device__ void stage_weights(const MlpView &m, float *sw) {
     if (m.params == nullptr) return;
     const int F = m.in_dim, H = m.hidden, A = m.out_dim;
-    if (PACK8) {
+    if (PACK8 && m.n_hidden == 1) {
         for (int i = threadIdx.x; i < H * 8; i += blockDim.x) {
             const int j = i >> 3, c = i & 7;
             float v = 0.0f;
@@ -147,7 +147,7 @@ __device__ void stage_weights(const MlpView &m, float *sw) {
         }
         if (threadIdx.x < 2) sw[H * 8 + threadIdx.x] = (int)threadIdx.x < A ? m.b2()[threadIdx.x] : 0.0f;
     } else {
-        const uint64_t np = rl_mlp::count(F, H, A);
+        const uint64_t np = m.n_params;
         for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
     }
 }
@@ -155,6 +155,10 @@ __device__ void stage_weights(const MlpView &m, float *sw) {
 template <class EnvT, bool PACK8>
 __device__ __forceinline__ void mlp_logits(const MlpView &m, const float *sw, const float *obs, float *z) {
     const int F = m.in_dim, H = m.hidden, A = m.out_dim;
+    if (m.n_hidden > 1) {  // MlpConfig::hidden_sizes with two or three entries: flat layout, layer-generic forward
+        rl_mlp_eval_deep(m, sw, obs, z);
+        return;
+    }
     if constexpr (PACK8) {
         float z0 = sw[H * 8], z1 = sw[H * 8 + 1];
         const float4 *w4 = reinterpret_cast<const float4 *>(sw);
@@ -1405,7 +1409,7 @@ template <class EnvT>
 size_t rollout_smem_bytes(const rl_mlp *net) {
     if (!net) return 16;
     constexpr bool PACK8 = EnvT::MAXF <= 5 && EnvT::MAXA <= 2;
-    return PACK8 ? ((size_t)net->hidden * 8 + 4) * sizeof(float) : net->n_params * sizeof(float);
+    return (PACK8 && net->n_hidden == 1) ? ((size_t)net->hidden * 8 + 4) * sizeof(float) : net->n_params * sizeof(float);
 }
 
 template <class EnvT>
@@ -1814,11 +1818,11 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
         int lanes = actor->lanes_per_env;
         // K2c serves the two network actors on the reference's default module (MlpConfig: one hidden layer of
         // 128, ReLU); anything else takes the generic thread-per-env kernel K2a.
-        const bool group_ok = net && net->hidden == GK_H && net->act == RL_ACT_RELU && es.num_actions == 2 &&
+        const bool group_ok = net && net->n_hidden == 1 && net->hidden == GK_H && net->act == RL_ACT_RELU && es.num_actions == 2 &&
                               (es.num_features == 5 || es.num_features == 4) && env->cartpole.max_angle <= 0.5;
         static const bool legacy = getenv("RL_ROLLOUT_LEGACY") != nullptr;
         if (!group_ok || legacy) {
-            const bool coop_ok = net && net->hidden == 128 && es.num_actions == 2;
+            const bool coop_ok = net && net->n_hidden == 1 && net->hidden == 128 && es.num_actions == 2;
             if (lanes == 0) lanes = 1;
             if (lanes > 1 && !coop_ok)
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: lanes_per_env > 1 needs a 128-unit MLP on CartPole");

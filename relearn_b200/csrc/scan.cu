@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) value_forward_kernel(MlpView m, const flo
                                                            const uint8_t *__restrict__ succ, uint64_t T, uint64_t E,
                                                            float *__restrict__ v, float *__restrict__ v_next) {
     extern __shared__ float sw[];
-    const uint64_t np = rl_mlp::count(m.in_dim, m.hidden, m.out_dim);
+    const uint64_t np = m.n_params;
     for (uint64_t i = threadIdx.x; i < np; i += blockDim.x) sw[i] = m.params[i];
     __syncthreads();
     const uint64_t n = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,6 +90,16 @@ __global__ void __launch_bounds__(256) value_forward_kernel(MlpView m, const flo
     for (int f = 0; f < FT; ++f) {
         xi[f] = f < F ? obs[(t * F + f) * E + e] : 0.0f;
         xn[f] = (f < F && intr) ? next_obs[(t * F + f) * E + e] : 0.0f;
+    }
+    if (m.n_hidden > 1) {  // MlpConfig::hidden_sizes with two or three entries
+        float zd;
+        rl_mlp_eval_deep(m, sw, xi, &zd);
+        v[n] = zd;
+        if (intr) {
+            rl_mlp_eval_deep(m, sw, xn, &zd);
+            v_next[n] = zd;
+        }
+        return;
     }
     float z = b2[0], zn = b2[0];
     for (int j = 0; j < H; ++j) {
@@ -276,7 +286,7 @@ rl_status rl_gae(rl_traj *traj, rl_mlp *value_fn, float gamma, float lambda, flo
         float *v;
         RL_TRY(rl_ctx_scratch(ctx, 2 * T * E * sizeof(float), (void **)&v));
         float *v_next = v + T * E;
-        if (value_fn->hidden == 128 && value_fn->in_dim <= 5 && value_fn->act == RL_ACT_RELU) {
+        if (value_fn->n_hidden == 1 && value_fn->hidden == 128 && value_fn->in_dim <= 5 && value_fn->act == RL_ACT_RELU) {
             RL_LAUNCH(ctx, value_forward_pairs_kernel, rl_grid_for(T * E, 256), 256, 0, rl_mlp_view(value_fn), traj->obs,
                       traj->next_obs, traj->succ, T, E, v, v_next);
         } else {

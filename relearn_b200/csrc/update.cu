@@ -519,9 +519,57 @@ constexpr int ANY_MAXA = 16, ANY_MAXF = 64, ANY_MAXH = 1024, ANY_THREADS = 128;
 constexpr size_t ANY_SMEM_CAP = 200 * 1024;
 struct AnyShape {
     int F, H, A, act;
+    int L;      // hidden layers (MlpConfig::hidden_sizes); H = Hs[0]
+    int Hs[3];
 };
 
+// Layer-generic (L = 2 or 3) form of the same kernel: every Linear's weights sit in shared memory TRANSPOSED as
+// [input][unit] with an odd row pitch, so that both the forward sweep (lanes over units, fixed input) and the backward
+// sweep of the layer above (lanes over inputs, fixed unit) are conflict-free; the warp's f64 totals use the same layout;
+// activations, tangents and deltas of the sample in flight live in per-warp buffers of ANY_DEEP_MAXH floats.
+constexpr int ANY_DEEP_MAXH = 256;
+struct DeepLayout {
+    int n_layers;                  // Linear layers = L + 1
+    int in[4], out[4], ld[4];      // per Linear: inputs, units, pitch (odd)
+    int off_w[4], off_b[4];        // offsets in the padded layout
+    int nat_w[4];                  // offsets in Module::variables() order
+    int P, P_pad, maxH;
+};
+__host__ __device__ inline DeepLayout deep_layout(const AnyShape &sh) {
+    DeepLayout d{};
+    d.n_layers = sh.L + 1;
+    int prev = sh.F, off = 0, nat = 0, maxH = 0;
+    for (int l = 0; l <= sh.L; ++l) {
+        const int out = l < sh.L ? sh.Hs[l] : sh.A;
+        d.in[l] = prev; d.out[l] = out; d.ld[l] = out | 1;
+        d.off_w[l] = off; off += prev * d.ld[l];
+        d.off_b[l] = off; off += out;
+        d.nat_w[l] = nat; nat += prev * out + out;
+        if (l < sh.L && out > maxH) maxH = out;
+        prev = out;
+    }
+    d.P = nat; d.P_pad = off; d.maxH = maxH;
+    return d;
+}
+// natural parameter index -> index in the padded transposed layout
+__host__ __device__ inline int deep_pidx(const DeepLayout &d, int i) {
+    for (int l = 0; l < d.n_layers; ++l) {
+        const int r = i - d.nat_w[l], nw = d.in[l] * d.out[l];
+        if (r < nw) return d.off_w[l] + (r % d.in[l]) * d.ld[l] + r / d.in[l];
+        if (r < nw + d.out[l]) return d.off_b[l] + (r - nw);
+    }
+    return 0;
+}
+
 __host__ __device__ inline size_t any_smem_bytes(const AnyShape &sh, int nwarps, bool backward, bool fvp) {
+    if (sh.L > 1) {
+        const DeepLayout d = deep_layout(sh);
+        const size_t Pp = (size_t)d.P_pad;
+        // totals | scalars | theta (+ direction) | tile observations | per-warp buffers: h[L], tangent[L], delta[2]
+        return (backward ? (size_t)nwarps * Pp * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
+               Pp * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float) +
+               (size_t)nwarps * (2 * sh.L + 2) * ANY_DEEP_MAXH * sizeof(float);
+    }
     const size_t P = (size_t)sh.H * sh.F + sh.H + (size_t)sh.A * sh.H + sh.A;
     return (backward ? (size_t)nwarps * P * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
            P * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float);
@@ -553,25 +601,30 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
     constexpr bool FVP = MODE == PASS_FVP;
     if (a.skip_flag && *a.skip_flag) return;
     const int F = sh.F, H = sh.H, A = sh.A, act = sh.act;
-    const int P = H * F + H + A * H + A, W = P + NSCALAR;
+    const bool deep = sh.L > 1;
+    const DeepLayout dl = deep_layout(sh);
+    const int P = deep ? dl.P : H * F + H + A * H + A, W = P + NSCALAR;
+    const int PL = deep ? dl.P_pad : P;  // entries of the shared-memory copies (padded when deep)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     extern __shared__ __align__(16) unsigned char any_smem[];
-    double *tot_all = reinterpret_cast<double *>(any_smem);                        // [nwarps][P], W1 part as [F][H]
-    double *red = tot_all + (BACKWARD ? (size_t)nwarps * P : 0);                   // [nwarps][NSCALAR + ANY_MAXA]
+    double *tot_all = reinterpret_cast<double *>(any_smem);                        // [nwarps][PL], W1 part as [F][H]
+    double *red = tot_all + (BACKWARD ? (size_t)nwarps * PL : 0);                  // [nwarps][NSCALAR + ANY_MAXA]
     float *th = reinterpret_cast<float *>(red + (size_t)nwarps * (NSCALAR + ANY_MAXA));  // theta, W1 as [F][H]
-    float *tv = th + P;                                                            // FVP: the direction, same layout
-    float *xs_all = th + (FVP ? 2 : 1) * (size_t)P;
+    float *tv = th + PL;                                                           // FVP: the direction, same layout
+    float *xs_all = th + (FVP ? 2 : 1) * (size_t)PL;
     float *xs = xs_all + (size_t)warp * 32 * F;
-    double *tot = tot_all + (size_t)warp * P;
+    float *dbuf = xs_all + (size_t)nwarps * 32 * F + (size_t)warp * (2 * sh.L + 2) * ANY_DEEP_MAXH;  // deep: h | tangent | delta
+    double *tot = tot_all + (size_t)warp * PL;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
         int dst = i;
-        if (i < H * F) dst = (i % F) * H + i / F;  // W1[j][f] -> [f][j]
+        if (deep) dst = deep_pidx(dl, i);
+        else if (i < H * F) dst = (i % F) * H + i / F;  // W1[j][f] -> [f][j]
         th[dst] = a.theta[i];
         if (FVP) tv[dst] = a.vec[i];
     }
     if (BACKWARD)
-        for (int i = lane; i < P; i += 32) tot[i] = 0.0;
+        for (int i = lane; i < PL; i += 32) tot[i] = 0.0;
     __syncthreads();
     const float *w1t = th, *b1 = th + H * F, *w2 = b1 + H, *b2 = w2 + A * H;
     const float *vw1t = tv, *vb1 = tv + H * F, *vw2 = vb1 + H, *vb2 = vw2 + A * H;
@@ -607,7 +660,7 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                 pz[k] = 0.0f;
                 if (FVP) pzd[k] = 0.0f;
             }
-            for (int j = lane; j < H; j += 32) {
+            for (int j = lane; j < (deep ? 0 : H); j += 32) {
                 float pre = b1[j];
                 for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
                 const float h = rl_activate(act, pre);
@@ -624,11 +677,51 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                         if (FVP) pzd[k] = fmaf(vw2[k * H + j], h, fmaf(w2[k * H + j], dh, pzd[k]));
                     }
             }
+            if (deep) {
+                // hidden layers: lane j owns units {j + 32 u}; the layer's output (and its tangent) goes to the warp's buffers
+                const float *vin = x, *dvin = nullptr;
+                for (int l = 0; l < sh.L; ++l) {
+                    const int n_in = dl.in[l], n_out = dl.out[l], ld = dl.ld[l];
+                    const float *Wt = th + dl.off_w[l], *bb = th + dl.off_b[l];
+                    const float *vWt = tv + dl.off_w[l], *vbb = tv + dl.off_b[l];
+                    float *hout = dbuf + l * ANY_DEEP_MAXH, *dout = dbuf + (sh.L + l) * ANY_DEEP_MAXH;
+                    for (int j = lane; j < n_out; j += 32) {
+                        float pre = bb[j];
+                        for (int f = 0; f < n_in; ++f) pre = fmaf(Wt[f * ld + j], vin[f], pre);
+                        const float h = rl_activate(act, pre);
+                        hout[j] = h;
+                        if (FVP) {
+                            float dpre = vbb[j];
+                            for (int f = 0; f < n_in; ++f) {
+                                dpre = fmaf(vWt[f * ld + j], vin[f], dpre);
+                                if (dvin) dpre = fmaf(Wt[f * ld + j], dvin[f], dpre);
+                            }
+                            dout[j] = any_act_grad(act, h, h) * dpre;
+                        }
+                    }
+                    __syncwarp();
+                    vin = hout;
+                    dvin = dout;
+                }
+                // output Linear: partial sums over this lane's units of the last hidden layer
+                const int n_in = dl.in[sh.L], ld = dl.ld[sh.L];
+                const float *Wt = th + dl.off_w[sh.L], *vWt = tv + dl.off_w[sh.L];
+                for (int j = lane; j < n_in; j += 32) {
+                    const float h = vin[j], dh = FVP ? dvin[j] : 0.0f;
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k)
+                        if (k < A) {
+                            pz[k] = fmaf(Wt[j * ld + k], h, pz[k]);
+                            if (FVP) pzd[k] = fmaf(vWt[j * ld + k], h, fmaf(Wt[j * ld + k], dh, pzd[k]));
+                        }
+                }
+            }
+            const float *b_out = deep ? th + dl.off_b[sh.L] : b2, *vb_out = deep ? tv + dl.off_b[sh.L] : vb2;
             float z[ANY_MAXA], zd[FVP ? ANY_MAXA : 1];
 #pragma unroll
             for (int k = 0; k < ANY_MAXA; ++k) {
-                z[k] = k < A ? warp_allsum_f32(pz[k]) + b2[k] : 0.0f;
-                if (FVP) zd[k] = k < A ? warp_allsum_f32(pzd[k]) + vb2[k] : 0.0f;
+                z[k] = k < A ? warp_allsum_f32(pz[k]) + b_out[k] : 0.0f;
+                if (FVP) zd[k] = k < A ? warp_allsum_f32(pzd[k]) + vb_out[k] : 0.0f;
             }
             const int act_s = __shfl_sync(0xffffffffu, my_act, s);
             const float adv_s = __shfl_sync(0xffffffffu, my_adv, s), tgt_s = __shfl_sync(0xffffffffu, my_tgt, s);
@@ -732,7 +825,48 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
             for (int k = 0; k < ANY_MAXA; ++k) gb2[k] += (double)dz[k];
 
             // ---- backward: this lane's units, straight into the warp's f64 totals ----
-            if (BACKWARD) {
+            if (BACKWARD && deep) {
+                // output Linear: gradients of its weights, delta of the last hidden layer
+                const int LL = sh.L;
+                float *delta = dbuf + 2 * LL * ANY_DEEP_MAXH, *delta2 = delta + ANY_DEEP_MAXH;
+                {
+                    const int n_in = dl.in[LL], ld = dl.ld[LL];
+                    const float *Wt = th + dl.off_w[LL], *hin = dbuf + (LL - 1) * ANY_DEEP_MAXH;
+                    for (int j = lane; j < n_in; j += 32) {
+                        const float h = hin[j];
+                        float dh = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) {
+                                dh = fmaf(dz[k], Wt[j * ld + k], dh);
+                                tot[dl.off_w[LL] + j * ld + k] += (double)(dz[k] * h);
+                            }
+                        delta[j] = dh * any_act_grad(act, h, h);
+                    }
+                    __syncwarp();
+                }
+                for (int l = LL - 1; l >= 0; --l) {
+                    const int n_in = dl.in[l], n_out = dl.out[l], ld = dl.ld[l];
+                    const float *vin = l == 0 ? x : dbuf + (l - 1) * ANY_DEEP_MAXH;
+                    for (int j = lane; j < n_out; j += 32) {
+                        const float dj = delta[j];
+                        tot[dl.off_b[l] + j] += (double)dj;
+                        for (int f = 0; f < n_in; ++f) tot[dl.off_w[l] + f * ld + j] += (double)(dj * vin[f]);
+                    }
+                    if (l > 0) {  // delta of the layer below: lane i owns ITS unit i (= input i of this layer)
+                        const float *Wt = th + dl.off_w[l];
+                        for (int i2 = lane; i2 < n_in; i2 += 32) {
+                            float acc = 0.0f;
+                            for (int j = 0; j < n_out; ++j) acc = fmaf(Wt[i2 * ld + j], delta[j], acc);
+                            delta2[i2] = acc * any_act_grad(act, vin[i2], vin[i2]);
+                        }
+                        __syncwarp();
+                        float *t = delta; delta = delta2; delta2 = t;
+                    }
+                }
+                __syncwarp();
+            }
+            if (BACKWARD && !deep) {
                 for (int j = lane; j < H; j += 32) {
                     float pre = b1[j];
                     for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
@@ -764,9 +898,9 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         double s = 0.0;
         if (i < P - A) {
-            const int src = i < H * F ? (i % F) * H + i / F : i;
+            const int src = deep ? deep_pidx(dl, i) : i < H * F ? (i % F) * H + i / F : i;
             if (BACKWARD)
-                for (int w = 0; w < nwarps; ++w) s += tot_all[(size_t)w * P + src];
+                for (int w = 0; w < nwarps; ++w) s += tot_all[(size_t)w * PL + src];
         } else if (i < P) {
             if (BACKWARD)
                 for (int w = 0; w < nwarps; ++w) s += red[w * (NSCALAR + ANY_MAXA) + NSCALAR + (i - (P - A))];
@@ -1389,8 +1523,17 @@ rl_status pass_net_for(rl_ctx *ctx, const rl_mlp *m, int F_data, const char *wha
     if (m->in_dim != F_data)
         return rl_fail(ctx, RL_ERR_INVALID_ARG, "%s: a %d->%d->%d module does not match observations of %d features", what,
                        m->in_dim, m->hidden, m->out_dim, F_data);
-    out->sh = AnyShape{m->in_dim, m->hidden, m->out_dim, (int)m->act};
-    out->deflt = F_data == 5 && m->hidden == 128 && m->act == RL_ACT_RELU && (m->out_dim == 1 || m->out_dim == 2);
+    out->sh = AnyShape{m->in_dim, m->hidden, m->out_dim, (int)m->act, m->n_hidden, {m->hid[0], m->hid[1], m->hid[2]}};
+    out->deflt = m->n_hidden == 1 && F_data == 5 && m->hidden == 128 && m->act == RL_ACT_RELU && (m->out_dim == 1 || m->out_dim == 2);
+    if (m->n_hidden > 1) {
+        bool ok = m->in_dim >= 1 && m->in_dim <= ANY_MAXF && m->out_dim >= 1 && m->out_dim <= ANY_MAXA;
+        for (int l = 0; l < m->n_hidden; ++l) ok = ok && m->hid[l] >= 1 && m->hid[l] <= ANY_DEEP_MAXH;
+        if (!ok || any_smem_bytes(out->sh, 1, true, true) > ANY_SMEM_CAP)
+            return rl_fail(ctx, RL_ERR_UNSUPPORTED,
+                           "%s: modules with two or three hidden layers are built for <= %d features, <= %d units per layer, <= %d "
+                           "outputs and <= ~12 K parameters", what, ANY_MAXF, ANY_DEEP_MAXH, ANY_MAXA);
+        return RL_OK;
+    }
     if (!out->deflt && !(m->in_dim >= 1 && m->in_dim <= ANY_MAXF && m->hidden >= 1 && m->hidden <= ANY_MAXH && m->out_dim >= 1 &&
                          m->out_dim <= ANY_MAXA && any_smem_bytes(out->sh, 1, true, true) <= ANY_SMEM_CAP))
         return rl_fail(ctx, RL_ERR_UNSUPPORTED,

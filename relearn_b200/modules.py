@@ -23,16 +23,23 @@ class MlpConfig:
         return Mlp(ctx, in_dim, self.hidden_sizes, out_dim, self.activation)
 
 
+def _layer_dims(in_dim, hidden, out_dim):
+    sizes = [hidden] if isinstance(hidden, (int, np.integer)) else list(hidden)
+    dims = [in_dim] + [int(h) for h in sizes] + [out_dim]
+    return list(zip(dims[:-1], dims[1:]))
+
+
 def num_params(in_dim, hidden, out_dim):
-    return hidden * in_dim + hidden + out_dim * hidden + out_dim
+    """`hidden`: MlpConfig::hidden_sizes (an int for one hidden layer)."""
+    return sum(o * i + o for i, o in _layer_dims(in_dim, hidden, out_dim))
 
 
-def init_params(rng: np.random.Generator, in_dim: int, hidden: int, out_dim: int) -> np.ndarray:
+def init_params(rng: np.random.Generator, in_dim: int, hidden, out_dim: int) -> np.ndarray:
     """Initializer::Uniform(FanAvg) with Linear's fan_in = in_dim + 1 (initializers.rs:31-38,159-163;
     linear.rs:56): every tensor of a Linear ~ U(+-sqrt(6 / (in+1+out))).  libtorch's generator is not
-    reproducible from relearn, so values come from numpy and are injected."""
+    reproducible from relearn, so values come from numpy and are injected.  `hidden`: an int or hidden_sizes."""
     parts = []
-    for (i, o) in ((in_dim, hidden), (hidden, out_dim)):
+    for (i, o) in _layer_dims(in_dim, hidden, out_dim):
         lim = np.sqrt(6.0 / (i + 1 + o))
         parts.append(rng.uniform(-lim, lim, size=(o, i)).astype(np.float32).ravel())
         parts.append(rng.uniform(-lim, lim, size=(o,)).astype(np.float32))

@@ -123,7 +123,27 @@ def random_words(rng: np.random.Generator, E: int, n: int) -> np.ndarray:
     return rng.integers(0, 2**32, size=(E, n), dtype=np.uint64).astype(np.uint32)
 
 
-def check_policy_consistency(host: dict, params, hidden, A, actor_words, atol=2e-6):
+def mlp_forward_any(params, F, hidden, A, x, activation="relu"):
+    """Mlp::forward (mlp.rs:139-151): the C oracle for one ReLU hidden layer, numpy (f64 accumulation, rounded to f32) for
+    `hidden_sizes` with several entries or another activation."""
+    if isinstance(hidden, (int, np.integer)) and activation == "relu":
+        return O.mlp_forward(params, F, hidden, A, x)
+    sizes = [hidden] if isinstance(hidden, (int, np.integer)) else list(hidden)
+    act = {"relu": lambda v: np.maximum(v, 0.0), "tanh": np.tanh, "sigmoid": lambda v: 1.0 / (1.0 + np.exp(-v)),
+           "identity": lambda v: v}[activation]
+    h = np.asarray(x, np.float64).reshape(-1, F)
+    o, prev = 0, F
+    for li, width in enumerate(sizes + [A]):
+        w = np.asarray(params[o:o + width * prev], np.float64).reshape(width, prev); o += width * prev
+        b = np.asarray(params[o:o + width], np.float64); o += width
+        h = h @ w.T + b
+        if li < len(sizes):
+            h = act(h)
+        prev = width
+    return h.astype(np.float32)
+
+
+def check_policy_consistency(host: dict, params, hidden, A, actor_words, atol=2e-6, activation="relu"):
     """Every sampled action must be the inverse-CDF choice of the oracle's softmax for the observation the kernel
     recorded, unless the uniform lies within `atol` of a CDF boundary (rounding near-tie)."""
     T, E, F = host["obs"].shape
@@ -132,7 +152,7 @@ def check_policy_consistency(host: dict, params, hidden, A, actor_words, atol=2e
     for e in range(E):
         n = int(host["lane_len"][e])
         # the dropped dangling step also consumed a uniform: n_taken = n or n + 1; index by step
-        logits = O.mlp_forward(params, F, hidden, A, host["obs"][:n, e])
+        logits = mlp_forward_any(params, F, hidden, A, host["obs"][:n, e], activation)
         m = logits.max(axis=1, keepdims=True)
         lse = m + np.log(np.exp(logits - m).sum(axis=1, keepdims=True))
         p = np.exp(logits - lse)

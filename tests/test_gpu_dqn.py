@@ -249,18 +249,20 @@ def test_dqn_update_matches_oracle(ctx, filled, pass_kernel, td):
 _DRAWS = {}
 
 
+@pytest.mark.parametrize("hidden", [64, [32, 24]], ids=["one-hidden-layer", "two-hidden-layers"])
 @pytest.mark.parametrize("td", [False, True])
-def test_dqn_update_other_network_shape(ctx, td):
+def test_dqn_update_other_network_shape(ctx, td, hidden):
     """DqnAgent::batch_update with a module the default kernels do not serve (MemoryGame: 7 features, 4 actions; 64 tanh
     units -> mlp_pass_any_kernel's Q-loss pass): same sampled episodes, same bound as the default-network test."""
     cfg = R.MemoryGame(4, 3)
-    E, hidden, act = 24, 64, "tanh"
+    E, act = 24, "tanh"
     env, rb, models = _fill(ctx, cfg, 0, E, 80, R.HistoryDataBound(24, 4), periods=3, seed=44)
     lanes = [rb.read_lane(e) for e in range(E)]
     F, A = env.num_features, env.num_actions
     params = R.init_params(np.random.default_rng(9), F, hidden, A)
     steps, minibatch, seed = 5, 300, 77
-    agent = R.DqnConfig(action_value_fn_config=R.MlpConfig(hidden_sizes=[hidden], activation=act), minibatch_steps=minibatch,
+    hs = [hidden] if isinstance(hidden, int) else hidden
+    agent = R.DqnConfig(action_value_fn_config=R.MlpConfig(hidden_sizes=hs, activation=act), minibatch_steps=minibatch,
                         opt_steps_per_update=steps, target_one_step_td=td, sample_seed=seed, buffer_capacity=80).build_agent(env)
     agent.action_value_fn.set_weights(params)
     stats = agent.batch_update(rb, {})

@@ -2,7 +2,7 @@
 
 `mlp_pass_any_kernel` (update.cu) serves every one-hidden-layer MlpConfig (mlp.rs:21-61): other observation sizes
 (MemoryGame, the bandit meta-env), other action counts, other hidden sizes and the Tanh / Sigmoid activations
-(ff/activation.rs:11).  Same oracle and same bounds as tests/test_gpu_update.py: loss / gradient / Fisher-vector product
+(ff/activation.rs:11) -- and, in its layer-generic form, `hidden_sizes` with two or three entries (mlp.rs:25-34,139-151).  Same oracle and same bounds as tests/test_gpu_update.py: loss / gradient / Fisher-vector product
 against the f64 autograd run at rtol 1e-5; whole updates against the f64 run within max(2e-4, 4 x the torch-f32 run's own
 distance from it).
 """
@@ -24,7 +24,16 @@ SHAPES = [
     pytest.param(R.Chain(), 32, "sigmoid", id="chain-5-32-2-sigmoid"),
     pytest.param(R.CartPoleConfig().wrap(R.VisibleStepLimit(40)), 256, "relu", id="cartpole-5-256-2-relu"),
     pytest.param(R.CartPoleConfig().wrap(R.LatentStepLimit(30)), 100, "relu", id="cartpole-4-100-2-relu"),
+    # MlpConfig::hidden_sizes with two and three entries (even / odd layer widths, widths below and above a warp)
+    pytest.param(R.CartPoleConfig().wrap(R.VisibleStepLimit(40)), [32, 16], "tanh", id="cartpole-5-32-16-2-tanh"),
+    pytest.param(R.MemoryGame(4, 3), [64, 33], "relu", id="memory-7-64-33-4-relu"),
+    pytest.param(R.MetaEnv(R.UniformBernoulliBandits(10), 7), [24, 40, 12], "sigmoid", id="bandit-14-24-40-12-10-sigmoid"),
 ]
+DEEP = SHAPES[5:]
+
+
+def _hs(hidden):
+    return [hidden] if isinstance(hidden, int) else list(hidden)
 
 
 def _rel(a, b):
@@ -37,7 +46,7 @@ def _collect(ctx, cfg, hidden, activation, E, T, seed, scale=1.5):
     env = R.build_env(ctx, cfg, E, seed=seed)
     F, A = env.num_features, env.num_actions
     params = (R.init_params(rng, F, hidden, A) * scale).astype(np.float32)
-    net = R.Mlp(ctx, F, [hidden], A, activation)
+    net = R.Mlp(ctx, F, _hs(hidden), A, activation)
     net.set_weights(params)
     traj = R.Trajectory(env, T)
     R.rollout(env, R.ActorSpec(kind=L.RL_ACTOR_CATEGORICAL_POLICY, net=net), R.HistoryDataBound(T, 0), traj)
@@ -68,7 +77,7 @@ def test_policy_probe_any_shape(ctx, cfg, hidden, activation):
     assert _rel(got["fvp"], hv64) <= 1e-5
 
 
-@pytest.mark.parametrize("cfg,hidden,activation", SHAPES[:3])
+@pytest.mark.parametrize("cfg,hidden,activation", SHAPES[:3] + DEEP)
 def test_trpo_update_any_shape(ctx, cfg, hidden, activation):
     """The whole trust-region step (CG, step size, line search) on a well-conditioned problem (hpv_reg_coeff 0.1)."""
     E, T, reg = 90, 60, 0.1
@@ -94,14 +103,14 @@ def test_trpo_update_any_shape(ctx, cfg, hidden, activation):
     assert _rel(d, d64) <= max(2e-5, 1.25 * _rel(d32, d64)) and _rel(d, d64) <= 1e-4
 
 
-@pytest.mark.parametrize("cfg,hidden,activation", [SHAPES[0], SHAPES[1], SHAPES[4]])
+@pytest.mark.parametrize("cfg,hidden,activation", [SHAPES[0], SHAPES[1], SHAPES[4]] + DEEP)
 def test_value_update_any_shape(ctx, cfg, hidden, activation):
     """ValuesOpt::update (opt.rs:100-127) with a non-default state-value module: 15 Adam steps on the reward-to-go MSE."""
     E, T, steps = 80, 50, 15
     env, traj, net, params, host, valid, adv, F, A = _collect(ctx, cfg, hidden, activation, E, T, seed=9)
     rng = np.random.default_rng(10)
     vparams = R.init_params(rng, F, hidden, 1)
-    vcfg = R.ValuesOptConfig(state_value_fn_config=R.MlpConfig(hidden_sizes=[hidden], activation=activation),
+    vcfg = R.ValuesOptConfig(state_value_fn_config=R.MlpConfig(hidden_sizes=_hs(hidden), activation=activation),
                              opt_steps_per_update=steps)
     critic = R.ValuesOpt(ctx, vcfg, F, float(env.discount_factor))
     critic.state_value_fn.set_weights(vparams)
@@ -124,7 +133,7 @@ def test_value_update_any_shape(ctx, cfg, hidden, activation):
     assert _rel(d, d64) <= max(2e-4, 4 * _rel(d32, d64) + 1e-5)
 
 
-@pytest.mark.parametrize("cfg,hidden,activation", [SHAPES[1], SHAPES[2]])
+@pytest.mark.parametrize("cfg,hidden,activation", [SHAPES[1], SHAPES[2], DEEP[0], DEEP[2]])
 def test_ppo_and_reinforce_any_shape(ctx, cfg, hidden, activation):
     """Ppo::update / Reinforce::update (ppo.rs:97-147, reinforce.rs:64-89) with non-default policies."""
     E, T, steps, clip = 64, 50, 8, 0.1
@@ -156,18 +165,19 @@ def test_ppo_and_reinforce_any_shape(ctx, cfg, hidden, activation):
     assert _rel(d, d64) <= max(2e-3, 4 * _rel(d32, d64) + 1e-5)
 
 
-def test_actor_critic_learns_chain_with_small_tanh_mlp(ctx):
+@pytest.mark.parametrize("hidden", [[32], [24, 16]], ids=["one-hidden-layer", "two-hidden-layers"])
+def test_actor_critic_learns_chain_with_small_tanh_mlp(ctx, hidden):
     """agents/testing.rs:14-64 in spirit, on an env and modules the default kernels do not serve: TRPO with 32-unit
     tanh networks on Chain (chain.rs: always going right pays 10 at the end of the chain, going left pays 2 at once)
     raises the mean step reward."""
     E, T = 512, 64
     env = R.build_env(ctx, R.Chain(), E, seed=3)
-    mc = R.MlpConfig(hidden_sizes=[32], activation="tanh")
+    mc = R.MlpConfig(hidden_sizes=hidden, activation="tanh")
     agent = R.ActorCriticConfig(policy_config=R.TrpoConfig(policy_fn_config=mc),
                                 critic_config=R.ValuesOptConfig(state_value_fn_config=mc)).build_agent(env)
     rng = np.random.default_rng(0)
-    agent.policy.policy_fn.set_weights(R.init_params(rng, env.num_features, 32, 2))
-    agent.critic.state_value_fn.set_weights(R.init_params(rng, env.num_features, 32, 1))
+    agent.policy.policy_fn.set_weights(R.init_params(rng, env.num_features, hidden, 2))
+    agent.critic.state_value_fn.set_weights(R.init_params(rng, env.num_features, hidden, 1))
     traj = R.Trajectory(env, T)
     rewards = []
     for period in range(12):
