@@ -61,6 +61,7 @@ typedef struct rl_mlp rl_mlp;
 typedef struct rl_adam rl_adam;
 typedef struct rl_traj rl_traj;
 typedef struct rl_tabq rl_tabq;
+typedef struct rl_ucb1 rl_ucb1;
 typedef struct rl_replay rl_replay;
 typedef struct rl_grunet rl_grunet;
 
@@ -260,7 +261,8 @@ typedef enum {
     RL_ACTOR_RANDOM = 1,             /* RandomAgent: action_space.sample (src/agents/random.rs) */
     RL_ACTOR_CATEGORICAL_POLICY = 2, /* PolicyActor::act (src/torch/agents/policies/actor.rs:42-55) */
     RL_ACTOR_EPS_GREEDY_Q = 3,       /* DqnActor::act (src/torch/agents/dqn.rs:360-379) */
-    RL_ACTOR_TABULAR_EPS_GREEDY = 4  /* BaseTabularQLearningActor::act (src/agents/tabular.rs:222-232) */
+    RL_ACTOR_TABULAR_EPS_GREEDY = 4, /* BaseTabularQLearningActor::act (src/agents/tabular.rs:222-232) */
+    RL_ACTOR_UCB1 = 5                /* BaseUCB1Actor::act (src/agents/bandits/ucb.rs:214-243) */
 } rl_actor_kind;
 
 /* rl_actor_cfg.lanes_per_env value selecting the tensor-core rollout kernel (CartPole + 5/4-128-2 ReLU network) */
@@ -278,6 +280,7 @@ typedef struct rl_actor_cfg {
     int32_t lanes_per_env;        /* 0 = auto; threads cooperating on one env's MLP (1,2,4,8,16,32), or
                                    * RL_LANES_TENSOR_CORE: 128-env tiles, hidden layer on tcgen05 (K2t) */
     rl_grunet *seq_net;           /* CATEGORICAL_POLICY with a recurrent module (Chain<Gru, Linear>) instead of `net` */
+    rl_ucb1 *ucb;                 /* UCB1 (training: maximise the upper confidence bound; evaluation: the most selected action) */
 } rl_actor_cfg;
 
 /* HistoryDataBound (src/agents/buffers/mod.rs:25-113), per lane */
@@ -438,6 +441,20 @@ rl_status rl_tabq_update(rl_tabq *t, rl_traj *traj);
 /* q: f64 [R][S][A], counts: u64 [R][S][A] (host) */
 rl_status rl_tabq_get_table(rl_tabq *t, double *q_host, uint64_t *counts_host);
 rl_status rl_tabq_set_table(rl_tabq *t, const double *q_host, const uint64_t *counts_host);
+
+/* UCB1Agent (src/agents/bandits/ucb.rs:20-243): UCB1 applied independently to each state of a finite observation space.
+ * Tables per replica: mean reward f64 [S][A] (rewards scaled to [0, 1] by the env's reward range, :118-123), selection
+ * count u64 [S][A], visit count u64 [S]; initialised to one success and one failure per arm (:125-128).  As for rl_tabq,
+ * num_replicas = 1 is the reference under train_parallel (every lane acts from the one table, rl_ucb1_update folds lane 0,
+ * lane 1, ... into it in order, :186-199), num_replicas = num_envs trains independent agents.  The actor is deterministic
+ * given the tables; ties go to the LAST maximal action (utils/iter/cmp.rs:58-76). */
+rl_status rl_ucb1_create(rl_ctx *ctx, uint64_t num_replicas, int32_t num_observations, int32_t num_actions, double reward_lo,
+                         double reward_hi, double exploration_rate, rl_ucb1 **out);
+rl_status rl_ucb1_destroy(rl_ucb1 *u);
+rl_status rl_ucb1_update(rl_ucb1 *u, rl_traj *traj);
+rl_status rl_ucb1_get_tables(rl_ucb1 *u, double *mean_host, uint64_t *action_count_host, uint64_t *visit_count_host);
+rl_status rl_ucb1_set_tables(rl_ucb1 *u, const double *mean_host, const uint64_t *action_count_host,
+                             const uint64_t *visit_count_host);
 
 /* ------------------------------------------------------------------------------------------ */
 /* DQN (ReplayBuffer src/agents/buffers/replay.rs:11-126; DqnAgent::batch_update                 */

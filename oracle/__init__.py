@@ -498,3 +498,44 @@ def pack_episodes(episodes):
         steps += row
         batch_sizes.append(len(row))
     return {"steps": steps, "batch_sizes": batch_sizes, "order": order}
+
+
+# ------------------------------------------------------------------------------------------------
+# UCB1 (src/agents/bandits/ucb.rs) -- small-case Python restatement (scalar f64 arithmetic, libm log as f64::ln)
+# ------------------------------------------------------------------------------------------------
+class Ucb1Oracle:
+    """BaseUCB1Agent + BaseUCB1Actor (ucb.rs:78-243)."""
+
+    def __init__(self, num_observations: int, num_actions: int, reward_range, exploration_rate: float = 0.2):
+        lo, hi = float(reward_range[0]), float(reward_range[1])
+        width = hi - lo
+        if not np.isfinite(width):
+            raise ValueError("UnboundedReward")  # ucb.rs:112-117
+        self.exploration_rate = float(exploration_rate)
+        self.reward_scale_factor = 1.0 / width   # :118
+        self.reward_shift = -lo                  # :119
+        # one success and one failure for each arm (:125-128)
+        self.mean = np.full((num_observations, num_actions), 0.5, np.float64)
+        self.count = np.full((num_observations, num_actions), 2, np.uint64)
+        self.visits = np.full((num_observations,), 2 * num_actions, np.uint64)
+
+    def step_update(self, obs: int, action: int, reward: float):  # :143-160
+        scaled = (float(reward) + self.reward_shift) * self.reward_scale_factor
+        self.visits[obs] += np.uint64(1)
+        self.count[obs, action] += np.uint64(1)
+        m = float(self.mean[obs, action])
+        self.mean[obs, action] = m + (scaled - m) / float(self.count[obs, action])
+
+    def ucb(self, obs: int):  # :219-231
+        import math
+
+        lsv = 2.0 * math.log(float(self.visits[obs]))
+        return [math.sqrt(lsv / float(c)) * self.exploration_rate + float(m) for c, m in zip(self.count[obs], self.mean[obs])]
+
+    def act(self, obs: int, training: bool = True) -> int:  # :214-243; argmax_by returns the LAST maximum (cmp.rs:58-76)
+        vals = self.ucb(obs) if training else [int(c) for c in self.count[obs]]
+        best, bv = 0, vals[0]
+        for k, v in enumerate(vals):
+            if v >= bv:
+                best, bv = k, v
+        return best

@@ -13,7 +13,7 @@ from .simulation import (ActorSpec, HistoryDataBound, TrainParallelConfig, Traje
 from .logging import DisplayLogger, HistoryLogger, NullLogger, StatsLogger  # noqa: F401
 
 __version__ = "0.1.0"
-from .agents import TabularQ  # noqa: F401,E402
+from .agents import TabularQ, UCB1Agent, UCB1AgentConfig  # noqa: F401,E402
 from .torch_agents import (ActorCriticAgent, ActorCriticConfig, Adam, AdamConfig,  # noqa: F401,E402
                            ConjugateGradientOptimizerConfig, DataCollectionSchedule, DqnAgent, DqnConfig,
                            ExplorationRateSchedule, OptimizerStepError, Ppo, PpoConfig, Reinforce, ReinforceConfig,

@@ -136,6 +136,16 @@ struct rl_tabq {
     unsigned long long *counts = nullptr;  // u64 [R][S][A]
 };
 
+struct rl_ucb1 {
+    rl_ctx *ctx = nullptr;
+    uint64_t R = 0;
+    int S = 0, A = 0;
+    double rate = 0.2, scale = 1.0, shift = 0.0;  // exploration_rate; reward_scale_factor, reward_shift (ucb.rs:118-123)
+    double *mean = nullptr;                  // f64 [R][S][A]
+    unsigned long long *count = nullptr;     // u64 [R][S][A]
+    unsigned long long *visits = nullptr;    // u64 [R][S]
+};
+
 // Mlp weights passed by value into kernels
 struct MlpView {
     const float *params;

@@ -37,6 +37,9 @@ struct RolloutArgs {
     int training;
     const double *qtable;
     uint64_t qtable_lane_stride;  // S * A with one table per lane, 0 with one table shared by every lane (tabular.rs:148-156)
+    const double *ucb_mean;       // UCB1: tables (ucb.rs:96-103), per-lane strides as for qtable (visits: S or 0)
+    const unsigned long long *ucb_count, *ucb_visits;
+    double ucb_rate;
     int S, A, F;
     double *partials;  // f64 [gridDim.x][ST_COUNT]
     int sm_count;      // K2w: CTAs past the first per SM put their dynamics warp on another sub-partition
@@ -224,6 +227,26 @@ __device__ __forceinline__ uint32_t actor_act(const RolloutArgs &a, const typena
         double bv = row[0];
         for (int k = 1; k < a.A; ++k)
             if (row[k] > bv) { bv = row[k]; best = (uint32_t)k; }
+        return best;
+    }
+    case RL_ACTOR_UCB1: {  // ucb.rs:214-243; argmax_by keeps the LAST maximal element (utils/iter/cmp.rs:58-76)
+        const uint32_t o = EnvT::observe_index(p, s);
+        const unsigned long long *cnt = a.ucb_count + (uint64_t)e * a.qtable_lane_stride + (uint64_t)o * a.A;
+        uint32_t best = 0;
+        if (a.training) {
+            const double *mean = a.ucb_mean + (uint64_t)e * a.qtable_lane_stride + (uint64_t)o * a.A;
+            const uint64_t vstride = a.qtable_lane_stride ? (uint64_t)a.S : 0;
+            const double lsv = __dmul_rn(2.0, log((double)a.ucb_visits[(uint64_t)e * vstride + o]));
+            double bv = 0.0;
+            for (int k = 0; k < a.A; ++k) {
+                const double u = __dadd_rn(__dmul_rn(__dsqrt_rn(__ddiv_rn(lsv, (double)cnt[k])), a.ucb_rate), mean[k]);
+                if (k == 0 || u >= bv) { bv = u; best = (uint32_t)k; }
+            }
+        } else {
+            unsigned long long bc = 0;
+            for (int k = 0; k < a.A; ++k)
+                if (k == 0 || cnt[k] >= bc) { bc = cnt[k]; best = (uint32_t)k; }
+        }
         return best;
     }
     }
@@ -1790,6 +1813,12 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
                             actor->table->A == es.num_actions,
                    "rl_rollout: table shape does not match the environment (one replica per lane, or one shared table)");
     }
+    if (actor->kind == RL_ACTOR_UCB1) {
+        RL_REQUIRE(ctx, actor->ucb, "rl_rollout: ucb is NULL");
+        RL_REQUIRE(ctx, (actor->ucb->R == env->E || actor->ucb->R == 1) && actor->ucb->S == es.num_observations &&
+                            actor->ucb->A == es.num_actions,
+                   "rl_rollout: UCB1 tables do not match the environment (one replica per lane, or one shared set)");
+    }
     RolloutArgs a{};
     a.E = env->E; a.lane_offset = env->lane_offset; a.Tcap = traj->T;
     a.noise = env->noise;
@@ -1804,6 +1833,11 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
     a.training = actor->training;
     a.qtable = actor->table ? actor->table->q : nullptr;
     a.qtable_lane_stride = (actor->table && actor->table->R == env->E) ? (uint64_t)actor->table->S * actor->table->A : 0;
+    if (actor->kind == RL_ACTOR_UCB1) {
+        a.ucb_mean = actor->ucb->mean; a.ucb_count = actor->ucb->count; a.ucb_visits = actor->ucb->visits;
+        a.ucb_rate = actor->ucb->rate;
+        a.qtable_lane_stride = actor->ucb->R == env->E ? (uint64_t)actor->ucb->S * actor->ucb->A : 0;
+    }
     a.S = es.num_observations; a.A = es.num_actions; a.F = es.num_features;
 
     RL_CUDA(ctx, cudaMemsetAsync(traj->succ, RL_PAD, (size_t)traj->T * traj->E, ctx->stream));

@@ -49,6 +49,7 @@ class ActorSpec:
     training: bool = True
     lanes_per_env: int = 0
     seq_net: object = None             # modules.GruLinear (recurrent CATEGORICAL_POLICY)
+    ucb: object = None                 # agents.UCB1Agent
 
 
 class Trajectory:
@@ -127,6 +128,7 @@ def rollout(env: BatchedEnv, actor: ActorSpec, bound: HistoryDataBound, traj: Tr
     cfg.training = 1 if actor.training else 0
     cfg.lanes_per_env = actor.lanes_per_env
     cfg.seq_net = actor.seq_net.handle if actor.seq_net is not None else None
+    cfg.ucb = actor.ucb.handle if actor.ucb is not None else None
     summ = L.StepsSummary() if want_summary else None
     L.check(lib.rl_rollout(env.handle, C.byref(cfg), L.Bound(bound.min_steps, bound.slack_steps), traj.handle,
                            C.byref(summ) if want_summary else None), env.ctx.handle)

@@ -721,3 +721,22 @@ def test_gru_linear_packed_matches_iterated_steps():
     # identical inputs in different episodes give identical outputs (modules/testing.rs:80-122)
     same = TO.gru_packed_episodes(flat, F, H, A, [eps[0], eps[0][:3]])
     np.testing.assert_allclose(same[0][:3], same[1], rtol=0, atol=1e-6)
+
+
+def test_ucb1_oracle_restates_the_reference_rules():
+    """ucb.rs: initial tables (:125-128), reward scaling (:118-123,:145), incremental mean (:157-159), the confidence bound
+    (:219-231) and argmax_by's last-maximum tie rule (utils/iter/cmp.rs:58-76)."""
+    import math
+
+    o = O.Ucb1Oracle(3, 4, (-1.0, 3.0), 0.2)
+    assert (o.mean == 0.5).all() and (o.count == 2).all() and (o.visits == 8).all()
+    assert o.act(0, training=True) == 3 and o.act(0, training=False) == 3  # all equal: the LAST maximal element
+    o.step_update(1, 2, 3.0)  # scaled reward (3 - (-1)) / 4 = 1
+    assert o.visits[1] == 9 and o.count[1, 2] == 3 and o.mean[1, 2] == 0.5 + (1.0 - 0.5) / 3.0
+    want = math.sqrt(2.0 * math.log(9.0) / 3.0) * 0.2 + o.mean[1, 2]
+    assert o.ucb(1)[2] == want and o.act(1) == 2
+    o.step_update(1, 0, -1.0)  # scaled 0
+    assert o.mean[1, 0] == 0.5 + (0.0 - 0.5) / 3.0
+    assert o.act(1, training=False) == 2  # counts [3, 2, 3, 2]: last maximum
+    with pytest.raises(ValueError):
+        O.Ucb1Oracle(2, 2, (0.0, float("inf")))
