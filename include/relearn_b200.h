@@ -209,6 +209,22 @@ typedef enum {
 rl_status rl_encode_features(rl_ctx *ctx, rl_space_kind kind, uint64_t size, const void *elems_dev, uint64_t n,
                              float *out_dev);
 
+/* LazyHistoryFeatures (src/torch/agents/features.rs:70-215) over the stored episodes of `traj`, in the packed order of
+ * PackedStructure / PackedSeqIter (src/torch/packed.rs:346-420): episodes sorted by length descending (ties in buffer
+ * order: lane, then time; the reference's sort_unstable leaves ties unordered), interleaved time-major.  The update
+ * kernels of this library read the [T][F][E] planes directly and never need this; it materialises the reference's own
+ * layout for callers that do (a libtorch module on the other side of the boundary, checks against the reference).
+ * Device outputs, any may be NULL; N = num_steps, M = num_episodes, L = max_len:
+ *   obs f32 [N][F] (observation_features), ext_obs f32 [N + M][F] and ext_invalid u8 [N + M]
+ *   (extended_observation_features: per episode one more row -- the successor observation on Interrupt, zeros and
+ *   invalid = 1 on Terminate), action i64 [N] (actions), reward f32 [N] (rewards), batch_sizes i64 [L],
+ *   ext_batch_sizes i64 [L + 1].  Sizing by the trajectory's capacity (T E rows, 2 T E for ext) is always enough. */
+typedef struct rl_packed_info {
+    uint64_t num_steps, num_episodes, max_len;
+} rl_packed_info;
+rl_status rl_pack_history(rl_traj *traj, float *obs_dev, float *ext_obs_dev, uint8_t *ext_invalid_dev, int64_t *action_dev,
+                          float *reward_dev, int64_t *batch_sizes_dev, int64_t *ext_batch_sizes_dev, rl_packed_info *info);
+
 /* ------------------------------------------------------------------------------------------ */
 /* MLP module (BuildModule / Module::variables src/torch/modules/mod.rs:21-235, ff/mlp.rs)      */
 /* ------------------------------------------------------------------------------------------ */

@@ -8,7 +8,7 @@ from .envs import (BatchedEnv, CartPole, CartPoleConfig, Chain, LatentStepLimit,
                    TrialEpisodeLimit, UniformBernoulliBandits, VisibleStepLimit, build_env)
 from .modules import (GruLinear, GruLinearConfig, Mlp, MlpConfig, init_gru_linear_params, init_params, num_params)  # noqa: F401
 from .runtime import Context, DeviceBuffer  # noqa: F401
-from .simulation import (ActorSpec, HistoryDataBound, TrainParallelConfig, Trajectory, rollout, train_device,  # noqa: F401
+from .simulation import (ActorSpec, HistoryDataBound, TrainParallelConfig, Trajectory, pack_history, rollout, train_device,  # noqa: F401
                          train_serial)
 from .logging import DisplayLogger, HistoryLogger, NullLogger, StatsLogger  # noqa: F401
 

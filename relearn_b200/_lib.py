@@ -65,6 +65,10 @@ class ActorCfg(C.Structure):
                 ("seq_net", vp), ("ucb", vp)]
 
 
+class PackedInfo(C.Structure):
+    _fields_ = [("num_steps", C.c_uint64), ("num_episodes", C.c_uint64), ("max_len", C.c_uint64)]
+
+
 class Bound(C.Structure):
     _fields_ = [("min_steps", C.c_uint64), ("slack_steps", C.c_uint64)]
 
@@ -215,6 +219,7 @@ SIGNATURES = {
     "rl_ppo_cfg_default": (None, [P(PpoCfg)]),
     "rl_ppo_update": (st, [vp, vp, vp, vp, P(PpoCfg), P(PolicyOptStats)]),
     "rl_reinforce_update": (st, [vp, vp, vp, vp, P(PolicyOptStats)]),
+    "rl_pack_history": (st, [vp, vp, vp, vp, vp, vp, vp, vp, P(PackedInfo)]),
     "rl_tabq_create": (st, [vp, C.c_uint64, C.c_int32, C.c_int32, C.c_double, P(vp)]),
     "rl_tabq_destroy": (st, [vp]),
     "rl_tabq_update": (st, [vp, vp]),

@@ -269,3 +269,29 @@ class _ScopeDict(dict):
     def update(self, other=(), **kw):
         for k, v in dict(other, **kw).items():
             self[k] = v
+
+
+def pack_history(traj: Trajectory) -> dict:
+    """LazyHistoryFeatures (src/torch/agents/features.rs:70-215) of the stored episodes, built on the device by
+    `rl_pack_history` and read back: packed observation features [N, F], extended observation features [N + M, F] with
+    their is_invalid flags, actions (i64), rewards, and the batch sizes of the two PackedStructures."""
+    ctx, lib = traj.ctx, traj.ctx._lib
+    v = traj.view()
+    T, E, F = int(v.step_capacity), int(v.num_lanes), int(v.num_features)
+    cap = max(T * E, 1)
+    obs, ext, inv = ctx.alloc(cap * F * 4), ctx.alloc(2 * cap * F * 4), ctx.alloc(2 * cap)
+    act, rew = ctx.alloc(cap * 8), ctx.alloc(cap * 4)
+    bs, ebs = ctx.alloc((T + 1) * 8), ctx.alloc((T + 2) * 8)
+    info = L.PackedInfo()
+    L.check(lib.rl_pack_history(traj.handle, obs.c, ext.c, inv.c, act.c, rew.c, bs.c, ebs.c, C.byref(info)), ctx.handle)
+    N, M, Lmax = int(info.num_steps), int(info.num_episodes), int(info.max_len)
+    out = {
+        "num_steps": N, "num_episodes": M, "max_len": Lmax,
+        "obs": obs.download((N, F), np.float32), "ext_obs": ext.download((N + M, F), np.float32),
+        "ext_invalid": inv.download((N + M,), np.uint8).astype(bool), "action": act.download((N,), np.int64),
+        "reward": rew.download((N,), np.float32), "batch_sizes": bs.download((Lmax,), np.int64),
+        "ext_batch_sizes": ebs.download((Lmax + 1 if M else 0,), np.int64),
+    }
+    for b in (obs, ext, inv, act, rew, bs, ebs):
+        b.free()
+    return out

@@ -31,6 +31,7 @@ STRUCTS = {
     "TrajView": "rl_traj_view", "TrpoCfg": "rl_trpo_cfg", "TrpoStats": "rl_trpo_stats", "AdamCfg": "rl_adam_cfg",
     "OptStats": "rl_opt_stats", "PpoCfg": "rl_ppo_cfg", "PolicyOptStats": "rl_policy_opt_stats",
     "ReplayStats": "rl_replay_stats", "DqnCfg": "rl_dqn_cfg", "MinibatchView": "rl_minibatch_view",
+    "PackedInfo": "rl_packed_info",
 }
 
 
