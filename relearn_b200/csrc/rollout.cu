@@ -1898,12 +1898,13 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
             if (replay || a.actor_kind != RL_ACTOR_CATEGORICAL_POLICY)
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
             {
-                // K2v while its 16-env CTAs fit one per SM (E = 1024: 0.123 ms per period against K2w's 0.131), K2q while its
-                // 32-env CTAs do (E = 4096: 0.127 ms against K2w's 0.156), K2w beyond (two and more CTAs per SM).
-                // RL_WS_VARIANT = 1 | 3 | 4 | 5 | 6 forces K2w / K2y / K2v / K2z / K2q (measurements: profiles/r2_summary.md).
+                // K2z while its 16-env CTAs fit one per SM (E = 1024: 0.115 .. 0.118 ms per period against K2v's 0.123 and
+                // K2w's 0.131), K2q while its 32-env CTAs do (E = 4096: 0.127 ms against K2w's 0.156), K2w beyond (two and
+                // more CTAs per SM).  RL_WS_VARIANT = 1 | 3 | 4 | 5 | 6 forces K2w / K2y / K2v / K2z / K2q (measurements:
+                // profiles/r2_summary.md).
                 static const char *ws_variant = getenv("RL_WS_VARIANT");
                 const char v = ws_variant ? ws_variant[0]
-                               : a.E <= (uint64_t)VK_ENVS * ctx->sm_count ? '4'
+                               : a.E <= (uint64_t)VK_ENVS * ctx->sm_count ? '5'
                                : a.E <= (uint64_t)QK_ENVS * ctx->sm_count ? '6' : '1';
                 if (v == '6') RL_TRY(launch_ws6(ctx, env->cartpole, a, &nblocks));
                 else if (v == '5') RL_TRY(launch_ws5(ctx, env->cartpole, a, &nblocks));

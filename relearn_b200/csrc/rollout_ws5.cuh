@@ -62,6 +62,8 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws5_kernel(Car
     LaneStats st;
     st.init();
     bool contributes = false;
+    uint32_t fin_steps = 0;                                      // dynamics lanes: what finalize_last_episode needs after the loops
+    int fin_succ_last = RL_TERMINATE, fin_succ_prev = RL_TERMINATE;
 
     // ---- aux: one chunk = VK_CHUNK steps x 16 envs; lane = (env, half) handles steps k0 + 2 half + {0, 1} ----
     auto aux_fill = [&](uint32_t k0) {
@@ -118,7 +120,6 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws5_kernel(Car
             k0 += VK_CHUNK;
             if (lane == 0) yk_stu(sb + ZK_OFF(prod), k0);
         }
-        __syncthreads();  // (matches the barrier that ends the dynamics / policy loops)
     } else if (is_dyn) {
         // ------------------------------ dynamics warp: lane = (env el, action act) ------------------------------
         const int el = lane & 15, act = lane >> 4;
@@ -252,33 +253,9 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws5_kernel(Car
                    (double)ck[2] / ck[4], (double)ck[3] / ck[4]);
 #endif
         if (lane == 0) yk_stu(sb + ZK_OFF(done), 1u);
-        __syncthreads();  // the policy warps' stores of the step records are visible from here on
         st.v[ST_STEPS] = st.v[ST_R] = st.v[ST_R2] = (double)i;
         st.v[ST_EPS] = (double)n_eps; st.v[ST_ER] = st.v[ST_EL] = (double)sum_el; st.v[ST_ER2] = st.v[ST_EL2] = (double)sum_el2;
-        if (valid && act == 0) {
-            // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
-            uint32_t len = i, flags = 0;
-            double eps = (double)n_eps;
-            if (i > 0 && succ_last == RL_CONTINUE) {
-                len = i - 1;
-                flags = 1;
-                a.succ[(uint64_t)len * a.E + e] = RL_PAD;
-                if (len > 0 && succ_prev == RL_CONTINUE) {
-                    flags = 3;
-                    a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
-                    // next_obs of the new last step = the observation of the dropped one (stored by the policy warps)
-#pragma unroll
-                    for (int f = 0; f < 5; ++f)
-                        if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = __ldcg(a.obs + ((uint64_t)len * F + f) * a.E + e);
-                    eps += 1.0;
-                }
-            }
-            a.lane_len[e] = len;
-            a.lane_flags[e] = (uint8_t)flags;
-            st.v[ST_STORED_STEPS] = (double)len;
-            st.v[ST_STORED_EPS] = eps;
-            contributes = true;
-        }
+        fin_steps = i; fin_succ_last = succ_last; fin_succ_prev = succ_prev;
     } else {
         // ------------------------------ policy warps: 4 envs x 8 threads (K2c<8>) ------------------------------
         const int grp = lane >> 3, sub = lane & 7, el = 4 * warp + grp;
@@ -379,7 +356,37 @@ __global__ void __launch_bounds__(VK_THREADS, 2) rollout_cartpole_ws5_kernel(Car
             pk[0] += q1 - q0; pk[1] += q2 - q1; pk[2] += q3 - q2; pk[3] += 1;
 #endif
         }
-        __syncthreads();
+    }
+    __syncthreads();  // one barrier for every role: the policy warps' stores of the step records are visible from here on
+    if (is_dyn) {
+        const int act = lane >> 4;
+        const uint64_t e = e_base + (lane & 15);
+        if (e < a.E && act == 0) {
+            // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
+            const uint32_t i = fin_steps;
+            const int succ_last = fin_succ_last, succ_prev = fin_succ_prev;
+            uint32_t len = i, flags = 0;
+            double eps = st.v[ST_EPS];
+            if (i > 0 && succ_last == RL_CONTINUE) {
+                len = i - 1;
+                flags = 1;
+                a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+                if (len > 0 && succ_prev == RL_CONTINUE) {
+                    flags = 3;
+                    a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+                    // next_obs of the new last step = the observation of the dropped one (stored by the policy warps)
+#pragma unroll
+                    for (int f = 0; f < 5; ++f)
+                        if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = __ldcg(a.obs + ((uint64_t)len * F + f) * a.E + e);
+                    eps += 1.0;
+                }
+            }
+            a.lane_len[e] = len;
+            a.lane_flags[e] = (uint8_t)flags;
+            st.v[ST_STORED_STEPS] = (double)len;
+            st.v[ST_STORED_EPS] = eps;
+            contributes = true;
+        }
     }
     block_reduce_stats(st, contributes, a.partials);
 }
