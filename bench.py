@@ -534,6 +534,30 @@ def kernel_rooflines(ctx, R, L, hbm_peak):
     gbs = 9 * T * E2 / (ms * 1e-3) / 1e9
     out.append({"kernel": "cumsum_kernel (discounted_cumsum_from_end)", "steps": T * E2, "bytes_per_step": 9, "ms": ms,
                 "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+    # LazyHistoryFeatures' packed tensors from the same 33.5 M-step trajectory (rl_pack_history: episode scan, stable radix
+    # sort by length, gather).  Algorithmic bytes per stored step: read obs 20 + action 1 + reward 4 + succ 1, write
+    # obs 20 + extended obs 20 + is_invalid 1 + action (i64) 8 + reward 4 = 79 (the per-episode extra rows and the sort's
+    # own traffic -- 24 B per EPISODE -- come on top and are not counted).
+    cap = T * E2
+    p_obs, p_ext, p_inv = ctx.alloc(cap * 5 * 4), ctx.alloc(2 * cap * 5 * 4), ctx.alloc(2 * cap)
+    p_act, p_rew, p_bs, p_ebs = ctx.alloc(cap * 8), ctx.alloc(cap * 4), ctx.alloc((T + 1) * 8), ctx.alloc((T + 2) * 8)
+    info = L.PackedInfo()
+    pack = lambda: L.check(lib.rl_pack_history(traj.handle, p_obs.c, p_ext.c, p_inv.c, p_act.c, p_rew.c, p_bs.c, p_ebs.c,
+                                               C.byref(info)), ctx.handle)
+    for _ in range(2):
+        pack()
+    reps = 5
+    e0 = ctx.event().record()
+    for _ in range(reps):
+        pack()
+    e1 = ctx.event().record()
+    ms = e0.elapsed_ms(e1) / reps
+    gbs = 79 * info.num_steps / (ms * 1e-3) / 1e9
+    out.append({"kernel": "rl_pack_history (LazyHistoryFeatures: packed observations, extended observations, actions, rewards)",
+                "steps": int(info.num_steps), "episodes": int(info.num_episodes), "bytes_per_step": 79, "ms": ms,
+                "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak})
+    for b in (p_obs, p_ext, p_inv, p_act, p_rew, p_bs, p_ebs):
+        b.free()
     # large-E fused rollout (config 5's throughput end): K2c with one thread per env on the FP32 pipe, and K2t with the
     # policy's hidden layer on tcgen05 (what `lanes_per_env = 0` picks at this size)
     E3, T3 = 1 << 20, 64
