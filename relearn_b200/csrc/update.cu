@@ -590,6 +590,32 @@ __device__ __forceinline__ float warp_allsum_f32(float x) {
     return x;
 }
 
+// The kernel's inner loops, written with four independent partial results: one warp per scheduler runs this kernel (its
+// f64 totals fill shared memory), so a dependent chain of LDS -> FMA (or LDS.64 -> DADD -> STS.64) per element would
+// expose every shared-memory latency.  Same products, additions regrouped.
+__device__ __forceinline__ float any_dot(const float *__restrict__ w, int stride, const float *__restrict__ v, int n, float init) {
+    float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+    int f = 0;
+    for (; f + 3 < n; f += 4) {
+        a0 = fmaf(w[(f + 0) * stride], v[f + 0], a0);
+        a1 = fmaf(w[(f + 1) * stride], v[f + 1], a1);
+        a2 = fmaf(w[(f + 2) * stride], v[f + 2], a2);
+        a3 = fmaf(w[(f + 3) * stride], v[f + 3], a3);
+    }
+    for (; f < n; ++f) a0 = fmaf(w[f * stride], v[f], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+// tot[f * stride] += d * v[f]  (f64 totals, each entry owned by this lane)
+__device__ __forceinline__ void any_axpy(double *__restrict__ tot, int stride, float d, const float *__restrict__ v, int n) {
+    int f = 0;
+    for (; f + 3 < n; f += 4) {
+        double t0 = tot[(f + 0) * stride], t1 = tot[(f + 1) * stride], t2 = tot[(f + 2) * stride], t3 = tot[(f + 3) * stride];
+        t0 += (double)(d * v[f + 0]); t1 += (double)(d * v[f + 1]); t2 += (double)(d * v[f + 2]); t3 += (double)(d * v[f + 3]);
+        tot[(f + 0) * stride] = t0; tot[(f + 1) * stride] = t1; tot[(f + 2) * stride] = t2; tot[(f + 3) * stride] = t3;
+    }
+    for (; f < n; ++f) tot[f * stride] += (double)(d * v[f]);
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, AnyShape sh) {
     constexpr bool BACKWARD = MODE == PASS_GRAD || MODE == PASS_FVP || MODE == PASS_VALUE || MODE == PASS_QLOSS ||
@@ -661,15 +687,10 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                 if (FVP) pzd[k] = 0.0f;
             }
             for (int j = lane; j < (deep ? 0 : H); j += 32) {
-                float pre = b1[j];
-                for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
+                const float pre = any_dot(w1t + j, H, x, F, b1[j]);
                 const float h = rl_activate(act, pre);
                 float dh = 0.0f;
-                if (FVP) {
-                    float dpre = vb1[j];
-                    for (int f = 0; f < F; ++f) dpre = fmaf(vw1t[f * H + j], x[f], dpre);
-                    dh = any_act_grad(act, pre, h) * dpre;
-                }
+                if (FVP) dh = any_act_grad(act, pre, h) * any_dot(vw1t + j, H, x, F, vb1[j]);
 #pragma unroll
                 for (int k = 0; k < ANY_MAXA; ++k)
                     if (k < A) {
@@ -686,16 +707,12 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                     const float *vWt = tv + dl.off_w[l], *vbb = tv + dl.off_b[l];
                     float *hout = dbuf + l * ANY_DEEP_MAXH, *dout = dbuf + (sh.L + l) * ANY_DEEP_MAXH;
                     for (int j = lane; j < n_out; j += 32) {
-                        float pre = bb[j];
-                        for (int f = 0; f < n_in; ++f) pre = fmaf(Wt[f * ld + j], vin[f], pre);
+                        const float pre = any_dot(Wt + j, ld, vin, n_in, bb[j]);
                         const float h = rl_activate(act, pre);
                         hout[j] = h;
                         if (FVP) {
-                            float dpre = vbb[j];
-                            for (int f = 0; f < n_in; ++f) {
-                                dpre = fmaf(vWt[f * ld + j], vin[f], dpre);
-                                if (dvin) dpre = fmaf(Wt[f * ld + j], dvin[f], dpre);
-                            }
+                            float dpre = any_dot(vWt + j, ld, vin, n_in, vbb[j]);
+                            if (dvin) dpre = any_dot(Wt + j, ld, dvin, n_in, dpre);
                             dout[j] = any_act_grad(act, h, h) * dpre;
                         }
                     }
@@ -851,13 +868,12 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                     for (int j = lane; j < n_out; j += 32) {
                         const float dj = delta[j];
                         tot[dl.off_b[l] + j] += (double)dj;
-                        for (int f = 0; f < n_in; ++f) tot[dl.off_w[l] + f * ld + j] += (double)(dj * vin[f]);
+                        any_axpy(tot + dl.off_w[l] + j, ld, dj, vin, n_in);
                     }
                     if (l > 0) {  // delta of the layer below: lane i owns ITS unit i (= input i of this layer)
                         const float *Wt = th + dl.off_w[l];
                         for (int i2 = lane; i2 < n_in; i2 += 32) {
-                            float acc = 0.0f;
-                            for (int j = 0; j < n_out; ++j) acc = fmaf(Wt[i2 * ld + j], delta[j], acc);
+                            const float acc = any_dot(Wt + i2 * ld, 1, delta, n_out, 0.0f);
                             delta2[i2] = acc * any_act_grad(act, vin[i2], vin[i2]);
                         }
                         __syncwarp();
@@ -868,8 +884,7 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
             }
             if (BACKWARD && !deep) {
                 for (int j = lane; j < H; j += 32) {
-                    float pre = b1[j];
-                    for (int f = 0; f < F; ++f) pre = fmaf(w1t[f * H + j], x[f], pre);
+                    const float pre = any_dot(w1t + j, H, x, F, b1[j]);
                     const float h = rl_activate(act, pre);
                     float dh = 0.0f;
 #pragma unroll
@@ -880,7 +895,7 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
                         }
                     const float dp = dh * any_act_grad(act, pre, h);
                     tot[H * F + j] += (double)dp;
-                    for (int f = 0; f < F; ++f) tot[f * H + j] += (double)(dp * x[f]);
+                    any_axpy(tot + j, H, dp, x, F);
                 }
             }
         }
