@@ -561,18 +561,16 @@ __host__ __device__ inline int deep_pidx(const DeepLayout &d, int i) {
     return 0;
 }
 
+// floats per activation / tangent / delta buffer: the widest hidden layer, rounded up to a multiple of 32
+__host__ __device__ inline int any_buf_stride(const DeepLayout &d) { return (d.maxH + 31) / 32 * 32; }
+
 __host__ __device__ inline size_t any_smem_bytes(const AnyShape &sh, int nwarps, bool backward, bool fvp) {
-    if (sh.L > 1) {
-        const DeepLayout d = deep_layout(sh);
-        const size_t Pp = (size_t)d.P_pad;
-        // totals | scalars | theta (+ direction) | tile observations | per-warp buffers: h[L], tangent[L], delta[2]
-        return (backward ? (size_t)nwarps * Pp * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
-               Pp * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float) +
-               (size_t)nwarps * (2 * sh.L + 2) * ANY_DEEP_MAXH * sizeof(float);
-    }
-    const size_t P = (size_t)sh.H * sh.F + sh.H + (size_t)sh.A * sh.H + sh.A;
-    return (backward ? (size_t)nwarps * P * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
-           P * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float);
+    const DeepLayout d = deep_layout(sh);
+    const size_t Pp = (size_t)d.P_pad;
+    // totals | scalars | theta (+ direction) | tile observations | per warp, for two samples in flight: h[L], tangent[L], delta[2]
+    return (backward ? (size_t)nwarps * Pp * sizeof(double) : 0) + (size_t)nwarps * (NSCALAR + ANY_MAXA) * sizeof(double) +
+           Pp * sizeof(float) * (fvp ? 2 : 1) + (size_t)nwarps * 32 * sh.F * sizeof(float) +
+           (size_t)nwarps * 2 * (2 * sh.L + 2) * any_buf_stride(d) * sizeof(float);
 }
 
 __device__ __forceinline__ float any_act_grad(int act, float pre, float h) {
@@ -590,30 +588,37 @@ __device__ __forceinline__ float warp_allsum_f32(float x) {
     return x;
 }
 
-// The kernel's inner loops, written with four independent partial results: one warp per scheduler runs this kernel (its
-// f64 totals fill shared memory), so a dependent chain of LDS -> FMA (or LDS.64 -> DADD -> STS.64) per element would
-// expose every shared-memory latency.  Same products, additions regrouped.
-__device__ __forceinline__ float any_dot(const float *__restrict__ w, int stride, const float *__restrict__ v, int n, float init) {
-    float a0 = init, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+// The kernel's inner loops.  One warp per scheduler runs this kernel (its f64 totals fill shared memory), so the loops are
+// written for instruction economy and independent work: TWO samples share every weight / total they touch, and each
+// result is built from two independent partial sums (same products, additions regrouped).
+__device__ __forceinline__ void any_dot2(const float *__restrict__ w, int stride, const float *__restrict__ v0,
+                                         const float *__restrict__ v1, int n, float init0, float init1, float &r0, float &r1) {
+    float a0 = init0, a1 = 0.0f, b0 = init1, b1 = 0.0f;
     int f = 0;
-    for (; f + 3 < n; f += 4) {
-        a0 = fmaf(w[(f + 0) * stride], v[f + 0], a0);
-        a1 = fmaf(w[(f + 1) * stride], v[f + 1], a1);
-        a2 = fmaf(w[(f + 2) * stride], v[f + 2], a2);
-        a3 = fmaf(w[(f + 3) * stride], v[f + 3], a3);
+    for (; f + 1 < n; f += 2) {
+        const float w0 = w[f * stride], w1 = w[(f + 1) * stride];
+        a0 = fmaf(w0, v0[f], a0); b0 = fmaf(w0, v1[f], b0);
+        a1 = fmaf(w1, v0[f + 1], a1); b1 = fmaf(w1, v1[f + 1], b1);
     }
-    for (; f < n; ++f) a0 = fmaf(w[f * stride], v[f], a0);
-    return (a0 + a1) + (a2 + a3);
+    if (f < n) {
+        const float w0 = w[f * stride];
+        a0 = fmaf(w0, v0[f], a0); b0 = fmaf(w0, v1[f], b0);
+    }
+    r0 = a0 + a1;
+    r1 = b0 + b1;
 }
-// tot[f * stride] += d * v[f]  (f64 totals, each entry owned by this lane)
-__device__ __forceinline__ void any_axpy(double *__restrict__ tot, int stride, float d, const float *__restrict__ v, int n) {
+// tot[f * stride] += d0 * v0[f] + d1 * v1[f]  (f64 totals, each entry owned by this lane)
+__device__ __forceinline__ void any_axpy2(double *__restrict__ tot, int stride, float d0, const float *__restrict__ v0, float d1,
+                                          const float *__restrict__ v1, int n) {
     int f = 0;
-    for (; f + 3 < n; f += 4) {
-        double t0 = tot[(f + 0) * stride], t1 = tot[(f + 1) * stride], t2 = tot[(f + 2) * stride], t3 = tot[(f + 3) * stride];
-        t0 += (double)(d * v[f + 0]); t1 += (double)(d * v[f + 1]); t2 += (double)(d * v[f + 2]); t3 += (double)(d * v[f + 3]);
-        tot[(f + 0) * stride] = t0; tot[(f + 1) * stride] = t1; tot[(f + 2) * stride] = t2; tot[(f + 3) * stride] = t3;
+    for (; f + 1 < n; f += 2) {
+        double t0 = tot[f * stride], t1 = tot[(f + 1) * stride];
+        t0 += (double)fmaf(d1, v1[f], d0 * v0[f]);
+        t1 += (double)fmaf(d1, v1[f + 1], d0 * v0[f + 1]);
+        tot[f * stride] = t0;
+        tot[(f + 1) * stride] = t1;
     }
-    for (; f < n; ++f) tot[f * stride] += (double)(d * v[f]);
+    if (f < n) tot[f * stride] += (double)fmaf(d1, v1[f], d0 * v0[f]);
 }
 
 template <int MODE>
@@ -625,35 +630,32 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
     constexpr bool USES_ADV = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO || MODE == PASS_REINFORCE;
     constexpr bool USES_LP0 = MODE == PASS_EVAL || MODE == PASS_GRAD || MODE == PASS_PPO;
     constexpr bool FVP = MODE == PASS_FVP;
+    constexpr int SB = 2;  // samples in flight per warp
     if (a.skip_flag && *a.skip_flag) return;
-    const int F = sh.F, H = sh.H, A = sh.A, act = sh.act;
-    const bool deep = sh.L > 1;
+    const int F = sh.F, A = sh.A, act = sh.act, LL = sh.L;
     const DeepLayout dl = deep_layout(sh);
-    const int P = deep ? dl.P : H * F + H + A * H + A, W = P + NSCALAR;
-    const int PL = deep ? dl.P_pad : P;  // entries of the shared-memory copies (padded when deep)
+    const int P = dl.P, W = P + NSCALAR, PL = dl.P_pad, HB = any_buf_stride(dl);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
 
     extern __shared__ __align__(16) unsigned char any_smem[];
-    double *tot_all = reinterpret_cast<double *>(any_smem);                        // [nwarps][PL], W1 part as [F][H]
+    double *tot_all = reinterpret_cast<double *>(any_smem);                        // [nwarps][PL], every Linear as [input][unit]
     double *red = tot_all + (BACKWARD ? (size_t)nwarps * PL : 0);                  // [nwarps][NSCALAR + ANY_MAXA]
-    float *th = reinterpret_cast<float *>(red + (size_t)nwarps * (NSCALAR + ANY_MAXA));  // theta, W1 as [F][H]
+    float *th = reinterpret_cast<float *>(red + (size_t)nwarps * (NSCALAR + ANY_MAXA));  // theta, same layout
     float *tv = th + PL;                                                           // FVP: the direction, same layout
     float *xs_all = th + (FVP ? 2 : 1) * (size_t)PL;
     float *xs = xs_all + (size_t)warp * 32 * F;
-    float *dbuf = xs_all + (size_t)nwarps * 32 * F + (size_t)warp * (2 * sh.L + 2) * ANY_DEEP_MAXH;  // deep: h | tangent | delta
+    // per warp and sample in flight: activations h[L], their tangents [L], two delta buffers; HB floats each
+    float *bufs = xs_all + (size_t)nwarps * 32 * F + (size_t)warp * SB * (2 * LL + 2) * HB;
+    auto buf = [&](int which, int b) { return bufs + ((size_t)b * (2 * LL + 2) + which) * HB; };
     double *tot = tot_all + (size_t)warp * PL;
     for (int i = threadIdx.x; i < P; i += blockDim.x) {
-        int dst = i;
-        if (deep) dst = deep_pidx(dl, i);
-        else if (i < H * F) dst = (i % F) * H + i / F;  // W1[j][f] -> [f][j]
+        const int dst = deep_pidx(dl, i);
         th[dst] = a.theta[i];
         if (FVP) tv[dst] = a.vec[i];
     }
     if (BACKWARD)
         for (int i = lane; i < PL; i += 32) tot[i] = 0.0;
     __syncthreads();
-    const float *w1t = th, *b1 = th + H * F, *w2 = b1 + H, *b2 = w2 + A * H;
-    const float *vw1t = tv, *vb1 = tv + H * F, *vw2 = vb1 + H, *vb2 = vw2 + A * H;
 
     double gb2[ANY_MAXA], sc[NSCALAR];  // lane 0's copies are the ones reported (every lane computes the same values)
 #pragma unroll
@@ -673,230 +675,225 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
         const int my_act = ((IS_POLICY || MODE == PASS_QLOSS) && valid) ? (int)a.action[n] : 0;
         const float my_adv = (USES_ADV && valid) ? a.adv[n] : 0.0f;
         const float my_tgt = ((MODE == PASS_VALUE || MODE == PASS_QLOSS) && valid) ? a.target[n] : 0.0f;
-        const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+        unsigned todo = __ballot_sync(0xffffffffu, valid);
         __syncwarp();
-        for (int s = 0; s < 32; ++s) {
-            if (!((valid_mask >> s) & 1u)) continue;  // warp-uniform
-            const float *x = xs + s * F;
-            const uint64_t ns = tile * 32 + s;
-            // ---- forward: this lane's units -> partial outputs (and their tangents along `vec`) ----
-            float pz[ANY_MAXA], pzd[FVP ? ANY_MAXA : 1];
-#pragma unroll
-            for (int k = 0; k < ANY_MAXA; ++k) {
-                pz[k] = 0.0f;
-                if (FVP) pzd[k] = 0.0f;
-            }
-            for (int j = lane; j < (deep ? 0 : H); j += 32) {
-                const float pre = any_dot(w1t + j, H, x, F, b1[j]);
-                const float h = rl_activate(act, pre);
-                float dh = 0.0f;
-                if (FVP) dh = any_act_grad(act, pre, h) * any_dot(vw1t + j, H, x, F, vb1[j]);
-#pragma unroll
-                for (int k = 0; k < ANY_MAXA; ++k)
-                    if (k < A) {
-                        pz[k] = fmaf(w2[k * H + j], h, pz[k]);
-                        if (FVP) pzd[k] = fmaf(vw2[k * H + j], h, fmaf(w2[k * H + j], dh, pzd[k]));
+        while (todo) {  // warp-uniform: the next two valid samples of the tile (the last one may be alone)
+            const int s0 = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const bool two = todo != 0;
+            const int s1 = two ? __ffs(todo) - 1 : s0;
+            if (two) todo &= todo - 1;
+            const int sidx[SB] = {s0, s1};
+            const float *x0 = xs + s0 * F, *x1 = xs + s1 * F;
+            // ---- forward: lane j owns units {j + 32 u} of every layer; outputs (and tangents) go to the warp's buffers ----
+            const float *vin0 = x0, *vin1 = x1, *dvin0 = nullptr, *dvin1 = nullptr;
+            for (int l = 0; l < LL; ++l) {
+                const int n_in = dl.in[l], n_out = dl.out[l], ld = dl.ld[l];
+                const float *Wt = th + dl.off_w[l], *bb = th + dl.off_b[l];
+                const float *vWt = tv + dl.off_w[l], *vbb = tv + dl.off_b[l];
+                float *h0 = buf(l, 0), *h1 = buf(l, 1), *d0 = buf(LL + l, 0), *d1 = buf(LL + l, 1);
+                for (int j = lane; j < n_out; j += 32) {
+                    float p0, p1;
+                    any_dot2(Wt + j, ld, vin0, vin1, n_in, bb[j], bb[j], p0, p1);
+                    const float a0 = rl_activate(act, p0), a1 = rl_activate(act, p1);
+                    h0[j] = a0;
+                    h1[j] = a1;
+                    if (FVP) {
+                        float q0, q1;
+                        any_dot2(vWt + j, ld, vin0, vin1, n_in, vbb[j], vbb[j], q0, q1);
+                        if (dvin0) any_dot2(Wt + j, ld, dvin0, dvin1, n_in, q0, q1, q0, q1);
+                        d0[j] = any_act_grad(act, a0, a0) * q0;
+                        d1[j] = any_act_grad(act, a1, a1) * q1;
                     }
-            }
-            if (deep) {
-                // hidden layers: lane j owns units {j + 32 u}; the layer's output (and its tangent) goes to the warp's buffers
-                const float *vin = x, *dvin = nullptr;
-                for (int l = 0; l < sh.L; ++l) {
-                    const int n_in = dl.in[l], n_out = dl.out[l], ld = dl.ld[l];
-                    const float *Wt = th + dl.off_w[l], *bb = th + dl.off_b[l];
-                    const float *vWt = tv + dl.off_w[l], *vbb = tv + dl.off_b[l];
-                    float *hout = dbuf + l * ANY_DEEP_MAXH, *dout = dbuf + (sh.L + l) * ANY_DEEP_MAXH;
-                    for (int j = lane; j < n_out; j += 32) {
-                        const float pre = any_dot(Wt + j, ld, vin, n_in, bb[j]);
-                        const float h = rl_activate(act, pre);
-                        hout[j] = h;
-                        if (FVP) {
-                            float dpre = any_dot(vWt + j, ld, vin, n_in, vbb[j]);
-                            if (dvin) dpre = any_dot(Wt + j, ld, dvin, n_in, dpre);
-                            dout[j] = any_act_grad(act, h, h) * dpre;
-                        }
-                    }
-                    __syncwarp();
-                    vin = hout;
-                    dvin = dout;
                 }
-                // output Linear: partial sums over this lane's units of the last hidden layer
-                const int n_in = dl.in[sh.L], ld = dl.ld[sh.L];
-                const float *Wt = th + dl.off_w[sh.L], *vWt = tv + dl.off_w[sh.L];
+                __syncwarp();
+                vin0 = h0; vin1 = h1;
+                dvin0 = d0; dvin1 = d1;
+            }
+            // output Linear: partial sums over this lane's units of the last hidden layer, then a butterfly
+            float zz[SB][ANY_MAXA], zzd[SB][FVP ? ANY_MAXA : 1], dzz[SB][ANY_MAXA];
+            {
+                float pz[SB][ANY_MAXA], pzd[SB][FVP ? ANY_MAXA : 1];
+#pragma unroll
+                for (int b = 0; b < SB; ++b)
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k) {
+                        pz[b][k] = 0.0f;
+                        if (FVP) pzd[b][k] = 0.0f;
+                    }
+                const int n_in = dl.in[LL], ld = dl.ld[LL];
+                const float *Wt = th + dl.off_w[LL], *vWt = tv + dl.off_w[LL];
                 for (int j = lane; j < n_in; j += 32) {
-                    const float h = vin[j], dh = FVP ? dvin[j] : 0.0f;
+                    const float hv[SB] = {vin0[j], vin1[j]};
+                    const float dv[SB] = {FVP ? dvin0[j] : 0.0f, FVP ? dvin1[j] : 0.0f};
 #pragma unroll
                     for (int k = 0; k < ANY_MAXA; ++k)
                         if (k < A) {
-                            pz[k] = fmaf(Wt[j * ld + k], h, pz[k]);
-                            if (FVP) pzd[k] = fmaf(vWt[j * ld + k], h, fmaf(Wt[j * ld + k], dh, pzd[k]));
+                            const float wk = Wt[j * ld + k], vwk = FVP ? vWt[j * ld + k] : 0.0f;
+#pragma unroll
+                            for (int b = 0; b < SB; ++b) {
+                                pz[b][k] = fmaf(wk, hv[b], pz[b][k]);
+                                if (FVP) pzd[b][k] = fmaf(vwk, hv[b], fmaf(wk, dv[b], pzd[b][k]));
+                            }
                         }
                 }
-            }
-            const float *b_out = deep ? th + dl.off_b[sh.L] : b2, *vb_out = deep ? tv + dl.off_b[sh.L] : vb2;
-            float z[ANY_MAXA], zd[FVP ? ANY_MAXA : 1];
+                const float *b_out = th + dl.off_b[LL], *vb_out = tv + dl.off_b[LL];
 #pragma unroll
-            for (int k = 0; k < ANY_MAXA; ++k) {
-                z[k] = k < A ? warp_allsum_f32(pz[k]) + b_out[k] : 0.0f;
-                if (FVP) zd[k] = k < A ? warp_allsum_f32(pzd[k]) + vb_out[k] : 0.0f;
+                for (int b = 0; b < SB; ++b)
+#pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k) {
+                        zz[b][k] = k < A ? warp_allsum_f32(pz[b][k]) + b_out[k] : 0.0f;
+                        if (FVP) zzd[b][k] = k < A ? warp_allsum_f32(pzd[b][k]) + vb_out[k] : 0.0f;
+                    }
             }
-            const int act_s = __shfl_sync(0xffffffffu, my_act, s);
-            const float adv_s = __shfl_sync(0xffffffffu, my_adv, s), tgt_s = __shfl_sync(0xffffffffu, my_tgt, s);
-
             // ---- per-sample algebra (every lane computes the same values) ----
-            float dz[ANY_MAXA];
 #pragma unroll
-            for (int k = 0; k < ANY_MAXA; ++k) dz[k] = 0.0f;
-            float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
-            if (IS_POLICY) {
-                // log_softmax over the A outputs
-                float m = z[0];
+            for (int b = 0; b < SB; ++b) {
 #pragma unroll
-                for (int k = 1; k < ANY_MAXA; ++k)
-                    if (k < A) m = fmaxf(m, z[k]);
-                float sum = 0.0f;
-#pragma unroll
-                for (int k = 0; k < ANY_MAXA; ++k)
-                    if (k < A) sum += expf(z[k] - m);
-                const float lse = m + logf(sum);
-                float lp[ANY_MAXA], pr[ANY_MAXA], lp0[USES_LP0 ? ANY_MAXA : 1];
-                float lpa = 0.0f, lp0a = 0.0f;
-#pragma unroll
-                for (int k = 0; k < ANY_MAXA; ++k) {
-                    lp[k] = k < A ? z[k] - lse : 0.0f;
-                    pr[k] = k < A ? expf(lp[k]) : 0.0f;
-                    if (USES_LP0) lp0[k] = k < A ? a.logp0[ns * A + k] : 0.0f;
-                    if (k == act_s) {
-                        lpa = lp[k];
-                        if (USES_LP0) lp0a = lp0[k];
-                    }
-                }
-                if (MODE == PASS_STATS) {  // trpo.rs:112-122, categorical.rs:62-68
-#pragma unroll
+                for (int k = 0; k < ANY_MAXA; ++k) dzz[b][k] = 0.0f;
+                if (b == 1 && !two) continue;  // (warp-uniform) no second sample: its logit gradients stay zero
+                const uint64_t ns = tile * 32 + sidx[b];
+                const int act_s = __shfl_sync(0xffffffffu, my_act, sidx[b]);
+                const float adv_s = __shfl_sync(0xffffffffu, my_adv, sidx[b]), tgt_s = __shfl_sync(0xffffffffu, my_tgt, sidx[b]);
+                float loss_s = 0.0f, kl_s = 0.0f, ent_s = 0.0f;
+                if (IS_POLICY) {
+                    // log_softmax over the A outputs
+                    float m = zz[b][0];
+    #pragma unroll
+                    for (int k = 1; k < ANY_MAXA; ++k)
+                        if (k < A) m = fmaxf(m, zz[b][k]);
+                    float sum = 0.0f;
+    #pragma unroll
                     for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) {
-                            ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
-                            if (lane == k) a.logp0[ns * A + k] = lp[k];
+                        if (k < A) sum += expf(zz[b][k] - m);
+                    const float lse = m + logf(sum);
+                    float lp[ANY_MAXA], pr[ANY_MAXA], lp0[USES_LP0 ? ANY_MAXA : 1];
+                    float lpa = 0.0f, lp0a = 0.0f;
+    #pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k) {
+                        lp[k] = k < A ? zz[b][k] - lse : 0.0f;
+                        pr[k] = k < A ? expf(lp[k]) : 0.0f;
+                        if (USES_LP0) lp0[k] = k < A ? a.logp0[ns * A + k] : 0.0f;
+                        if (k == act_s) {
+                            lpa = lp[k];
+                            if (USES_LP0) lp0a = lp0[k];
                         }
-                }
-                if (MODE == PASS_EVAL || MODE == PASS_GRAD) {  // trpo.rs:129-144
-                    const float ratio = expf(lpa - lp0a);
-                    loss_s = -(ratio * adv_s);
-#pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
-                    if (MODE == PASS_GRAD) {
-#pragma unroll
+                    }
+                    if (MODE == PASS_STATS) {  // trpo.rs:112-122, categorical.rs:62-68
+    #pragma unroll
                         for (int k = 0; k < ANY_MAXA; ++k)
-                            if (k < A) dz[k] = loss_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                            if (k < A) {
+                                ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
+                                if (lane == k) a.logp0[ns * A + k] = lp[k];
+                            }
                     }
-                }
-                if (MODE == PASS_PPO) {  // ppo.rs:124-138 (backward as libtorch, see mlp_pass_kernel)
-                    const float ratio = expf(lpa - lp0a);
-                    const float clipped = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
-                    const float t1 = ratio * adv_s, t2 = clipped * adv_s;
-                    loss_s = -fminf(t1, t2);
-                    const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
-                    const float g = (inside || t1 < t2) ? -t1 : 0.0f;
-#pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) dz[k] = g * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
-                }
-                if (MODE == PASS_REINFORCE) {  // reinforce.rs:72-79
-                    loss_s = -(lpa * adv_s);
-#pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) {
-                            ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
-                            dz[k] = -adv_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                    if (MODE == PASS_EVAL || MODE == PASS_GRAD) {  // trpo.rs:129-144
+                        const float ratio = expf(lpa - lp0a);
+                        loss_s = -(ratio * adv_s);
+    #pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) kl_s += fmaxf(lp0[k] - lp[k], F32_LOWEST) * expf(lp0[k]);
+                        if (MODE == PASS_GRAD) {
+    #pragma unroll
+                            for (int k = 0; k < ANY_MAXA; ++k)
+                                if (k < A) dzz[b][k] = loss_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
                         }
+                    }
+                    if (MODE == PASS_PPO) {  // ppo.rs:124-138 (backward as libtorch, see mlp_pass_kernel)
+                        const float ratio = expf(lpa - lp0a);
+                        const float clipped = fminf(fmaxf(ratio, a.clip_lo), a.clip_hi);
+                        const float t1 = ratio * adv_s, t2 = clipped * adv_s;
+                        loss_s = -fminf(t1, t2);
+                        const bool inside = ratio >= a.clip_lo && ratio <= a.clip_hi;
+                        const float g = (inside || t1 < t2) ? -t1 : 0.0f;
+    #pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) dzz[b][k] = g * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                    }
+                    if (MODE == PASS_REINFORCE) {  // reinforce.rs:72-79
+                        loss_s = -(lpa * adv_s);
+    #pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) {
+                                ent_s -= fmaxf(lp[k], F32_LOWEST) * pr[k];
+                                dzz[b][k] = -adv_s * ((act_s == k ? 1.0f : 0.0f) - pr[k]);
+                            }
+                    }
+                    if (FVP) {  // u = (diag p - p p^T) zdot
+                        float pd = 0.0f;
+    #pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) pd = fmaf(pr[k], zzd[b][k], pd);
+    #pragma unroll
+                        for (int k = 0; k < ANY_MAXA; ++k)
+                            if (k < A) dzz[b][k] = pr[k] * (zzd[b][k] - pd);
+                    }
+                } else if (MODE == PASS_VALUE) {  // opt.rs:109-115
+                    const float diff = zz[b][0] - tgt_s;
+                    loss_s = diff * diff;
+                    dzz[b][0] = 2.0f * diff;
+                } else {  // PASS_QLOSS, dqn.rs:316-326
+                    float qv = zz[b][0];
+    #pragma unroll
+                    for (int k = 1; k < ANY_MAXA; ++k)
+                        if (k == act_s) qv = zz[b][k];
+                    const float diff = qv - tgt_s;
+                    loss_s = diff * diff;
+    #pragma unroll
+                    for (int k = 0; k < ANY_MAXA; ++k) dzz[b][k] = (k == act_s && k < A) ? 2.0f * diff : 0.0f;
                 }
-                if (FVP) {  // u = (diag p - p p^T) zdot
-                    float pd = 0.0f;
+                sc[SC_COUNT] += 1.0;
+                sc[SC_LOSS] += (double)loss_s;
+                sc[SC_KL] += (double)kl_s;
+                sc[SC_ENTROPY] += (double)ent_s;
 #pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) pd = fmaf(pr[k], zd[k], pd);
-#pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) dz[k] = pr[k] * (zd[k] - pd);
-                }
-            } else if (MODE == PASS_VALUE) {  // opt.rs:109-115
-                const float diff = z[0] - tgt_s;
-                loss_s = diff * diff;
-                dz[0] = 2.0f * diff;
-            } else {  // PASS_QLOSS, dqn.rs:316-326
-                float qv = z[0];
-#pragma unroll
-                for (int k = 1; k < ANY_MAXA; ++k)
-                    if (k == act_s) qv = z[k];
-                const float diff = qv - tgt_s;
-                loss_s = diff * diff;
-#pragma unroll
-                for (int k = 0; k < ANY_MAXA; ++k) dz[k] = (k == act_s && k < A) ? 2.0f * diff : 0.0f;
+                for (int k = 0; k < ANY_MAXA; ++k) gb2[k] += (double)dzz[b][k];
             }
-            sc[SC_COUNT] += 1.0;
-            sc[SC_LOSS] += (double)loss_s;
-            sc[SC_KL] += (double)kl_s;
-            sc[SC_ENTROPY] += (double)ent_s;
-#pragma unroll
-            for (int k = 0; k < ANY_MAXA; ++k) gb2[k] += (double)dz[k];
 
-            // ---- backward: this lane's units, straight into the warp's f64 totals ----
-            if (BACKWARD && deep) {
-                // output Linear: gradients of its weights, delta of the last hidden layer
-                const int LL = sh.L;
-                float *delta = dbuf + 2 * LL * ANY_DEEP_MAXH, *delta2 = delta + ANY_DEEP_MAXH;
-                {
+            // ---- backward: this lane's units, straight into the warp's f64 totals (one update per entry for both samples) ----
+            if (BACKWARD) {
+                float *delta0 = buf(2 * LL, 0), *delta1 = buf(2 * LL, 1), *next0 = buf(2 * LL + 1, 0), *next1 = buf(2 * LL + 1, 1);
+                {   // output Linear: gradients of its weights, delta of the last hidden layer
                     const int n_in = dl.in[LL], ld = dl.ld[LL];
-                    const float *Wt = th + dl.off_w[LL], *hin = dbuf + (LL - 1) * ANY_DEEP_MAXH;
+                    const float *Wt = th + dl.off_w[LL];
                     for (int j = lane; j < n_in; j += 32) {
-                        const float h = hin[j];
-                        float dh = 0.0f;
+                        const float hv0 = vin0[j], hv1 = vin1[j];
+                        float dh0 = 0.0f, dh1 = 0.0f;
 #pragma unroll
                         for (int k = 0; k < ANY_MAXA; ++k)
                             if (k < A) {
-                                dh = fmaf(dz[k], Wt[j * ld + k], dh);
-                                tot[dl.off_w[LL] + j * ld + k] += (double)(dz[k] * h);
+                                const float wk = Wt[j * ld + k];
+                                dh0 = fmaf(dzz[0][k], wk, dh0);
+                                dh1 = fmaf(dzz[1][k], wk, dh1);
+                                tot[dl.off_w[LL] + j * ld + k] += (double)fmaf(dzz[1][k], hv1, dzz[0][k] * hv0);
                             }
-                        delta[j] = dh * any_act_grad(act, h, h);
+                        delta0[j] = dh0 * any_act_grad(act, hv0, hv0);
+                        delta1[j] = dh1 * any_act_grad(act, hv1, hv1);
                     }
                     __syncwarp();
                 }
                 for (int l = LL - 1; l >= 0; --l) {
                     const int n_in = dl.in[l], n_out = dl.out[l], ld = dl.ld[l];
-                    const float *vin = l == 0 ? x : dbuf + (l - 1) * ANY_DEEP_MAXH;
+                    const float *in0 = l == 0 ? x0 : buf(l - 1, 0), *in1 = l == 0 ? x1 : buf(l - 1, 1);
                     for (int j = lane; j < n_out; j += 32) {
-                        const float dj = delta[j];
-                        tot[dl.off_b[l] + j] += (double)dj;
-                        any_axpy(tot + dl.off_w[l] + j, ld, dj, vin, n_in);
+                        const float dj0 = delta0[j], dj1 = delta1[j];
+                        tot[dl.off_b[l] + j] += (double)(dj0 + dj1);
+                        any_axpy2(tot + dl.off_w[l] + j, ld, dj0, in0, dj1, in1, n_in);
                     }
                     if (l > 0) {  // delta of the layer below: lane i owns ITS unit i (= input i of this layer)
                         const float *Wt = th + dl.off_w[l];
                         for (int i2 = lane; i2 < n_in; i2 += 32) {
-                            const float acc = any_dot(Wt + i2 * ld, 1, delta, n_out, 0.0f);
-                            delta2[i2] = acc * any_act_grad(act, vin[i2], vin[i2]);
+                            float acc0, acc1;
+                            any_dot2(Wt + i2 * ld, 1, delta0, delta1, n_out, 0.0f, 0.0f, acc0, acc1);
+                            next0[i2] = acc0 * any_act_grad(act, in0[i2], in0[i2]);
+                            next1[i2] = acc1 * any_act_grad(act, in1[i2], in1[i2]);
                         }
                         __syncwarp();
-                        float *t = delta; delta = delta2; delta2 = t;
+                        float *t0 = delta0; delta0 = next0; next0 = t0;
+                        float *t1 = delta1; delta1 = next1; next1 = t1;
                     }
                 }
                 __syncwarp();
-            }
-            if (BACKWARD && !deep) {
-                for (int j = lane; j < H; j += 32) {
-                    const float pre = any_dot(w1t + j, H, x, F, b1[j]);
-                    const float h = rl_activate(act, pre);
-                    float dh = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < ANY_MAXA; ++k)
-                        if (k < A) {
-                            dh = fmaf(dz[k], w2[k * H + j], dh);
-                            tot[H * F + H + k * H + j] += (double)(dz[k] * h);
-                        }
-                    const float dp = dh * any_act_grad(act, pre, h);
-                    tot[H * F + j] += (double)dp;
-                    any_axpy(tot + j, H, dp, x, F);
-                }
             }
         }
     }
@@ -913,7 +910,7 @@ __global__ void __launch_bounds__(ANY_THREADS) mlp_pass_any_kernel(PassArgs a, A
     for (int i = threadIdx.x; i < W; i += blockDim.x) {
         double s = 0.0;
         if (i < P - A) {
-            const int src = deep ? deep_pidx(dl, i) : i < H * F ? (i % F) * H + i / F : i;
+            const int src = deep_pidx(dl, i);
             if (BACKWARD)
                 for (int w = 0; w < nwarps; ++w) s += tot_all[(size_t)w * PL + src];
         } else if (i < P) {
