@@ -121,8 +121,13 @@ rl_status rl_ucb1_create(rl_ctx *ctx, uint64_t num_replicas, int32_t num_observa
     // one success and one failure for each arm (ucb.rs:125-128)
     std::vector<double> m(n, 0.5);
     std::vector<unsigned long long> c(n, 2ull), v(ns, 2ull * (unsigned long long)num_actions);
+    const rl_status st = rl_ucb1_set_tables(u, m.data(), (const uint64_t *)c.data(), (const uint64_t *)v.data());
+    if (st != RL_OK) {
+        rl_ucb1_destroy(u);
+        return st;
+    }
     *out = u;
-    return rl_ucb1_set_tables(u, m.data(), (const uint64_t *)c.data(), (const uint64_t *)v.data());
+    return RL_OK;
 }
 
 rl_status rl_ucb1_destroy(rl_ucb1 *u) {
