@@ -39,8 +39,10 @@ __global__ void __launch_bounds__(128) seq_owner_init_kernel(typename EnvT::Para
 }
 
 // One step of every env that still collects: logits from h' (hnew plane), sample, record, env step, next observation.
+// (Two CTAs per SM: at 157 registers only one fitted and the 296 CTAs of 18 944 envs ran as two waves -- 10.28 -> 8.66 ms
+// per 199-step rollout.  A unit-major weight layout read with LDS.128 was measured slower: 9.12 ms.)
 template <class EnvT, bool REPLAY>
-__global__ void __launch_bounds__(256) seq_owner_step_kernel(typename EnvT::Params p, SeqArgs a, GtOwner<EnvT, REPLAY> *owners,
+__global__ void __launch_bounds__(256, 2) seq_owner_step_kernel(typename EnvT::Params p, SeqArgs a, GtOwner<EnvT, REPLAY> *owners,
                                                             float *__restrict__ xplane, float *__restrict__ hnew) {
     constexpr int MF = EnvT::MAXF, MA = EnvT::MAXA;
     extern __shared__ float osm[];  // lin_w [A][128], lin_b [A]
