@@ -1899,13 +1899,14 @@ rl_status rl_rollout(rl_env *env, const rl_actor_cfg *actor, rl_bound bound, rl_
                 return rl_fail(ctx, RL_ERR_UNSUPPORTED, "rl_rollout: RL_LANES_WARP_SPECIALIZED serves the categorical actor on Philox noise");
             {
                 // K2z while its 16-env CTAs fit one per SM (E = 1024: 0.115 .. 0.118 ms per period against K2v's 0.123 and
-                // K2w's 0.131), K2q while its 32-env CTAs do (E = 4096: 0.127 ms against K2w's 0.156), K2w beyond (two and
-                // more CTAs per SM).  RL_WS_VARIANT = 1 | 3 | 4 | 5 | 6 forces K2w / K2y / K2v / K2z / K2q (measurements:
-                // profiles/r2_summary.md).
+                // K2w's 0.131), K2q through two waves of its 32-env CTAs (E = 4096: 0.127 ms against K2w's 0.156; E = 4800 ..
+                // 9472: 0.239 .. 0.242 ms against K2w's 0.268 .. 0.301 and K2t's 0.322), K2w beyond (explicit requests only:
+                // `lanes_per_env = 0` switches to K2t there).  RL_WS_VARIANT = 1 | 3 | 4 | 5 | 6 forces K2w / K2y / K2v / K2z /
+                // K2q (measurements: profiles/r2_summary.md).
                 static const char *ws_variant = getenv("RL_WS_VARIANT");
                 const char v = ws_variant ? ws_variant[0]
                                : a.E <= (uint64_t)VK_ENVS * ctx->sm_count ? '5'
-                               : a.E <= (uint64_t)QK_ENVS * ctx->sm_count ? '6' : '1';
+                               : a.E <= 2ull * QK_ENVS * ctx->sm_count ? '6' : '1';
                 if (v == '6') RL_TRY(launch_ws6(ctx, env->cartpole, a, &nblocks));
                 else if (v == '5') RL_TRY(launch_ws5(ctx, env->cartpole, a, &nblocks));
                 else if (v == '3') RL_TRY(launch_ws3(ctx, env->cartpole, a, &nblocks));

@@ -422,9 +422,10 @@ def test_fused_rollout_policy_other_envs_consistent(ctx, cfg):
 @pytest.mark.parametrize("E,T,slack,limit,visible", [(4096, 64, 0, 500, True), (1000, 70, 9, 20, True), (37, 45, 3, 15, False),
                                                      (16, 33, 0, 500, True), (300, 50, 2, 0, False),
                                                      # K2q's range (2368 < E <= 4736): 28-env CTAs with a ragged last one, 32-env CTAs
-                                                     (2400, 40, 5, 20, True), (4700, 33, 0, 15, False), (4736, 21, 2, 9, True)])
+                                                     (2400, 40, 5, 20, True), (4700, 33, 0, 15, False), (4736, 21, 2, 9, True),
+                                                     (5000, 20, 3, 9, True), (9472, 12, 0, 500, True)])  # two waves of K2q
 def test_warp_specialized_rollout_is_bit_identical_to_k2c(ctx, E, T, slack, limit, visible):
-    """The warp-specialised kernels `RL_LANES_WARP_SPECIALIZED` picks by size (K2z up to 2368 envs, K2q up to 4736, K2w beyond:
+    """The warp-specialised kernels `RL_LANES_WARP_SPECIALIZED` picks by size (K2z up to 2368 envs, K2q up to 9472, K2w beyond:
     policy and dynamics of an env on different warps, hand-off through named barriers) perform the same
     operations on the same operands as K2c with 8 threads per env: under Philox noise every stored byte, the lane
     lengths and the summary must be identical -- ragged last CTA, slack, step-limit Interrupts, latent limit (F = 4),
