@@ -158,6 +158,42 @@ struct MlpView {
     __device__ const float *b2() const { return w2() + (size_t)out_dim * hidden; }
 };
 
+// Shared-memory layout of an Mlp for the warp-cooperative kernels (update.cu's run-time-sized passes, rollout.cu's
+// warp-per-env rollout): every Linear's weights TRANSPOSED as [input][unit] with an odd row pitch, so that a sweep with the
+// lanes over units (fixed input) and a sweep with the lanes over inputs (fixed unit) are both conflict-free.
+struct DeepLayout {
+    int n_layers;                  // Linear layers = hidden layers + 1
+    int in[4], out[4], ld[4];      // per Linear: inputs, units, pitch (odd)
+    int off_w[4], off_b[4];        // offsets in the padded layout
+    int nat_w[4];                  // offsets in Module::variables() order
+    int P, P_pad, maxH;
+};
+__host__ __device__ inline DeepLayout rl_mlp_layout(int F, int L, const int *Hs, int A) {
+    DeepLayout d{};
+    d.n_layers = L + 1;
+    int prev = F, off = 0, nat = 0, maxH = 0;
+    for (int l = 0; l <= L; ++l) {
+        const int out = l < L ? Hs[l] : A;
+        d.in[l] = prev; d.out[l] = out; d.ld[l] = out | 1;
+        d.off_w[l] = off; off += prev * d.ld[l];
+        d.off_b[l] = off; off += out;
+        d.nat_w[l] = nat; nat += prev * out + out;
+        if (l < L && out > maxH) maxH = out;
+        prev = out;
+    }
+    d.P = nat; d.P_pad = off; d.maxH = maxH;
+    return d;
+}
+// natural parameter index -> index in the padded transposed layout
+__host__ __device__ inline int deep_pidx(const DeepLayout &d, int i) {
+    for (int l = 0; l < d.n_layers; ++l) {
+        const int r = i - d.nat_w[l], nw = d.in[l] * d.out[l];
+        if (r < nw) return d.off_w[l] + (r % d.in[l]) * d.ld[l] + r / d.in[l];
+        if (r < nw + d.out[l]) return d.off_b[l] + (r - nw);
+    }
+    return 0;
+}
+
 inline MlpView rl_mlp_view(const rl_mlp *m) {
     MlpView v;
     v.params = m ? m->params : nullptr;

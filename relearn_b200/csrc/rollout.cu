@@ -350,6 +350,168 @@ __global__ void __launch_bounds__(128) rollout_kernel(typename EnvT::Params p, R
 }
 
 // ------------------------------------------------------------------------------------------------
+// K2g: one WARP per lane, for the network actors on modules the specialised kernels do not serve (any MlpConfig: one to
+// three hidden layers, any activation) while the lanes are few: K2a evaluates the module serially in one thread (4096 envs
+// are 128 warps on 148 SMs: 5-64-64-2 tanh: 16 ms per 256-step period), here the 32 threads of an env's warp split every
+// layer's units (weights transposed with an odd pitch in shared memory, activations of deeper layers in a per-warp
+// buffer, outputs combined by a butterfly so that every thread holds the same logits) and all of them carry the env, the
+// noise state and the actor redundantly -- same values in every thread, no divergence; thread 0 stores.
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 128, WG_MAX_ENVS = 65536;
+__host__ __device__ inline size_t rollout_warp_smem_bytes(const DeepLayout &d, int nwarps) {
+    return ((size_t)d.P_pad + (size_t)nwarps * 2 * ((d.maxH + 31) / 32 * 32)) * sizeof(float);
+}
+
+template <class EnvT>
+__device__ __forceinline__ void mlp_logits_warp(const MlpView &m, const DeepLayout &d, const float *__restrict__ th, float *__restrict__ hb,
+                                                int HB, const float *obs, float *z) {
+    const int lane = threadIdx.x & 31, L = m.n_hidden, A = m.out_dim;
+    const float *vin = nullptr;  // layer 0 reads the observation from registers
+    for (int l = 0; l < L; ++l) {
+        const int n_in = d.in[l], n_out = d.out[l], ld = d.ld[l];
+        const float *Wt = th + d.off_w[l], *bb = th + d.off_b[l];
+        float *hout = hb + (l & 1) * HB;
+        for (int j = lane; j < n_out; j += 32) {
+            float a0 = bb[j], a1 = 0.0f;
+            if (l == 0) {
+#pragma unroll
+                for (int f = 0; f < EnvT::MAXF; ++f)
+                    if (f < n_in) a0 = fmaf(Wt[f * ld + j], obs[f], a0);
+            } else {
+                int f = 0;
+                for (; f + 1 < n_in; f += 2) {
+                    a0 = fmaf(Wt[f * ld + j], vin[f], a0);
+                    a1 = fmaf(Wt[(f + 1) * ld + j], vin[f + 1], a1);
+                }
+                if (f < n_in) a0 = fmaf(Wt[f * ld + j], vin[f], a0);
+            }
+            hout[j] = rl_activate(m.act, a0 + a1);
+        }
+        __syncwarp();
+        vin = hout;
+    }
+    const int n_in = d.in[L], ld = d.ld[L];
+    const float *Wt = th + d.off_w[L], *bb = th + d.off_b[L];
+    float pz[EnvT::MAXA];
+#pragma unroll
+    for (int k = 0; k < EnvT::MAXA; ++k) pz[k] = 0.0f;
+    for (int j = lane; j < n_in; j += 32) {
+        const float h = vin[j];
+#pragma unroll
+        for (int k = 0; k < EnvT::MAXA; ++k)
+            if (k < A) pz[k] = fmaf(Wt[j * ld + k], h, pz[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < EnvT::MAXA; ++k) {
+        float v = pz[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        z[k] = k < A ? v + bb[k] : 0.0f;
+    }
+    __syncwarp();  // the buffers are reused by the next step
+}
+
+template <class EnvT, bool REPLAY>
+__global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT::Params p, RolloutArgs a) {
+    extern __shared__ __align__(16) float sw[];
+    const DeepLayout d = rl_mlp_layout(a.net.in_dim, a.net.n_hidden, a.net.hid, a.net.out_dim);
+    const int HB = (d.maxH + 31) / 32 * 32;
+    for (int i = threadIdx.x; i < d.P; i += blockDim.x) sw[deep_pidx(d, i)] = a.net.params[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    float *hb = sw + d.P_pad + (size_t)warp * 2 * HB;
+
+    const uint64_t e = (uint64_t)blockIdx.x * nwarps + warp;
+    const bool valid = e < a.E;
+    LaneStats st;
+    st.init();
+    if (valid) {
+        const int F = a.F;
+        LaneNoise<REPLAY> nz;
+        nz.init(a.noise, a.lane_offset + e, e);
+        const uint32_t t0 = a.noise.step_counter;
+        typename EnvT::State s;
+        float obs[EnvT::MAXF], last_obs[EnvT::MAXF];
+#pragma unroll
+        for (int f = 0; f < EnvT::MAXF; ++f) obs[f] = last_obs[f] = 0.0f;
+        uint32_t n = a.min_steps ? a.min_steps + a.slack : 0;  // take_steps.rs:20-31
+        uint32_t i = 0;
+        int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+        if (n > 0) {  // train.rs:135: every period starts fresh episodes
+            nz.set_step(t0);
+            EnvT::template reset<REPLAY>(p, s, nz);
+            EnvT::observe(p, s, obs);
+        }
+        while (n > 0) {
+            nz.set_step(t0 + i);
+            float z[EnvT::MAXA];
+            mlp_logits_warp<EnvT>(a.net, d, sw, hb, HB, obs, z);
+            const uint32_t action = actor_act<EnvT, REPLAY>(a, p, s, nz, e, i, z);
+            if (lane == 0) {
+#pragma unroll
+                for (int f = 0; f < EnvT::MAXF; ++f)
+                    if (f < F) a.obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
+            }
+#pragma unroll
+            for (int f = 0; f < EnvT::MAXF; ++f) last_obs[f] = obs[f];
+            float r;
+            const int sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
+            if (sc == RL_INTERRUPT) {
+                EnvT::observe(p, s, obs);
+                if (lane == 0) {
+#pragma unroll
+                    for (int f = 0; f < EnvT::MAXF; ++f)
+                        if (f < F) a.next_obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
+                }
+            }
+            if (sc != RL_CONTINUE) {
+                nz.set_step(t0 + i + 1);
+                EnvT::template reset<REPLAY>(p, s, nz);
+            }
+            EnvT::observe(p, s, obs);
+            if (lane == 0) {
+                a.action[(uint64_t)i * a.E + e] = (uint8_t)action;
+                a.reward[(uint64_t)i * a.E + e] = r;
+                a.succ[(uint64_t)i * a.E + e] = (uint8_t)sc;
+            }
+            st.push(r, sc);
+            succ_prev = succ_last;
+            succ_last = sc;
+            i += 1;
+            n -= 1;
+            if (sc != RL_CONTINUE && n <= a.slack) n = 0;  // take_steps.rs:83-88
+        }
+        // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
+        uint32_t len = i;
+        uint32_t flags = 0;
+        double eps = st.v[ST_EPS];
+        if (i > 0 && succ_last == RL_CONTINUE) {
+            len = i - 1;
+            flags = 1;
+            if (lane == 0) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (len > 0 && succ_prev == RL_CONTINUE) {
+                flags = 3;
+                if (lane == 0) {
+                    a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
+#pragma unroll
+                    for (int f = 0; f < EnvT::MAXF; ++f)
+                        if (f < F) a.next_obs[((uint64_t)(len - 1) * F + f) * a.E + e] = last_obs[f];
+                }
+                eps += 1.0;
+            }
+        }
+        if (lane == 0) {
+            a.lane_len[e] = len;
+            a.lane_flags[e] = (uint8_t)flags;
+            nz.finish(a.noise, e);
+        }
+        st.v[ST_STORED_STEPS] = (double)len;
+        st.v[ST_STORED_EPS] = eps;
+    }
+    block_reduce_stats(st, valid && lane == 0, a.partials);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K2b: CartPole, LANES threads per lane, H = 128 hidden units split across them, weights in registers.
 // Every thread of a group carries the full (redundant) f64 physics so that no state is exchanged;
 // only the two partial logits cross lanes (log2(LANES) xor-shuffles each).
@@ -1438,6 +1600,40 @@ size_t rollout_smem_bytes(const rl_mlp *net) {
 template <class EnvT>
 rl_status launch_rollout(rl_ctx *ctx, const typename EnvT::Params &p, RolloutArgs &a, const rl_mlp *net, bool replay,
                          int *nblocks_out) {
+    // Network actors on few lanes: one warp per lane (K2g).  K2a's serial evaluation wins back once its E / 32 warps fill the
+    // GPU (scripts/time_rollout_shapes.py); RL_ROLLOUT_WARP=0 | 1 forces the choice (measurements).
+    const bool uses_net = net && (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY || (a.actor_kind == RL_ACTOR_EPS_GREEDY_Q && a.eps < 1.0));
+    if (uses_net) {
+        const DeepLayout d = rl_mlp_layout(net->in_dim, net->n_hidden, net->hid, net->out_dim);
+        const size_t wsmem = rollout_warp_smem_bytes(d, WG_THREADS / 32);
+        static const char *force = getenv("RL_ROLLOUT_WARP");
+        // Cost model fitted to scripts/time_rollout_shapes.py (profiles/r2T_rollout_shapes.txt, r2U_rollout_shapes.txt), in clocks
+        // per step.  K2a is latency-bound -- ~3000 for env + noise + actor + record, plus the module evaluated serially: 80
+        // per unit in its packed one-hidden-layer form (160 with tanh / sigmoid), 26 per parameter otherwise -- until its
+        // E / 32 warps fill the GPU (~40 K envs).  K2g issues for 28 resident warps per SM: ~8000 + 1.4 per parameter + 600
+        // per hidden layer for every wave of 148 x 28 envs.
+        constexpr bool PACK8 = EnvT::MAXF <= 5 && EnvT::MAXA <= 2;
+        const bool smooth = !(net->act == RL_ACT_RELU || net->act == RL_ACT_IDENTITY);
+        const double ka = 3000.0 + ((PACK8 && net->n_hidden == 1) ? (smooth ? 160.0 : 80.0) * net->hidden : 26.0 * (double)net->n_params);
+        const double kg = 8000.0 + 1.4 * (double)net->n_params + 600.0 * net->n_hidden;
+        const double waves_g = (double)((a.E + 148ull * 28 - 1) / (148ull * 28)), fill_a = a.E > 40000 ? (double)a.E / 40000.0 : 1.0;
+        const bool pick = force ? force[0] == '1' : (a.E <= (uint64_t)WG_MAX_ENVS && kg * waves_g < ka * fill_a);
+        if (pick && wsmem <= 200 * 1024) {
+            const unsigned wgrid = rl_grid_for(a.E, WG_THREADS / 32);
+            double *wpartials;
+            RL_TRY(rl_ctx_scratch(ctx, ((size_t)wgrid + 1) * ST_COUNT * sizeof(double), (void **)&wpartials));
+            a.partials = wpartials + ST_COUNT;
+            *nblocks_out = (int)wgrid;
+            if (replay) {
+                RL_CUDA(ctx, cudaFuncSetAttribute(rollout_warp_kernel<EnvT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                RL_LAUNCH(ctx, (rollout_warp_kernel<EnvT, true>), wgrid, WG_THREADS, wsmem, p, a);
+            } else {
+                RL_CUDA(ctx, cudaFuncSetAttribute(rollout_warp_kernel<EnvT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+                RL_LAUNCH(ctx, (rollout_warp_kernel<EnvT, false>), wgrid, WG_THREADS, wsmem, p, a);
+            }
+            return RL_OK;
+        }
+    }
     const unsigned block = 128, grid = rl_grid_for(a.E, block);
     const size_t smem = rollout_smem_bytes<EnvT>(net);
     double *partials;

@@ -528,38 +528,7 @@ struct AnyShape {
 // sweep of the layer above (lanes over inputs, fixed unit) are conflict-free; the warp's f64 totals use the same layout;
 // activations, tangents and deltas of the sample in flight live in per-warp buffers of ANY_DEEP_MAXH floats.
 constexpr int ANY_DEEP_MAXH = 256;
-struct DeepLayout {
-    int n_layers;                  // Linear layers = L + 1
-    int in[4], out[4], ld[4];      // per Linear: inputs, units, pitch (odd)
-    int off_w[4], off_b[4];        // offsets in the padded layout
-    int nat_w[4];                  // offsets in Module::variables() order
-    int P, P_pad, maxH;
-};
-__host__ __device__ inline DeepLayout deep_layout(const AnyShape &sh) {
-    DeepLayout d{};
-    d.n_layers = sh.L + 1;
-    int prev = sh.F, off = 0, nat = 0, maxH = 0;
-    for (int l = 0; l <= sh.L; ++l) {
-        const int out = l < sh.L ? sh.Hs[l] : sh.A;
-        d.in[l] = prev; d.out[l] = out; d.ld[l] = out | 1;
-        d.off_w[l] = off; off += prev * d.ld[l];
-        d.off_b[l] = off; off += out;
-        d.nat_w[l] = nat; nat += prev * out + out;
-        if (l < sh.L && out > maxH) maxH = out;
-        prev = out;
-    }
-    d.P = nat; d.P_pad = off; d.maxH = maxH;
-    return d;
-}
-// natural parameter index -> index in the padded transposed layout
-__host__ __device__ inline int deep_pidx(const DeepLayout &d, int i) {
-    for (int l = 0; l < d.n_layers; ++l) {
-        const int r = i - d.nat_w[l], nw = d.in[l] * d.out[l];
-        if (r < nw) return d.off_w[l] + (r % d.in[l]) * d.ld[l] + r / d.in[l];
-        if (r < nw + d.out[l]) return d.off_b[l] + (r - nw);
-    }
-    return 0;
-}
+__host__ __device__ inline DeepLayout deep_layout(const AnyShape &sh) { return rl_mlp_layout(sh.F, sh.L, sh.Hs, sh.A); }
 
 // floats per activation / tangent / delta buffer: the widest hidden layer, rounded up to a multiple of 32
 __host__ __device__ inline int any_buf_stride(const DeepLayout &d) { return (d.maxH + 31) / 32 * 32; }
