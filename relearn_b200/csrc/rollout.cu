@@ -358,20 +358,22 @@ __global__ void __launch_bounds__(128) rollout_kernel(typename EnvT::Params p, R
 // noise state and the actor redundantly -- same values in every thread, no divergence; thread 0 stores.
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 128, WG_MAX_ENVS = 65536;
-__host__ __device__ inline size_t rollout_warp_smem_bytes(const DeepLayout &d, int nwarps) {
-    return ((size_t)d.P_pad + (size_t)nwarps * 2 * ((d.maxH + 31) / 32 * 32)) * sizeof(float);
+// GL threads of a warp per env (32 / GL envs per warp): the redundant part of a step is shared by fewer threads as GL shrinks,
+// the module's serial part per thread grows.
+__host__ __device__ inline size_t rollout_warp_smem_bytes(const DeepLayout &d, int nwarps, int GL) {
+    return ((size_t)d.P_pad + (size_t)nwarps * (32 / GL) * 2 * ((d.maxH + 31) / 32 * 32)) * sizeof(float);
 }
 
-template <class EnvT>
+template <class EnvT, int GL>
 __device__ __forceinline__ void mlp_logits_warp(const MlpView &m, const DeepLayout &d, const float *__restrict__ th, float *__restrict__ hb,
                                                 int HB, const float *obs, float *z) {
-    const int lane = threadIdx.x & 31, L = m.n_hidden, A = m.out_dim;
+    const int sub = threadIdx.x & (GL - 1), L = m.n_hidden, A = m.out_dim;
     const float *vin = nullptr;  // layer 0 reads the observation from registers
     for (int l = 0; l < L; ++l) {
         const int n_in = d.in[l], n_out = d.out[l], ld = d.ld[l];
         const float *Wt = th + d.off_w[l], *bb = th + d.off_b[l];
         float *hout = hb + (l & 1) * HB;
-        for (int j = lane; j < n_out; j += 32) {
+        for (int j = sub; j < n_out; j += GL) {
             float a0 = bb[j], a1 = 0.0f;
             if (l == 0) {
 #pragma unroll
@@ -395,7 +397,7 @@ __device__ __forceinline__ void mlp_logits_warp(const MlpView &m, const DeepLayo
     float pz[EnvT::MAXA];
 #pragma unroll
     for (int k = 0; k < EnvT::MAXA; ++k) pz[k] = 0.0f;
-    for (int j = lane; j < n_in; j += 32) {
+    for (int j = sub; j < n_in; j += GL) {
         const float h = vin[j];
 #pragma unroll
         for (int k = 0; k < EnvT::MAXA; ++k)
@@ -405,49 +407,52 @@ __device__ __forceinline__ void mlp_logits_warp(const MlpView &m, const DeepLayo
     for (int k = 0; k < EnvT::MAXA; ++k) {
         float v = pz[k];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);  // stays inside the env's GL threads
         z[k] = k < A ? v + bb[k] : 0.0f;
     }
     __syncwarp();  // the buffers are reused by the next step
 }
 
-template <class EnvT, bool REPLAY>
+template <class EnvT, bool REPLAY, int GL>
 __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT::Params p, RolloutArgs a) {
     extern __shared__ __align__(16) float sw[];
     const DeepLayout d = rl_mlp_layout(a.net.in_dim, a.net.n_hidden, a.net.hid, a.net.out_dim);
     const int HB = (d.maxH + 31) / 32 * 32;
     for (int i = threadIdx.x; i < d.P; i += blockDim.x) sw[deep_pidx(d, i)] = a.net.params[i];
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    float *hb = sw + d.P_pad + (size_t)warp * 2 * HB;
+    const int lane = threadIdx.x & 31, sub = lane & (GL - 1), grp = threadIdx.x / GL;  // grp: env slot in the CTA
+    float *hb = sw + d.P_pad + (size_t)grp * 2 * HB;
 
-    const uint64_t e = (uint64_t)blockIdx.x * nwarps + warp;
+    const uint64_t e = (uint64_t)blockIdx.x * (WG_THREADS / GL) + grp;
     const bool valid = e < a.E;
+    const uint64_t e_safe = valid ? e : 0;
     LaneStats st;
     st.init();
-    if (valid) {
-        const int F = a.F;
-        LaneNoise<REPLAY> nz;
-        nz.init(a.noise, a.lane_offset + e, e);
-        const uint32_t t0 = a.noise.step_counter;
-        typename EnvT::State s;
-        float obs[EnvT::MAXF], last_obs[EnvT::MAXF];
+    const int F = a.F;
+    LaneNoise<REPLAY> nz;
+    nz.init(a.noise, a.lane_offset + e_safe, e_safe);
+    const uint32_t t0 = a.noise.step_counter;
+    typename EnvT::State s;
+    float obs[EnvT::MAXF], last_obs[EnvT::MAXF];
 #pragma unroll
-        for (int f = 0; f < EnvT::MAXF; ++f) obs[f] = last_obs[f] = 0.0f;
-        uint32_t n = a.min_steps ? a.min_steps + a.slack : 0;  // take_steps.rs:20-31
-        uint32_t i = 0;
-        int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
-        if (n > 0) {  // train.rs:135: every period starts fresh episodes
-            nz.set_step(t0);
-            EnvT::template reset<REPLAY>(p, s, nz);
-            EnvT::observe(p, s, obs);
-        }
-        while (n > 0) {
+    for (int f = 0; f < EnvT::MAXF; ++f) obs[f] = last_obs[f] = 0.0f;
+    uint32_t n = (valid && a.min_steps) ? a.min_steps + a.slack : 0;  // take_steps.rs:20-31
+    uint32_t i = 0;
+    int succ_last = RL_TERMINATE, succ_prev = RL_TERMINATE;
+    if (n > 0) {  // train.rs:135: every period starts fresh episodes
+        nz.set_step(t0);
+        EnvT::template reset<REPLAY>(p, s, nz);
+        EnvT::observe(p, s, obs);
+    }
+    // The envs of a warp may stop at different steps (slack): the warp leaves the loop together, the module is evaluated for
+    // every env of the warp (it holds the warp's shuffles and barriers), everything else only for the envs still collecting.
+    while (__any_sync(0xffffffffu, n > 0)) {
+        float z[EnvT::MAXA];
+        mlp_logits_warp<EnvT, GL>(a.net, d, sw, hb, HB, obs, z);
+        if (n > 0) {
             nz.set_step(t0 + i);
-            float z[EnvT::MAXA];
-            mlp_logits_warp<EnvT>(a.net, d, sw, hb, HB, obs, z);
             const uint32_t action = actor_act<EnvT, REPLAY>(a, p, s, nz, e, i, z);
-            if (lane == 0) {
+            if (sub == 0) {
 #pragma unroll
                 for (int f = 0; f < EnvT::MAXF; ++f)
                     if (f < F) a.obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
@@ -458,7 +463,7 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
             const int sc = EnvT::template step<REPLAY>(p, s, action, nz, r);
             if (sc == RL_INTERRUPT) {
                 EnvT::observe(p, s, obs);
-                if (lane == 0) {
+                if (sub == 0) {
 #pragma unroll
                     for (int f = 0; f < EnvT::MAXF; ++f)
                         if (f < F) a.next_obs[((uint64_t)i * F + f) * a.E + e] = obs[f];
@@ -469,7 +474,7 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
                 EnvT::template reset<REPLAY>(p, s, nz);
             }
             EnvT::observe(p, s, obs);
-            if (lane == 0) {
+            if (sub == 0) {
                 a.action[(uint64_t)i * a.E + e] = (uint8_t)action;
                 a.reward[(uint64_t)i * a.E + e] = r;
                 a.succ[(uint64_t)i * a.E + e] = (uint8_t)sc;
@@ -481,6 +486,8 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
             n -= 1;
             if (sc != RL_CONTINUE && n <= a.slack) n = 0;  // take_steps.rs:83-88
         }
+    }
+    if (valid) {
         // VecBuffer::end_experience -> finalize_last_episode (buffers/mod.rs:237-261)
         uint32_t len = i;
         uint32_t flags = 0;
@@ -488,10 +495,10 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
         if (i > 0 && succ_last == RL_CONTINUE) {
             len = i - 1;
             flags = 1;
-            if (lane == 0) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
+            if (sub == 0) a.succ[(uint64_t)len * a.E + e] = RL_PAD;
             if (len > 0 && succ_prev == RL_CONTINUE) {
                 flags = 3;
-                if (lane == 0) {
+                if (sub == 0) {
                     a.succ[(uint64_t)(len - 1) * a.E + e] = RL_INTERRUPT;
 #pragma unroll
                     for (int f = 0; f < EnvT::MAXF; ++f)
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
                 eps += 1.0;
             }
         }
-        if (lane == 0) {
+        if (sub == 0) {
             a.lane_len[e] = len;
             a.lane_flags[e] = (uint8_t)flags;
             nz.finish(a.noise, e);
@@ -508,7 +515,7 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
         st.v[ST_STORED_STEPS] = (double)len;
         st.v[ST_STORED_EPS] = eps;
     }
-    block_reduce_stats(st, valid && lane == 0, a.partials);
+    block_reduce_stats(st, valid && sub == 0, a.partials);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1605,32 +1612,43 @@ rl_status launch_rollout(rl_ctx *ctx, const typename EnvT::Params &p, RolloutArg
     const bool uses_net = net && (a.actor_kind == RL_ACTOR_CATEGORICAL_POLICY || (a.actor_kind == RL_ACTOR_EPS_GREEDY_Q && a.eps < 1.0));
     if (uses_net) {
         const DeepLayout d = rl_mlp_layout(net->in_dim, net->n_hidden, net->hid, net->out_dim);
-        const size_t wsmem = rollout_warp_smem_bytes(d, WG_THREADS / 32);
+        // eight threads per env (four envs per warp) for the smaller modules once that still gives every scheduler a few warps
+        // (E = 4096: 5-128 tanh 1.31 -> 0.94 ms per period, 5-256 ReLU 1.51 -> 1.22; 5-64-64 tanh 2.07 -> 3.06: its serial part per
+        // thread grows fourfold), a whole warp per env otherwise
+        const int GL = (a.E >= 2368 && net->n_params <= 3000) ? 8 : 32;
+        const size_t wsmem = rollout_warp_smem_bytes(d, WG_THREADS / 32, GL);
         static const char *force = getenv("RL_ROLLOUT_WARP");
-        // Cost model fitted to scripts/time_rollout_shapes.py (profiles/r2T_rollout_shapes.txt, r2U_rollout_shapes.txt), in clocks
-        // per step.  K2a is latency-bound -- ~3000 for env + noise + actor + record, plus the module evaluated serially: 80
-        // per unit in its packed one-hidden-layer form (160 with tanh / sigmoid), 26 per parameter otherwise -- until its
-        // E / 32 warps fill the GPU (~40 K envs).  K2g issues for 28 resident warps per SM: ~8000 + 1.4 per parameter + 600
-        // per hidden layer for every wave of 148 x 28 envs.
+        // Cost model fitted to scripts/time_rollout_shapes.py (profiles/r2_summary.md section 7), in clocks per step.  K2a is
+        // latency-bound -- ~3000 for env + noise + actor + record, plus the module evaluated serially: 80 per unit in its packed
+        // one-hidden-layer form (160 with tanh / sigmoid), 26 per parameter otherwise -- until its E / 32 warps fill the GPU
+        // (~40 K envs).  K2g issues for its resident warps: per wave of 148 x 28 warps ~8000 + 1.4 per parameter + 600 per hidden
+        // layer with a warp per env; with four envs per warp the fixed part is shared and the module's part grows fourfold.
         constexpr bool PACK8 = EnvT::MAXF <= 5 && EnvT::MAXA <= 2;
         const bool smooth = !(net->act == RL_ACT_RELU || net->act == RL_ACT_IDENTITY);
         const double ka = 3000.0 + ((PACK8 && net->n_hidden == 1) ? (smooth ? 160.0 : 80.0) * net->hidden : 26.0 * (double)net->n_params);
-        const double kg = 8000.0 + 1.4 * (double)net->n_params + 600.0 * net->n_hidden;
-        const double waves_g = (double)((a.E + 148ull * 28 - 1) / (148ull * 28)), fill_a = a.E > 40000 ? (double)a.E / 40000.0 : 1.0;
+        const double kg = 8000.0 + (1.4 * (double)net->n_params + 600.0 * net->n_hidden) * (32 / GL);
+        const uint64_t envs_per_wave = 148ull * 28 * (32 / GL);
+        const double waves_g = (double)((a.E + envs_per_wave - 1) / envs_per_wave), fill_a = a.E > 40000 ? (double)a.E / 40000.0 : 1.0;
         const bool pick = force ? force[0] == '1' : (a.E <= (uint64_t)WG_MAX_ENVS && kg * waves_g < ka * fill_a);
         if (pick && wsmem <= 200 * 1024) {
-            const unsigned wgrid = rl_grid_for(a.E, WG_THREADS / 32);
+            const unsigned wgrid = rl_grid_for(a.E, WG_THREADS / GL);
             double *wpartials;
             RL_TRY(rl_ctx_scratch(ctx, ((size_t)wgrid + 1) * ST_COUNT * sizeof(double), (void **)&wpartials));
             a.partials = wpartials + ST_COUNT;
             *nblocks_out = (int)wgrid;
+#define RL_WARP_LAUNCH(RP, G)                                                                                                          \
+    do {                                                                                                                               \
+        RL_CUDA(ctx, cudaFuncSetAttribute(rollout_warp_kernel<EnvT, RP, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem)); \
+        RL_LAUNCH(ctx, (rollout_warp_kernel<EnvT, RP, G>), wgrid, WG_THREADS, wsmem, p, a);                                            \
+    } while (0)
             if (replay) {
-                RL_CUDA(ctx, cudaFuncSetAttribute(rollout_warp_kernel<EnvT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-                RL_LAUNCH(ctx, (rollout_warp_kernel<EnvT, true>), wgrid, WG_THREADS, wsmem, p, a);
+                if (GL == 8) RL_WARP_LAUNCH(true, 8);
+                else RL_WARP_LAUNCH(true, 32);
             } else {
-                RL_CUDA(ctx, cudaFuncSetAttribute(rollout_warp_kernel<EnvT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-                RL_LAUNCH(ctx, (rollout_warp_kernel<EnvT, false>), wgrid, WG_THREADS, wsmem, p, a);
+                if (GL == 8) RL_WARP_LAUNCH(false, 8);
+                else RL_WARP_LAUNCH(false, 32);
             }
+#undef RL_WARP_LAUNCH
             return RL_OK;
         }
     }
