@@ -1628,8 +1628,12 @@ rl_status launch_rollout(rl_ctx *ctx, const typename EnvT::Params &p, RolloutArg
         const double ka = 3000.0 + ((PACK8 && net->n_hidden == 1) ? (smooth ? 160.0 : 80.0) * net->hidden : 26.0 * (double)net->n_params);
         const double kg = 8000.0 + (1.4 * (double)net->n_params + 600.0 * net->n_hidden) * (32 / GL);
         const uint64_t envs_per_wave = 148ull * 28 * (32 / GL);
-        const double waves_g = (double)((a.E + envs_per_wave - 1) / envs_per_wave), fill_a = a.E > 40000 ? (double)a.E / 40000.0 : 1.0;
-        const bool pick = force ? force[0] == '1' : (a.E <= (uint64_t)WG_MAX_ENVS && kg * waves_g < ka * fill_a);
+        // (below a full wave K2g is latency-bound too: ~4.2 clk per instruction of one env's step)
+        int units = 0;
+        for (int l = 0; l < net->n_hidden; ++l) units += net->hid[l];
+        const double lat_g = 4.2 * (700.0 + (3.0 * (double)net->n_params + (smooth ? 40.0 : 0.0) * units) / GL);
+        const double thr_g = kg * (double)a.E / (double)envs_per_wave, fill_a = a.E > 40000 ? (double)a.E / 40000.0 : 1.0;
+        const bool pick = force ? force[0] == '1' : (a.E <= (uint64_t)WG_MAX_ENVS && (lat_g > thr_g ? lat_g : thr_g) < ka * fill_a);
         if (pick && wsmem <= 200 * 1024) {
             const unsigned wgrid = rl_grid_for(a.E, WG_THREADS / GL);
             double *wpartials;
