@@ -740,3 +740,35 @@ def test_ucb1_oracle_restates_the_reference_rules():
     assert o.act(1, training=False) == 2  # counts [3, 2, 3, 2]: last maximum
     with pytest.raises(ValueError):
         O.Ucb1Oracle(2, 2, (0.0, float("inf")))
+
+
+def test_deep_mlp_restatement_and_parameter_order():
+    """Mlp::forward with several hidden layers (mlp.rs:139-151: activation between Linear layers, none on the output) and
+    Module::variables() order ([W, b] per Linear, layers in order: mlp.rs:126-128, linear.rs:108-110): the torch restatement,
+    the numpy one used by the GPU tests and a hand-written loop agree; the host-side parameter count matches."""
+    torch = pytest.importorskip("torch")
+    from oracle import tensor_oracle as TO
+    import relearn_b200.modules as M
+    from tests import parity as P
+
+    rng = np.random.default_rng(3)
+    F, hidden, A = 6, [9, 4, 7], 3
+    flat = M.init_params(rng, F, hidden, A)
+    assert flat.size == M.num_params(F, hidden, A) == 6 * 9 + 9 + 9 * 4 + 4 + 4 * 7 + 7 + 7 * 3 + 3
+    assert M.num_params(5, 128, 2) == M.num_params(5, [128], 2) == 5 * 128 + 128 + 128 * 2 + 2
+    x = rng.normal(size=(11, F)).astype(np.float32)
+    params = TO.unflatten_mlp(torch.tensor(flat, dtype=torch.float64), F, hidden, A)
+    assert [tuple(p.shape) for p in params] == [(9, 6), (9,), (4, 9), (4,), (7, 4), (7,), (3, 7), (3,)]
+    with TO.mlp_activation("tanh"):
+        got = TO.mlp_forward(params, torch.tensor(x, dtype=torch.float64)).numpy()
+    h = x.astype(np.float64)
+    o = 0
+    dims = [F] + hidden + [A]
+    for li in range(len(dims) - 1):
+        w = flat[o:o + dims[li + 1] * dims[li]].astype(np.float64).reshape(dims[li + 1], dims[li]); o += w.size
+        b = flat[o:o + dims[li + 1]].astype(np.float64); o += b.size
+        h = np.stack([[sum(w[j, f] * row[f] for f in range(dims[li])) + b[j] for j in range(dims[li + 1])] for row in h])
+        if li < len(dims) - 2:
+            h = np.tanh(h)
+    np.testing.assert_allclose(got, h, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(P.mlp_forward_any(flat, F, hidden, A, x, "tanh"), h.astype(np.float32), rtol=1e-6, atol=1e-7)
