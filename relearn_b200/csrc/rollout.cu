@@ -361,7 +361,7 @@ constexpr int WG_THREADS = 128, WG_MAX_ENVS = 65536;
 // GL threads of a warp per env (32 / GL envs per warp): the redundant part of a step is shared by fewer threads as GL shrinks,
 // the module's serial part per thread grows.
 __host__ __device__ inline size_t rollout_warp_smem_bytes(const DeepLayout &d, int nwarps, int GL) {
-    return ((size_t)d.P_pad + (size_t)nwarps * (32 / GL) * 2 * ((d.maxH + 31) / 32 * 32)) * sizeof(float);
+    return ((size_t)((d.P_pad + 3) & ~3) + (size_t)nwarps * (32 / GL) * 2 * ((d.maxH + 31) / 32 * 32)) * sizeof(float);
 }
 
 template <class EnvT, int GL>
@@ -381,6 +381,13 @@ __device__ __forceinline__ void mlp_logits_warp(const MlpView &m, const DeepLayo
                     if (f < n_in) a0 = fmaf(Wt[f * ld + j], obs[f], a0);
             } else {
                 int f = 0;
+                for (; f + 3 < n_in; f += 4) {  // four inputs per broadcast LDS.128 (the buffers are 16-byte aligned)
+                    const float4 v = *reinterpret_cast<const float4 *>(vin + f);
+                    a0 = fmaf(Wt[f * ld + j], v.x, a0);
+                    a1 = fmaf(Wt[(f + 1) * ld + j], v.y, a1);
+                    a0 = fmaf(Wt[(f + 2) * ld + j], v.z, a0);
+                    a1 = fmaf(Wt[(f + 3) * ld + j], v.w, a1);
+                }
                 for (; f + 1 < n_in; f += 2) {
                     a0 = fmaf(Wt[f * ld + j], vin[f], a0);
                     a1 = fmaf(Wt[(f + 1) * ld + j], vin[f + 1], a1);
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(WG_THREADS) rollout_warp_kernel(typename EnvT:
     for (int i = threadIdx.x; i < d.P; i += blockDim.x) sw[deep_pidx(d, i)] = a.net.params[i];
     __syncthreads();
     const int lane = threadIdx.x & 31, sub = lane & (GL - 1), grp = threadIdx.x / GL;  // grp: env slot in the CTA
-    float *hb = sw + d.P_pad + (size_t)grp * 2 * HB;
+    float *hb = sw + ((d.P_pad + 3) & ~3) + (size_t)grp * 2 * HB;
 
     const uint64_t e = (uint64_t)blockIdx.x * (WG_THREADS / GL) + grp;
     const bool valid = e < a.E;
